@@ -1,0 +1,611 @@
+// Batched GEMM for the AVMoE token resampler (conv_adapter + fc) and its gradients.
+//
+// Product path: a persistent, warp-specialised tcgen05 kernel for sm_100a
+//   warp 0     TMA producer   (cp.async.bulk.tensor 3-D tiles, 128/64/32-byte swizzle, OOB zero fill)
+//   warp 1     MMA issuer     (one elected lane: tcgen05.mma.cta_group::1, M=128, N<=256, fp32 accum in TMEM)
+//   warps 2-5  epilogue       (tcgen05.ld 32x32b -> bias/scale -> vectorised or atomic global stores)
+// with a multi-stage smem ring (full/empty mbarriers) and TWO accumulator stages in TMEM so the
+// epilogue of tile i overlaps the main loop of tile i+1.
+//
+// Both operands may be K-major or MN-major (UMMA descriptors support either for BF16 and TF32), which
+// is what lets every gradient GEMM of the resampler consume the token-major activations in place,
+// with no transposed copies (see DESIGN.md "resampler").
+//
+// Replaces: nn.Conv2d(Nx->N,1x1) over the token axis + nn.Linear(Cx->C)
+//           (AVMOE/AVE/nets/net_trans_v3.py:445-446,469-471) and their autograd.
+#include <mutex>
+
+#include "common.cuh"
+
+namespace avmoe {
+
+// ------------------------------------------------------------------------------------------------
+// PTX wrappers
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred P1;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, P1;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// Bounded wait: a protocol bug must surface as a trapped kernel (cudaErrorLaunchFailure), never as a hung GPU.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    if (clock64() - t0 > 4000000000ll) {  // ~2 s at 2 GHz
+      printf("avmoe gemm: mbarrier wait timed out (block %d thread %d bar %u parity %u)\n", blockIdx.x, threadIdx.x, bar, parity);
+      __trap();
+    }
+  }
+}
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(dst),
+      "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tcgen05_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+template <bool kTf32>
+__device__ __forceinline__ void tcgen05_mma(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  if constexpr (kTf32) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+  } else {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+  }
+}
+__device__ __forceinline__ void tmem_ld_32x32b_x32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// ------------------------------------------------------------------------------------------------
+// kernel parameters
+// ------------------------------------------------------------------------------------------------
+struct OperandTile {
+  int kmajor;          // 1: [rows][K] tile (one TMA box); 0: MN-major, tile = nchunks boxes of [BK rows][chunk]
+  int nchunks;         // boxes per stage
+  int chunk_elems;     // MN elements per box (MN-major only)
+  int batch_extent;    // MN-major batched over N: per-batch MN extent (Nb); else 0
+  uint32_t chunk_bytes;  // smem bytes per box
+  uint32_t k_advance;    // descriptor start-address advance per MMA (bytes)
+  uint64_t desc_base;    // descriptor without the start address
+};
+
+struct GemmParams {
+  CUtensorMap tmA, tmB;
+  OperandTile a, b;
+  int BN;              // tile N (multiple of 32, <= 256)
+  int BK;              // K elements per stage
+  int mma_per_stage;
+  int num_stages;
+  uint32_t stage_bytes_a, stage_bytes_b;
+  uint32_t idesc;
+  int tmem_cols;       // power of two >= 2*BN
+  int tiles_m, tiles_n, splits;
+  int k_iters;         // total stages over the whole (batch,K) reduction
+  int k_iters_per_batch;  // batched-K: stages per batch element; else k_iters
+  int k_iters_per_split;
+  // epilogue
+  void* D;
+  int d_bf16;
+  long long M, N, Nb, ldd, d_bstride;
+  int n_batched;       // D is [b][M][Nb]
+  float alpha;
+  const float* row_bias;
+  const float* col_scale;
+  const float* col_bias;
+  int atomic;
+};
+
+static constexpr int kGemmThreads = 192;
+static constexpr int kBM = 128;
+
+template <bool kTf32>
+__global__ void __launch_bounds__(kGemmThreads, 1) gemm_tcgen05_kernel(const __grid_constant__ GemmParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  // carve: [stages][A tile][B tile] (1024-aligned), then barriers
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const uint32_t stage_bytes = p.stage_bytes_a + p.stage_bytes_b;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)p.num_stages * stage_bytes);
+  uint64_t* full_bar = bars;                       // [num_stages]
+  uint64_t* empty_bar = bars + p.num_stages;       // [num_stages]
+  uint64_t* tmem_full = bars + 2 * p.num_stages;   // [2]
+  uint64_t* tmem_empty = tmem_full + 2;            // [2]
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&p.tmA) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&p.tmB) : "memory");
+    for (int s = 0; s < p.num_stages; ++s) {
+      mbar_init(smem_u32(&full_bar[s]), 1);
+      mbar_init(smem_u32(&empty_bar[s]), 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(smem_u32(&tmem_full[s]), 1);
+      mbar_init(smem_u32(&tmem_empty[s]), 4);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_smem)),
+                 "r"((uint32_t)p.tmem_cols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  const int tiles_mn = p.tiles_m * p.tiles_n;
+  const int num_tiles = tiles_mn * p.splits;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int split = tile / tiles_mn;
+        const int mn = tile - split * tiles_mn;
+        const int m0 = (mn % p.tiles_m) * kBM;
+        const int n0 = (mn / p.tiles_m) * p.BN;
+        const int k_begin = split * p.k_iters_per_split;
+        const int k_end = min(p.k_iters, k_begin + p.k_iters_per_split);
+        for (int kit = k_begin; kit < k_end; ++kit) {
+          mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1);
+          const uint32_t fb = smem_u32(&full_bar[stage]);
+          mbar_expect_tx(fb, stage_bytes);
+          const uint32_t sa = smem_u32(smem + (size_t)stage * stage_bytes);
+          const uint32_t sb = sa + p.stage_bytes_a;
+          const int kb = kit / p.k_iters_per_batch;
+          const int kc = (kit - kb * p.k_iters_per_batch) * p.BK;
+          if (p.a.kmajor) {
+            tma_load_3d(sa, &p.tmA, fb, kc, m0, kb);
+          } else {
+            for (int i = 0; i < p.a.nchunks; ++i)
+              tma_load_3d(sa + i * p.a.chunk_bytes, &p.tmA, fb, m0 + i * p.a.chunk_elems, kc, 0);
+          }
+          if (p.b.kmajor) {
+            tma_load_3d(sb, &p.tmB, fb, kc, n0, kb);
+          } else {
+            for (int i = 0; i < p.b.nchunks; ++i) {
+              int n = n0 + i * p.b.chunk_elems;
+              int bb = 0;
+              if (p.b.batch_extent) { bb = n / p.b.batch_extent; n -= bb * p.b.batch_extent; }
+              tma_load_3d(sb + i * p.b.chunk_bytes, &p.tmB, fb, n, kc, bb);
+            }
+          }
+          if (++stage == p.num_stages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    int stage = 0;
+    uint32_t phase = 0;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int split = tile / tiles_mn;
+      const int k_begin = split * p.k_iters_per_split;
+      const int k_end = min(p.k_iters, k_begin + p.k_iters_per_split);
+      mbar_wait(smem_u32(&tmem_empty[acc]), acc_phase ^ 1);
+      tcgen05_fence_after();
+      const uint32_t d_tmem = tmem_base + (uint32_t)(acc * p.BN);
+      for (int kit = k_begin; kit < k_end; ++kit) {
+        mbar_wait(smem_u32(&full_bar[stage]), phase);
+        tcgen05_fence_after();
+        if (lane == 0) {
+          const uint32_t sa = smem_u32(smem + (size_t)stage * stage_bytes);
+          const uint32_t sb = sa + p.stage_bytes_a;
+          for (int j = 0; j < p.mma_per_stage; ++j) {
+            const uint64_t adesc = p.a.desc_base | (uint64_t)(((sa + j * p.a.k_advance) & 0x3FFFF) >> 4);
+            const uint64_t bdesc = p.b.desc_base | (uint64_t)(((sb + j * p.b.k_advance) & 0x3FFFF) >> 4);
+            tcgen05_mma<kTf32>(d_tmem, adesc, bdesc, p.idesc, (kit > k_begin || j > 0) ? 1u : 0u);
+          }
+          tcgen05_commit(smem_u32(&empty_bar[stage]));
+          if (kit == k_end - 1) tcgen05_commit(smem_u32(&tmem_full[acc]));
+        }
+        __syncwarp();
+        if (++stage == p.num_stages) { stage = 0; phase ^= 1; }
+      }
+      if (k_end <= k_begin && lane == 0) tcgen05_commit(smem_u32(&tmem_full[acc]));  // empty split: still signal
+      __syncwarp();
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  } else {
+    // ===================== epilogue (warps 2..5) =====================
+    const int quarter = warp & 3;  // TMEM lane quarter this warp may access
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int split = tile / tiles_mn;
+      const int mn = tile - split * tiles_mn;
+      const int m0 = (mn % p.tiles_m) * kBM;
+      const int n0 = (mn / p.tiles_m) * p.BN;
+      const int k_begin = split * p.k_iters_per_split;
+      const bool has_k = k_begin < p.k_iters;
+      mbar_wait(smem_u32(&tmem_full[acc]), acc_phase);
+      tcgen05_fence_after();
+      const long long m = m0 + quarter * 32 + lane;
+      const bool add_bias = (split == 0);
+      const float rb = (add_bias && p.row_bias && m < p.M) ? p.row_bias[m] : 0.f;
+      for (int g = 0; g < p.BN / 32; ++g) {
+        uint32_t r[32];
+        const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * p.BN + g * 32);
+        tmem_ld_32x32b_x32(taddr, r);
+        if (m < p.M) {
+#pragma unroll
+          for (int v = 0; v < 8; ++v) {
+            const long long n = (long long)n0 + g * 32 + v * 4;
+            if (n >= p.N) break;
+            long long bb = 0, c = n;
+            if (p.n_batched) { bb = n / p.Nb; c = n - bb * p.Nb; }
+            float o[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              float val = has_k ? __uint_as_float(r[v * 4 + e]) * p.alpha : 0.f;
+              if (add_bias) {
+                // a 4-vector never straddles a batch boundary when Nb % 4 == 0 (checked on the host)
+                const long long ce = c + e;
+                if (p.row_bias) val += rb * (p.col_scale ? p.col_scale[ce < p.Nb ? ce : 0] : 1.f);
+                if (p.col_bias) val += p.col_bias[ce < p.Nb ? ce : 0];
+              }
+              o[e] = val;
+            }
+            const long long off = bb * p.d_bstride + m * p.ldd + c;
+            const int valid = (int)min((long long)4, p.N - n);
+            if (p.atomic) {
+              float* dp = reinterpret_cast<float*>(p.D) + off;
+              for (int e = 0; e < valid; ++e) atomicAdd(dp + e, o[e]);
+            } else if (p.d_bf16) {
+              __nv_bfloat16* dp = reinterpret_cast<__nv_bfloat16*>(p.D) + off;
+              if (valid == 4) store4<__nv_bfloat16>(dp, o);
+              else for (int e = 0; e < valid; ++e) dp[e] = __float2bfloat16_rn(o[e]);
+            } else {
+              float* dp = reinterpret_cast<float*>(p.D) + off;
+              if (valid == 4) store4<float>(dp, o);
+              else for (int e = 0; e < valid; ++e) dp[e] = o[e];
+            }
+          }
+        }
+      }
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(&tmem_empty[acc]));
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)p.tmem_cols) : "memory");
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// SIMT cross-check kernel (same semantics, arbitrary strides).  impl=1 only; not a product path.
+// ------------------------------------------------------------------------------------------------
+struct SimtParams {
+  const void* A; const void* B; void* D;
+  int bf16, d_bf16;
+  long long M, N, K, Nb;
+  int a_kmajor, b_kmajor, a_batch, b_batch, n_batched;
+  long long lda, ldb, ldd, a_bstride, b_bstride, d_bstride;
+  float alpha;
+  const float* row_bias; const float* col_scale; const float* col_bias;
+  int accumulate;
+};
+
+template <typename T>
+__global__ void gemm_simt_kernel(const SimtParams p) {
+  const long long n = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  const long long m = blockIdx.y * (long long)blockDim.y + threadIdx.y;
+  if (m >= p.M || n >= p.N) return;
+  const T* A = reinterpret_cast<const T*>(p.A);
+  const T* B = reinterpret_cast<const T*>(p.B);
+  long long bb = 0, c = n;
+  if (p.n_batched) { bb = n / p.Nb; c = n - bb * p.Nb; }
+  const int kbatches = (p.a_kmajor && p.b_kmajor) ? p.a_batch : 1;
+  float acc = 0.f;
+  for (int kb = 0; kb < kbatches; ++kb) {
+    for (long long k = 0; k < p.K; ++k) {
+      float a = p.a_kmajor ? to_f32(A[kb * p.a_bstride + m * p.lda + k]) : to_f32(A[k * p.lda + m]);
+      float b = p.b_kmajor ? to_f32(B[kb * p.b_bstride + n * p.ldb + k]) : to_f32(B[bb * p.b_bstride + k * p.ldb + c]);
+      acc = fmaf(a, b, acc);
+    }
+  }
+  float val = acc * p.alpha;
+  if (p.row_bias) val += p.row_bias[m] * (p.col_scale ? p.col_scale[c] : 1.f);
+  if (p.col_bias) val += p.col_bias[c];
+  const long long off = bb * p.d_bstride + m * p.ldd + c;
+  if (p.d_bf16) reinterpret_cast<__nv_bfloat16*>(p.D)[off] = __float2bfloat16_rn(val);
+  else if (p.accumulate) reinterpret_cast<float*>(p.D)[off] += val;
+  else reinterpret_cast<float*>(p.D)[off] = val;
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                    const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static PFN_encodeTiled get_encode_fn() {
+  static PFN_encodeTiled fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_encodeTiled>(ptr);
+  });
+  return fn;
+}
+
+static int swizzle_for(long long contiguous_bytes_per_batch, bool may_overrun) {
+  // may_overrun: the extent is bounded by the tensor map (OOB zero fill) so any swizzle is correct.
+  if (may_overrun || contiguous_bytes_per_batch % 128 == 0) return 128;
+  if (contiguous_bytes_per_batch % 64 == 0) return 64;
+  if (contiguous_bytes_per_batch % 32 == 0) return 32;
+  return 0;
+}
+
+static CUtensorMapSwizzle cu_swizzle(int s) {
+  return s == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : s == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B;
+}
+static uint64_t layout_bits(int s) { return (uint64_t)(s == 128 ? 2 : s == 64 ? 4 : 6) << 61; }
+
+static int encode_map(CUtensorMap* map, const void* base, bool bf16, const cuuint64_t dims[3], const cuuint64_t strides_bytes[2],
+                      const cuuint32_t box[3], int swz) {
+  PFN_encodeTiled fn = get_encode_fn();
+  if (!fn) { set_error("cuTensorMapEncodeTiled not available from the driver"); return AVMOE_E_NODRIVER; }
+  const cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = fn(map, bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_TFLOAT32, 3, const_cast<void*>(base), dims,
+                  strides_bytes, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, cu_swizzle(swz), CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed (CUresult %d) dims=(%llu,%llu,%llu) strides=(%llu,%llu) box=(%u,%u,%u) swz=%d", (int)r,
+              (unsigned long long)dims[0], (unsigned long long)dims[1], (unsigned long long)dims[2],
+              (unsigned long long)strides_bytes[0], (unsigned long long)strides_bytes[1], box[0], box[1], box[2], swz);
+    return AVMOE_E_BADARG;
+  }
+  return 0;
+}
+
+static int launch_simt(const avmoe_gemm_args* a, cudaStream_t st) {
+  SimtParams p;
+  p.A = a->A; p.B = a->B; p.D = a->D;
+  p.bf16 = a->dtype == AVMOE_BF16; p.d_bf16 = a->d_dtype == AVMOE_BF16;
+  p.M = a->M; p.N = a->N; p.K = a->K; p.Nb = a->Nb > 0 ? a->Nb : a->N;
+  p.a_kmajor = a->a_kmajor; p.b_kmajor = a->b_kmajor; p.a_batch = a->a_batch; p.b_batch = a->b_batch;
+  p.n_batched = (!a->b_kmajor && a->b_batch > 1);
+  p.lda = a->lda; p.ldb = a->ldb; p.ldd = a->ldd;
+  p.a_bstride = a->a_bstride; p.b_bstride = a->b_bstride; p.d_bstride = a->d_bstride;
+  p.alpha = a->alpha; p.row_bias = a->row_bias; p.col_scale = a->col_scale; p.col_bias = a->col_bias;
+  p.accumulate = a->accumulate;
+  dim3 block(32, 8);
+  dim3 grid((unsigned)((a->N + 31) / 32), (unsigned)((a->M + 7) / 8));
+  if (p.bf16) gemm_simt_kernel<__nv_bfloat16><<<grid, block, 0, st>>>(p);
+  else gemm_simt_kernel<float><<<grid, block, 0, st>>>(p);
+  AVMOE_LAUNCH_CHECK("gemm_simt_kernel");
+  return 0;
+}
+
+int gemm_dispatch(const avmoe_gemm_args* a, cudaStream_t st) {
+  AVMOE_CHECK_ARG(a && a->A && a->B && a->D, "gemm: null pointer");
+  AVMOE_CHECK_ARG(a->M > 0 && a->N > 0 && a->K > 0, "gemm: empty problem M=%lld N=%lld K=%lld", (long long)a->M, (long long)a->N, (long long)a->K);
+  AVMOE_CHECK_ARG(a->dtype == AVMOE_F32 || a->dtype == AVMOE_BF16, "gemm: bad dtype");
+  AVMOE_CHECK_ARG(a->a_batch >= 1 && a->b_batch >= 1, "gemm: batch counts must be >= 1");
+  const bool kbatched = a->a_kmajor && a->b_kmajor && a->a_batch > 1;
+  if (a->a_kmajor && a->b_kmajor) AVMOE_CHECK_ARG(a->a_batch == a->b_batch, "gemm: K-batched operands need equal batch counts");
+  if (!a->a_kmajor) AVMOE_CHECK_ARG(a->a_batch == 1, "gemm: MN-major A cannot be batched");
+  if (!a->b_kmajor && a->a_kmajor) AVMOE_CHECK_ARG(a->a_batch == 1, "gemm: N-batched B needs an unbatched A");
+  const bool n_batched = (!a->b_kmajor && a->b_batch > 1);
+  const long long Nb = n_batched ? a->Nb : a->N;
+  if (n_batched) AVMOE_CHECK_ARG(Nb > 0 && Nb * a->b_batch == a->N, "gemm: N must equal b_batch*Nb");
+  const bool atomic = a->split_k > 1 || a->accumulate;
+  if (atomic) AVMOE_CHECK_ARG(a->d_dtype == AVMOE_F32, "gemm: split-K / accumulate need an fp32 D");
+  if (a->impl == 1) return launch_simt(a, st);
+  AVMOE_CHECK_ARG(a->ldd % 4 == 0 && a->d_bstride % 4 == 0 && ((uintptr_t)a->D % 16) == 0,
+                  "gemm: D needs a 16-byte aligned base and pitches that are multiples of 4 elements");
+
+  const bool bf16 = a->dtype == AVMOE_BF16;
+  const int es = bf16 ? 2 : 4;
+  const int umma_k = 32 / es;  // 16 (bf16) / 8 (tf32)
+  // ---- pick swizzles / BK -------------------------------------------------------------------
+  int swzA, swzB;
+  if (a->a_kmajor) swzA = swizzle_for(a->K * es, true);  // OOB zero fill inside the per-batch extent
+  else swzA = swizzle_for(a->M * es, true);
+  if (a->b_kmajor) swzB = swizzle_for(a->K * es, true);
+  else swzB = swizzle_for(Nb * es, !n_batched);
+  // K-batched with a per-batch K that is not a multiple of the 128-byte stage: use a narrower swizzle to avoid
+  // multiplying zero padding (K=96 bf16 -> 64B rows).
+  if (kbatched && (a->K * es) % 128 != 0) {
+    int s = swizzle_for(a->K * es, false);
+    if (s) { swzA = s; swzB = s; }
+  }
+  AVMOE_CHECK_ARG(swzA && swzB, "gemm: contiguous extents must be multiples of 32 bytes for batched MN-major operands");
+  int BK;  // elements per stage
+  {
+    int bka = a->a_kmajor ? swzA / es : 128 / es;
+    int bkb = a->b_kmajor ? swzB / es : 128 / es;
+    BK = bka < bkb ? bka : bkb;
+    if (a->a_kmajor && swzA / es != BK) swzA = BK * es;
+    if (a->b_kmajor && swzB / es != BK) swzB = BK * es;
+  }
+  AVMOE_CHECK_ARG(BK % umma_k == 0, "gemm: internal BK error");
+  // ---- tile N ---------------------------------------------------------------------------------
+  int BN = 256;
+  if (a->N < 256) BN = (int)((a->N + 31) / 32) * 32;
+  const int chunkB = a->b_kmajor ? 0 : swzB / es;
+  if (!a->b_kmajor) {
+    AVMOE_CHECK_ARG(!n_batched || Nb % chunkB == 0, "gemm: per-batch N (%lld) must be a multiple of %d", Nb, chunkB);
+    BN = (BN / chunkB) * chunkB;
+    if (BN == 0) BN = chunkB;
+    if (BN % 32) BN = ((BN + 31) / 32) * 32;
+  }
+  AVMOE_CHECK_ARG(Nb % 4 == 0 || !n_batched, "gemm: per-batch N must be a multiple of 4");
+  const int chunkA = a->a_kmajor ? 0 : swzA / es;
+
+  GemmParams p;
+  memset(&p, 0, sizeof(p));
+  p.BN = BN; p.BK = BK; p.mma_per_stage = BK / umma_k;
+  // ---- operand A ------------------------------------------------------------------------------
+  {
+    cuuint64_t dims[3]; cuuint64_t strides[2]; cuuint32_t box[3];
+    if (a->a_kmajor) {
+      dims[0] = a->K; dims[1] = a->M; dims[2] = a->a_batch;
+      strides[0] = a->lda * es; strides[1] = (a->a_batch > 1 ? a->a_bstride : a->lda * a->M) * es;
+      box[0] = BK; box[1] = kBM; box[2] = 1;
+      p.a.kmajor = 1; p.a.nchunks = 1; p.a.chunk_bytes = kBM * swzA; p.a.k_advance = 32;
+      p.a.desc_base = layout_bits(swzA) | (1ull << 46) | ((uint64_t)((8 * swzA) >> 4) << 32) | (1ull << 16);
+      p.stage_bytes_a = kBM * swzA;
+    } else {
+      dims[0] = a->M; dims[1] = a->K; dims[2] = 1;
+      strides[0] = a->lda * es; strides[1] = a->lda * a->K * es;
+      box[0] = chunkA; box[1] = BK; box[2] = 1;
+      p.a.kmajor = 0; p.a.nchunks = kBM / chunkA; p.a.chunk_elems = chunkA; p.a.chunk_bytes = BK * swzA;
+      p.a.k_advance = umma_k * swzA;
+      p.a.desc_base = layout_bits(swzA) | (1ull << 46) | ((uint64_t)((8 * swzA) >> 4) << 32) | ((uint64_t)((BK * swzA) >> 4) << 16);
+      p.stage_bytes_a = p.a.nchunks * p.a.chunk_bytes;
+    }
+    AVMOE_CHECK_ARG((strides[0] % 16) == 0 && (strides[1] % 16) == 0 && ((uintptr_t)a->A % 16) == 0,
+                    "gemm: operand A needs 16-byte aligned base and pitches (lda=%lld)", (long long)a->lda);
+    int rc = encode_map(&p.tmA, a->A, bf16, dims, strides, box, swzA);
+    if (rc) return rc;
+  }
+  // ---- operand B ------------------------------------------------------------------------------
+  {
+    cuuint64_t dims[3]; cuuint64_t strides[2]; cuuint32_t box[3];
+    if (a->b_kmajor) {
+      dims[0] = a->K; dims[1] = a->N; dims[2] = a->b_batch;
+      strides[0] = a->ldb * es; strides[1] = (a->b_batch > 1 ? a->b_bstride : a->ldb * a->N) * es;
+      box[0] = BK; box[1] = BN; box[2] = 1;
+      p.b.kmajor = 1; p.b.nchunks = 1; p.b.chunk_bytes = BN * swzB; p.b.k_advance = 32;
+      p.b.desc_base = layout_bits(swzB) | (1ull << 46) | ((uint64_t)((8 * swzB) >> 4) << 32) | (1ull << 16);
+      p.stage_bytes_b = BN * swzB;
+    } else {
+      dims[0] = Nb; dims[1] = a->K; dims[2] = a->b_batch;
+      strides[0] = a->ldb * es; strides[1] = (a->b_batch > 1 ? a->b_bstride : a->ldb * a->K) * es;
+      box[0] = chunkB; box[1] = BK; box[2] = 1;
+      p.b.kmajor = 0; p.b.nchunks = BN / chunkB; p.b.chunk_elems = chunkB; p.b.chunk_bytes = BK * swzB;
+      p.b.batch_extent = n_batched ? (int)Nb : 0;
+      p.b.k_advance = umma_k * swzB;
+      p.b.desc_base = layout_bits(swzB) | (1ull << 46) | ((uint64_t)((8 * swzB) >> 4) << 32) | ((uint64_t)((BK * swzB) >> 4) << 16);
+      p.stage_bytes_b = p.b.nchunks * p.b.chunk_bytes;
+    }
+    AVMOE_CHECK_ARG((strides[0] % 16) == 0 && (strides[1] % 16) == 0 && ((uintptr_t)a->B % 16) == 0,
+                    "gemm: operand B needs 16-byte aligned base and pitches (ldb=%lld)", (long long)a->ldb);
+    int rc = encode_map(&p.tmB, a->B, bf16, dims, strides, box, swzB);
+    if (rc) return rc;
+  }
+  // stage sizes must keep every tile base 1024-byte aligned (swizzle atom = 8 rows x swizzle bytes)
+  p.stage_bytes_a = (p.stage_bytes_a + 1023) & ~1023u;
+  p.stage_bytes_b = (p.stage_bytes_b + 1023) & ~1023u;
+  // ---- instruction descriptor -----------------------------------------------------------------
+  //  [4,6) D fmt = 1 (f32) | [7,10) A fmt | [10,13) B fmt (bf16=1, tf32=2) | bit15 A MN-major | bit16 B MN-major
+  //  [17,23) N>>3 | [24,29) M>>4
+  const uint32_t fmt = bf16 ? 1u : 2u;
+  p.idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((a->a_kmajor ? 0u : 1u) << 15) | ((a->b_kmajor ? 0u : 1u) << 16) |
+            ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(kBM >> 4) << 24);
+  // ---- K schedule -----------------------------------------------------------------------------
+  const int kpb = (int)((a->K + BK - 1) / BK);
+  p.k_iters_per_batch = kpb;
+  p.k_iters = kbatched ? kpb * a->a_batch : kpb;
+  p.splits = a->split_k > 1 ? a->split_k : 1;
+  if (p.splits > p.k_iters) p.splits = p.k_iters;
+  p.k_iters_per_split = (p.k_iters + p.splits - 1) / p.splits;
+  p.splits = (p.k_iters + p.k_iters_per_split - 1) / p.k_iters_per_split;
+  p.tiles_m = (int)((a->M + kBM - 1) / kBM);
+  p.tiles_n = (int)((a->N + BN - 1) / BN);
+  int tc = 32;
+  while (tc < 2 * BN) tc <<= 1;
+  p.tmem_cols = tc;
+  // ---- epilogue -------------------------------------------------------------------------------
+  p.D = a->D; p.d_bf16 = a->d_dtype == AVMOE_BF16;
+  p.M = a->M; p.N = a->N; p.Nb = Nb; p.ldd = a->ldd; p.d_bstride = a->d_bstride; p.n_batched = n_batched;
+  p.alpha = a->alpha; p.row_bias = a->row_bias; p.col_scale = a->col_scale; p.col_bias = a->col_bias;
+  p.atomic = atomic;
+  if (p.splits > 1 && !a->accumulate) {
+    if (n_batched) {
+      AVMOE_CHECK_ARG(a->d_bstride == a->M * a->ldd && a->ldd == Nb, "gemm: split-K needs a dense D");
+      AVMOE_CUDA(cudaMemsetAsync(a->D, 0, sizeof(float) * a->M * a->N, st));
+    } else {
+      AVMOE_CUDA(cudaMemset2DAsync(a->D, a->ldd * sizeof(float), 0, a->N * sizeof(float), a->M, st));
+    }
+  }
+  // ---- smem / launch --------------------------------------------------------------------------
+  const uint32_t stage_bytes = p.stage_bytes_a + p.stage_bytes_b;
+  const int max_smem = 227 * 1024;
+  int stages = (max_smem - 1024 /*align slack*/ - 256 /*barriers*/) / (int)stage_bytes;
+  if (stages > 8) stages = 8;
+  AVMOE_CHECK_ARG(stages >= 2, "gemm: tile does not fit shared memory");
+  p.num_stages = stages;
+  const size_t smem_bytes = 1024 + (size_t)stages * stage_bytes + 256;
+  const int tiles = p.tiles_m * p.tiles_n * p.splits;
+  int grid = num_sms();
+  if (grid > tiles) grid = tiles;
+  static std::once_flag attr_once;
+  static cudaError_t attr_err = cudaSuccess;
+  std::call_once(attr_once, [&] {
+    attr_err = cudaFuncSetAttribute(gemm_tcgen05_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
+    if (attr_err == cudaSuccess)
+      attr_err = cudaFuncSetAttribute(gemm_tcgen05_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
+  });
+  AVMOE_CUDA(attr_err);
+  if (bf16) gemm_tcgen05_kernel<false><<<grid, kGemmThreads, smem_bytes, st>>>(p);
+  else gemm_tcgen05_kernel<true><<<grid, kGemmThreads, smem_bytes, st>>>(p);
+  AVMOE_LAUNCH_CHECK("gemm_tcgen05_kernel");
+  return 0;
+}
+
+}  // namespace avmoe
+
+extern "C" int avmoe_gemm(const avmoe_gemm_args* args, avmoe_stream_t stream) {
+  return avmoe::gemm_dispatch(args, reinterpret_cast<cudaStream_t>(stream));
+}

@@ -1,0 +1,112 @@
+"""GPU: tcgen05 GEMM (every operand-major / batching / swizzle mode the resampler uses) vs torch fp32."""
+import pytest
+import torch
+
+from tests import util
+
+pytestmark = pytest.mark.gpu
+
+
+def _mk(shape, dtype, seed):
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    return torch.randn(shape, generator=g).to("cuda").to(dtype)
+
+
+def _tol(dtype):
+    return 2e-3 if dtype == torch.float32 else 1e-2   # TF32 operands / bf16 output rounding
+
+
+CASES = [
+    # name, M, N, K
+    ("small", 128, 64, 64),
+    ("ragged", 200, 96, 144),
+    ("multi_tile", 384, 512, 320),
+    ("tiny_n", 64, 32, 36 * 4),
+]
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32])
+@pytest.mark.parametrize("impl", [0, 1])
+@pytest.mark.parametrize("name,M,N,K", CASES)
+def test_gemm_kmajor_kmajor(dtype, impl, name, M, N, K):
+    from avmoe_b200 import ops
+    A, B = _mk((M, K), dtype, 1), _mk((N, K), dtype, 2)
+    rb, cs, cb = _mk((M,), torch.float32, 3), _mk((N,), torch.float32, 4), _mk((N,), torch.float32, 5)
+    D = ops.gemm(A, B, out_dtype=torch.float32, row_bias=rb, col_scale=cs, col_bias=cb, alpha=0.5, impl=impl)
+    ref = 0.5 * (A.float() @ B.float().t()) + rb[:, None] * cs[None, :] + cb[None, :]
+    assert util.rel_err(D, ref) < _tol(dtype)
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32])
+@pytest.mark.parametrize("impl", [0, 1])
+@pytest.mark.parametrize("Nb", [96, 64, 256, 48])
+def test_gemm_nbatched_mnmajor_b(dtype, impl, Nb):
+    """resampler forward: D[b] = W[M,K] · P[b][K,Nb]  (B MN-major, N-batched)."""
+    from avmoe_b200 import ops
+    b, M, K = 5, 200, 144
+    W, P = _mk((M, K), dtype, 1), _mk((b, K, Nb), dtype, 2)
+    rb, cs, cb = _mk((M,), torch.float32, 3), _mk((Nb,), torch.float32, 4), _mk((Nb,), torch.float32, 5)
+    D = ops.gemm(W, P, b_kmajor=False, row_bias=rb, col_scale=cs, col_bias=cb, impl=impl)
+    ref = torch.einsum("mk,bkn->bmn", W.float(), P.float()) + rb[None, :, None] * cs[None, None, :] + cb[None, None, :]
+    assert D.shape == (b, M, Nb) and D.dtype == dtype
+    assert util.rel_err(D, ref) < _tol(dtype)
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32])
+@pytest.mark.parametrize("impl", [0, 1])
+@pytest.mark.parametrize("Nb", [96, 128])
+def test_gemm_mnmajor_a_and_b(dtype, impl, Nb):
+    """input gradient: dP[b] = Wᵀ[K=N_tok rows, M] · dV[b][K, Nb]  (A stored [K,M], B MN-major batched)."""
+    from avmoe_b200 import ops
+    b, M, K = 3, 144, 256
+    Wt, dV = _mk((K, M), dtype, 1), _mk((b, K, Nb), dtype, 2)
+    D = ops.gemm(Wt, dV, a_kmajor=False, b_kmajor=False, impl=impl)
+    ref = torch.einsum("km,bkn->bmn", Wt.float(), dV.float())
+    assert util.rel_err(D, ref) < _tol(dtype)
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32])
+@pytest.mark.parametrize("impl", [0, 1])
+@pytest.mark.parametrize("Kb", [96, 64, 384])
+def test_gemm_kbatched(dtype, impl, Kb):
+    """weight gradient: dW[M,N] = sum_b dV[b][M,Kb] · P[b][N,Kb]ᵀ."""
+    from avmoe_b200 import ops
+    b, M, N = 6, 256, 144
+    dV, P = _mk((b, M, Kb), dtype, 1), _mk((b, N, Kb), dtype, 2)
+    D = ops.gemm(dV, P, out_dtype=torch.float32, impl=impl)
+    ref = torch.einsum("bmk,bnk->mn", dV.float(), P.float())
+    assert util.rel_err(D, ref) < _tol(dtype)
+    if impl == 0:
+        D2 = ops.gemm(dV, P, out_dtype=torch.float32, split_k=4)
+        assert util.rel_err(D2, ref) < _tol(dtype)
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32])
+@pytest.mark.parametrize("impl", [0, 1])
+def test_gemm_mnmajor_both_flat_splitk(dtype, impl):
+    """fc weight gradient: dWfc[C,Cx] = dPᵀ · O with rows flattened over (b,n): both operands MN-major, split-K."""
+    from avmoe_b200 import ops
+    rows, C, Cx = 1000, 96, 192
+    dP, O = _mk((rows, C), dtype, 1), _mk((rows, Cx), dtype, 2)
+    D = ops.gemm(dP, O, a_kmajor=False, b_kmajor=False, out_dtype=torch.float32, split_k=1 if impl else 8, impl=impl)
+    ref = dP.float().t() @ O.float()
+    assert util.rel_err(D, ref) < _tol(dtype)
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32])
+def test_gemm_kmajor_a_mnmajor_b_flat(dtype):
+    """dU = dV[rows,C] · Wfc[C,Cx]  (B MN-major, unbatched)."""
+    from avmoe_b200 import ops
+    rows, C, Cx = 700, 192, 96
+    dV, W = _mk((rows, C), dtype, 1), _mk((C, Cx), dtype, 2)
+    D = ops.gemm(dV, W, b_kmajor=False)
+    assert util.rel_err(D, dV.float() @ W.float()) < _tol(dtype)
+
+
+def test_gemm_resampler_shape_bf16():
+    """stage-1 audio adapter forward shape at BT=8 (M=4096, K=2304, Nb=96), bf16."""
+    from avmoe_b200 import ops
+    W, P = _mk((4096, 2304), torch.bfloat16, 1), _mk((8, 2304, 96), torch.bfloat16, 2)
+    D = ops.gemm(W, P, b_kmajor=False)
+    ref = torch.einsum("mk,bkn->bmn", W.float(), P.float())
+    assert util.rel_err(D, ref) < 1e-2
