@@ -395,13 +395,19 @@ static int swizzle_for(long long contiguous_bytes_per_batch, bool may_overrun) {
   return 0;
 }
 
+// swizzle code: 128/64/32 = classic 16-byte-atom swizzles; 129 = 128-byte span with 32-byte atoms
+// (UMMA SWIZZLE_128B_BASE32B / TMA SWIZZLE_128B_ATOM_32B), the only layout tcgen05 accepts for MN-major TF32.
 static CUtensorMapSwizzle cu_swizzle(int s) {
-  return s == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : s == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B;
+  return s == 129 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B
+       : s == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : s == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B;
 }
-static uint64_t layout_bits(int s) { return (uint64_t)(s == 128 ? 2 : s == 64 ? 4 : 6) << 61; }
+static uint64_t layout_bits(int s) { return (uint64_t)(s == 129 ? 1 : s == 128 ? 2 : s == 64 ? 4 : 6) << 61; }
+static int swz_bytes(int s) { return s == 129 ? 128 : s; }
+static int swz_atom_rows(int s) { return s == 129 ? 4 : 8; }
 
 static int encode_map(CUtensorMap* map, const void* base, bool bf16, const cuuint64_t dims[3], const cuuint64_t strides_bytes[2],
-                      const cuuint32_t box[3], int swz) {
+                      const cuuint32_t box[3], int swz_code) {
+  const int swz = swz_code;
   PFN_encodeTiled fn = get_encode_fn();
   if (!fn) { set_error("cuTensorMapEncodeTiled not available from the driver"); return AVMOE_E_NODRIVER; }
   const cuuint32_t estr[3] = {1, 1, 1};
@@ -436,6 +442,34 @@ static int launch_simt(const avmoe_gemm_args* a, cudaStream_t st) {
   return 0;
 }
 
+// Tile plan of one operand.  `code` is a swizzle code (see cu_swizzle); returns false when tcgen05/TMA cannot
+// express the operand (the caller then uses the generic SIMT kernel).
+struct OperandPlan {
+  int code = 0;       // swizzle code
+  int chunk = 0;      // MN elements per TMA box (MN-major)
+};
+
+static bool plan_operand(bool kmajor, bool bf16, long long contiguous_extent, bool bounded_by_map, OperandPlan* out) {
+  const int es = bf16 ? 2 : 4;
+  if (kmajor) { out->code = 128; return true; }  // narrowed later if the per-batch K needs it
+  if (!bf16) {  // TF32 MN-major: only the 128B-span / 32B-atom layout exists
+    if (!bounded_by_map && (contiguous_extent * es) % 128 != 0) return false;
+    out->code = 129; out->chunk = 32;
+    return true;
+  }
+  int sw = swizzle_for(contiguous_extent * es, bounded_by_map);
+  if (!sw) return false;
+  out->code = sw; out->chunk = sw / es;
+  return true;
+}
+
+static uint64_t make_desc_base(int code, bool kmajor, int BK) {
+  const int sb = swz_bytes(code);
+  const uint64_t sbo = (uint64_t)((swz_atom_rows(code) * sb) >> 4);
+  const uint64_t lbo = kmajor ? 1ull : (uint64_t)((BK * sb) >> 4);
+  return layout_bits(code) | (1ull << 46) | (sbo << 32) | (lbo << 16);
+}
+
 int gemm_dispatch(const avmoe_gemm_args* a, cudaStream_t st) {
   AVMOE_CHECK_ARG(a && a->A && a->B && a->D, "gemm: null pointer");
   AVMOE_CHECK_ARG(a->M > 0 && a->N > 0 && a->K > 0, "gemm: empty problem M=%lld N=%lld K=%lld", (long long)a->M, (long long)a->N, (long long)a->K);
@@ -451,46 +485,43 @@ int gemm_dispatch(const avmoe_gemm_args* a, cudaStream_t st) {
   const bool atomic = a->split_k > 1 || a->accumulate;
   if (atomic) AVMOE_CHECK_ARG(a->d_dtype == AVMOE_F32, "gemm: split-K / accumulate need an fp32 D");
   if (a->impl == 1) return launch_simt(a, st);
-  AVMOE_CHECK_ARG(a->ldd % 4 == 0 && a->d_bstride % 4 == 0 && ((uintptr_t)a->D % 16) == 0,
-                  "gemm: D needs a 16-byte aligned base and pitches that are multiples of 4 elements");
 
   const bool bf16 = a->dtype == AVMOE_BF16;
   const int es = bf16 ? 2 : 4;
   const int umma_k = 32 / es;  // 16 (bf16) / 8 (tf32)
-  // ---- pick swizzles / BK -------------------------------------------------------------------
-  int swzA, swzB;
-  if (a->a_kmajor) swzA = swizzle_for(a->K * es, true);  // OOB zero fill inside the per-batch extent
-  else swzA = swizzle_for(a->M * es, true);
-  if (a->b_kmajor) swzB = swizzle_for(a->K * es, true);
-  else swzB = swizzle_for(Nb * es, !n_batched);
+  // ---- can the tensor-core path express this problem? ------------------------------------------
+  OperandPlan pa, pb;
+  const char* why = nullptr;
+  if (!plan_operand(a->a_kmajor, bf16, a->a_kmajor ? a->K : a->M, true, &pa)) why = "operand A extent";
+  if (!why && !plan_operand(a->b_kmajor, bf16, a->b_kmajor ? a->K : Nb, !n_batched, &pb)) why = "operand B per-batch extent";
+  if (!why && ((a->lda * es) % 16 || (a->ldb * es) % 16 || ((uintptr_t)a->A % 16) || ((uintptr_t)a->B % 16))) why = "operand alignment";
+  if (!why && (a->a_batch > 1 && (a->a_bstride * es) % 16)) why = "A batch pitch";
+  if (!why && (a->b_batch > 1 && (a->b_bstride * es) % 16)) why = "B batch pitch";
+  if (!why && (a->ldd % 4 || a->d_bstride % 4 || ((uintptr_t)a->D % 16))) why = "D alignment";
+  if (!why && n_batched && Nb % 4) why = "per-batch N not a multiple of 4";
+  if (why) {
+    if (a->impl == 2) { set_error("gemm: tcgen05 path unsupported (%s)", why); return AVMOE_E_UNSUPPORTED; }
+    return launch_simt(a, st);  // generic small-shape kernel (still CUDA; there is no CPU path)
+  }
   // K-batched with a per-batch K that is not a multiple of the 128-byte stage: use a narrower swizzle to avoid
   // multiplying zero padding (K=96 bf16 -> 64B rows).
   if (kbatched && (a->K * es) % 128 != 0) {
     int s = swizzle_for(a->K * es, false);
-    if (s) { swzA = s; swzB = s; }
+    if (s) { pa.code = s; pb.code = s; }
   }
-  AVMOE_CHECK_ARG(swzA && swzB, "gemm: contiguous extents must be multiples of 32 bytes for batched MN-major operands");
-  int BK;  // elements per stage
-  {
-    int bka = a->a_kmajor ? swzA / es : 128 / es;
-    int bkb = a->b_kmajor ? swzB / es : 128 / es;
-    BK = bka < bkb ? bka : bkb;
-    if (a->a_kmajor && swzA / es != BK) swzA = BK * es;
-    if (a->b_kmajor && swzB / es != BK) swzB = BK * es;
-  }
-  AVMOE_CHECK_ARG(BK % umma_k == 0, "gemm: internal BK error");
+  int BK = 128 / es;
+  if (a->a_kmajor && pa.code / es < BK) BK = pa.code / es;
+  if (a->b_kmajor && pb.code / es < BK) BK = pb.code / es;
+  if (a->a_kmajor) pa.code = BK * es;
+  if (a->b_kmajor) pb.code = BK * es;
   // ---- tile N ---------------------------------------------------------------------------------
   int BN = 256;
   if (a->N < 256) BN = (int)((a->N + 31) / 32) * 32;
-  const int chunkB = a->b_kmajor ? 0 : swzB / es;
   if (!a->b_kmajor) {
-    AVMOE_CHECK_ARG(!n_batched || Nb % chunkB == 0, "gemm: per-batch N (%lld) must be a multiple of %d", Nb, chunkB);
-    BN = (BN / chunkB) * chunkB;
-    if (BN == 0) BN = chunkB;
-    if (BN % 32) BN = ((BN + 31) / 32) * 32;
+    BN = (BN / pb.chunk) * pb.chunk;
+    if (BN == 0) BN = pb.chunk;
+    if (BN % 32) BN = ((BN + 31) / 32) * 32;   // chunk is 16 only for 32B swizzle; keep the epilogue granularity
   }
-  AVMOE_CHECK_ARG(Nb % 4 == 0 || !n_batched, "gemm: per-batch N must be a multiple of 4");
-  const int chunkA = a->a_kmajor ? 0 : swzA / es;
 
   GemmParams p;
   memset(&p, 0, sizeof(p));
@@ -498,53 +529,49 @@ int gemm_dispatch(const avmoe_gemm_args* a, cudaStream_t st) {
   // ---- operand A ------------------------------------------------------------------------------
   {
     cuuint64_t dims[3]; cuuint64_t strides[2]; cuuint32_t box[3];
+    const int sb = swz_bytes(pa.code);
+    p.a.desc_base = make_desc_base(pa.code, a->a_kmajor, BK);
     if (a->a_kmajor) {
       dims[0] = a->K; dims[1] = a->M; dims[2] = a->a_batch;
       strides[0] = a->lda * es; strides[1] = (a->a_batch > 1 ? a->a_bstride : a->lda * a->M) * es;
       box[0] = BK; box[1] = kBM; box[2] = 1;
-      p.a.kmajor = 1; p.a.nchunks = 1; p.a.chunk_bytes = kBM * swzA; p.a.k_advance = 32;
-      p.a.desc_base = layout_bits(swzA) | (1ull << 46) | ((uint64_t)((8 * swzA) >> 4) << 32) | (1ull << 16);
-      p.stage_bytes_a = kBM * swzA;
+      p.a.kmajor = 1; p.a.nchunks = 1; p.a.chunk_bytes = kBM * sb; p.a.k_advance = 32;
+      p.stage_bytes_a = kBM * sb;
     } else {
       dims[0] = a->M; dims[1] = a->K; dims[2] = 1;
       strides[0] = a->lda * es; strides[1] = a->lda * a->K * es;
-      box[0] = chunkA; box[1] = BK; box[2] = 1;
-      p.a.kmajor = 0; p.a.nchunks = kBM / chunkA; p.a.chunk_elems = chunkA; p.a.chunk_bytes = BK * swzA;
-      p.a.k_advance = umma_k * swzA;
-      p.a.desc_base = layout_bits(swzA) | (1ull << 46) | ((uint64_t)((8 * swzA) >> 4) << 32) | ((uint64_t)((BK * swzA) >> 4) << 16);
+      box[0] = pa.chunk; box[1] = BK; box[2] = 1;
+      p.a.kmajor = 0; p.a.nchunks = kBM / pa.chunk; p.a.chunk_elems = pa.chunk; p.a.chunk_bytes = BK * sb;
+      p.a.k_advance = umma_k * sb;
       p.stage_bytes_a = p.a.nchunks * p.a.chunk_bytes;
     }
-    AVMOE_CHECK_ARG((strides[0] % 16) == 0 && (strides[1] % 16) == 0 && ((uintptr_t)a->A % 16) == 0,
-                    "gemm: operand A needs 16-byte aligned base and pitches (lda=%lld)", (long long)a->lda);
-    int rc = encode_map(&p.tmA, a->A, bf16, dims, strides, box, swzA);
+    int rc = encode_map(&p.tmA, a->A, bf16, dims, strides, box, pa.code);
     if (rc) return rc;
   }
   // ---- operand B ------------------------------------------------------------------------------
   {
     cuuint64_t dims[3]; cuuint64_t strides[2]; cuuint32_t box[3];
+    const int sb = swz_bytes(pb.code);
+    p.b.desc_base = make_desc_base(pb.code, a->b_kmajor, BK);
     if (a->b_kmajor) {
       dims[0] = a->K; dims[1] = a->N; dims[2] = a->b_batch;
       strides[0] = a->ldb * es; strides[1] = (a->b_batch > 1 ? a->b_bstride : a->ldb * a->N) * es;
       box[0] = BK; box[1] = BN; box[2] = 1;
-      p.b.kmajor = 1; p.b.nchunks = 1; p.b.chunk_bytes = BN * swzB; p.b.k_advance = 32;
-      p.b.desc_base = layout_bits(swzB) | (1ull << 46) | ((uint64_t)((8 * swzB) >> 4) << 32) | (1ull << 16);
-      p.stage_bytes_b = BN * swzB;
+      p.b.kmajor = 1; p.b.nchunks = 1; p.b.chunk_bytes = BN * sb; p.b.k_advance = 32;
+      p.stage_bytes_b = BN * sb;
     } else {
       dims[0] = Nb; dims[1] = a->K; dims[2] = a->b_batch;
       strides[0] = a->ldb * es; strides[1] = (a->b_batch > 1 ? a->b_bstride : a->ldb * a->K) * es;
-      box[0] = chunkB; box[1] = BK; box[2] = 1;
-      p.b.kmajor = 0; p.b.nchunks = BN / chunkB; p.b.chunk_elems = chunkB; p.b.chunk_bytes = BK * swzB;
+      box[0] = pb.chunk; box[1] = BK; box[2] = 1;
+      p.b.kmajor = 0; p.b.nchunks = BN / pb.chunk; p.b.chunk_elems = pb.chunk; p.b.chunk_bytes = BK * sb;
       p.b.batch_extent = n_batched ? (int)Nb : 0;
-      p.b.k_advance = umma_k * swzB;
-      p.b.desc_base = layout_bits(swzB) | (1ull << 46) | ((uint64_t)((8 * swzB) >> 4) << 32) | ((uint64_t)((BK * swzB) >> 4) << 16);
+      p.b.k_advance = umma_k * sb;
       p.stage_bytes_b = p.b.nchunks * p.b.chunk_bytes;
     }
-    AVMOE_CHECK_ARG((strides[0] % 16) == 0 && (strides[1] % 16) == 0 && ((uintptr_t)a->B % 16) == 0,
-                    "gemm: operand B needs 16-byte aligned base and pitches (ldb=%lld)", (long long)a->ldb);
-    int rc = encode_map(&p.tmB, a->B, bf16, dims, strides, box, swzB);
+    int rc = encode_map(&p.tmB, a->B, bf16, dims, strides, box, pb.code);
     if (rc) return rc;
   }
-  // stage sizes must keep every tile base 1024-byte aligned (swizzle atom = 8 rows x swizzle bytes)
+  // stage sizes must keep every tile base 1024-byte aligned (swizzle atom <= 8 rows x 128 bytes)
   p.stage_bytes_a = (p.stage_bytes_a + 1023) & ~1023u;
   p.stage_bytes_b = (p.stage_bytes_b + 1023) & ~1023u;
   // ---- instruction descriptor -----------------------------------------------------------------

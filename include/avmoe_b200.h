@@ -72,8 +72,10 @@ const char* avmoe_last_error(void);
  *   Otherwise D is [M][N] with pitch ldd.  d_dtype: AVMOE_F32 or AVMOE_BF16.
  *   split_k>1: K range is split over split_k CTAs that atomically add into a zero-initialised
  *               fp32 D (the call zeroes it); biases are added once.
- *   impl: 0 = tcgen05 (product path), 1 = plain SIMT kernel with the same semantics (used by the
- *         tests to cross-check the tensor-core path; never selected by the host layer).
+ *   impl: 0 = tcgen05 whenever TMA/UMMA can express the operands (16-byte pitches, per-batch MN extents
+ *             that are multiples of the swizzle chunk), else the generic SIMT kernel (tiny/odd shapes only);
+ *         1 = force the SIMT kernel (tests cross-check the tensor-core path against it);
+ *         2 = tcgen05 or fail with AVMOE_E_UNSUPPORTED (tests prove the hot shapes stay on tensor cores).
  * ------------------------------------------------------------------------------------------ */
 typedef struct {
   const void* A; const void* B; void* D;

@@ -103,6 +103,20 @@ def test_gemm_kmajor_a_mnmajor_b_flat(dtype):
     assert util.rel_err(D, dV.float() @ W.float()) < _tol(dtype)
 
 
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32])
+def test_hot_shapes_stay_on_tensor_cores(dtype):
+    """impl=2 refuses to fall back: the real backbone shapes must be expressible on tcgen05."""
+    from avmoe_b200 import ops
+    for (N, Nx, C) in ((4096, 2304, 96), (2304, 4096, 96), (256, 144, 384), (144, 256, 384)):
+        W, P, dV = _mk((N, Nx), dtype, 1), _mk((2, Nx, C), dtype, 2), _mk((2, N, C), dtype, 3)
+        V = ops.gemm(W, P, b_kmajor=False, impl=2)
+        assert util.rel_err(V, torch.einsum("mk,bkn->bmn", W.float(), P.float())) < _tol(dtype)
+        dP = ops.gemm(W, dV, a_kmajor=False, b_kmajor=False, impl=2)
+        assert util.rel_err(dP, torch.einsum("km,bkn->bmn", W.float(), dV.float())) < _tol(dtype)
+        dW = ops.gemm(dV, P, out_dtype=torch.float32, impl=2)
+        assert util.rel_err(dW, torch.einsum("bmk,bnk->mn", dV.float(), P.float())) < _tol(dtype)
+
+
 def test_gemm_resampler_shape_bf16():
     """stage-1 audio adapter forward shape at BT=8 (M=4096, K=2304, Nb=96), bf16."""
     from avmoe_b200 import ops
