@@ -61,6 +61,23 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map
       "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
       : "memory");
 }
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, uint32_t src, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.tile.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(map), "r"(src),
+               "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
+__device__ __forceinline__ void tma_reduce_add_3d(const CUtensorMap* map, uint32_t src, int c0, int c1, int c2) {
+  asm volatile("cp.reduce.async.bulk.tensor.3d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(map),
+               "r"(src), "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int kPending>
+__device__ __forceinline__ void tma_store_wait_read() {
+  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(kPending) : "memory");
+}
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tcgen05_commit(uint32_t bar) {
@@ -109,7 +126,8 @@ struct OperandTile {
 };
 
 struct GemmParams {
-  CUtensorMap tmA, tmB;
+  CUtensorMap tmA, tmB, tmD;
+  int tma_store;       // 1: epilogue stages 32x32 slabs in swizzled smem and TMA-stores / TMA-reduces them
   OperandTile a, b;
   int BN;              // tile N (multiple of 32, <= 256)
   int BK;              // K elements per stage
@@ -136,6 +154,7 @@ struct GemmParams {
 
 static constexpr int kGemmThreads = 192;
 static constexpr int kBM = 128;
+static constexpr int kStagingBytes = 4 * 2 * 4096;
 
 template <bool kTf32>
 __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tcgen05_kernel(const __grid_constant__ GemmParams p) {
@@ -143,7 +162,8 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tcgen05_kernel(const __g
   // carve: [stages][A tile][B tile] (1024-aligned), then barriers
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const uint32_t stage_bytes = p.stage_bytes_a + p.stage_bytes_b;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)p.num_stages * stage_bytes);
+  uint8_t* staging = smem + (size_t)p.num_stages * stage_bytes;          // 4 warps x 2 x 4 KiB (1024-aligned)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(staging + kStagingBytes);
   uint64_t* full_bar = bars;                       // [num_stages]
   uint64_t* empty_bar = bars + p.num_stages;       // [num_stages]
   uint64_t* tmem_full = bars + 2 * p.num_stages;   // [2]
@@ -156,6 +176,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tcgen05_kernel(const __g
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&p.tmA) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&p.tmB) : "memory");
+    if (p.tma_store) asm volatile("prefetch.tensormap [%0];" ::"l"(&p.tmD) : "memory");
     for (int s = 0; s < p.num_stages; ++s) {
       mbar_init(smem_u32(&full_bar[s]), 1);
       mbar_init(smem_u32(&empty_bar[s]), 1);
@@ -259,6 +280,8 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tcgen05_kernel(const __g
     const int quarter = warp & 3;  // TMEM lane quarter this warp may access
     int acc = 0;
     uint32_t acc_phase = 0;
+    uint8_t* my_stage = staging + (warp - 2) * 8192;
+    int sbuf = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int split = tile / tiles_mn;
       const int mn = tile - split * tiles_mn;
@@ -268,33 +291,83 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tcgen05_kernel(const __g
       const bool has_k = k_begin < p.k_iters;
       mbar_wait(smem_u32(&tmem_full[acc]), acc_phase);
       tcgen05_fence_after();
-      const long long m = m0 + quarter * 32 + lane;
+      const int mrow0 = m0 + quarter * 32;
+      const long long m = mrow0 + lane;
       const bool add_bias = (split == 0);
       const float rb = (add_bias && p.row_bias && m < p.M) ? p.row_bias[m] : 0.f;
       for (int g = 0; g < p.BN / 32; ++g) {
+        const long long ng = (long long)n0 + g * 32;
+        if (ng >= p.N || mrow0 >= p.M) break;   // warp-uniform
         uint32_t r[32];
         const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * p.BN + g * 32);
         tmem_ld_32x32b_x32(taddr, r);
-        if (m < p.M) {
+        long long bb = 0, c0 = ng;
+        if (p.n_batched) { bb = ng / p.Nb; c0 = ng - bb * p.Nb; }
+        if (p.tma_store) {
+          // ---- fast path: regs -> swizzled smem slab [32 rows][32 cols] -> TMA store / reduce-add ----
+          uint8_t* buf = my_stage + sbuf * 4096;
+          tma_store_wait_read<1>();     // the slab issued two steps ago has been read out of this buffer
+          __syncwarp();
+          float o[32];
+#pragma unroll
+          for (int e = 0; e < 32; ++e) {
+            float val = has_k ? __uint_as_float(r[e]) * p.alpha : 0.f;
+            if (add_bias) {
+              const long long ce = (c0 + e < p.Nb) ? c0 + e : 0;
+              if (p.row_bias) val += rb * (p.col_scale ? __ldg(p.col_scale + ce) : 1.f);
+              if (p.col_bias) val += __ldg(p.col_bias + ce);
+            }
+            o[e] = val;
+          }
+          if (p.d_bf16) {   // rows of 64 B, SWIZZLE_64B: 16-byte chunk j of row r lives at chunk j ^ ((r>>1)&3)
+            uint8_t* row = buf + lane * 64;
+            const int x = (lane >> 1) & 3;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              uint4 q;
+              __nv_bfloat162 h0 = __floats2bfloat162_rn(o[8 * j + 0], o[8 * j + 1]);
+              __nv_bfloat162 h1 = __floats2bfloat162_rn(o[8 * j + 2], o[8 * j + 3]);
+              __nv_bfloat162 h2 = __floats2bfloat162_rn(o[8 * j + 4], o[8 * j + 5]);
+              __nv_bfloat162 h3 = __floats2bfloat162_rn(o[8 * j + 6], o[8 * j + 7]);
+              q.x = *reinterpret_cast<uint32_t*>(&h0); q.y = *reinterpret_cast<uint32_t*>(&h1);
+              q.z = *reinterpret_cast<uint32_t*>(&h2); q.w = *reinterpret_cast<uint32_t*>(&h3);
+              *reinterpret_cast<uint4*>(row + ((j ^ x) << 4)) = q;
+            }
+          } else {          // rows of 128 B, SWIZZLE_128B: chunk j of row r lives at chunk j ^ (r&7)
+            uint8_t* row = buf + lane * 128;
+            const int x = lane & 7;
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              *reinterpret_cast<float4*>(row + ((j ^ x) << 4)) = make_float4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
+          }
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            if (p.atomic) tma_reduce_add_3d(&p.tmD, smem_u32(buf), (int)c0, mrow0, (int)bb);
+            else tma_store_3d(&p.tmD, smem_u32(buf), (int)c0, mrow0, (int)bb);
+            tma_store_commit();
+          }
+          sbuf ^= 1;
+        } else if (m < p.M) {
+          // ---- generic path (per-batch N not a multiple of 32): direct 4-wide stores ----
 #pragma unroll
           for (int v = 0; v < 8; ++v) {
-            const long long n = (long long)n0 + g * 32 + v * 4;
+            const long long n = ng + v * 4;
             if (n >= p.N) break;
-            long long bb = 0, c = n;
-            if (p.n_batched) { bb = n / p.Nb; c = n - bb * p.Nb; }
+            long long b2 = 0, c = n;
+            if (p.n_batched) { b2 = n / p.Nb; c = n - b2 * p.Nb; }
             float o[4];
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
               float val = has_k ? __uint_as_float(r[v * 4 + e]) * p.alpha : 0.f;
               if (add_bias) {
-                // a 4-vector never straddles a batch boundary when Nb % 4 == 0 (checked on the host)
                 const long long ce = c + e;
                 if (p.row_bias) val += rb * (p.col_scale ? p.col_scale[ce < p.Nb ? ce : 0] : 1.f);
                 if (p.col_bias) val += p.col_bias[ce < p.Nb ? ce : 0];
               }
               o[e] = val;
             }
-            const long long off = bb * p.d_bstride + m * p.ldd + c;
+            const long long off = b2 * p.d_bstride + m * p.ldd + c;
             const int valid = (int)min((long long)4, p.N - n);
             if (p.atomic) {
               float* dp = reinterpret_cast<float*>(p.D) + off;
@@ -316,6 +389,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tcgen05_kernel(const __g
       if (lane == 0) mbar_arrive(smem_u32(&tmem_empty[acc]));
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
+    if (p.tma_store) tma_store_wait_all();   // smem must outlive the bulk reads; global writes complete before exit
   }
 
   tcgen05_fence_before();
@@ -333,7 +407,7 @@ struct SimtParams {
   const void* A; const void* B; void* D;
   int bf16, d_bf16;
   long long M, N, K, Nb;
-  int a_kmajor, b_kmajor, a_batch, b_batch, n_batched;
+  int a_kmajor, b_kmajor, a_batch, b_batch, n_batched, b_nbatched;
   long long lda, ldb, ldd, a_bstride, b_bstride, d_bstride;
   float alpha;
   const float* row_bias; const float* col_scale; const float* col_bias;
@@ -354,7 +428,8 @@ __global__ void gemm_simt_kernel(const SimtParams p) {
   for (int kb = 0; kb < kbatches; ++kb) {
     for (long long k = 0; k < p.K; ++k) {
       float a = p.a_kmajor ? to_f32(A[kb * p.a_bstride + m * p.lda + k]) : to_f32(A[k * p.lda + m]);
-      float b = p.b_kmajor ? to_f32(B[kb * p.b_bstride + n * p.ldb + k]) : to_f32(B[bb * p.b_bstride + k * p.ldb + c]);
+      float b = p.b_kmajor ? to_f32(B[kb * p.b_bstride + n * p.ldb + k])
+                           : (p.b_nbatched ? to_f32(B[bb * p.b_bstride + k * p.ldb + c]) : to_f32(B[k * p.ldb + n]));
       acc = fmaf(a, b, acc);
     }
   }
@@ -429,7 +504,8 @@ static int launch_simt(const avmoe_gemm_args* a, cudaStream_t st) {
   p.bf16 = a->dtype == AVMOE_BF16; p.d_bf16 = a->d_dtype == AVMOE_BF16;
   p.M = a->M; p.N = a->N; p.K = a->K; p.Nb = a->Nb > 0 ? a->Nb : a->N;
   p.a_kmajor = a->a_kmajor; p.b_kmajor = a->b_kmajor; p.a_batch = a->a_batch; p.b_batch = a->b_batch;
-  p.n_batched = (!a->b_kmajor && a->b_batch > 1);
+  p.n_batched = (!a->b_kmajor && a->b_batch > 1) || (a->Nb > 0 && a->Nb < a->N);
+  p.b_nbatched = (!a->b_kmajor && a->b_batch > 1);
   p.lda = a->lda; p.ldb = a->ldb; p.ldd = a->ldd;
   p.a_bstride = a->a_bstride; p.b_bstride = a->b_bstride; p.d_bstride = a->d_bstride;
   p.alpha = a->alpha; p.row_bias = a->row_bias; p.col_scale = a->col_scale; p.col_bias = a->col_bias;
@@ -479,9 +555,11 @@ int gemm_dispatch(const avmoe_gemm_args* a, cudaStream_t st) {
   if (a->a_kmajor && a->b_kmajor) AVMOE_CHECK_ARG(a->a_batch == a->b_batch, "gemm: K-batched operands need equal batch counts");
   if (!a->a_kmajor) AVMOE_CHECK_ARG(a->a_batch == 1, "gemm: MN-major A cannot be batched");
   if (!a->b_kmajor && a->a_kmajor) AVMOE_CHECK_ARG(a->a_batch == 1, "gemm: N-batched B needs an unbatched A");
-  const bool n_batched = (!a->b_kmajor && a->b_batch > 1);
+  const bool b_nbatched = (!a->b_kmajor && a->b_batch > 1);      // B is [b][K][Nb]
+  const bool n_batched = b_nbatched || (a->Nb > 0 && a->Nb < a->N);  // D is [N/Nb][M][Nb]
   const long long Nb = n_batched ? a->Nb : a->N;
-  if (n_batched) AVMOE_CHECK_ARG(Nb > 0 && Nb * a->b_batch == a->N, "gemm: N must equal b_batch*Nb");
+  if (n_batched) AVMOE_CHECK_ARG(Nb > 0 && a->N % Nb == 0, "gemm: N must be a multiple of Nb");
+  if (b_nbatched) AVMOE_CHECK_ARG(Nb * a->b_batch == a->N, "gemm: N must equal b_batch*Nb");
   const bool atomic = a->split_k > 1 || a->accumulate;
   if (atomic) AVMOE_CHECK_ARG(a->d_dtype == AVMOE_F32, "gemm: split-K / accumulate need an fp32 D");
   if (a->impl == 1) return launch_simt(a, st);
@@ -493,7 +571,7 @@ int gemm_dispatch(const avmoe_gemm_args* a, cudaStream_t st) {
   OperandPlan pa, pb;
   const char* why = nullptr;
   if (!plan_operand(a->a_kmajor, bf16, a->a_kmajor ? a->K : a->M, true, &pa)) why = "operand A extent";
-  if (!why && !plan_operand(a->b_kmajor, bf16, a->b_kmajor ? a->K : Nb, !n_batched, &pb)) why = "operand B per-batch extent";
+  if (!why && !plan_operand(a->b_kmajor, bf16, a->b_kmajor ? a->K : Nb, !b_nbatched, &pb)) why = "operand B per-batch extent";
   if (!why && ((a->lda * es) % 16 || (a->ldb * es) % 16 || ((uintptr_t)a->A % 16) || ((uintptr_t)a->B % 16))) why = "operand alignment";
   if (!why && (a->a_batch > 1 && (a->a_bstride * es) % 16)) why = "A batch pitch";
   if (!why && (a->b_batch > 1 && (a->b_bstride * es) % 16)) why = "B batch pitch";
@@ -564,7 +642,7 @@ int gemm_dispatch(const avmoe_gemm_args* a, cudaStream_t st) {
       strides[0] = a->ldb * es; strides[1] = (a->b_batch > 1 ? a->b_bstride : a->ldb * a->K) * es;
       box[0] = pb.chunk; box[1] = BK; box[2] = 1;
       p.b.kmajor = 0; p.b.nchunks = BN / pb.chunk; p.b.chunk_elems = pb.chunk; p.b.chunk_bytes = BK * sb;
-      p.b.batch_extent = n_batched ? (int)Nb : 0;
+      p.b.batch_extent = b_nbatched ? (int)Nb : 0;
       p.b.k_advance = umma_k * sb;
       p.stage_bytes_b = p.b.nchunks * p.b.chunk_bytes;
     }
@@ -606,14 +684,32 @@ int gemm_dispatch(const avmoe_gemm_args* a, cudaStream_t st) {
       AVMOE_CUDA(cudaMemset2DAsync(a->D, a->ldd * sizeof(float), 0, a->N * sizeof(float), a->M, st));
     }
   }
+  // ---- D tensor map for the TMA-store epilogue (32x32 slabs; needs slabs that never straddle a batch) ----
+  p.tma_store = (!n_batched || Nb % 32 == 0) ? 1 : 0;
+  if (p.tma_store) {
+    const int des = p.d_bf16 ? 2 : 4;
+    cuuint64_t dims[3] = {(cuuint64_t)(n_batched ? Nb : a->N), (cuuint64_t)a->M, (cuuint64_t)(n_batched ? a->N / Nb : 1)};
+    cuuint64_t strides[2] = {(cuuint64_t)(a->ldd * des), (cuuint64_t)((n_batched ? a->d_bstride : a->ldd * a->M) * des)};
+    cuuint32_t box[3] = {32, 32, 1};
+    if ((strides[0] % 16) || (strides[1] % 16)) p.tma_store = 0;
+    else {
+      PFN_encodeTiled fn = get_encode_fn();
+      if (!fn) { set_error("cuTensorMapEncodeTiled not available from the driver"); return AVMOE_E_NODRIVER; }
+      const cuuint32_t estr[3] = {1, 1, 1};
+      CUresult r = fn(&p.tmD, p.d_bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, a->D, dims, strides, box, estr,
+                      CU_TENSOR_MAP_INTERLEAVE_NONE, p.d_bf16 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B,
+                      CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(D) failed (CUresult %d)", (int)r); return AVMOE_E_BADARG; }
+    }
+  }
   // ---- smem / launch --------------------------------------------------------------------------
   const uint32_t stage_bytes = p.stage_bytes_a + p.stage_bytes_b;
   const int max_smem = 227 * 1024;
-  int stages = (max_smem - 1024 /*align slack*/ - 256 /*barriers*/) / (int)stage_bytes;
+  int stages = (max_smem - 1024 /*align slack*/ - 256 /*barriers*/ - kStagingBytes) / (int)stage_bytes;
   if (stages > 8) stages = 8;
   AVMOE_CHECK_ARG(stages >= 2, "gemm: tile does not fit shared memory");
   p.num_stages = stages;
-  const size_t smem_bytes = 1024 + (size_t)stages * stage_bytes + 256;
+  const size_t smem_bytes = 1024 + (size_t)stages * stage_bytes + kStagingBytes + 256;
   const int tiles = p.tiles_m * p.tiles_n * p.splits;
   int grid = num_sms();
   if (grid > tiles) grid = tiles;

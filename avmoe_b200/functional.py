@@ -1,0 +1,460 @@
+"""Host-side orchestration of the AVMoE adapter forward/backward over the C-ABI kernels.
+
+One ``torch.autograd.Function`` per MoEAdapter call.  Everything numeric happens inside the
+kernel namespace ``K`` (``avmoe_b200.ops`` = CUDA kernels behind the C ABI; the tests swap in a
+torch emulation of each kernel to validate this orchestration on CPU).  This file only decides
+which kernels run, with which buffers, and routes gradients to the reference's parameters.
+
+Pass structure (DESIGN.md "passes"):
+  forward   resample (2 GEMMs) -> pool -> router -> latent (tokens<-kv) -> expert_front (z)
+            -> [BN: stats, moments, finalize] -> expert_back (out)
+  backward  [BN: expert_back_bwd_stats] -> expert_back_bwd (dz~, dprobs, d{Wu,ln_post,gate})
+            -> router_bwd -> expert_front_bwd (dx, dtok', d{Wd,ln_before,gate_av})
+            -> latent_bwd (dV, dtokens) -> resample_bwd (GEMMs: dO, dW_tok, dW_fc, biases)
+
+Reference semantics: AVMOE/AVE/nets/net_trans_v3.py:376-435 (ExpertAdapter.forward),
+:468-487 (MoEAdapter.forward) and the four sibling copies.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import torch
+
+BN_EPS = 1e-5
+LN_EPS = 1e-5
+BN_MOMENTUM = 0.1
+
+# expert pre-transform kinds (what happens to x before ln_before)
+PRE_NONE, PRE_LATENT, PRE_AUX_ADD, PRE_AUX_REPLACE = 0, 1, 2, 3
+# batch-norm modes
+BN_OFF, BN_TRAIN, BN_EVAL = 0, 1, 2
+
+
+@dataclass
+class AdapterConfig:
+    """Static shape/flag description of one MoEAdapter (mirrors the reference ctor arguments + opt)."""
+    C: int
+    N: int
+    Cx: int
+    Nx: int
+    r: int
+    G: int
+    T: int
+    Mm: int
+    Ms: int
+    use_bn: bool
+    use_gate: bool
+    ln_before: bool
+    ln_post: bool
+    self_attn: str = "none"      # none | mha | latent | nxn   (single-modal experts)
+    lb_loss: bool = False
+
+    @property
+    def E(self) -> int:
+        return self.Mm + self.Ms
+
+    @property
+    def Cr(self) -> int:
+        return self.C // self.r
+
+    @property
+    def n_latent(self) -> int:
+        """number of experts that own latent tokens (multimodal + latent-self single-modal)."""
+        return self.Mm + (self.Ms if self.self_attn == "latent" else 0)
+
+    def expert_kinds(self) -> List[Tuple[int, bool]]:
+        """(pre_kind, relu) per expert, multimodal first (net_trans_v3.py:482)."""
+        kinds = [(PRE_LATENT, True)] * self.Mm
+        um = {"none": PRE_NONE, "latent": PRE_LATENT, "nxn": PRE_AUX_ADD, "mha": PRE_AUX_REPLACE}[self.self_attn]
+        return kinds + [(um, False)] * self.Ms
+
+
+def param_names(cfg: AdapterConfig) -> List[str]:
+    """Canonical flat ordering of the reference parameter names used by this adapter."""
+    names = ["conv_adapter.weight", "conv_adapter.bias", "fc.weight", "fc.bias"]
+    names += [f"router.{i}.{w}" for i in (0, 2, 4) for w in ("weight", "bias")]
+
+    def expert(p, multimodal):
+        out = []
+        if cfg.use_gate:
+            out.append(p + "gate")
+        if multimodal:
+            out += [p + "my_tokens", p + "gate_av"]
+        elif cfg.self_attn == "nxn":
+            out.append(p + "gate_av")
+        elif cfg.self_attn == "latent":
+            out += [p + "my_tokens", p + "gate_self"]
+        elif cfg.self_attn == "mha":
+            out += [p + "self_attention.in_proj_weight", p + "self_attention.in_proj_bias",
+                    p + "self_attention.out_proj.weight", p + "self_attention.out_proj.bias"]
+        out += [p + "down_sampler.weight", p + "up_sampler.weight"]
+        if cfg.use_bn:
+            out += [p + "bn1.weight", p + "bn1.bias", p + "bn2.weight", p + "bn2.bias"]
+        if cfg.ln_before:
+            out += [p + "ln_before.weight", p + "ln_before.bias"]
+        if cfg.ln_post:
+            out += [p + "ln_post.weight", p + "ln_post.bias"]
+        return out
+
+    for m in range(cfg.Mm):
+        names += expert(f"multimodal_experts.{m}.", True)
+    for s in range(cfg.Ms):
+        names += expert(f"singlemodal_experts.{s}.", False)
+    return names
+
+
+def expert_prefixes(cfg: AdapterConfig) -> List[str]:
+    return [f"multimodal_experts.{m}." for m in range(cfg.Mm)] + [f"singlemodal_experts.{s}." for s in range(cfg.Ms)]
+
+
+@dataclass
+class ExpertPack:
+    """Per-expert tensors handed to the expert kernels (all fp32, contiguous; None = feature absent)."""
+    pre_kind: int
+    relu: bool
+    latent_slot: int = -1                    # index into tokp's expert axis
+    gate_pre: Optional[torch.Tensor] = None  # gate_av / gate_self  [1]
+    aux: Optional[torch.Tensor] = None       # [BT,N,C] activation dtype (PRE_AUX_*)
+    ln1_w: Optional[torch.Tensor] = None
+    ln1_b: Optional[torch.Tensor] = None
+    wd: Optional[torch.Tensor] = None        # [Cr, C/G]
+    wu: Optional[torch.Tensor] = None        # [C, Cr/G]
+    ln2_w: Optional[torch.Tensor] = None
+    ln2_b: Optional[torch.Tensor] = None
+    gate: Optional[torch.Tensor] = None      # [1]
+
+
+@dataclass
+class ExpertGrads:
+    """fp32 gradient accumulators the backward kernels atomically add into (zero-initialised)."""
+    gate_pre: Optional[torch.Tensor] = None
+    aux: Optional[torch.Tensor] = None
+    ln1_w: Optional[torch.Tensor] = None
+    ln1_b: Optional[torch.Tensor] = None
+    wd: Optional[torch.Tensor] = None
+    wu: Optional[torch.Tensor] = None
+    ln2_w: Optional[torch.Tensor] = None
+    ln2_b: Optional[torch.Tensor] = None
+    gate: Optional[torch.Tensor] = None
+
+
+# -------------------------------------------------------------------------------------------------
+# resampler: vis' = fc(conv_adapter(other))          (net_trans_v3.py:469-471)
+# -------------------------------------------------------------------------------------------------
+def resample_fwd(K, cfg: AdapterConfig, o: torch.Tensor, w_tok, b_tok, w_fc, b_fc):
+    """o [BT,Nx,Cx] -> v [BT,N,C].  Returns (v, saved) where saved holds the GEMM intermediate.
+
+    Association is chosen by FLOPs: with Cx > C the channel projection runs first
+        P = o·W_fcᵀ                      [BT,Nx,C]
+        v = W_tok·P + b_tok⊗s + 1⊗b_fc   with s = rowsum(W_fc)
+    otherwise the token resampling runs first
+        U = W_tok·o + b_tok⊗1            [BT,N,Cx]
+        v = U·W_fcᵀ + 1⊗b_fc.
+    The token-resampling GEMM always runs in K-major x K-major form on the tensor cores: its activation operand is
+    re-laid out channel-major ([BT,c,Nx], one bandwidth-bound transpose) because tcgen05 reads MN-major operands at
+    well under half the K-major rate (profiles/r01_gemm_microbench.md)."""
+    BT = o.shape[0]
+    dt = o.dtype
+    N, Nx, C, Cx = cfg.N, cfg.Nx, cfg.C, cfg.Cx
+    wt_l = K.prep_weight(w_tok.reshape(N, Nx), dt, False)                       # [N,Nx]  activation dtype
+    wf_l = K.prep_weight(w_fc, dt, False)                                       # [C,Cx]
+    fc_first = Cx > C
+    if fc_first:
+        P = K.gemm(o.reshape(BT * Nx, Cx), wf_l).reshape(BT, Nx, C)
+        Pt = K.transpose(P)                                                     # [BT,C,Nx]
+        s = K.rowsum(w_fc)                                                      # [C] fp32
+        v = K.gemm(wt_l, Pt.reshape(BT * C, Nx), d_nbatch=C, row_bias=b_tok, col_scale=s, col_bias=b_fc)
+        return v, (fc_first, P, s)
+    Ot = K.transpose(o)                                                         # [BT,Cx,Nx]
+    U = K.gemm(wt_l, Ot.reshape(BT * Cx, Nx), d_nbatch=Cx, row_bias=b_tok)      # [BT,N,Cx]
+    v = K.gemm(U.reshape(BT * N, Cx), wf_l, col_bias=b_fc).reshape(BT, N, C)
+    return v, (fc_first, U, None)
+
+
+def resample_bwd(K, cfg: AdapterConfig, o: torch.Tensor, dv: torch.Tensor, saved, w_tok, b_tok, w_fc, need_do: bool = True):
+    """Gradients of resample_fwd.  dv [BT,N,C] (activation dtype).  Returns (do, dw_tok, db_tok, dw_fc, db_fc)."""
+    fc_first, mid, s = saved
+    BT = o.shape[0]
+    dt = o.dtype
+    N, Nx, C, Cx = cfg.N, cfg.Nx, cfg.C, cfg.Cx
+    f32 = torch.float32
+    wt_T = K.prep_weight(w_tok.reshape(N, Nx), dt, True)                        # [Nx,N]
+    wf_T = K.prep_weight(w_fc, dt, True)                                        # [Cx,C]
+    if fc_first:
+        P = mid
+        # bias grads: db_fc[c] = sum dv ; db_tok[n] = sum_c dv*s[c] ; ds[c] = sum_n dv*b_tok[n]  (d rowsum(W_fc))
+        db_tok, db_fc, ds = K.reduce_bias(dv, col_weight=s, row_weight=b_tok)
+        dw_tok = K.gemm(dv, P, out_dtype=f32)                                   # sum_b dv[b]·P[b]ᵀ        [N,Nx]
+        dVt = K.transpose(dv)                                                   # [BT,C,N]
+        dP = K.gemm(wt_T, dVt.reshape(BT * C, N), d_nbatch=C)                   # W_tokᵀ·dv[b]             [BT,Nx,C]
+        dP2 = dP.reshape(BT * Nx, C)
+        dw_fc = K.gemm(dP2, o.reshape(BT * Nx, Cx), a_kmajor=False, b_kmajor=False, out_dtype=f32,
+                       split_k=K.split_k_hint(BT * Nx, C, Cx), row_bias=ds)      # dPᵀ·o + ds⊗1             [C,Cx]
+        do = K.gemm(dP2, wf_T).reshape(BT, Nx, Cx) if need_do else None         # dP·W_fc
+        return do, dw_tok.reshape(N, Nx, 1, 1), db_tok, dw_fc, db_fc
+    U = mid
+    dv2 = dv.reshape(BT * N, C)
+    _, db_fc, _ = K.reduce_bias(dv)
+    dw_fc = K.gemm(dv2, U.reshape(BT * N, Cx), a_kmajor=False, b_kmajor=False, out_dtype=f32,
+                   split_k=K.split_k_hint(BT * N, C, Cx))                        # dvᵀ·U                    [C,Cx]
+    dU = K.gemm(dv2, wf_T).reshape(BT, N, Cx)                                    # dv·W_fc                  [BT,N,Cx]
+    db_tok, _, _ = K.reduce_bias(dU)
+    dw_tok = K.gemm(dU, o, out_dtype=f32)                                        # sum_b dU[b]·o[b]ᵀ        [N,Nx]
+    do = None
+    if need_do:
+        dUt = K.transpose(dU)                                                    # [BT,Cx,N]
+        do = K.gemm(wt_T, dUt.reshape(BT * Cx, N), d_nbatch=Cx)                  # W_tokᵀ·dU[b]             [BT,Nx,Cx]
+    return do, dw_tok.reshape(N, Nx, 1, 1), db_tok, dw_fc, db_fc
+
+
+# -------------------------------------------------------------------------------------------------
+# the fused adapter function
+# -------------------------------------------------------------------------------------------------
+def _bn_mode(cfg: AdapterConfig, training: bool) -> int:
+    if not cfg.use_bn:
+        return BN_OFF
+    return BN_TRAIN if training else BN_EVAL
+
+
+class MoEAdapterFunction(torch.autograd.Function):
+    """(x, o, *params) -> (out [BT,N,C], probs [BT,E], lb_loss [])  with expert_indices as a non-differentiable extra.
+
+    ``state`` carries non-tensor context: cfg, kernel namespace K, training flag, the BatchNorm buffers (updated in
+    place in training mode, exactly like nn.BatchNorm2d), the optional router noise tensor, and receives ``idx``."""
+
+    @staticmethod
+    def forward(ctx, state: dict, x: torch.Tensor, o: torch.Tensor, *params: torch.Tensor):
+        cfg: AdapterConfig = state["cfg"]
+        K = state["K"]
+        training: bool = state["training"]
+        names = param_names(cfg)
+        assert len(params) == len(names), (len(params), len(names))
+        P: Dict[str, torch.Tensor] = dict(zip(names, params))
+        bufs: Dict[str, torch.Tensor] = state.get("buffers", {})
+        BT, N, C = x.shape
+        assert (N, C) == (cfg.N, cfg.C) and o.shape[1:] == (cfg.Nx, cfg.Cx), "token shapes do not match the adapter"
+        assert x.is_contiguous() and o.is_contiguous()
+        E, Cr, G, T = cfg.E, cfg.Cr, cfg.G, cfg.T
+        bn_mode = _bn_mode(cfg, training)
+        f32 = torch.float32
+        dev = x.device
+
+        # 1. resampler
+        v, rs_saved = resample_fwd(K, cfg, o, P["conv_adapter.weight"], P["conv_adapter.bias"], P["fc.weight"], P["fc.bias"])
+        # 2. router
+        pool_x, pool_v = K.pool(x), K.pool(v)                                    # [BT,C] fp32 sums
+        rw = [P[f"router.{i}.{w}"] for i in (0, 2, 4) for w in ("weight", "bias")]
+        probs, idx, h1, h2 = K.router_fwd(pool_x, pool_v, 1.0 / N, rw, state.get("noise"))
+        # 3. per-expert pre-transforms that are separate kernels
+        prefixes = expert_prefixes(cfg)
+        kinds = cfg.expert_kinds()
+        packs: List[ExpertPack] = []
+        latent_tokens, latent_kv_is_x = [], []
+        aux_saved = {}
+        for e, (pfx, (pre, relu)) in enumerate(zip(prefixes, kinds)):
+            pk = ExpertPack(pre_kind=pre, relu=relu)
+            multimodal = e < cfg.Mm
+            if pre == PRE_LATENT:
+                pk.latent_slot = len(latent_tokens)
+                latent_tokens.append(P[pfx + "my_tokens"])
+                latent_kv_is_x.append(not multimodal)
+                pk.gate_pre = P[pfx + ("gate_av" if multimodal else "gate_self")]
+            elif pre == PRE_AUX_ADD:      # AVVP NxN token self-attention (mgn.py:132-139)
+                pk.aux, lse_rows = K.selfattn_nxn_fwd(x)
+                aux_saved[e] = lse_rows
+                pk.gate_pre = P[pfx + "gate_av"]
+            elif pre == PRE_AUX_REPLACE:  # AVS v1 MHA over the BT axis (PVT_AVSModel_v2.py:212-215)
+                mp = [P[pfx + "self_attention." + n] for n in ("in_proj_weight", "in_proj_bias", "out_proj.weight", "out_proj.bias")]
+                pk.aux, mha_saved = K.mha_fwd(x, mp)
+                aux_saved[e] = mha_saved
+            if cfg.ln_before:
+                pk.ln1_w, pk.ln1_b = P[pfx + "ln_before.weight"], P[pfx + "ln_before.bias"]
+            if cfg.ln_post:
+                pk.ln2_w, pk.ln2_b = P[pfx + "ln_post.weight"], P[pfx + "ln_post.bias"]
+            pk.wd = P[pfx + "down_sampler.weight"].reshape(Cr, C // G)
+            pk.wu = P[pfx + "up_sampler.weight"].reshape(C, Cr // G)
+            if cfg.use_gate:
+                pk.gate = P[pfx + "gate"]
+            packs.append(pk)
+        # 4. latent tokens attend to their key/value stream (v for multimodal, x for latent-self)
+        tokp = lse = None
+        nl = len(latent_tokens)
+        if nl:
+            tokp = torch.empty((BT, nl, T, C), device=dev, dtype=f32)
+            lse = torch.empty((BT, nl, T), device=dev, dtype=f32)
+            for kv_is_x in (False, True):
+                slots = [i for i in range(nl) if latent_kv_is_x[i] == kv_is_x]
+                if slots:
+                    K.latent_fwd(x if kv_is_x else v, [latent_tokens[i] for i in slots], slots, tokp, lse)
+        # 5. expert front: pre-transform, ln_before, grouped down projection -> z (pre-BN), BN1 batch sums
+        z = torch.empty((BT, N, E, Cr), device=dev, dtype=f32)
+        stats1 = torch.zeros((E, Cr, 2), device=dev, dtype=torch.float64) if bn_mode == BN_TRAIN else None
+        K.expert_front_fwd(cfg, x, tokp, packs, z, stats1)
+        # 6. BatchNorm statistics -> per-channel affine + (mean, invstd) for both norms
+        bn = None
+        if bn_mode != BN_OFF:
+            bn_w = [[P[p + f"bn{i}.{w}"] for i in (1, 2) for w in ("weight", "bias")] for p in prefixes]
+            bn_b = [[bufs[p + f"bn{i}.{w}"] for i in (1, 2) for w in ("running_mean", "running_var")] for p in prefixes]
+            moments = None
+            if bn_mode == BN_TRAIN:
+                aff1, save1 = K.bn1_finalize(cfg, stats1, BT * N, bn_w, bn_b, True)
+                moments = K.bn_moments(cfg, z, aff1, packs)                       # sums of a and a aᵀ per group (float64)
+            else:
+                aff1, save1 = K.bn1_finalize(cfg, None, BT * N, bn_w, bn_b, False)
+            aff2, save2 = K.bn2_finalize(cfg, moments, BT * N, packs, bn_w, bn_b, bn_mode == BN_TRAIN)
+            if bn_mode == BN_TRAIN:
+                for p in prefixes:
+                    bufs[p + "bn1.num_batches_tracked"] += 1
+                    bufs[p + "bn2.num_batches_tracked"] += 1
+            bn = (aff1, save1, aff2, save2)
+        # 7. expert back: activation, up projection, bn2, ln_post, gate, probability-weighted combine
+        out = torch.empty_like(x)
+        K.expert_back_fwd(cfg, z, bn, packs, probs, out)
+        lb = K.lb_loss_fwd(probs) if cfg.lb_loss else torch.zeros((), device=dev, dtype=f32)
+
+        state["idx"] = idx
+        ctx.state = state
+        ctx.names = names
+        ctx.bn_mode = bn_mode
+        ctx.rs_saved = rs_saved
+        ctx.aux_saved = aux_saved
+        ctx.latent_kv_is_x = latent_kv_is_x
+        ctx.packs_meta = [(pk.pre_kind, pk.relu, pk.latent_slot) for pk in packs]
+        ctx.bn = bn
+        ctx.aux = [pk.aux for pk in packs]
+        ctx.save_for_backward(x, o, v, pool_x, pool_v, probs, h1, h2, tokp, lse, z, *params)
+        ctx.mark_non_differentiable(idx)
+        return out, probs, lb, idx
+
+    @staticmethod
+    def backward(ctx, dout, dprobs_ext, dlb, _didx):
+        state = ctx.state
+        cfg: AdapterConfig = state["cfg"]
+        K = state["K"]
+        names = ctx.names
+        x, o, v, pool_x, pool_v, probs, h1, h2, tokp, lse, z, *params = ctx.saved_tensors
+        P: Dict[str, torch.Tensor] = dict(zip(names, params))
+        BT, N, C = x.shape
+        E, Cr, G, T = cfg.E, cfg.Cr, cfg.G, cfg.T
+        f32 = torch.float32
+        dev = x.device
+        bn_mode = ctx.bn_mode
+        prefixes = expert_prefixes(cfg)
+        grads: Dict[str, Optional[torch.Tensor]] = {n: None for n in names}
+        dout = dout.contiguous()
+
+        # rebuild packs (parameters come from saved tensors)
+        packs: List[ExpertPack] = []
+        egr: List[ExpertGrads] = []
+        for e, (pfx, (pre, relu, slot)) in enumerate(zip(prefixes, ctx.packs_meta)):
+            multimodal = e < cfg.Mm
+            pk = ExpertPack(pre_kind=pre, relu=relu, latent_slot=slot, aux=ctx.aux[e])
+            g = ExpertGrads()
+            if pre == PRE_LATENT:
+                pk.gate_pre = P[pfx + ("gate_av" if multimodal else "gate_self")]
+            elif pre == PRE_AUX_ADD:
+                pk.gate_pre = P[pfx + "gate_av"]
+            if pk.gate_pre is not None:
+                g.gate_pre = torch.zeros(1, device=dev, dtype=f32)
+            if pre in (PRE_AUX_ADD, PRE_AUX_REPLACE):
+                g.aux = torch.empty((BT, N, C), device=dev, dtype=x.dtype)
+            if cfg.ln_before:
+                pk.ln1_w, pk.ln1_b = P[pfx + "ln_before.weight"], P[pfx + "ln_before.bias"]
+                g.ln1_w, g.ln1_b = torch.zeros(C, device=dev, dtype=f32), torch.zeros(C, device=dev, dtype=f32)
+            if cfg.ln_post:
+                pk.ln2_w, pk.ln2_b = P[pfx + "ln_post.weight"], P[pfx + "ln_post.bias"]
+                g.ln2_w, g.ln2_b = torch.zeros(C, device=dev, dtype=f32), torch.zeros(C, device=dev, dtype=f32)
+            pk.wd = P[pfx + "down_sampler.weight"].reshape(Cr, C // G)
+            pk.wu = P[pfx + "up_sampler.weight"].reshape(C, Cr // G)
+            g.wd = torch.zeros((Cr, C // G), device=dev, dtype=f32)
+            g.wu = torch.zeros((C, Cr // G), device=dev, dtype=f32)
+            if cfg.use_gate:
+                pk.gate = P[pfx + "gate"]
+                g.gate = torch.zeros(1, device=dev, dtype=f32)
+            packs.append(pk)
+            egr.append(g)
+
+        # 1. expert back (BN2 batch reductions first when training with BN)
+        red2 = None
+        if bn_mode == BN_TRAIN:
+            red2 = torch.zeros((E, C, 2), device=dev, dtype=torch.float64)
+            K.expert_back_bwd_stats(cfg, dout, z, ctx.bn, packs, probs, red2)
+        dzt = torch.empty((BT, N, E, Cr), device=dev, dtype=f32)
+        dprobs = torch.zeros((BT, E), device=dev, dtype=f32)
+        red1 = torch.zeros((E, Cr, 2), device=dev, dtype=torch.float64) if bn_mode != BN_OFF else None
+        red2b = torch.zeros((E, C, 2), device=dev, dtype=torch.float64) if bn_mode == BN_EVAL else red2
+        K.expert_back_bwd(cfg, dout, z, ctx.bn, bn_mode, red2, red2b, packs, probs, dzt, dprobs, red1, egr)
+        # 2. router backward (dprobs from the combine + external grads on gating_probs + lb-loss)
+        if dprobs_ext is not None:
+            dprobs = dprobs + dprobs_ext.to(f32)
+        if cfg.lb_loss and dlb is not None:
+            K.lb_loss_bwd(probs, dlb.to(f32), dprobs)                            # accumulates into dprobs
+        rw = [P[f"router.{i}.{w}"] for i in (0, 2, 4) for w in ("weight", "bias")]
+        dpool_x, dpool_v, drw = K.router_bwd(dprobs, probs, h1, h2, pool_x, pool_v, 1.0 / N, rw)
+        for (i, w), g in zip([(i, w) for i in (0, 2, 4) for w in ("weight", "bias")], drw):
+            grads[f"router.{i}.{w}"] = g
+        # 3. expert front backward
+        nl = 0 if tokp is None else tokp.shape[1]
+        dtokp = torch.zeros((BT, nl, T, C), device=dev, dtype=f32) if nl else None
+        dx = torch.empty_like(x)
+        K.expert_front_bwd(cfg, x, tokp, dzt, z, ctx.bn, bn_mode, red1, packs, dpool_x, dx, dtokp, egr)
+        # 4. separate pre-transform kernels
+        for e, (pfx, pk) in enumerate(zip(prefixes, packs)):
+            if pk.pre_kind == PRE_AUX_ADD:
+                K.selfattn_nxn_bwd(x, ctx.aux_saved[e], egr[e].aux, dx)          # accumulates into dx
+            elif pk.pre_kind == PRE_AUX_REPLACE:
+                mp = [P[pfx + "self_attention." + n] for n in ("in_proj_weight", "in_proj_bias", "out_proj.weight", "out_proj.bias")]
+                dmp = K.mha_bwd(x, mp, ctx.aux_saved[e], egr[e].aux, dx)         # accumulates into dx
+                for n, g in zip(("in_proj_weight", "in_proj_bias", "out_proj.weight", "out_proj.bias"), dmp):
+                    grads[pfx + "self_attention." + n] = g
+        # 5. latent attention backward -> dv (and dx for latent-self), d my_tokens
+        dv = None
+        if nl:
+            dtokens = [torch.zeros((T, C), device=dev, dtype=f32) for _ in range(nl)]
+            toks = [None] * nl
+            for e, (pfx, pk) in enumerate(zip(prefixes, packs)):
+                if pk.pre_kind == PRE_LATENT:
+                    toks[pk.latent_slot] = P[pfx + "my_tokens"]
+            for kv_is_x in (False, True):
+                slots = [i for i in range(nl) if ctx.latent_kv_is_x[i] == kv_is_x]
+                if not slots:
+                    continue
+                if kv_is_x:
+                    K.latent_bwd(x, [toks[i] for i in slots], slots, tokp, lse, dtokp, None, dx, True, [dtokens[i] for i in slots])
+                else:
+                    dv = torch.empty_like(v)
+                    K.latent_bwd(v, [toks[i] for i in slots], slots, tokp, lse, dtokp, dpool_v, dv, False, [dtokens[i] for i in slots])
+            for e, (pfx, pk) in enumerate(zip(prefixes, packs)):
+                if pk.pre_kind == PRE_LATENT:
+                    grads[pfx + "my_tokens"] = dtokens[pk.latent_slot]
+        if dv is None:   # no multimodal expert: v only feeds the router
+            dv = K.broadcast_rows(dpool_v, N, v.dtype)
+        # 6. resampler backward
+        need_do = ctx.needs_input_grad[2]
+        do, dw_tok, db_tok, dw_fc, db_fc = resample_bwd(K, cfg, o, dv, ctx.rs_saved, P["conv_adapter.weight"],
+                                                        P["conv_adapter.bias"], P["fc.weight"], need_do)
+        grads["conv_adapter.weight"], grads["conv_adapter.bias"] = dw_tok, db_tok
+        grads["fc.weight"], grads["fc.bias"] = dw_fc, db_fc
+        # 7. scatter expert gradients to the reference parameter names
+        if bn_mode != BN_OFF:
+            r1 = red1.to(f32)
+            r2 = red2b.to(f32)
+        for e, (pfx, g) in enumerate(zip(prefixes, egr)):
+            multimodal = e < cfg.Mm
+            if g.gate is not None:
+                grads[pfx + "gate"] = g.gate
+            if g.gate_pre is not None:
+                key = "gate_av" if (multimodal or cfg.self_attn == "nxn") else "gate_self"
+                grads[pfx + key] = g.gate_pre
+            grads[pfx + "down_sampler.weight"] = g.wd.reshape(Cr, C // G, 1, 1)
+            grads[pfx + "up_sampler.weight"] = g.wu.reshape(C, Cr // G, 1, 1)
+            if cfg.ln_before:
+                grads[pfx + "ln_before.weight"], grads[pfx + "ln_before.bias"] = g.ln1_w, g.ln1_b
+            if cfg.ln_post:
+                grads[pfx + "ln_post.weight"], grads[pfx + "ln_post.bias"] = g.ln2_w, g.ln2_b
+            if bn_mode != BN_OFF:
+                grads[pfx + "bn1.weight"], grads[pfx + "bn1.bias"] = r1[e, :, 1], r1[e, :, 0]
+                grads[pfx + "bn2.weight"], grads[pfx + "bn2.bias"] = r2[e, :, 1], r2[e, :, 0]
+        return (None, dx, do) + tuple(grads[n] for n in names)

@@ -41,12 +41,13 @@ def gemm(A: torch.Tensor, B: torch.Tensor, *, a_kmajor: bool = True, b_kmajor: b
          out_dtype: Optional[torch.dtype] = None, alpha: float = 1.0,
          row_bias: Optional[torch.Tensor] = None, col_scale: Optional[torch.Tensor] = None,
          col_bias: Optional[torch.Tensor] = None, split_k: int = 1, out: Optional[torch.Tensor] = None,
-         accumulate: bool = False, impl: int = 0) -> torch.Tensor:
+         accumulate: bool = False, impl: int = 0, d_nbatch: int = 0) -> torch.Tensor:
     """D = alpha * A·Bᵀ (+ biases) on the tcgen05 GEMM.  Supported operand forms:
 
       A [M,K] (a_kmajor) | A [b,M,K] with B [b,N,K]  (sum over b: "K-batched")
       A [K,M] (a_kmajor=False: stored transposed)
       B [N,K] (b_kmajor) | B [K,N] (b_kmajor=False) | B [b,K,Nb] (b_kmajor=False: "N-batched", D is [b,M,Nb])
+      d_nbatch=Nb with a K-major B [b*Nb, K]: rows are (batch, n) pairs and D is written as [b, M, Nb]
     Inner dimension must be contiguous; row/batch pitches are taken from the strides."""
     _require_cuda(A, B)
     assert A.dtype == B.dtype
@@ -88,9 +89,12 @@ def gemm(A: torch.Tensor, B: torch.Tensor, *, a_kmajor: bool = True, b_kmajor: b
             a.ldb = B.stride(0)
             N = Nb
     assert K == Kb, f"K mismatch {K} vs {Kb}"
+    if d_nbatch:
+        assert b_kmajor and B.dim() == 2 and N % d_nbatch == 0
+        Nb = d_nbatch
     a.M, a.N, a.K, a.Nb = M, N, K, Nb
     if out is None:
-        shape = (a.b_batch, M, Nb) if (not b_kmajor and B.dim() == 3) else (M, N)
+        shape = (N // Nb, M, Nb) if ((not b_kmajor and B.dim() == 3) or d_nbatch) else (M, N)
         out = torch.empty(shape, device=A.device, dtype=out_dtype)
     assert out.stride(-1) == 1
     if out.dim() == 3:

@@ -69,7 +69,9 @@ const char* avmoe_last_error(void);
  *   b_kmajor=0: B is [b_batch][K][Nb]  (Nb contiguous, pitch ldb, batch pitch b_bstride); the
  *               GEMM N axis is the concatenation (b, nb), N = b_batch*Nb, and D is written
  *               as [b_batch][M][Nb] (pitch ldd, batch pitch d_bstride).
- *   Otherwise D is [M][N] with pitch ldd.  d_dtype: AVMOE_F32 or AVMOE_BF16.
+ *   Nb: 0 (or N) = D is [M][N] with pitch ldd.  0 < Nb < N = the N axis is a concatenation of N/Nb batches
+ *               and D is written as [N/Nb][M][Nb] (pitch ldd, batch pitch d_bstride) — also valid with a
+ *               K-major B whose rows are the flattened (batch, n) pairs.  d_dtype: AVMOE_F32 or AVMOE_BF16.
  *   split_k>1: K range is split over split_k CTAs that atomically add into a zero-initialised
  *               fp32 D (the call zeroes it); biases are added once.
  *   impl: 0 = tcgen05 whenever TMA/UMMA can express the operands (16-byte pitches, per-batch MN extents
@@ -85,7 +87,7 @@ typedef struct {
   int64_t lda, ldb, ldd;
   int32_t a_batch, b_batch;   /* see above */
   int64_t a_bstride, b_bstride, d_bstride;
-  int64_t Nb;                 /* per-batch N extent when b_kmajor=0 and b_batch>1, else N */
+  int64_t Nb;                 /* per-batch N extent of D (see above); 0 = unbatched */
   float alpha;
   const float* row_bias;      /* [M] or NULL */
   const float* col_scale;     /* [Nb] or NULL (=1) ; multiplies row_bias */

@@ -1,0 +1,485 @@
+"""TEST INFRASTRUCTURE — torch emulation of every kernel in the C ABI (device-agnostic).
+
+Each function has exactly the signature of its counterpart in ``avmoe_b200.ops`` and states, in
+plain torch, what that CUDA kernel must compute.  Two uses:
+  * CPU tests run ``avmoe_b200.functional`` with ``K = kernel_emulation`` to validate the host
+    orchestration (pass structure, BatchNorm-from-moments algebra, hand-derived backward) against
+    the oracle / golden vectors without a GPU;
+  * GPU tests compare each CUDA kernel against its emulation on random inputs (unit parity).
+It is never imported by the product package.
+"""
+from __future__ import annotations
+
+import math
+from typing import List, Optional
+
+import torch
+import torch.nn.functional as F
+
+from avmoe_b200.functional import (BN_EPS, BN_EVAL, BN_MOMENTUM, BN_OFF, BN_TRAIN, LN_EPS, PRE_AUX_ADD, PRE_AUX_REPLACE,
+                                   PRE_LATENT, PRE_NONE, AdapterConfig, ExpertGrads, ExpertPack)
+
+MHA_HEADS = 4
+
+
+# ------------------------------------------------------------------------------------------------ GEMM & small helpers
+def prep_weight(w: torch.Tensor, act_dtype, transpose: bool) -> torch.Tensor:
+    w = w.t() if transpose else w
+    return w.to(act_dtype).contiguous()
+
+
+def transpose(t: torch.Tensor) -> torch.Tensor:
+    return t.transpose(1, 2).contiguous()
+
+
+def gemm(A, B, *, a_kmajor=True, b_kmajor=True, out_dtype=None, alpha=1.0, row_bias=None, col_scale=None, col_bias=None,
+         split_k=1, out=None, accumulate=False, impl=0, d_nbatch=0):
+    out_dtype = out_dtype or A.dtype
+    Af, Bf = A.float(), B.float()
+    if not a_kmajor:
+        Af = Af.t()
+    if b_kmajor:
+        if Bf.dim() == 3:
+            D = torch.einsum("bmk,bnk->mn", Af, Bf)
+        else:
+            D = Af @ Bf.t()
+    else:
+        D = Af @ Bf if Bf.dim() == 2 else torch.einsum("mk,bkn->bmn", Af, Bf)
+    if d_nbatch:
+        D = D.reshape(D.shape[0], -1, d_nbatch).permute(1, 0, 2)
+    D = alpha * D
+    if row_bias is not None:
+        rb = row_bias[:, None] * (col_scale[None, :] if col_scale is not None else 1.0)
+        D = D + rb
+    if col_bias is not None:
+        D = D + col_bias
+    if out is not None:
+        if accumulate:
+            out += D.to(out.dtype)
+        else:
+            out.copy_(D.to(out.dtype))
+        return out
+    return D.to(out_dtype)
+
+
+def rowsum(w):
+    return w.float().sum(dim=1)
+
+
+def reduce_bias(dt, col_weight=None, row_weight=None):
+    d = dt.float()
+    rows_w = (d * (col_weight if col_weight is not None else 1.0)).sum(dim=(0, 2))
+    cols = d.sum(dim=(0, 1))
+    cols_w = (d * row_weight[None, :, None]).sum(dim=(0, 1)) if row_weight is not None else None
+    return rows_w, cols, cols_w
+
+
+def split_k_hint(k_rows, m, n):
+    return 1
+
+
+def pool(x):
+    return x.float().sum(dim=1)
+
+
+def broadcast_rows(dpool, n, dtype):
+    return dpool[:, None, :].expand(-1, n, -1).to(dtype).contiguous()
+
+
+# ------------------------------------------------------------------------------------------------ router
+def router_fwd(pool_x, pool_v, inv_n, rw, noise):
+    w0, b0, w2, b2, w4, b4 = rw
+    rin = torch.cat((pool_x, pool_v), dim=-1) * inv_n
+    h1 = torch.relu(rin @ w0.t() + b0)
+    h2 = torch.relu(h1 @ w2.t() + b2)
+    logits = h2 @ w4.t() + b4
+    if noise is not None:
+        logits = logits + noise
+    probs = torch.softmax(logits, dim=-1)
+    idx = torch.argmax(probs, dim=-1)
+    return probs, idx, h1, h2
+
+
+def router_bwd(dprobs, probs, h1, h2, pool_x, pool_v, inv_n, rw):
+    w0, b0, w2, b2, w4, b4 = rw
+    C = pool_x.shape[1]
+    rin = torch.cat((pool_x, pool_v), dim=-1) * inv_n
+    dlogits = probs * (dprobs - (dprobs * probs).sum(-1, keepdim=True))
+    dw4, db4 = dlogits.t() @ h2, dlogits.sum(0)
+    dh2 = (dlogits @ w4) * (h2 > 0)
+    dw2, db2 = dh2.t() @ h1, dh2.sum(0)
+    dh1 = (dh2 @ w2) * (h1 > 0)
+    dw0, db0 = dh1.t() @ rin, dh1.sum(0)
+    drin = (dh1 @ w0) * inv_n
+    return drin[:, :C].contiguous(), drin[:, C:].contiguous(), [dw0, db0, dw2, db2, dw4, db4]
+
+
+def lb_loss_fwd(probs):
+    return -(probs.mean(dim=0).log()).sum()
+
+
+def lb_loss_bwd(probs, dlb, dprobs):
+    bt = probs.shape[0]
+    dprobs += -dlb / (bt * probs.mean(dim=0, keepdim=True))
+
+
+# ------------------------------------------------------------------------------------------------ latent attention
+def latent_fwd(kv, tokens: List[torch.Tensor], slots: List[int], tokp, lse):
+    """tok' = tok + softmax_N(tok·kvᵀ)·kv ; lse = logsumexp_N(tok·kvᵀ).   (net_trans_v3.py:379-383)"""
+    kvf = kv.float()
+    for tok, s in zip(tokens, slots):
+        logits = torch.einsum("tc,bnc->btn", tok, kvf)
+        lse[:, s] = torch.logsumexp(logits, dim=-1)
+        tokp[:, s] = tok[None] + torch.softmax(logits, dim=-1) @ kvf
+
+
+def latent_bwd(kv, tokens, slots, tokp, lse, dtokp, dpool, dkv, accumulate, dtokens):
+    kvf = kv.float()
+    total = dkv.float() if accumulate else torch.zeros_like(kvf)
+    for tok, s, dtok in zip(tokens, slots, dtokens):
+        dR = dtokp[:, s]                                            # [BT,T,C]
+        R = tokp[:, s] - tok[None]
+        a1 = torch.exp(torch.einsum("tc,bnc->btn", tok, kvf) - lse[:, s][..., None])
+        dA = torch.einsum("btc,bnc->btn", dR, kvf)
+        dS = a1 * (dA - (dR * R).sum(-1, keepdim=True))
+        total = total + torch.einsum("btn,btc->bnc", a1, dR) + torch.einsum("btn,tc->bnc", dS, tok)
+        dtok += dR.sum(0) + torch.einsum("btn,bnc->tc", dS, kvf)
+    if dpool is not None:
+        total = total + dpool[:, None, :]
+    dkv.copy_(total.to(dkv.dtype))
+
+
+# ------------------------------------------------------------------------------------------------ AVVP NxN self-attention
+def selfattn_nxn_fwd(x):
+    """aux_j = sum_i softmax_j(x_i·x_·)[j] x_i   (mgn.py:132-137).  Saves the row log-sum-exps."""
+    xf = x.float()
+    s = xf @ xf.transpose(1, 2)
+    lse_rows = torch.logsumexp(s, dim=-1)                            # [BT,N]
+    att = torch.exp(s - lse_rows[..., None])
+    return (att.transpose(1, 2) @ xf).to(x.dtype), lse_rows
+
+
+def selfattn_nxn_bwd(x, lse_rows, daux, dx):
+    xf, g = x.float(), daux.float()
+    s = xf @ xf.transpose(1, 2)
+    att = torch.exp(s - lse_rows[..., None])                          # att[i,j]
+    # aux_j = sum_i att[i,j] x_i
+    datt = xf @ g.transpose(1, 2)                                     # datt[i,j] = x_i · g_j
+    ds = att * (datt - (att * datt).sum(-1, keepdim=True))
+    d = att @ g + ds @ xf + ds.transpose(1, 2) @ xf
+    dx += d.to(dx.dtype)
+
+
+# ------------------------------------------------------------------------------------------------ AVS v1 MHA over the BT axis
+def mha_fwd(x, mp):
+    w_in, b_in, w_out, b_out = mp
+    L, B, C = x.shape
+    hd = C // MHA_HEADS
+    xf = x.float()
+    qkv = xf @ w_in.t() + b_in
+    q, k, v = qkv.split(C, dim=-1)
+
+    def heads(t):
+        return t.reshape(L, B * MHA_HEADS, hd).transpose(0, 1)
+    qh, kh, vh = heads(q), heads(k), heads(v)
+    att = torch.softmax((qh / math.sqrt(hd)) @ kh.transpose(1, 2), dim=-1)
+    ctxv = (att @ vh).transpose(0, 1).reshape(L, B, C)
+    out = ctxv @ w_out.t() + b_out
+    return out.to(x.dtype), (qkv, att, ctxv)
+
+
+def mha_bwd(x, mp, saved, daux, dx):
+    w_in, b_in, w_out, b_out = mp
+    qkv, att, ctxv = saved
+    L, B, C = x.shape
+    hd = C // MHA_HEADS
+    g = daux.float()
+    dw_out = g.reshape(-1, C).t() @ ctxv.reshape(-1, C)
+    db_out = g.sum(dim=(0, 1))
+    dctx = g @ w_out
+
+    def heads(t):
+        return t.reshape(L, B * MHA_HEADS, hd).transpose(0, 1)
+    q, k, v = qkv.split(C, dim=-1)
+    qh, kh, vh, dch = heads(q), heads(k), heads(v), heads(dctx)
+    datt = dch @ vh.transpose(1, 2)
+    dvh = att.transpose(1, 2) @ dch
+    ds = att * (datt - (att * datt).sum(-1, keepdim=True))
+    dqh = (ds @ kh) / math.sqrt(hd)
+    dkh = ds.transpose(1, 2) @ (qh / math.sqrt(hd))
+
+    def unheads(t):
+        return t.transpose(0, 1).reshape(L, B, C)
+    dqkv = torch.cat((unheads(dqh), unheads(dkh), unheads(dvh)), dim=-1)
+    dw_in = dqkv.reshape(-1, 3 * C).t() @ x.float().reshape(-1, C)
+    db_in = dqkv.sum(dim=(0, 1))
+    dx += (dqkv @ w_in).to(dx.dtype)
+    return [dw_in, db_in, dw_out, db_out]
+
+
+# ------------------------------------------------------------------------------------------------ expert kernels
+def _ln_stats(t):
+    mean = t.mean(-1, keepdim=True)
+    rstd = torch.rsqrt(t.var(-1, unbiased=False, keepdim=True) + LN_EPS)
+    return mean, rstd
+
+
+def _grouped(x, w, G):
+    """x [...,Cin], w [Cout, Cin/G] -> [...,Cout]"""
+    Cout, Cin_g = w.shape
+    lead = x.shape[:-1]
+    xg = x.reshape(*lead, G, Cin_g)
+    wg = w.reshape(G, Cout // G, Cin_g)
+    return torch.einsum("...gi,goi->...go", xg, wg).reshape(*lead, Cout)
+
+
+def _grouped_t(dy, w, G):
+    """dy [...,Cout], w [Cout, Cin/G] -> dx [...,Cin]"""
+    Cout, Cin_g = w.shape
+    lead = dy.shape[:-1]
+    dyg = dy.reshape(*lead, G, Cout // G)
+    wg = w.reshape(G, Cout // G, Cin_g)
+    return torch.einsum("...go,goi->...gi", dyg, wg).reshape(*lead, G * Cin_g)
+
+
+def _grouped_wgrad(dy, x, G):
+    """sum over leading dims of dy^T x per group -> [Cout, Cin/G]"""
+    Cout, Cin = dy.shape[-1], x.shape[-1]
+    dyg = dy.reshape(-1, G, Cout // G)
+    xg = x.reshape(-1, G, Cin // G)
+    return torch.einsum("ngo,ngi->goi", dyg, xg).reshape(Cout, Cin // G)
+
+
+def _pre_transform(x, tokp, pk: ExpertPack):
+    """returns (xa, cache) with xa = the tensor ln_before sees."""
+    xf = x.float()
+    if pk.pre_kind == PRE_NONE:
+        return xf, None
+    if pk.pre_kind == PRE_LATENT:
+        tp = tokp[:, pk.latent_slot]                                  # [BT,T,C]
+        a2 = torch.softmax(xf @ tp.transpose(1, 2), dim=-1)           # [BT,N,T]
+        xr = a2 @ tp
+        return xf + pk.gate_pre * xr, (a2, xr, tp)
+    if pk.pre_kind == PRE_AUX_ADD:
+        return xf + pk.gate_pre * pk.aux.float(), None
+    return pk.aux.float(), None
+
+
+def expert_front_fwd(cfg: AdapterConfig, x, tokp, packs: List[ExpertPack], z, stats1):
+    for e, pk in enumerate(packs):
+        xa, _ = _pre_transform(x, tokp, pk)
+        xn = F.layer_norm(xa, (cfg.C,), pk.ln1_w, pk.ln1_b, LN_EPS) if pk.ln1_w is not None else xa
+        ze = _grouped(xn, pk.wd, cfg.G)
+        z[:, :, e, :] = ze
+        if stats1 is not None:
+            stats1[e, :, 0] += ze.double().sum(dim=(0, 1))
+            stats1[e, :, 1] += (ze.double() ** 2).sum(dim=(0, 1))
+
+
+def _running_update(rm, rv, mean, var_biased, n):
+    rm.mul_(1 - BN_MOMENTUM).add_(BN_MOMENTUM * mean.to(rm.dtype))
+    rv.mul_(1 - BN_MOMENTUM).add_(BN_MOMENTUM * (var_biased * (n / max(n - 1, 1))).to(rv.dtype))
+
+
+def bn1_finalize(cfg, stats1, n, bn_w, bn_b, train):
+    E, Cr = cfg.E, cfg.Cr
+    dev = bn_w[0][0].device
+    aff = torch.empty((E, Cr, 2), device=dev, dtype=torch.float32)
+    save = torch.empty((E, Cr, 2), device=dev, dtype=torch.float32)
+    for e in range(E):
+        w1, b1 = bn_w[e][0], bn_w[e][1]
+        rm1, rv1 = bn_b[e][0], bn_b[e][1]
+        if train:
+            mean = stats1[e, :, 0] / n
+            var = (stats1[e, :, 1] / n - mean * mean).clamp_min(0)
+            _running_update(rm1, rv1, mean, var, n)
+        else:
+            mean, var = rm1.double(), rv1.double()
+        invstd = torch.rsqrt(var + BN_EPS)
+        aff[e, :, 0] = (w1.double() * invstd).float()
+        aff[e, :, 1] = (b1.double() - mean * w1.double() * invstd).float()
+        save[e, :, 0], save[e, :, 1] = mean.float(), invstd.float()
+    return aff, save
+
+
+def _act(zt, relu):
+    return torch.relu(zt) if relu else zt
+
+
+def bn_moments(cfg, z, aff1, packs):
+    E, Cr, G = cfg.E, cfg.Cr, cfg.G
+    crg = Cr // G
+    m1 = torch.zeros((E, Cr), device=z.device, dtype=torch.float64)
+    m2 = torch.zeros((E, G, crg, crg), device=z.device, dtype=torch.float64)
+    for e, pk in enumerate(packs):
+        a = _act(z[:, :, e, :] * aff1[e, :, 0] + aff1[e, :, 1], pk.relu).double().reshape(-1, G, crg)
+        m1[e] = a.sum(0).reshape(Cr)
+        m2[e] = torch.einsum("ngj,ngk->gjk", a, a)
+    return m1, m2
+
+
+def bn2_finalize(cfg, moments, n, packs, bn_w, bn_b, train):
+    E, C, Cr, G = cfg.E, cfg.C, cfg.Cr, cfg.G
+    crg, cg = Cr // G, C // G
+    dev = bn_w[0][0].device
+    aff = torch.empty((E, C, 2), device=dev, dtype=torch.float32)
+    save = torch.empty((E, C, 2), device=dev, dtype=torch.float32)
+    for e, pk in enumerate(packs):
+        w2, b2 = bn_w[e][2], bn_w[e][3]
+        rm2, rv2 = bn_b[e][2], bn_b[e][3]
+        if train:
+            m1, m2 = moments
+            wu = pk.wu.double().reshape(G, cg, crg)                   # [g, c_local, j]
+            ea = (m1[e] / n).reshape(G, crg)
+            eaa = m2[e] / n                                           # [g, j, k]
+            mean = torch.einsum("gcj,gj->gc", wu, ea).reshape(C)
+            ey2 = torch.einsum("gcj,gjk,gck->gc", wu, eaa, wu).reshape(C)
+            var = (ey2 - mean * mean).clamp_min(0)
+            _running_update(rm2, rv2, mean, var, n)
+        else:
+            mean, var = rm2.double(), rv2.double()
+        invstd = torch.rsqrt(var + BN_EPS)
+        aff[e, :, 0] = (w2.double() * invstd).float()
+        aff[e, :, 1] = (b2.double() - mean * w2.double() * invstd).float()
+        save[e, :, 0], save[e, :, 1] = mean.float(), invstd.float()
+    return aff, save
+
+
+def _back_recompute(cfg, z, bn, pk, e):
+    """from z recompute a, y, yt (post-bn2), ln2 stats"""
+    ze = z[:, :, e, :]
+    if bn is not None:
+        aff1, save1, aff2, save2 = bn
+        zt = ze * aff1[e, :, 0] + aff1[e, :, 1]
+    else:
+        zt = ze
+    a = _act(zt, pk.relu)
+    y = _grouped(a, pk.wu, cfg.G)
+    yt = y * bn[2][e, :, 0] + bn[2][e, :, 1] if bn is not None else y
+    return zt, a, y, yt
+
+
+def expert_back_fwd(cfg, z, bn, packs, probs, out):
+    acc = torch.zeros(z.shape[0], z.shape[1], cfg.C, device=z.device, dtype=torch.float32)
+    for e, pk in enumerate(packs):
+        _, _, _, yt = _back_recompute(cfg, z, bn, pk, e)
+        q = F.layer_norm(yt, (cfg.C,), pk.ln2_w, pk.ln2_b, LN_EPS) if pk.ln2_w is not None else yt
+        if pk.gate is not None:
+            q = q * pk.gate
+        acc = acc + probs[:, e, None, None] * q
+    out.copy_(acc.to(out.dtype))
+
+
+def _back_dyt(cfg, dout, z, bn, pk, e, probs):
+    """shared by the stats pass and the main backward: returns intermediates up to dyt."""
+    zt, a, y, yt = _back_recompute(cfg, z, bn, pk, e)
+    g = dout.float()
+    if pk.ln2_w is not None:
+        mean, rstd = _ln_stats(yt)
+        qhat = (yt - mean) * rstd
+        q = qhat * pk.ln2_w + pk.ln2_b
+    else:
+        qhat, q = None, yt
+    gate = pk.gate if pk.gate is not None else 1.0
+    dq = g * (probs[:, e, None, None] * gate)
+    if pk.ln2_w is not None:
+        dqh = dq * pk.ln2_w
+        dyt = rstd * (dqh - dqh.mean(-1, keepdim=True) - qhat * (dqh * qhat).mean(-1, keepdim=True))
+    else:
+        dyt = dq
+    return zt, a, y, yt, q, qhat, dq, dyt, g
+
+
+def expert_back_bwd_stats(cfg, dout, z, bn, packs, probs, red2):
+    for e, pk in enumerate(packs):
+        zt, a, y, yt, q, qhat, dq, dyt, g = _back_dyt(cfg, dout, z, bn, pk, e, probs)
+        yhat = (y - bn[3][e, :, 0]) * bn[3][e, :, 1]
+        red2[e, :, 0] += dyt.double().sum(dim=(0, 1))
+        red2[e, :, 1] += (dyt * yhat).double().sum(dim=(0, 1))
+
+
+def expert_back_bwd(cfg, dout, z, bn, bn_mode, red2, red2b, packs, probs, dzt, dprobs, red1, egr: List[ExpertGrads]):
+    n = z.shape[0] * z.shape[1]
+    for e, (pk, gr) in enumerate(zip(packs, egr)):
+        zt, a, y, yt, q, qhat, dq, dyt, g = _back_dyt(cfg, dout, z, bn, pk, e, probs)
+        gq = (g * q).sum(dim=(1, 2))                                  # [BT]  sum dout*q (q before gate)
+        gate = pk.gate if pk.gate is not None else 1.0
+        dprobs[:, e] += gq * gate
+        if gr.gate is not None:
+            gr.gate += (gq * probs[:, e]).sum()
+        if pk.ln2_w is not None:
+            gr.ln2_w += (dq * qhat).sum(dim=(0, 1))
+            gr.ln2_b += dq.sum(dim=(0, 1))
+        if bn_mode != BN_OFF:
+            aff2, save2 = bn[2], bn[3]
+            yhat = (y - save2[e, :, 0]) * save2[e, :, 1]
+            if bn_mode == BN_TRAIN:
+                m_d = (red2[e, :, 0] / n).float()
+                m_dy = (red2[e, :, 1] / n).float()
+                dy = aff2[e, :, 0] * (dyt - m_d - yhat * m_dy)
+            else:
+                dy = aff2[e, :, 0] * dyt
+                red2b[e, :, 0] += dyt.double().sum(dim=(0, 1))
+                red2b[e, :, 1] += (dyt * yhat).double().sum(dim=(0, 1))
+        else:
+            dy = dyt
+        gr.wu += _grouped_wgrad(dy, a, cfg.G)
+        da = _grouped_t(dy, pk.wu, cfg.G)
+        d = da * (zt > 0) if pk.relu else da
+        dzt[:, :, e, :] = d
+        if bn_mode != BN_OFF:
+            save1 = bn[1]
+            zhat = (z[:, :, e, :] - save1[e, :, 0]) * save1[e, :, 1]
+            red1[e, :, 0] += d.double().sum(dim=(0, 1))
+            red1[e, :, 1] += (d * zhat).double().sum(dim=(0, 1))
+
+
+def expert_front_bwd(cfg, x, tokp, dzt, z, bn, bn_mode, red1, packs, dpool_x, dx, dtokp, egr: List[ExpertGrads]):
+    n = x.shape[0] * x.shape[1]
+    xf = x.float()
+    dxa_total = dpool_x[:, None, :].expand_as(xf).clone()
+    for e, (pk, gr) in enumerate(zip(packs, egr)):
+        d = dzt[:, :, e, :]
+        if bn_mode != BN_OFF:
+            aff1, save1 = bn[0], bn[1]
+            if bn_mode == BN_TRAIN:
+                zhat = (z[:, :, e, :] - save1[e, :, 0]) * save1[e, :, 1]
+                dz = aff1[e, :, 0] * (d - (red1[e, :, 0] / n).float() - zhat * (red1[e, :, 1] / n).float())
+            else:
+                dz = aff1[e, :, 0] * d
+        else:
+            dz = d
+        xa, cache = _pre_transform(x, tokp, pk)
+        if pk.ln1_w is not None:
+            mean, rstd = _ln_stats(xa)
+            xhat = (xa - mean) * rstd
+            xn = xhat * pk.ln1_w + pk.ln1_b
+        else:
+            xn = xa
+        gr.wd += _grouped_wgrad(dz, xn, cfg.G)
+        dxn = _grouped_t(dz, pk.wd, cfg.G)
+        if pk.ln1_w is not None:
+            gr.ln1_w += (dxn * xhat).sum(dim=(0, 1))
+            gr.ln1_b += dxn.sum(dim=(0, 1))
+            dh = dxn * pk.ln1_w
+            dxa = rstd * (dh - dh.mean(-1, keepdim=True) - xhat * (dh * xhat).mean(-1, keepdim=True))
+        else:
+            dxa = dxn
+        if pk.pre_kind == PRE_NONE:
+            dxa_total += dxa
+        elif pk.pre_kind == PRE_LATENT:
+            a2, xr, tp = cache
+            dxa_total += dxa
+            gr.gate_pre += (dxa * xr).sum()
+            dxr = dxa * pk.gate_pre
+            da2 = dxr @ tp.transpose(1, 2)                            # [BT,N,T]
+            ds2 = a2 * (da2 - (a2 * da2).sum(-1, keepdim=True))
+            dxa_total += ds2 @ tp
+            dtokp[:, pk.latent_slot] += a2.transpose(1, 2) @ dxr + ds2.transpose(1, 2) @ xf
+        elif pk.pre_kind == PRE_AUX_ADD:
+            dxa_total += dxa
+            gr.gate_pre += (dxa * pk.aux.float()).sum()
+            gr.aux.copy_((dxa * pk.gate_pre).to(gr.aux.dtype))
+        else:
+            gr.aux.copy_(dxa.to(gr.aux.dtype))
+    dx.copy_(dxa_total.to(dx.dtype))

@@ -104,6 +104,21 @@ def test_gemm_kmajor_a_mnmajor_b_flat(dtype):
 
 
 @pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32])
+@pytest.mark.parametrize("impl", [0, 1])
+@pytest.mark.parametrize("Nb", [96, 64, 384])
+def test_gemm_kmajor_b_nbatched_output(dtype, impl, Nb):
+    """resampler forward in TN form: D[b][m][c] = sum_k W[m,k] * Pt[(b,c),k]  (B K-major, N-batched D)."""
+    from avmoe_b200 import ops
+    b, M, K = 5, 200, 144
+    W, Pt = _mk((M, K), dtype, 1), _mk((b * Nb, K), dtype, 2)
+    rb, cs, cb = _mk((M,), torch.float32, 3), _mk((Nb,), torch.float32, 4), _mk((Nb,), torch.float32, 5)
+    D = ops.gemm(W, Pt, d_nbatch=Nb, row_bias=rb, col_scale=cs, col_bias=cb, impl=impl)
+    ref = torch.einsum("mk,bnk->bmn", W.float(), Pt.float().reshape(b, Nb, K)) + rb[None, :, None] * cs[None, None, :] + cb[None, None, :]
+    assert D.shape == (b, M, Nb)
+    assert util.rel_err(D, ref) < _tol(dtype)
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32])
 def test_hot_shapes_stay_on_tensor_cores(dtype):
     """impl=2 refuses to fall back: the real backbone shapes must be expressible on tcgen05."""
     from avmoe_b200 import ops
