@@ -67,3 +67,44 @@ def exported_symbols():
     hdr = os.path.join(os.path.dirname(_build.PKG_DIR), "include", "avmoe_b200.h")
     txt = open(hdr).read()
     return sorted(set(re.findall(r"\b(avmoe_[a-z0-9_]+)\s*\(", txt)))
+
+
+MAX_EXPERTS = 8
+
+
+class Expert(C.Structure):
+    _fields_ = [
+        ("pre_kind", C.c_int32), ("relu", C.c_int32), ("latent_slot", C.c_int32), ("_pad", C.c_int32),
+        ("gate_pre", C.c_void_p), ("aux", C.c_void_p), ("ln1_w", C.c_void_p), ("ln1_b", C.c_void_p),
+        ("wd", C.c_void_p), ("wu", C.c_void_p), ("ln2_w", C.c_void_p), ("ln2_b", C.c_void_p), ("gate", C.c_void_p),
+        ("g_gate_pre", C.c_void_p), ("g_aux", C.c_void_p), ("g_ln1_w", C.c_void_p), ("g_ln1_b", C.c_void_p),
+        ("g_wd", C.c_void_p), ("g_wu", C.c_void_p), ("g_ln2_w", C.c_void_p), ("g_ln2_b", C.c_void_p), ("g_gate", C.c_void_p),
+    ]
+
+
+class ExpertArgs(C.Structure):
+    _fields_ = [
+        ("BT", C.c_int32), ("N", C.c_int32), ("C", C.c_int32), ("Cr", C.c_int32), ("G", C.c_int32), ("T", C.c_int32),
+        ("E", C.c_int32), ("nl", C.c_int32), ("dtype", C.c_int32), ("bn_mode", C.c_int32),
+        ("ex", Expert * MAX_EXPERTS),
+        ("x", C.c_void_p), ("tokp", C.c_void_p), ("z", C.c_void_p), ("stats1", C.c_void_p),
+        ("aff1", C.c_void_p), ("save1", C.c_void_p), ("aff2", C.c_void_p), ("save2", C.c_void_p),
+        ("probs", C.c_void_p), ("out", C.c_void_p), ("dout", C.c_void_p),
+        ("red2", C.c_void_p), ("red2b", C.c_void_p), ("red1", C.c_void_p),
+        ("dzt", C.c_void_p), ("dprobs", C.c_void_p), ("dpool_x", C.c_void_p), ("dx", C.c_void_p), ("dtokp", C.c_void_p),
+    ]
+
+
+_PtrArr = C.c_void_p * MAX_EXPERTS
+
+
+class BnArgs(C.Structure):
+    _fields_ = [
+        ("E", C.c_int32), ("C", C.c_int32), ("Cr", C.c_int32), ("G", C.c_int32), ("train", C.c_int32), ("_pad", C.c_int32),
+        ("n", C.c_int64),
+        ("w1", _PtrArr), ("b1", _PtrArr), ("w2", _PtrArr), ("b2", _PtrArr),
+        ("rm1", _PtrArr), ("rv1", _PtrArr), ("rm2", _PtrArr), ("rv2", _PtrArr),
+        ("wu", _PtrArr),
+        ("stats1", C.c_void_p), ("m1", C.c_void_p), ("m2", C.c_void_p),
+        ("aff1", C.c_void_p), ("save1", C.c_void_p), ("aff2", C.c_void_p), ("save2", C.c_void_p),
+    ]

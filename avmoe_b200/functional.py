@@ -244,9 +244,9 @@ class MoEAdapterFunction(torch.autograd.Function):
         # 1. resampler
         v, rs_saved = resample_fwd(K, cfg, o, P["conv_adapter.weight"], P["conv_adapter.bias"], P["fc.weight"], P["fc.bias"])
         # 2. router
-        pool_x, pool_v = K.pool(x), K.pool(v)                                    # [BT,C] fp32 sums
+        pool_x, pool_v = K.pool(x), K.pool(v)                                    # [BT,chunks,C] fp32 partial sums
         rw = [P[f"router.{i}.{w}"] for i in (0, 2, 4) for w in ("weight", "bias")]
-        probs, idx, h1, h2 = K.router_fwd(pool_x, pool_v, 1.0 / N, rw, state.get("noise"))
+        probs, idx, h1, h2, rin = K.router_fwd(pool_x, pool_v, 1.0 / N, rw, state.get("noise"))
         # 3. per-expert pre-transforms that are separate kernels
         prefixes = expert_prefixes(cfg)
         kinds = cfg.expert_kinds()
@@ -324,7 +324,7 @@ class MoEAdapterFunction(torch.autograd.Function):
         ctx.packs_meta = [(pk.pre_kind, pk.relu, pk.latent_slot) for pk in packs]
         ctx.bn = bn
         ctx.aux = [pk.aux for pk in packs]
-        ctx.save_for_backward(x, o, v, pool_x, pool_v, probs, h1, h2, tokp, lse, z, *params)
+        ctx.save_for_backward(x, o, v, rin, probs, h1, h2, tokp, lse, z, *params)
         ctx.mark_non_differentiable(idx)
         return out, probs, lb, idx
 
@@ -334,7 +334,7 @@ class MoEAdapterFunction(torch.autograd.Function):
         cfg: AdapterConfig = state["cfg"]
         K = state["K"]
         names = ctx.names
-        x, o, v, pool_x, pool_v, probs, h1, h2, tokp, lse, z, *params = ctx.saved_tensors
+        x, o, v, rin, probs, h1, h2, tokp, lse, z, *params = ctx.saved_tensors
         P: Dict[str, torch.Tensor] = dict(zip(names, params))
         BT, N, C = x.shape
         E, Cr, G, T = cfg.E, cfg.Cr, cfg.G, cfg.T
@@ -392,7 +392,7 @@ class MoEAdapterFunction(torch.autograd.Function):
         if cfg.lb_loss and dlb is not None:
             K.lb_loss_bwd(probs, dlb.to(f32), dprobs)                            # accumulates into dprobs
         rw = [P[f"router.{i}.{w}"] for i in (0, 2, 4) for w in ("weight", "bias")]
-        dpool_x, dpool_v, drw = K.router_bwd(dprobs, probs, h1, h2, pool_x, pool_v, 1.0 / N, rw)
+        dpool_x, dpool_v, drw = K.router_bwd(dprobs, probs, h1, h2, rin, 1.0 / N, rw)
         for (i, w), g in zip([(i, w) for i in (0, 2, 4) for w in ("weight", "bias")], drw):
             grads[f"router.{i}.{w}"] = g
         # 3. expert front backward

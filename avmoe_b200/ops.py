@@ -110,3 +110,290 @@ def gemm(A: torch.Tensor, B: torch.Tensor, *, a_kmajor: bool = True, b_kmajor: b
     a.split_k, a.accumulate, a.impl = split_k, int(accumulate), impl
     _lib.check(_lib.load().avmoe_gemm(C.byref(a), _stream()), "gemm")
     return out
+
+
+# ------------------------------------------------------------------------------------------------ layout helpers
+def _lib_call(name, *args):
+    fn = getattr(_lib.load(), "avmoe_" + name)
+    _lib.check(fn(*args), name)
+
+
+def transpose(t: torch.Tensor, out_dtype: Optional[torch.dtype] = None) -> torch.Tensor:
+    """[b,R,C] -> [b,C,R] (contiguous)."""
+    _require_cuda(t)
+    assert t.dim() == 3 and t.is_contiguous()
+    b, R, Cc = t.shape
+    out = torch.empty((b, Cc, R), device=t.device, dtype=out_dtype or t.dtype)
+    _lib_call("transpose", _ptr(t), _ptr(out), b, R, Cc, C.c_int64(Cc), C.c_int64(R * Cc), C.c_int64(R), C.c_int64(R * Cc),
+              _dt(t), _dt(out), _stream())
+    return out
+
+
+def prep_weight(w: torch.Tensor, act_dtype: torch.dtype, transpose_: bool) -> torch.Tensor:
+    """fp32 master weight [R,C] -> GEMM operand in the activation dtype, optionally transposed to [C,R]."""
+    _require_cuda(w)
+    assert w.dim() == 2 and w.dtype == torch.float32
+    w = w.contiguous()
+    if transpose_:
+        return transpose(w.unsqueeze(0), act_dtype).squeeze(0)
+    if act_dtype == torch.float32:
+        return w
+    out = torch.empty(w.shape, device=w.device, dtype=act_dtype)
+    _lib_call("cast", _ptr(w), _ptr(out), C.c_int64(w.numel()), _dt(w), _dt(out), _stream())
+    return out
+
+
+def rowsum(w: torch.Tensor) -> torch.Tensor:
+    _require_cuda(w)
+    w = w.contiguous()
+    out = torch.empty(w.shape[0], device=w.device, dtype=torch.float32)
+    _lib_call("rowsum", _ptr(w), _ptr(out), w.shape[0], w.shape[1], _stream())
+    return out
+
+
+def reduce_bias(d: torch.Tensor, col_weight=None, row_weight=None):
+    _require_cuda(d)
+    assert d.dim() == 3 and d.is_contiguous()
+    BT, N, Cc = d.shape
+    f32 = dict(device=d.device, dtype=torch.float32)
+    rows_w = torch.empty(N, **f32)
+    cols = torch.empty(Cc, **f32)
+    cols_w = torch.empty(Cc, **f32) if row_weight is not None else None
+    _lib_call("reduce_bias", _ptr(d), _ptr(col_weight), _ptr(row_weight), _ptr(rows_w), _ptr(cols), _ptr(cols_w), BT, N, Cc, _dt(d), _stream())
+    return rows_w, cols, cols_w
+
+
+def split_k_hint(k_rows: int, m: int, n: int) -> int:
+    """split-K factor for the skinny weight-gradient GEMMs ([m,n] output, k_rows reduction)."""
+    tiles = ((m + 127) // 128) * ((n + 255) // 256)
+    want = max(1, (2 * 148) // tiles)
+    return int(min(want, max(1, k_rows // 256)))
+
+
+def pool(x: torch.Tensor) -> torch.Tensor:
+    _require_cuda(x)
+    assert x.dim() == 3 and x.is_contiguous()
+    BT, N, Cc = x.shape
+    chunks = _lib.load().avmoe_pool_chunks(BT, N)
+    part = torch.empty((BT, chunks, Cc), device=x.device, dtype=torch.float32)
+    _lib_call("pool", _ptr(x), _ptr(part), BT, N, Cc, chunks, _dt(x), _stream())
+    return part
+
+
+def broadcast_rows(dpool: torch.Tensor, n: int, dtype: torch.dtype) -> torch.Tensor:
+    BT, Cc = dpool.shape
+    out = torch.empty((BT, n, Cc), device=dpool.device, dtype=dtype)
+    _lib_call("broadcast_rows", _ptr(dpool), _ptr(out), BT, n, Cc, _dt(out), _stream())
+    return out
+
+
+# ------------------------------------------------------------------------------------------------ router
+def router_fwd(pool_x, pool_v, inv_n, rw, noise):
+    _require_cuda(pool_x, pool_v)
+    w0, b0, w2, b2, w4, b4 = [t.contiguous() for t in rw]
+    BT, chx, Cc = pool_x.shape
+    chv = pool_v.shape[1]
+    E = w4.shape[0]
+    f32 = dict(device=pool_x.device, dtype=torch.float32)
+    probs = torch.empty((BT, E), **f32)
+    idx = torch.empty((BT,), device=pool_x.device, dtype=torch.int64)
+    h1, h2, rin = torch.empty((BT, 128), **f32), torch.empty((BT, 32), **f32), torch.empty((BT, 2 * Cc), **f32)
+    if noise is not None:
+        noise = noise.to(torch.float32).contiguous()
+    _lib_call("router_fwd", _ptr(pool_x), _ptr(pool_v), chx, chv, BT, Cc, E, C.c_float(inv_n), _ptr(w0), _ptr(b0), _ptr(w2), _ptr(b2),
+              _ptr(w4), _ptr(b4), _ptr(noise), _ptr(probs), _ptr(idx), _ptr(h1), _ptr(h2), _ptr(rin), _stream())
+    return probs, idx, h1, h2, rin
+
+
+def router_bwd(dprobs, probs, h1, h2, rin, inv_n, rw):
+    w0, b0, w2, b2, w4, b4 = [t.contiguous() for t in rw]
+    BT, E = probs.shape
+    Cc = rin.shape[1] // 2
+    f32 = dict(device=probs.device, dtype=torch.float32)
+    ws = torch.empty(BT * (E + 32 + 128), **f32)
+    dpx, dpv = torch.empty((BT, Cc), **f32), torch.empty((BT, Cc), **f32)
+    grads = [torch.empty_like(t) for t in (w0, b0, w2, b2, w4, b4)]
+    _lib_call("router_bwd", _ptr(dprobs.contiguous()), _ptr(probs), _ptr(h1), _ptr(h2), _ptr(rin), BT, Cc, E, C.c_float(inv_n),
+              _ptr(w0), _ptr(w2), _ptr(w4), _ptr(ws), _ptr(dpx), _ptr(dpv), *[_ptr(g) for g in grads], _stream())
+    return dpx, dpv, grads
+
+
+def lb_loss_fwd(probs):
+    loss = torch.empty((), device=probs.device, dtype=torch.float32)
+    _lib_call("lb_loss_fwd", _ptr(probs), _ptr(loss), probs.shape[0], probs.shape[1], _stream())
+    return loss
+
+
+def lb_loss_bwd(probs, dlb, dprobs):
+    _lib_call("lb_loss_bwd", _ptr(probs), _ptr(dlb.contiguous()), _ptr(dprobs), probs.shape[0], probs.shape[1], _stream())
+
+
+# ------------------------------------------------------------------------------------------------ latent attention
+def _ptr_array(tensors):
+    arr = (C.c_void_p * len(tensors))(*[t.data_ptr() for t in tensors])
+    return arr
+
+
+def latent_fwd(kv, tokens, slots, tokp, lse):
+    _require_cuda(kv)
+    assert kv.is_contiguous()
+    BT, Nk, Cc = kv.shape
+    T = tokens[0].shape[0]
+    nl = tokp.shape[1]
+    tokens = [t.contiguous() for t in tokens]
+    lib = _lib.load()
+    lib.avmoe_latent_fwd_workspace.restype = C.c_int64
+    nws = lib.avmoe_latent_fwd_workspace(BT, Nk, Cc, T, len(tokens))
+    ws = torch.empty(nws, device=kv.device, dtype=torch.float32)
+    _lib_call("latent_fwd", _ptr(kv), _ptr_array(tokens), (C.c_int * len(slots))(*slots), len(tokens), nl, _ptr(tokp), _ptr(lse), _ptr(ws),
+              BT, Nk, Cc, T, _dt(kv), _stream())
+
+
+def latent_bwd(kv, tokens, slots, tokp, lse, dtokp, dpool, dkv, accumulate, dtokens):
+    BT, Nk, Cc = kv.shape
+    T = tokens[0].shape[0]
+    nl = tokp.shape[1]
+    tokens = [t.contiguous() for t in tokens]
+    _lib_call("latent_bwd", _ptr(kv), _ptr_array(tokens), (C.c_int * len(slots))(*slots), len(tokens), nl, _ptr(tokp), _ptr(lse), _ptr(dtokp),
+              _ptr(dpool), _ptr(dkv), int(bool(accumulate)), _ptr_array(dtokens), BT, Nk, Cc, T, _dt(kv), _stream())
+
+
+# ------------------------------------------------------------------------------------------------ expert kernels
+def _expert_args(cfg, packs, egr=None, *, BT, dtype, bn_mode=0, nl=0):
+    a = _lib.ExpertArgs()
+    a.BT, a.N, a.C, a.Cr, a.G, a.T, a.E, a.nl = BT, cfg.N, cfg.C, cfg.Cr, cfg.G, cfg.T, cfg.E, nl
+    a.dtype, a.bn_mode = dtype, bn_mode
+    keep = []
+    for e, pk in enumerate(packs):
+        ex = a.ex[e]
+        ex.pre_kind, ex.relu, ex.latent_slot = pk.pre_kind, int(pk.relu), pk.latent_slot
+        for name in ("gate_pre", "aux", "ln1_w", "ln1_b", "wd", "wu", "ln2_w", "ln2_b", "gate"):
+            t = getattr(pk, name)
+            if t is not None:
+                t = t.contiguous()
+                keep.append(t)
+                setattr(ex, name, t.data_ptr())
+        if egr is not None:
+            g = egr[e]
+            for name in ("gate_pre", "aux", "ln1_w", "ln1_b", "wd", "wu", "ln2_w", "ln2_b", "gate"):
+                t = getattr(g, name)
+                if t is not None:
+                    assert t.is_contiguous()
+                    setattr(ex, "g_" + name, t.data_ptr())
+    return a, keep
+
+
+def _set(a, **tensors):
+    for k, t in tensors.items():
+        if t is not None:
+            setattr(a, k, t.data_ptr())
+
+
+def _bn_tensors(a, bn):
+    if bn is not None:
+        _set(a, aff1=bn[0], save1=bn[1], aff2=bn[2], save2=bn[3])
+
+
+def expert_front_fwd(cfg, x, tokp, packs, z, stats1):
+    _require_cuda(x)
+    a, keep = _expert_args(cfg, packs, BT=x.shape[0], dtype=_dt(x), nl=0 if tokp is None else tokp.shape[1])
+    _set(a, x=x, tokp=tokp, z=z, stats1=stats1)
+    _lib_call("expert_front_fwd", C.byref(a), _stream())
+
+
+def bn1_finalize(cfg, stats1, n, bn_w, bn_b, train):
+    return _bn_finalize(cfg, 1, stats1, None, n, None, bn_w, bn_b, train)
+
+
+def bn2_finalize(cfg, moments, n, packs, bn_w, bn_b, train):
+    return _bn_finalize(cfg, 2, None, moments, n, packs, bn_w, bn_b, train)
+
+
+def _bn_finalize(cfg, which, stats1, moments, n, packs, bn_w, bn_b, train):
+    dev = bn_w[0][0].device
+    a = _lib.BnArgs()
+    a.E, a.C, a.Cr, a.G, a.train, a.n = cfg.E, cfg.C, cfg.Cr, cfg.G, int(train), n
+    keep = []
+    for e in range(cfg.E):
+        for name, t in zip(("w1", "b1", "w2", "b2"), bn_w[e]):
+            t = t.contiguous(); keep.append(t)
+            getattr(a, name)[e] = t.data_ptr()
+        for name, t in zip(("rm1", "rv1", "rm2", "rv2"), bn_b[e]):
+            assert t.is_contiguous()
+            getattr(a, name)[e] = t.data_ptr()
+        if packs is not None:
+            t = packs[e].wu.contiguous(); keep.append(t)
+            a.wu[e] = t.data_ptr()
+    ch = cfg.Cr if which == 1 else cfg.C
+    aff = torch.empty((cfg.E, ch, 2), device=dev, dtype=torch.float32)
+    save = torch.empty((cfg.E, ch, 2), device=dev, dtype=torch.float32)
+    if which == 1:
+        _set(a, stats1=stats1, aff1=aff, save1=save)
+        _lib_call("bn1_finalize", C.byref(a), _stream())
+    else:
+        if moments is not None:
+            _set(a, m1=moments[0], m2=moments[1])
+        _set(a, aff2=aff, save2=save)
+        _lib_call("bn2_finalize", C.byref(a), _stream())
+    return aff, save
+
+
+def bn_moments(cfg, z, aff1, packs):
+    crg = cfg.Cr // cfg.G
+    m1 = torch.empty((cfg.E, cfg.Cr), device=z.device, dtype=torch.float64)
+    m2 = torch.empty((cfg.E, cfg.G, crg, crg), device=z.device, dtype=torch.float64)
+    a, keep = _expert_args(cfg, packs, BT=z.shape[0], dtype=F32, bn_mode=1)
+    _set(a, z=z, aff1=aff1)
+    _lib_call("bn_moments", C.byref(a), _ptr(m1), _ptr(m2), _stream())
+    return m1, m2
+
+
+def _bn_mode_of(bn, explicit=None):
+    if explicit is not None:
+        return explicit
+    return 0 if bn is None else 1
+
+
+def expert_back_fwd(cfg, z, bn, packs, probs, out):
+    a, keep = _expert_args(cfg, packs, BT=z.shape[0], dtype=_dt(out), bn_mode=_bn_mode_of(bn))
+    _set(a, z=z, probs=probs, out=out)
+    _bn_tensors(a, bn)
+    _lib_call("expert_back_fwd", C.byref(a), _stream())
+
+
+def expert_back_bwd_stats(cfg, dout, z, bn, packs, probs, red2):
+    a, keep = _expert_args(cfg, packs, BT=z.shape[0], dtype=_dt(dout), bn_mode=1)
+    _set(a, z=z, probs=probs, dout=dout, red2=red2)
+    _bn_tensors(a, bn)
+    _lib_call("expert_back_bwd_stats", C.byref(a), _stream())
+
+
+def expert_back_bwd(cfg, dout, z, bn, bn_mode, red2, red2b, packs, probs, dzt, dprobs, red1, egr):
+    a, keep = _expert_args(cfg, packs, egr, BT=z.shape[0], dtype=_dt(dout), bn_mode=bn_mode)
+    _set(a, z=z, probs=probs, dout=dout, red2=red2, red2b=red2b, red1=red1, dzt=dzt, dprobs=dprobs)
+    _bn_tensors(a, bn)
+    _lib_call("expert_back_bwd", C.byref(a), _stream())
+
+
+def expert_front_bwd(cfg, x, tokp, dzt, z, bn, bn_mode, red1, packs, dpool_x, dx, dtokp, egr):
+    a, keep = _expert_args(cfg, packs, egr, BT=x.shape[0], dtype=_dt(x), bn_mode=bn_mode, nl=0 if tokp is None else tokp.shape[1])
+    _set(a, x=x, tokp=tokp, z=z, dzt=dzt, red1=red1, dpool_x=dpool_x, dx=dx, dtokp=dtokp)
+    _bn_tensors(a, bn)
+    _lib_call("expert_front_bwd", C.byref(a), _stream())
+
+
+# ------------------------------------------------------------------------------------------------ variant pre-transforms
+def selfattn_nxn_fwd(x):
+    raise RuntimeError("avmoe_b200: the AVVP NxN token self-attention kernel is not built yet")
+
+
+def selfattn_nxn_bwd(x, saved, daux, dx):
+    raise RuntimeError("avmoe_b200: the AVVP NxN token self-attention kernel is not built yet")
+
+
+def mha_fwd(x, mp):
+    raise RuntimeError("avmoe_b200: the AVS-v1 multi-head attention kernel is not built yet")
+
+
+def mha_bwd(x, mp, saved, daux, dx):
+    raise RuntimeError("avmoe_b200: the AVS-v1 multi-head attention kernel is not built yet")

@@ -99,6 +99,121 @@ typedef struct {
 
 int avmoe_gemm(const avmoe_gemm_args* args, avmoe_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Layout helpers feeding the GEMMs, router pooling, bias-gradient reductions.
+ * ------------------------------------------------------------------------------------------ */
+/* out[b][c][r] = in[b][r][c]  (dtype pairs: f32->f32, f32->bf16, bf16->bf16) */
+int avmoe_transpose(const void* in, void* out, int batch, int R, int C, int64_t in_ld, int64_t in_bstride, int64_t out_ld,
+                    int64_t out_bstride, int in_dtype, int out_dtype, avmoe_stream_t stream);
+int avmoe_cast(const void* in, void* out, int64_t n, int in_dtype, int out_dtype, avmoe_stream_t stream);
+/* partial[b][chunk][c] = sum of x[b][n][c] over the chunk's tokens; chunk count from avmoe_pool_chunks */
+int avmoe_pool_chunks(int BT, int N);
+int avmoe_pool(const void* x, float* partial, int BT, int N, int C, int chunks, int dtype, avmoe_stream_t stream);
+/* rows_w[n] = sum_{b,c} d*col_weight[c] ; cols[c] = sum_{b,n} d ; cols_w[c] = sum_{b,n} d*row_weight[n]  (outputs may be NULL) */
+int avmoe_reduce_bias(const void* d, const float* col_weight, const float* row_weight, float* rows_w, float* cols, float* cols_w,
+                      int BT, int N, int C, int dtype, avmoe_stream_t stream);
+int avmoe_rowsum(const float* w, float* out, int rows, int cols, avmoe_stream_t stream);
+int avmoe_broadcast_rows(const float* src, void* out, int BT, int N, int C, int dtype, avmoe_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Router (fp32, one CTA per sample, fixed reduction order) and the load-balancing loss.
+ *   rin = [mean_N x | mean_N vis'] ; probs = softmax(W4 relu(W2 relu(W0 rin + b0) + b2) + b4 (+noise))
+ *   idx = first argmax of probs (int64, bit-exact contract).
+ * ------------------------------------------------------------------------------------------ */
+int avmoe_router_fwd(const float* pool_x, const float* pool_v, int chunks_x, int chunks_v, int BT, int C, int E, float inv_n,
+                     const float* w0, const float* b0, const float* w2, const float* b2, const float* w4, const float* b4,
+                     const float* noise, float* probs, int64_t* idx, float* h1, float* h2, float* rin, avmoe_stream_t stream);
+/* ws: BT*(E+32+128) floats of scratch; dpool_* already carry the 1/N of the mean */
+int avmoe_router_bwd(const float* dprobs, const float* probs, const float* h1, const float* h2, const float* rin, int BT, int C,
+                     int E, float inv_n, const float* w0, const float* w2, const float* w4, float* ws, float* dpool_x,
+                     float* dpool_v, float* dw0, float* db0, float* dw2, float* db2, float* dw4, float* db4, avmoe_stream_t stream);
+int avmoe_lb_loss_fwd(const float* probs, float* loss, int BT, int E, avmoe_stream_t stream);
+int avmoe_lb_loss_bwd(const float* probs, const float* dloss, float* dprobs /* += */, int BT, int E, avmoe_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Latent tokens attend to a key/value stream:  tok' = tok + softmax_N(tok kv^T) kv ; lse = logsumexp_N.
+ *   tokens[i] [T,C] fp32 is written to slot slots[i] of tokp [BT,nl,T,C] / lse [BT,nl,T].
+ *   Backward: dkv (= or +=) d/dkv, plus dpool[b][c] broadcast to every token (router path);
+ *             dtokens[i] [T,C] += d/d tokens[i]  (zero-initialised by the caller).
+ * ------------------------------------------------------------------------------------------ */
+int64_t avmoe_latent_fwd_workspace(int BT, int Nk, int C, int T, int nexp);   /* floats */
+int avmoe_latent_fwd(const void* kv, const float* const* tokens, const int* slots, int nexp, int nl, float* tokp, float* lse,
+                     float* workspace, int BT, int Nk, int C, int T, int dtype, avmoe_stream_t stream);
+int avmoe_latent_bwd(const void* kv, const float* const* tokens, const int* slots, int nexp, int nl, const float* tokp,
+                     const float* lse, const float* dtokp, const float* dpool, void* dkv, int accumulate,
+                     float* const* dtokens, int BT, int Nk, int C, int T, int dtype, avmoe_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Expert kernels.  All experts of a MoEAdapter are evaluated per token tile in one launch.
+ * ------------------------------------------------------------------------------------------ */
+#define AVMOE_PRE_NONE 0        /* single-modal expert: x goes straight to ln_before                        */
+#define AVMOE_PRE_LATENT 1      /* x + gate_pre * softmax_T(x tok'^T) tok'   (multimodal / AVS-v2 latent-self) */
+#define AVMOE_PRE_AUX_ADD 2     /* x + gate_pre * aux                        (AVVP NxN self-attention result)  */
+#define AVMOE_PRE_AUX_REPLACE 3 /* aux replaces x                            (AVS-v1 MHA output)              */
+#define AVMOE_BN_OFF 0
+#define AVMOE_BN_TRAIN 1
+#define AVMOE_BN_EVAL 2
+
+typedef struct {
+  int32_t pre_kind, relu, latent_slot, _pad;
+  const float* gate_pre;               /* [1] gate_av / gate_self, or NULL */
+  const void* aux;                     /* [BT,N,C] activation dtype, or NULL */
+  const float* ln1_w; const float* ln1_b;   /* ln_before (NULL = absent) */
+  const float* wd;                     /* down_sampler.weight [Cr, C/G] */
+  const float* wu;                     /* up_sampler.weight   [C, Cr/G] */
+  const float* ln2_w; const float* ln2_b;   /* ln_post (NULL = absent) */
+  const float* gate;                   /* [1] or NULL */
+  /* fp32 gradient accumulators (+=, backward entry points only) */
+  float* g_gate_pre; void* g_aux; float* g_ln1_w; float* g_ln1_b; float* g_wd; float* g_wu;
+  float* g_ln2_w; float* g_ln2_b; float* g_gate;
+} avmoe_expert;
+
+typedef struct {
+  int32_t BT, N, C, Cr, G, T, E, nl;
+  int32_t dtype, bn_mode;
+  avmoe_expert ex[AVMOE_MAX_EXPERTS];
+  const void* x;            /* [BT,N,C] */
+  const float* tokp;        /* [BT,nl,T,C] updated latent tokens */
+  float* z;                 /* [BT,N,E,Cr] bottleneck activations before bn1 */
+  double* stats1;           /* [E,Cr,2] sum z, sum z^2 (bn train) */
+  const float* aff1; const float* save1;   /* [E,Cr,2] (scale,shift) / (mean,invstd) of bn1 */
+  const float* aff2; const float* save2;   /* [E,C,2] of bn2 */
+  const float* probs;       /* [BT,E] */
+  void* out;                /* [BT,N,C] */
+  const void* dout;         /* [BT,N,C] */
+  double* red2;             /* [E,C,2]  sum dyt, sum dyt*yhat over all tokens (bn train: input of the main backward) */
+  double* red2b;            /* [E,C,2]  same sums produced in eval mode (bn2 weight/bias grads) */
+  double* red1;             /* [E,Cr,2] sum dzt, sum dzt*zhat */
+  float* dzt;               /* [BT,N,E,Cr] grad wrt bn1 output (after the relu mask) */
+  float* dprobs;            /* [BT,E] += */
+  const float* dpool_x;     /* [BT,C] router-path grad per token (already /N) */
+  void* dx;                 /* [BT,N,C] */
+  float* dtokp;             /* [BT,nl,T,C] += */
+} avmoe_expert_args;
+
+int avmoe_expert_front_fwd(const avmoe_expert_args* a, avmoe_stream_t stream);
+int avmoe_expert_back_fwd(const avmoe_expert_args* a, avmoe_stream_t stream);
+int avmoe_expert_back_bwd_stats(const avmoe_expert_args* a, avmoe_stream_t stream);
+int avmoe_expert_back_bwd(const avmoe_expert_args* a, avmoe_stream_t stream);
+int avmoe_expert_front_bwd(const avmoe_expert_args* a, avmoe_stream_t stream);
+/* sums of a = act(bn1(z)) and of a a^T per conv group, used to derive bn2's batch statistics algebraically */
+int avmoe_bn_moments(const avmoe_expert_args* a, double* m1 /* [E,Cr] */, double* m2 /* [E,G,Cr/G,Cr/G] */, avmoe_stream_t stream);
+
+typedef struct {
+  int32_t E, C, Cr, G, train, _pad;
+  int64_t n;                                   /* BT*N */
+  const float* w1[AVMOE_MAX_EXPERTS]; const float* b1[AVMOE_MAX_EXPERTS];   /* bn1 weight / bias */
+  const float* w2[AVMOE_MAX_EXPERTS]; const float* b2[AVMOE_MAX_EXPERTS];   /* bn2 weight / bias */
+  float* rm1[AVMOE_MAX_EXPERTS]; float* rv1[AVMOE_MAX_EXPERTS];             /* running stats (updated when train) */
+  float* rm2[AVMOE_MAX_EXPERTS]; float* rv2[AVMOE_MAX_EXPERTS];
+  const float* wu[AVMOE_MAX_EXPERTS];          /* up_sampler weights [C, Cr/G] (bn2 train) */
+  const double* stats1;                        /* [E,Cr,2] */
+  const double* m1; const double* m2;          /* from avmoe_bn_moments */
+  float* aff1; float* save1; float* aff2; float* save2;
+} avmoe_bn_args;
+int avmoe_bn1_finalize(const avmoe_bn_args* a, avmoe_stream_t stream);
+int avmoe_bn2_finalize(const avmoe_bn_args* a, avmoe_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -79,7 +79,7 @@ def split_k_hint(k_rows, m, n):
 
 
 def pool(x):
-    return x.float().sum(dim=1)
+    return x.float().sum(dim=1, keepdim=True)          # [BT, chunks=1, C] partial sums
 
 
 def broadcast_rows(dpool, n, dtype):
@@ -89,7 +89,7 @@ def broadcast_rows(dpool, n, dtype):
 # ------------------------------------------------------------------------------------------------ router
 def router_fwd(pool_x, pool_v, inv_n, rw, noise):
     w0, b0, w2, b2, w4, b4 = rw
-    rin = torch.cat((pool_x, pool_v), dim=-1) * inv_n
+    rin = torch.cat((pool_x.sum(1), pool_v.sum(1)), dim=-1) * inv_n
     h1 = torch.relu(rin @ w0.t() + b0)
     h2 = torch.relu(h1 @ w2.t() + b2)
     logits = h2 @ w4.t() + b4
@@ -97,13 +97,12 @@ def router_fwd(pool_x, pool_v, inv_n, rw, noise):
         logits = logits + noise
     probs = torch.softmax(logits, dim=-1)
     idx = torch.argmax(probs, dim=-1)
-    return probs, idx, h1, h2
+    return probs, idx, h1, h2, rin
 
 
-def router_bwd(dprobs, probs, h1, h2, pool_x, pool_v, inv_n, rw):
+def router_bwd(dprobs, probs, h1, h2, rin, inv_n, rw):
     w0, b0, w2, b2, w4, b4 = rw
-    C = pool_x.shape[1]
-    rin = torch.cat((pool_x, pool_v), dim=-1) * inv_n
+    C = rin.shape[1] // 2
     dlogits = probs * (dprobs - (dprobs * probs).sum(-1, keepdim=True))
     dw4, db4 = dlogits.t() @ h2, dlogits.sum(0)
     dh2 = (dlogits @ w4) * (h2 > 0)
