@@ -536,6 +536,7 @@ __global__ void __launch_bounds__(kThreads) expert_back_bwd_kernel(const avmoe_e
           atomicAdd(&red[((long long)e * C + c) * 2], (double)s1);
           atomicAdd(&red[((long long)e * C + c) * 2 + 1], (double)s2v);
         }
+        __syncthreads();   // the sums read gs (dyt) before the loop below overwrites it with dy
       }
       if (!kStatsOnly) {
         for (int i = threadIdx.x; i < TN * C; i += blockDim.x) {

@@ -1,0 +1,79 @@
+"""Batch-sharded data parallelism for the adapter path: one process per GPU, adapters replicated, and ONE collective —
+the all-reduce (average) of the adapter + router gradients per optimizer step.
+
+The reference itself only has single-process ``nn.DataParallel`` (AVMOE/AVVP/main.py:420-421), whose gradient
+reduce-add onto GPU 0 this replaces.  Gradients are packed into a few large flat fp32 buckets (reverse execution
+order, so the first buckets are complete while the backward of earlier sites is still running) and reduced with
+NCCL over NVLink; with gradient accumulation call ``reduce()`` only on the boundary micro-step
+(AVMOE/AVE/main_trans_v3.py:133-138).  Works with the gloo backend on CPU for the host-logic tests."""
+from __future__ import annotations
+
+from typing import Iterable, List, Optional
+
+import torch
+import torch.distributed as dist
+
+
+class GradientAllReducer:
+    def __init__(self, params: Iterable[torch.nn.Parameter], bucket_bytes: int = 128 << 20, group=None):
+        self.params: List[torch.nn.Parameter] = [p for p in params if p.requires_grad]
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        # buckets in REVERSE registration order == the order gradients become ready in backward
+        self.buckets: List[List[torch.nn.Parameter]] = []
+        cur, size = [], 0
+        for p in reversed(self.params):
+            nbytes = p.numel() * 4
+            if cur and size + nbytes > bucket_bytes:
+                self.buckets.append(cur)
+                cur, size = [], 0
+            cur.append(p)
+            size += nbytes
+        if cur:
+            self.buckets.append(cur)
+        self._flat: List[Optional[torch.Tensor]] = [None] * len(self.buckets)
+
+    def num_bytes(self) -> int:
+        return sum(p.numel() * 4 for p in self.params)
+
+    def reduce(self, async_op: bool = False):
+        """Average .grad of every parameter across ranks (in place).  Returns the work handles when async_op."""
+        if self.world == 1:
+            return []
+        works = []
+        for bi, bucket in enumerate(self.buckets):
+            grads = [p.grad if p.grad is not None else torch.zeros_like(p) for p in bucket]
+            n = sum(g.numel() for g in grads)
+            flat = self._flat[bi]
+            if flat is None or flat.numel() != n or flat.device != grads[0].device:
+                flat = torch.empty(n, device=grads[0].device, dtype=torch.float32)
+                self._flat[bi] = flat
+            off = 0
+            views = []
+            for g in grads:
+                v = flat[off:off + g.numel()]
+                v.copy_(g.reshape(-1))
+                views.append(v)
+                off += g.numel()
+            w = dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
+            works.append((w, bucket, views))
+        if async_op:
+            return works
+        self.finish(works)
+        return []
+
+    def finish(self, works):
+        inv = 1.0 / self.world
+        for w, bucket, views in works:
+            w.wait()
+            for p, v in zip(bucket, views):
+                if p.grad is None:
+                    p.grad = torch.empty_like(p)
+                p.grad.copy_(v.view_as(p)).mul_(inv)
+
+
+def shard_batch(total: int, rank: int, world: int):
+    """[start, end) of this rank's contiguous slice of the BT axis (even split, remainder to the first ranks)."""
+    base, rem = divmod(total, world)
+    start = rank * base + min(rank, rem)
+    return start, start + base + (1 if rank < rem else 0)

@@ -13,6 +13,20 @@ import torch
 from . import _lib
 
 F32, BF16 = 0, 1
+# diagnostics only: AVMOE_GEMM_IMPL=1 forces the plain-fp32 SIMT GEMM (isolates TF32/bf16 tensor-core rounding in parity studies)
+import os as _os
+_GEMM_IMPL_OVERRIDE = int(_os.environ.get("AVMOE_GEMM_IMPL", "0"))
+
+
+# kernel-launch accounting (bench.py reports it as "gpu_launches") and optional per-GEMM CUDA-event profiling
+LAUNCHES = 0
+GEMM_PROFILE = None   # set to a list to collect (start_event, end_event, flops, bytes, tag) per tensor-core GEMM launch
+
+_KERNELS_PER_CALL = {"transpose": 1, "cast": 1, "pool": 1, "reduce_bias": 1, "rowsum": 1, "broadcast_rows": 1, "router_fwd": 1,
+                     "router_bwd": 4, "lb_loss_fwd": 1, "lb_loss_bwd": 1, "latent_fwd": 2, "latent_bwd": 1, "expert_front_fwd": 1,
+                     "bn1_finalize": 1, "bn2_finalize": 1, "bn_moments": 1, "expert_back_fwd": 1, "expert_back_bwd_stats": 1,
+                     "expert_back_bwd": 1, "expert_front_bwd": 1, "selfattn_nxn_fwd": 2, "selfattn_nxn_bwd": 2, "mha_attn_fwd": 1,
+                     "mha_attn_bwd": 1}
 
 
 def _dt(t: torch.Tensor) -> int:
@@ -107,13 +121,26 @@ def gemm(A: torch.Tensor, B: torch.Tensor, *, a_kmajor: bool = True, b_kmajor: b
         if t is not None:
             assert t.dtype == torch.float32 and t.is_contiguous()
             setattr(a, name, t.data_ptr())
-    a.split_k, a.accumulate, a.impl = split_k, int(accumulate), impl
+    a.split_k, a.accumulate, a.impl = split_k, int(accumulate), impl or _GEMM_IMPL_OVERRIDE
+    global LAUNCHES
+    LAUNCHES += 1
+    if GEMM_PROFILE is not None:
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
+        _lib.check(_lib.load().avmoe_gemm(C.byref(a), _stream()), "gemm")
+        ev1.record()
+        kb = a.a_batch if (a_kmajor and b_kmajor) else 1
+        nbytes = A.numel() * A.element_size() + B.numel() * B.element_size() + out.numel() * out.element_size()
+        GEMM_PROFILE.append((ev0, ev1, 2.0 * M * N * K * kb, nbytes, f"M{M}_N{N}_K{K * kb}"))
+        return out
     _lib.check(_lib.load().avmoe_gemm(C.byref(a), _stream()), "gemm")
     return out
 
 
 # ------------------------------------------------------------------------------------------------ layout helpers
 def _lib_call(name, *args):
+    global LAUNCHES
+    LAUNCHES += _KERNELS_PER_CALL.get(name, 1)
     fn = getattr(_lib.load(), "avmoe_" + name)
     _lib.check(fn(*args), name)
 

@@ -1,0 +1,264 @@
+#!/usr/bin/env python
+"""AVMoE adapter-layer fwd+bwd tokens/s (BASELINE.json metric) on N B200s of one node.
+
+    python bench.py --gpus N --steps K --warmup W                 # our CUDA path
+    python bench.py --impl reference --gpus N --steps K --warmup W  # the reference's CPU path on the host cores
+
+One step = forward + backward of the whole AVE adapter stack (8 adapted blocks x {p1,p2} x {audio,visual} = 32
+MoEAdapter calls; Swin-V2-L / HTS-AT token shapes; r=8 G=2 T=32 BN on) on one batch of
+synthetic backbone tokens of BT = 16 clips x 10 segments per GPU, bf16 activations, fp32 parameters/router/statistics,
+plus the gradient all-reduce when N > 1 (weak scaling: per-GPU batch fixed).  Rank 0 prints ONE JSON line.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "avmoe_adapter_fwd_bwd_tokens_per_s"
+UNIT = "tokens/s"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--variant", default="ave")
+    ap.add_argument("--clips", type=int, default=16, help="clips per GPU (x10 segments = BT)")
+    ap.add_argument("--segments", type=int, default=10)
+    ap.add_argument("--dtype", default="bf16", choices=["bf16", "f32"])
+    ap.add_argument("--cpu-sample-clips", type=int, default=1, help="clips in the bounded CPU-baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def workload_name(args):
+    return (f"{args.variant.upper()} adapter stack fwd+bwd, Swin-V2-L/HTS-AT token shapes, batch {args.clips} x {args.segments} "
+            f"segments per GPU, {args.dtype}")
+
+
+# ------------------------------------------------------------------------------------------------ reference (CPU) arm
+def cpu_baseline(args, steps, warmup):
+    """The reference's own CPU implementation of the path (unmodified reference modules when /root/reference exists,
+    else the oracle port) on all host cores, on a bounded sample of the same workload."""
+    import torch
+    from oracle import ref_loader, stack_oracle
+    use_ref = ref_loader.available()
+    bt = args.cpu_sample_clips * args.segments
+    tps, times, cores = stack_oracle.time_cpu(args.variant, bt, steps, warmup, use_reference=use_ref)
+    return {"value": tps, "unit": UNIT, "cores": cores, "kind": "reference" if use_ref else "port",
+            "sample": f"{args.variant.upper()} adapter stack fwd+bwd fp32, BT={bt} ({args.cpu_sample_clips} clip x {args.segments} segments), "
+                      f"{steps} timed steps after {warmup} warm-up, median {sorted(times)[len(times) // 2]:.3f} s/step"}, times
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    base, times = cpu_baseline(args, max(1, args.steps), max(1, min(args.warmup, 1)))
+    ms = 1e3 * sorted(times)[len(times) // 2]
+    line = {"impl": "reference", "metric": METRIC, "value": base["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic", "config": {"workload": workload_name(args), "sample": base["sample"]},
+            "cpu_baseline": base, "e2e": {"value": base["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------ clocks
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+
+    def start(self):
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.index)],
+                                      stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        if self.p is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        rows = [l.strip().split(", ") for l in open(self.f.name) if l.strip()]
+        os.unlink(self.f.name)
+        sm, smax, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in rows:
+            try:
+                sm.append(float(r[1])); smax.append(float(r[2]))
+                for name, v in zip(names, r[5:9]):
+                    if v.strip().lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                continue
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(smax) if smax else None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------ our arm
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from avmoe_b200 import ops, stack as S
+    from avmoe_b200.dist import GradientAllReducer
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a CUDA device: the product path has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    dtype = torch.bfloat16 if args.dtype == "bf16" else torch.float32
+    BT = args.clips * args.segments
+    model = S.AdapterStack(args.variant, seed=0).to(dev)
+    model.train()
+    params = [p for p in model.parameters() if p.requires_grad]
+    reducer = GradientAllReducer(params) if world > 1 else None
+    tokens_dev = S.make_stage_tokens(args.variant, BT, dtype, dev, seed=1000 + rank)
+    tokens_host = S.make_stage_tokens(args.variant, BT, dtype, None, seed=1000 + rank, pin=True)
+    tokens_per_step = S.tokens_per_segment(args.variant) * BT
+    h2d_bytes = sum(t.numel() * t.element_size() for pair in tokens_host.values() for t in pair)
+
+    def zero():
+        for p in params:
+            p.grad = None
+
+    def step(tok):
+        zero()
+        leaves = {s: (a.detach().requires_grad_(), v.detach().requires_grad_()) for s, (a, v) in tok.items()}
+        loss = model(leaves)
+        loss.backward()
+        if reducer is not None:
+            reducer.reduce()
+        return loss
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, n):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n):
+            fn()
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms
+
+    # ---- warm-up, then the device-resident timed region ---------------------------------------------------------
+    for _ in range(max(args.warmup, 3)):
+        step(tokens_dev)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ops.LAUNCHES = 0
+    ms_total = timed(lambda: step(tokens_dev), args.steps)
+    launches = ops.LAUNCHES
+    clocks = sampler.stop() if rank == 0 else None
+    ms_per_step = ms_total / args.steps
+    value = tokens_per_step * world / (ms_per_step * 1e-3)
+
+    # ---- end-to-end through the public module API with host buffers -----------------------------------------------
+    def e2e_step():
+        tok = {s: (a.to(dev, non_blocking=True), v.to(dev, non_blocking=True)) for s, (a, v) in tokens_host.items()}
+        loss = step(tok)
+        return float(loss.item())          # device -> host read of the step's result
+
+    e2e_step()
+    ms_e2e = timed(e2e_step, args.steps) / args.steps
+    e2e = {"value": tokens_per_step * world / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d_bytes * world,
+           "d2h_bytes_per_step": 4 * world, "ms_per_step": ms_e2e}
+
+    # ---- roofline of the dominant kernel (tcgen05 resampler GEMM), measured live with CUDA events -------------------
+    roofline = None
+    if rank == 0:
+        ops.GEMM_PROFILE = []
+        step(tokens_dev)
+        torch.cuda.synchronize()
+        prof, ops.GEMM_PROFILE = ops.GEMM_PROFILE, None
+        tot_ms = sum(a.elapsed_time(b) for a, b, *_ in prof)
+        tot_flops = sum(p[2] for p in prof)
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        peak = peaks.get("bf16_tflops_sustained") if dtype == torch.bfloat16 else None
+        peak_src = "MEASURED_PEAKS.json bf16_tflops_sustained (kernel timed inside a long step)"
+        if dtype == torch.bfloat16 and peak is None:
+            peak, peak_src = 1400.0, "fallback (B200_PROFILING.md sustained figure)"
+        if dtype == torch.float32:
+            peak = (peaks.get("bf16_tflops_sustained") or 1400.0) / 2.0
+            peak_src = "half of the measured bf16 sustained peak (TF32 runs at half the bf16 rate)"
+        ach = tot_flops / (tot_ms * 1e-3) / 1e12 if tot_ms > 0 else 0.0
+        roofline = {"bound": "tensor", "kernel": "gemm_tcgen05_kernel (token resampler conv_adapter+fc, fwd+dgrad+wgrad)",
+                    "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak if peak else None, "traffic": None,
+                    "launches_per_step": len(prof), "avg_launch_ms": tot_ms / max(len(prof), 1), "gemm_ms_per_step": tot_ms,
+                    "gemm_share_of_step": tot_ms / ms_per_step, "algorithmic_flops_per_step": tot_flops, "peak_source": peak_src}
+
+    # ---- CPU baseline (rank 0, N=1 only), bounded sample --------------------------------------------------------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        try:
+            cpu, _ = cpu_baseline(args, 2, 1)
+        except Exception as ex:  # the baseline is a report, never a dependency of the product path
+            cpu = {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "port", "sample": f"failed: {ex}"}
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+                "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "bf16" if dtype == torch.bfloat16 else "f32", "data": "synthetic",
+                "config": {"workload": workload_name(args), "variant": args.variant, "BT_per_gpu": BT, "tokens_per_step_per_gpu": tokens_per_step,
+                           "adapter_calls_per_step": 4 * len(model.sites), "parallelism": f"dp{world} (batch-sharded, grad all-reduce)" if world > 1 else "single GPU",
+                           "l2": f"inputs+weights per step ({(h2d_bytes + sum(p.numel() * 4 for p in params)) / 1e6:.0f} MB) exceed the 126 MB L2; no explicit flush"},
+                "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "roofline": roofline}
+        if cpu is not None:
+            line["cpu_baseline"] = cpu
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference_arm(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()
