@@ -12,6 +12,9 @@
 // Token tiles live in shared memory as fp32 [rows][C+1]; activations are read/written in their storage
 // dtype with 8/16-byte vectors.  Parameter gradients are accumulated with fp32 atomics, BatchNorm sums
 // with fp64 atomics.
+#include <type_traits>
+
+#include "block_mma.cuh"
 #include "common.cuh"
 
 namespace avmoe {
@@ -82,17 +85,11 @@ __device__ __forceinline__ float block_sum(float v, float* scratch /* >= 32 floa
   return r;  // valid in warp 0
 }
 
-// ---- token <- latent attention on a tile: probabilities into s2 [rows][T+1], xa = x + g * (A2 tok') into ws ----
+// ---- token <- latent attention on a tile: probabilities into s2 [rows][T+4], xa = x + g * (A2 tok') into ws ----
+template <bool kExact>
 __device__ __forceinline__ void latent_tile_fwd(const float* xs, float* ws, float* s2, const float* tp, float g, int rows, int C, int ld, int T) {
-  const int lt = T + 1;
-  for (int i = threadIdx.x; i < rows * T; i += blockDim.x) {
-    const int n = i % rows, t = i / rows;
-    const float* xr = xs + n * ld;
-    const float* tr = tp + (long long)t * C;
-    float s = 0.f;
-    for (int c = 0; c < C; ++c) s = fmaf(xr[c], __ldg(tr + c), s);
-    s2[n * lt + t] = s;
-  }
+  const int lt = T + 4;
+  contract<kExact>(rows, T, C, xs, ld, 1, tp, 1, C, [&](int n, int t, float v) { s2[n * lt + t] = v; });
   __syncthreads();
   for (int n = threadIdx.x; n < rows; n += blockDim.x) {
     float* r = s2 + n * lt;
@@ -104,24 +101,18 @@ __device__ __forceinline__ void latent_tile_fwd(const float* xs, float* ws, floa
     for (int t = 0; t < T; ++t) r[t] *= inv;
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < rows * C; i += blockDim.x) {
-    const int n = i / C, c = i - n * C;
-    const float* pr = s2 + n * lt;
-    float a = 0.f;
-    for (int t = 0; t < T; ++t) a = fmaf(pr[t], __ldg(tp + (long long)t * C + c), a);
-    ws[n * ld + c] = xs[n * ld + c] + g * a;
-  }
+  contract<kExact>(rows, C, T, s2, lt, 1, tp, C, 1, [&](int n, int c, float v) { ws[n * ld + c] = xs[n * ld + c] + g * v; });
   __syncthreads();
 }
 
 // builds ws = the tensor ln_before sees for expert `ex` (see AVMOE_PRE_*); leaves latent probabilities in s2
-template <typename T>
+template <typename T, bool kExact>
 __device__ __forceinline__ void pre_transform(const avmoe_expert& ex, const avmoe_expert_args& p, int b, int n0, int valid, int rows,
                                               const float* xs, float* ws, float* s2, int ld) {
   const int C = p.C;
   if (ex.pre_kind == AVMOE_PRE_LATENT) {
     const float* tp = p.tokp + ((long long)b * p.nl + ex.latent_slot) * p.T * C;
-    latent_tile_fwd(xs, ws, s2, tp, *ex.gate_pre, rows, C, ld, p.T);
+    latent_tile_fwd<kExact>(xs, ws, s2, tp, *ex.gate_pre, rows, C, ld, p.T);
   } else if (ex.pre_kind == AVMOE_PRE_NONE) {
     for (int i = threadIdx.x; i < rows * C; i += blockDim.x) { const int n = i / C, c = i - n * C; ws[n * ld + c] = xs[n * ld + c]; }
     __syncthreads();
@@ -142,23 +133,22 @@ __device__ __forceinline__ void pre_transform(const avmoe_expert& ex, const avmo
 template <typename T>
 __global__ void __launch_bounds__(kThreads) expert_front_fwd_kernel(const avmoe_expert_args p, int TN) {
   extern __shared__ float sm[];
-  const int C = p.C, Cr = p.Cr, G = p.G, Cg = C / G, Crg = Cr / G, ld = C + 1;
+  constexpr bool kExact = std::is_same<T, float>::value;
+  const int C = p.C, Cr = p.Cr, G = p.G, Cg = C / G, Crg = Cr / G, ld = C + 4, ECr = p.E * Cr, lz = ECr + 1;
   float* xs = sm;                      // [TN][ld]
   float* ws = xs + TN * ld;            // [TN][ld]
-  float* s2 = ws + TN * ld;            // [TN][T+1]
-  float* mean = s2 + TN * (p.T + 1);   // [TN]
+  float* s2 = ws + TN * ld;            // [TN][T+4]
+  float* zt = s2 + TN * (p.T + 4);     // [TN][E*Cr+1]  z tile of all experts
+  float* mean = zt + TN * lz;          // [TN]
   float* rstd = mean + TN;             // [TN]
-  float* sst = rstd + TN;              // [E*Cr*2] tile-local bn1 sums
   const int b = blockIdx.y, n0 = blockIdx.x * TN;
   const int valid = min(TN, p.N - n0);
   const T* xb = reinterpret_cast<const T*>(p.x) + ((long long)b * p.N + n0) * C;
   load_tile<T>(xs, xb, valid, TN, C, ld);
-  if (p.stats1) for (int i = threadIdx.x; i < p.E * Cr * 2; i += blockDim.x) sst[i] = 0.f;
   __syncthreads();
-  const int group = pow2_group(TN);
   for (int e = 0; e < p.E; ++e) {
     const avmoe_expert& ex = p.ex[e];
-    pre_transform<T>(ex, p, b, n0, valid, TN, xs, ws, s2, ld);
+    pre_transform<T, kExact>(ex, p, b, n0, valid, TN, xs, ws, s2, ld);
     if (ex.ln1_w) {
       row_stats(ws, TN, C, ld, mean, rstd);
       __syncthreads();
@@ -168,30 +158,23 @@ __global__ void __launch_bounds__(kThreads) expert_front_fwd_kernel(const avmoe_
       }
       __syncthreads();
     }
-    // grouped down projection: z[n][j] = sum_cl xn[n][g*Cg+cl] * wd[j][cl]
-    const int total = TN * Cr;
-    for (int i0 = 0; i0 < total; i0 += blockDim.x) {
-      const int i = i0 + threadIdx.x;
-      float zv = 0.f;
-      int n = 0, j = 0;
-      const bool active = i < total;
-      if (active) {
-        n = i % TN; j = i / TN;
-        const float* xr = ws + n * ld + (j / Crg) * Cg;
-        const float* wr = ex.wd + (long long)j * Cg;
-        for (int cl = 0; cl < Cg; ++cl) zv = fmaf(xr[cl], __ldg(wr + cl), zv);
-        if (n < valid) p.z[(((long long)b * p.N + n0 + n) * p.E + e) * Cr + j] = zv;
-        else zv = 0.f;
-      }
-      if (p.stats1) {
-        const float s1 = group_sum(zv, group), s2v = group_sum(zv * zv, group);
-        if (active && (n % group) == 0) { atomicAdd(&sst[(e * Cr + j) * 2], s1); atomicAdd(&sst[(e * Cr + j) * 2 + 1], s2v); }
-      }
-    }
+    // grouped down projection: z[n][g*Crg+jl] = sum_cl xn[n][g*Cg+cl] * wd[g*Crg+jl][cl]
+    for (int g = 0; g < G; ++g)
+      contract<kExact>(TN, Crg, Cg, ws + g * Cg, ld, 1, ex.wd + (long long)g * Crg * Cg, 1, Cg,
+                       [&](int n, int jl, float v) { zt[n * lz + e * Cr + g * Crg + jl] = v; });
     __syncthreads();
   }
-  if (p.stats1)
-    for (int i = threadIdx.x; i < p.E * Cr * 2; i += blockDim.x) atomicAdd(&p.stats1[i], (double)sst[i]);
+  // coalesced store of the z tile [valid][E*Cr] and the bn1 batch sums
+  float* zg = p.z + ((long long)b * p.N + n0) * ECr;
+  for (int i = threadIdx.x; i < valid * ECr; i += blockDim.x) { const int n = i / ECr, q = i - n * ECr; zg[i] = zt[n * lz + q]; }
+  if (p.stats1) {
+    for (int q = threadIdx.x; q < ECr; q += blockDim.x) {
+      float s1 = 0.f, s2v = 0.f;
+      for (int n = 0; n < valid; ++n) { const float v = zt[n * lz + q]; s1 += v; s2v = fmaf(v, v, s2v); }
+      atomicAdd(&p.stats1[q * 2], (double)s1);
+      atomicAdd(&p.stats1[q * 2 + 1], (double)s2v);
+    }
+  }
 }
 
 // ------------------------------------------------------------------------------------------------ bn moments
@@ -345,9 +328,10 @@ __global__ void bn2_finalize_kernel(const avmoe_bn_args a) {
 
 // ------------------------------------------------------------------------------------------------ back: shared recompute
 // as[n][j] = act(bn1(z)) for expert e (invalid rows 0); ys[n][c] = y = Wu a (pre-bn2)
+template <bool kExact>
 __device__ __forceinline__ void back_recompute(const avmoe_expert_args& p, const avmoe_expert& ex, int e, int b, int n0, int valid, int TN,
                                                float* as, float* ys, int ld) {
-  const int C = p.C, Cr = p.Cr, G = p.G, Cg = C / G, Crg = Cr / G, lda = Cr + 1;
+  const int C = p.C, Cr = p.Cr, G = p.G, Cg = C / G, Crg = Cr / G, lda = Cr + 4;
   const bool bn = p.bn_mode != AVMOE_BN_OFF;
   for (int i = threadIdx.x; i < TN * Cr; i += blockDim.x) {
     const int n = i / Cr, j = i - n * Cr;
@@ -360,14 +344,9 @@ __device__ __forceinline__ void back_recompute(const avmoe_expert_args& p, const
     as[n * lda + j] = a;
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < TN * C; i += blockDim.x) {
-    const int n = i / C, c = i - n * C;
-    const float* ar = as + n * lda + (c / Cg) * Crg;
-    const float* wr = ex.wu + (long long)c * Crg;
-    float y = 0.f;
-    for (int jl = 0; jl < Crg; ++jl) y = fmaf(ar[jl], __ldg(wr + jl), y);
-    ys[n * ld + c] = y;
-  }
+  for (int g = 0; g < G; ++g)
+    contract<kExact>(TN, Cg, Crg, as + g * Crg, lda, 1, ex.wu + (long long)g * Cg * Crg, 1, Crg,
+                     [&](int n, int cl, float v) { ys[n * ld + g * Cg + cl] = v; });
   __syncthreads();
 }
 
@@ -375,11 +354,12 @@ __device__ __forceinline__ void back_recompute(const avmoe_expert_args& p, const
 template <typename T>
 __global__ void __launch_bounds__(kThreads) expert_back_fwd_kernel(const avmoe_expert_args p, int TN) {
   extern __shared__ float sm[];
-  const int C = p.C, Cr = p.Cr, ld = C + 1;
+  constexpr bool kExact = std::is_same<T, float>::value;
+  const int C = p.C, Cr = p.Cr, ld = C + 4;
   float* ys = sm;                      // [TN][ld]
   float* acc = ys + TN * ld;           // [TN][ld]
-  float* as = acc + TN * ld;           // [TN][Cr+1]
-  float* mean = as + TN * (Cr + 1);
+  float* as = acc + TN * ld;           // [TN][Cr+4]
+  float* mean = as + TN * (Cr + 4);
   float* rstd = mean + TN;
   const int b = blockIdx.y, n0 = blockIdx.x * TN;
   const int valid = min(TN, p.N - n0);
@@ -387,7 +367,7 @@ __global__ void __launch_bounds__(kThreads) expert_back_fwd_kernel(const avmoe_e
   for (int i = threadIdx.x; i < TN * ld; i += blockDim.x) acc[i] = 0.f;
   for (int e = 0; e < p.E; ++e) {
     const avmoe_expert& ex = p.ex[e];
-    back_recompute(p, ex, e, b, n0, valid, TN, as, ys, ld);
+    back_recompute<kExact>(p, ex, e, b, n0, valid, TN, as, ys, ld);
     if (bn) {
       for (int i = threadIdx.x; i < TN * C; i += blockDim.x) {
         const int n = i / C, c = i - n * C;
@@ -414,7 +394,8 @@ __global__ void __launch_bounds__(kThreads) expert_back_fwd_kernel(const avmoe_e
 template <typename T, bool kStatsOnly>
 __global__ void __launch_bounds__(kThreads) expert_back_bwd_kernel(const avmoe_expert_args p, int TN) {
   extern __shared__ float sm[];
-  const int C = p.C, Cr = p.Cr, G = p.G, Cg = C / G, Crg = Cr / G, ld = C + 1, lda = Cr + 1;
+  constexpr bool kExact = std::is_same<T, float>::value;
+  const int C = p.C, Cr = p.Cr, G = p.G, Cg = C / G, Crg = Cr / G, ld = C + 4, lda = Cr + 4;
   float* gs0 = sm;                     // [TN][ld]  dout tile (kept)
   float* ys = gs0 + TN * ld;           // [TN][ld]  y (pre-bn2)
   float* gs = ys + TN * ld;            // [TN][ld]  working gradient (dq -> dyt -> dy)
@@ -424,7 +405,7 @@ __global__ void __launch_bounds__(kThreads) expert_back_bwd_kernel(const avmoe_e
   float* m1r = rstd + TN;              // row means of the LN backward
   float* m2r = m1r + TN;
   float* scratch = m2r + TN;           // [32]
-  float* sred = scratch + 32;          // [Cr*2] tile-local bn1-backward sums
+  float* dzs = scratch + 32;           // [TN][Cr+4] dzt tile of the current expert
   const int b = blockIdx.y, n0 = blockIdx.x * TN;
   const int valid = min(TN, p.N - n0);
   const int mode = p.bn_mode;
@@ -433,10 +414,9 @@ __global__ void __launch_bounds__(kThreads) expert_back_bwd_kernel(const avmoe_e
   load_tile<T>(gs0, gb, valid, TN, C, ld);
   __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
-  const int group = pow2_group(TN);
   for (int e = 0; e < p.E; ++e) {
     const avmoe_expert& ex = p.ex[e];
-    back_recompute(p, ex, e, b, n0, valid, TN, as, ys, ld);
+    back_recompute<kExact>(p, ex, e, b, n0, valid, TN, as, ys, ld);
     const float* aff2 = p.aff2 ? p.aff2 + (long long)e * C * 2 : nullptr;
     const float* sv2 = p.save2 ? p.save2 + (long long)e * C * 2 : nullptr;
     // ---- ln_post statistics of yt = bn2(y)
@@ -554,44 +534,37 @@ __global__ void __launch_bounds__(kThreads) expert_back_bwd_kernel(const avmoe_e
       __syncthreads();
     }
     if (kStatsOnly) continue;
-    // ---- d up_sampler.weight[c][jl] += sum_n dy[n][c] * a[n][g*Crg+jl]
-    for (int i = threadIdx.x; i < C * Crg; i += blockDim.x) {
-      const int c = i / Crg, jl = i - c * Crg;
-      const int j = (c / Cg) * Crg + jl;
-      float s = 0.f;
-      for (int n = 0; n < valid; ++n) s = fmaf(gs[n * ld + c], as[n * lda + j], s);
-      atomicAdd(ex.g_wu + i, s);
-    }
-    // ---- da -> dzt (relu mask), write, bn1-backward sums
-    if (mode != AVMOE_BN_OFF) for (int i = threadIdx.x; i < Cr * 2; i += blockDim.x) sred[i] = 0.f;
+    // ---- d up_sampler.weight[c][jl] += sum_n dy[n][c] * a[n][g*Crg+jl]      (rows >= valid of gs are zero)
+    for (int g = 0; g < G; ++g)
+      contract<kExact>(Cg, Crg, TN, gs + g * Cg, 1, ld, as + g * Crg, lda, 1,
+                       [&](int cl, int jl, float v) { atomicAdd(ex.g_wu + (long long)(g * Cg + cl) * Crg + jl, v); });
+    // ---- da[n][g*Crg+jl] = sum_cl dy[n][g*Cg+cl] * wu[g*Cg+cl][jl]
+    for (int g = 0; g < G; ++g)
+      contract<kExact>(TN, Crg, Cg, gs + g * Cg, ld, 1, ex.wu + (long long)g * Cg * Crg, Crg, 1,
+                       [&](int n, int jl, float v) { dzs[n * lda + g * Crg + jl] = v; });
     __syncthreads();
-    const int total = TN * Cr;
-    for (int i0 = 0; i0 < total; i0 += blockDim.x) {
-      const int i = i0 + threadIdx.x;
-      const bool active = i < total;
-      float d = 0.f, dzh = 0.f;
-      int n = 0, j = 0;
-      if (active) {
-        n = i % TN; j = i / TN;
-        if (n < valid) {
-          const int g = j / Crg, jl = j - g * Crg;
-          const float* dr = gs + n * ld + g * Cg;
-          const float* wr = ex.wu + (long long)g * Cg * Crg + jl;
-          for (int cl = 0; cl < Cg; ++cl) d = fmaf(dr[cl], __ldg(wr + (long long)cl * Crg), d);
-          if (ex.relu && !(as[n * lda + j] > 0.f)) d = 0.f;
-          const long long zi = (((long long)b * p.N + n0 + n) * p.E + e) * Cr + j;
-          p.dzt[zi] = d;
-          if (mode != AVMOE_BN_OFF) dzh = d * (p.z[zi] - p.save1[(e * Cr + j) * 2]) * p.save1[(e * Cr + j) * 2 + 1];
+    // ---- relu mask, store dzt, bn1-backward sums per channel
+    for (int i = threadIdx.x; i < valid * Cr; i += blockDim.x) {
+      const int n = i / Cr, j = i - n * Cr;
+      float d = dzs[n * lda + j];
+      if (ex.relu && !(as[n * lda + j] > 0.f)) d = 0.f;
+      dzs[n * lda + j] = d;
+      p.dzt[(((long long)b * p.N + n0 + n) * p.E + e) * Cr + j] = d;
+    }
+    __syncthreads();
+    if (mode != AVMOE_BN_OFF) {
+      for (int j = threadIdx.x; j < Cr; j += blockDim.x) {
+        const float mu = p.save1[(e * Cr + j) * 2], is = p.save1[(e * Cr + j) * 2 + 1];
+        float s1 = 0.f, s2v = 0.f;
+        for (int n = 0; n < valid; ++n) {
+          const float d = dzs[n * lda + j];
+          s1 += d;
+          s2v = fmaf(d, (p.z[(((long long)b * p.N + n0 + n) * p.E + e) * Cr + j] - mu) * is, s2v);
         }
-      }
-      if (mode != AVMOE_BN_OFF) {
-        const float s1 = group_sum(d, group), s2v = group_sum(dzh, group);
-        if (active && (n % group) == 0) { atomicAdd(&sred[j * 2], s1); atomicAdd(&sred[j * 2 + 1], s2v); }
+        atomicAdd(&p.red1[((long long)e * Cr + j) * 2], (double)s1);
+        atomicAdd(&p.red1[((long long)e * Cr + j) * 2 + 1], (double)s2v);
       }
     }
-    __syncthreads();
-    if (mode != AVMOE_BN_OFF)
-      for (int i = threadIdx.x; i < Cr * 2; i += blockDim.x) atomicAdd(&p.red1[(long long)e * Cr * 2 + i], (double)sred[i]);
     __syncthreads();
   }
 }
@@ -600,7 +573,8 @@ __global__ void __launch_bounds__(kThreads) expert_back_bwd_kernel(const avmoe_e
 template <typename T>
 __global__ void __launch_bounds__(kThreads) expert_front_bwd_kernel(const avmoe_expert_args p, int TN) {
   extern __shared__ float sm[];
-  const int C = p.C, Cr = p.Cr, G = p.G, Cg = C / G, Crg = Cr / G, ld = C + 1, lda = Cr + 1, lt = p.T + 1;
+  constexpr bool kExact = std::is_same<T, float>::value;
+  const int C = p.C, Cr = p.Cr, G = p.G, Cg = C / G, Crg = Cr / G, ld = C + 4, lda = Cr + 4, lt = p.T + 4;
   float* xs = sm;                      // [TN][ld] x tile
   float* ws = xs + TN * ld;            // [TN][ld] xa -> xhat
   float* t1 = ws + TN * ld;            // [TN][ld] dxn -> dxa
@@ -645,7 +619,7 @@ __global__ void __launch_bounds__(kThreads) expert_front_bwd_kernel(const avmoe_
       dzs[n * lda + j] = d;
     }
     // ---- recompute xa and its LN statistics
-    pre_transform<T>(ex, p, b, n0, valid, TN, xs, ws, s2, ld);
+    pre_transform<T, kExact>(ex, p, b, n0, valid, TN, xs, ws, s2, ld);
     if (ex.ln1_w) {
       row_stats(ws, TN, C, ld, mean, rstd);
       __syncthreads();
@@ -655,25 +629,20 @@ __global__ void __launch_bounds__(kThreads) expert_front_bwd_kernel(const avmoe_
       }
       __syncthreads();
     }
-    // ---- d down_sampler.weight[j][cl] += sum_n dz[n][j] * xn[n][g*Cg+cl]
-    for (int i = threadIdx.x; i < Cr * Cg; i += blockDim.x) {
-      const int j = i / Cg, cl = i - j * Cg;
-      const int c = (j / Crg) * Cg + cl;
-      const float w = ex.ln1_w ? __ldg(ex.ln1_w + c) : 1.f, bb = ex.ln1_w ? __ldg(ex.ln1_b + c) : 0.f;
-      float s = 0.f;
-      for (int n = 0; n < valid; ++n) s = fmaf(dzs[n * lda + j], fmaf(ws[n * ld + c], w, bb), s);
-      atomicAdd(ex.g_wd + i, s);
-    }
-    // ---- dxn[n][c] = sum_jl dz[n][g*Crg+jl] * wd[g*Crg+jl][cl]
+    // ---- d down_sampler.weight[g*Crg+jl][cl] += sum_n dz[n][g*Crg+jl] * xn[n][g*Cg+cl]   (xn staged in t1; dz rows >= valid are 0)
     for (int i = threadIdx.x; i < TN * C; i += blockDim.x) {
       const int n = i / C, c = i - n * C;
-      const int g = c / Cg, cl = c - g * Cg;
-      const float* dr = dzs + n * lda + g * Crg;
-      const float* wr = ex.wd + (long long)g * Crg * Cg + cl;
-      float s = 0.f;
-      for (int jl = 0; jl < Crg; ++jl) s = fmaf(dr[jl], __ldg(wr + (long long)jl * Cg), s);
-      t1[n * ld + c] = s;
+      t1[n * ld + c] = ex.ln1_w ? fmaf(ws[n * ld + c], __ldg(ex.ln1_w + c), __ldg(ex.ln1_b + c)) : ws[n * ld + c];
     }
+    __syncthreads();
+    for (int g = 0; g < G; ++g)
+      contract<kExact>(Crg, Cg, TN, dzs + g * Crg, 1, lda, t1 + g * Cg, ld, 1,
+                       [&](int jl, int cl, float v) { atomicAdd(ex.g_wd + (long long)(g * Crg + jl) * Cg + cl, v); });
+    __syncthreads();
+    // ---- dxn[n][g*Cg+cl] = sum_jl dz[n][g*Crg+jl] * wd[g*Crg+jl][cl]
+    for (int g = 0; g < G; ++g)
+      contract<kExact>(TN, Cg, Crg, dzs + g * Crg, lda, 1, ex.wd + (long long)g * Crg * Cg, Cg, 1,
+                       [&](int n, int cl, float v) { t1[n * ld + g * Cg + cl] = v; });
     __syncthreads();
     if (ex.ln1_w) {
       for (int c = threadIdx.x; c < C; c += blockDim.x) {
@@ -727,14 +696,7 @@ __global__ void __launch_bounds__(kThreads) expert_front_bwd_kernel(const avmoe_
       const float* tp = p.tokp + ((long long)b * p.nl + ex.latent_slot) * p.T * C;
       float* dtp = p.dtokp + ((long long)b * p.nl + ex.latent_slot) * p.T * C;
       // u[n][t] = dxa_n . tok'_t
-      for (int i = threadIdx.x; i < TN * p.T; i += blockDim.x) {
-        const int n = i % TN, t = i / TN;
-        const float* dr = t1 + n * ld;
-        const float* tr = tp + (long long)t * C;
-        float s = 0.f;
-        for (int c = 0; c < C; ++c) s = fmaf(dr[c], __ldg(tr + c), s);
-        ds2[n * lt + t] = s;
-      }
+      contract<kExact>(TN, p.T, C, t1, ld, 1, tp, 1, C, [&](int n, int t, float v) { ds2[n * lt + t] = v; });
       __syncthreads();
       // d gate_pre = sum A2*u ; dS2 = A2 * (g*u - sum_t A2*g*u)
       float dg = 0.f;
@@ -748,22 +710,10 @@ __global__ void __launch_bounds__(kThreads) expert_front_bwd_kernel(const avmoe_
       if (threadIdx.x == 0) atomicAdd(ex.g_gate_pre, tot);
       __syncthreads();
       // dx[n][c] += sum_t dS2[n][t] * tok'[t][c]
-      for (int i = threadIdx.x; i < TN * C; i += blockDim.x) {
-        const int n = i / C, c = i - n * C;
-        float s = 0.f;
-        for (int t = 0; t < p.T; ++t) s = fmaf(ds2[n * lt + t], __ldg(tp + (long long)t * C + c), s);
-        dxs[n * ld + c] += s;
-      }
-      // d tok'[t][c] += sum_n A2[n][t]*g*dxa[n][c] + dS2[n][t]*x[n][c]
-      for (int i = threadIdx.x; i < p.T * C; i += blockDim.x) {
-        const int t = i / C, c = i - t * C;
-        float s = 0.f;
-        for (int n = 0; n < valid; ++n) {
-          s = fmaf(s2[n * lt + t] * g, t1[n * ld + c], s);
-          s = fmaf(ds2[n * lt + t], xs[n * ld + c], s);
-        }
-        atomicAdd(dtp + i, s);
-      }
+      contract<kExact>(TN, C, p.T, ds2, lt, 1, tp, C, 1, [&](int n, int c, float v) { dxs[n * ld + c] += v; });
+      // d tok'[t][c] += sum_n A2[n][t]*g*dxa[n][c] + dS2[n][t]*x[n][c]       (rows >= valid of t1 / xs are zero)
+      contract<kExact>(p.T, C, TN, s2, 1, lt, t1, ld, 1, [&](int t, int c, float v) { atomicAdd(dtp + (long long)t * C + c, g * v); });
+      contract<kExact>(p.T, C, TN, ds2, 1, lt, xs, ld, 1, [&](int t, int c, float v) { atomicAdd(dtp + (long long)t * C + c, v); });
     }
     __syncthreads();
   }
@@ -774,7 +724,7 @@ __global__ void __launch_bounds__(kThreads) expert_front_bwd_kernel(const avmoe_
 // ------------------------------------------------------------------------------------------------ host side
 static int pow2_floor(int v) { int p = 1; while (p * 2 <= v) p *= 2; return p; }
 static int pick_tn(int C, int budget_floats) {
-  int tn = budget_floats / (C + 1);
+  int tn = budget_floats / (C + 4);
   if (tn < 1) tn = 1;
   if (tn > 64) tn = 64;
   return pow2_floor(tn);
@@ -806,7 +756,7 @@ extern "C" int avmoe_expert_front_fwd(const avmoe_expert_args* a, avmoe_stream_t
   AVMOE_CHECK_ARG(a->x && a->z, "expert_front_fwd: null tensor");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const int TN = pick_tn(a->C, 12288);
-  const size_t smem = sizeof(float) * (2 * (size_t)TN * (a->C + 1) + (size_t)TN * (a->T + 1) + 2 * TN + (size_t)a->E * a->Cr * 2);
+  const size_t smem = sizeof(float) * (2 * (size_t)TN * (a->C + 4) + (size_t)TN * (a->T + 4) + (size_t)TN * (a->E * a->Cr + 1) + 2 * TN);
   dim3 grid((a->N + TN - 1) / TN, a->BT);
   if (a->dtype == AVMOE_F32) {
     if (int rc = set_smem(expert_front_fwd_kernel<float>, smem, "expert_front_fwd")) return rc;
@@ -871,7 +821,7 @@ extern "C" int avmoe_expert_back_fwd(const avmoe_expert_args* a, avmoe_stream_t 
   AVMOE_CHECK_ARG(a->bn_mode == AVMOE_BN_OFF || (a->aff1 && a->aff2), "expert_back_fwd: batch-norm affine missing");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const int TN = pick_tn(a->C, 12288);
-  const size_t smem = sizeof(float) * (2 * (size_t)TN * (a->C + 1) + (size_t)TN * (a->Cr + 1) + 2 * TN);
+  const size_t smem = sizeof(float) * (2 * (size_t)TN * (a->C + 4) + (size_t)TN * (a->Cr + 4) + 2 * TN);
   dim3 grid((a->N + TN - 1) / TN, a->BT);
   if (a->dtype == AVMOE_F32) {
     if (int rc = set_smem(expert_back_fwd_kernel<float>, smem, "expert_back_fwd")) return rc;
@@ -897,7 +847,7 @@ static int launch_back_bwd(const avmoe_expert_args* a, cudaStream_t st, const ch
     AVMOE_CHECK_ARG(a->bn_mode == AVMOE_BN_OFF || a->red1, "%s: red1 missing", who);
   }
   const int TN = pick_tn(a->C, 8192);
-  const size_t smem = sizeof(float) * (3 * (size_t)TN * (a->C + 1) + (size_t)TN * (a->Cr + 1) + 4 * TN + 32 + 2 * (size_t)a->Cr);
+  const size_t smem = sizeof(float) * (3 * (size_t)TN * (a->C + 4) + 2 * (size_t)TN * (a->Cr + 4) + 4 * TN + 32);
   dim3 grid((a->N + TN - 1) / TN, a->BT);
   if (a->dtype == AVMOE_F32) {
     if (int rc = set_smem(expert_back_bwd_kernel<float, kStatsOnly>, smem, who)) return rc;
@@ -923,7 +873,7 @@ extern "C" int avmoe_expert_front_bwd(const avmoe_expert_args* a, avmoe_stream_t
   AVMOE_CHECK_ARG(a->bn_mode == AVMOE_BN_OFF || (a->aff1 && a->save1 && a->z && a->red1), "expert_front_bwd: batch-norm tensors missing");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const int TN = pick_tn(a->C, 6144);
-  const size_t smem = sizeof(float) * (4 * (size_t)TN * (a->C + 1) + 2 * (size_t)TN * (a->T + 1) + (size_t)TN * (a->Cr + 1) + 4 * TN + 32);
+  const size_t smem = sizeof(float) * (4 * (size_t)TN * (a->C + 4) + 2 * (size_t)TN * (a->T + 4) + (size_t)TN * (a->Cr + 4) + 4 * TN + 32);
   dim3 grid((a->N + TN - 1) / TN, a->BT);
   if (a->dtype == AVMOE_F32) {
     if (int rc = set_smem(expert_front_bwd_kernel<float>, smem, "expert_front_bwd")) return rc;

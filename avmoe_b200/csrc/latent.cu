@@ -8,6 +8,9 @@
 // Flash-style: the [T,N] attention matrix is never written to HBM.  Forward splits N over CTAs with an
 // online softmax and merges the partial (max, sum, acc) triples; backward recomputes the probabilities
 // from the saved log-sum-exp.  fp32 math; kv is read once per pass in its storage dtype.
+#include <type_traits>
+
+#include "block_mma.cuh"
 #include "common.cuh"
 
 namespace avmoe {
@@ -46,9 +49,10 @@ __device__ __forceinline__ void load_kv_tile(float* kvs, const T* kvb, int n0, i
 template <typename T>
 __global__ void __launch_bounds__(256) latent_fwd_kernel(const LatentParams p) {
   extern __shared__ float sm[];
-  const int ld = p.C + 1, lds = p.TN + 1;
-  float* kvs = sm;                            // [TN][C+1]
-  float* S = kvs + p.TN * ld;                 // [T][TN+1]
+  constexpr bool kExact = std::is_same<T, float>::value;
+  const int ld = p.C + 4, lds = p.TN + 4;
+  float* kvs = sm;                            // [TN][C+4]
+  float* S = kvs + p.TN * ld;                 // [T][TN+4]
   float* acc = S + p.T * lds;                 // [T][CC]
   float* mrun = acc + p.T * p.CC;             // [T]
   float* lrun = mrun + p.T;
@@ -68,17 +72,8 @@ __global__ void __launch_bounds__(256) latent_fwd_kernel(const LatentParams p) {
     load_kv_tile<T>(kvs, kvb, n0, ne, p.TN, p.C, ld);
     __syncthreads();
     // logits S[t][n] = tok_t . kv_n
-    for (int i = threadIdx.x; i < p.T * p.TN; i += blockDim.x) {
-      const int t = i / p.TN, n = i - t * p.TN;
-      float s = -INFINITY;
-      if (n0 + n < ne) {
-        const float* tr = tok + (long long)t * p.C;
-        const float* kr = kvs + n * ld;
-        s = 0.f;
-        for (int c = 0; c < p.C; ++c) s = fmaf(__ldg(tr + c), kr[c], s);
-      }
-      S[t * lds + n] = s;
-    }
+    contract<kExact>(p.T, p.TN, p.C, tok, p.C, 1, kvs, 1, ld,
+                     [&](int t, int n, float v) { S[t * lds + n] = (n0 + n < ne) ? v : -INFINITY; });
     __syncthreads();
     // online softmax per latent token (one warp per t)
     for (int t = warp; t < p.T; t += nwarps) {
@@ -102,14 +97,8 @@ __global__ void __launch_bounds__(256) latent_fwd_kernel(const LatentParams p) {
     }
     __syncthreads();
     // acc[t][c] = alpha[t]*acc[t][c] + sum_n P[t][n]*kv[n][c]   (this CTA's channel range only)
-    for (int i = threadIdx.x; i < p.T * cw; i += blockDim.x) {
-      const int t = i / cw, c = i - t * cw;
-      float a = 0.f;
-      const float* pr = S + t * lds;
-      const float* kc = kvs + c_lo + c;
-      for (int n = 0; n < p.TN; ++n) a = fmaf(pr[n], kc[n * ld], a);
-      acc[t * p.CC + c] = acc[t * p.CC + c] * alpha[t] + a;
-    }
+    contract<kExact>(p.T, cw, p.TN, S, lds, 1, kvs + c_lo, ld, 1,
+                     [&](int t, int c, float v) { acc[t * p.CC + c] = acc[t * p.CC + c] * alpha[t] + v; });
     __syncthreads();
   }
   float* pp = p.part + ((((long long)b * p.nexp + ei) * p.nsplit + split) * p.T) * p.C;
@@ -153,10 +142,11 @@ __global__ void latent_merge_kernel(const LatentParams p) {
 template <typename T>
 __global__ void __launch_bounds__(256) latent_bwd_kernel(const LatentParams p) {
   extern __shared__ float sm[];
-  const int ld = p.C + 1, lds = p.TN + 1;
-  float* kvs = sm;                            // [TN][C+1]
-  float* A1 = kvs + p.TN * ld;                // [T][TN+1]  probabilities
-  float* dS = A1 + p.T * lds;                 // [T][TN+1]
+  constexpr bool kExact = std::is_same<T, float>::value;
+  const int ld = p.C + 4, lds = p.TN + 4;
+  float* kvs = sm;                            // [TN][C+4]
+  float* A1 = kvs + p.TN * ld;                // [T][TN+4]  probabilities
+  float* dS = A1 + p.T * lds;                 // [T][TN+4]
   float* dkvt = dS + p.T * lds;               // [TN][CC]
   float* dtk = dkvt + p.TN * p.CC;            // [nexp][T][CC]
   float* Dt = dtk + p.nexp * p.T * p.CC;      // [nexp][T]
@@ -188,46 +178,19 @@ __global__ void __launch_bounds__(256) latent_bwd_kernel(const LatentParams p) {
       const float* tok = p.tok[ei];
       const long long sbase = ((long long)b * p.nl + p.slot[ei]) * p.T;
       const float* dR = p.dtokp + sbase * p.C;
-      // probabilities and dS from two dot products sharing the kv row
-      for (int i = threadIdx.x; i < p.T * p.TN; i += blockDim.x) {
-        const int t = i / p.TN, n = i - t * p.TN;
-        float a1 = 0.f, ds = 0.f;
-        if (n0 + n < ne) {
-          const float* tr = tok + (long long)t * p.C;
-          const float* dr = dR + (long long)t * p.C;
-          const float* kr = kvs + n * ld;
-          float s = 0.f, da = 0.f;
-          for (int c = 0; c < p.C; ++c) {
-            const float kvv = kr[c];
-            s = fmaf(__ldg(tr + c), kvv, s);
-            da = fmaf(__ldg(dr + c), kvv, da);
-          }
-          a1 = expf(s - p.lse[sbase + t]);
-          ds = a1 * (da - Dt[ei * p.T + t]);
-        }
-        A1[t * lds + n] = a1;
-        dS[t * lds + n] = ds;
-      }
+      // probabilities A1 = exp(tok.kv - lse) and dS = A1 * (dR.kv - D)
+      contract<kExact>(p.T, p.TN, p.C, tok, p.C, 1, kvs, 1, ld,
+                       [&](int t, int n, float v) { A1[t * lds + n] = (n0 + n < ne) ? expf(v - p.lse[sbase + t]) : 0.f; });
+      __syncthreads();
+      contract<kExact>(p.T, p.TN, p.C, dR, p.C, 1, kvs, 1, ld,
+                       [&](int t, int n, float v) { dS[t * lds + n] = A1[t * lds + n] * (v - Dt[ei * p.T + t]); });
       __syncthreads();
       // dkv[n][c] += sum_t A1[t][n]*dR[t][c] + dS[t][n]*tok[t][c]
-      for (int i = threadIdx.x; i < p.TN * cw; i += blockDim.x) {
-        const int n = i / cw, c = i - n * cw;
-        float a = 0.f;
-        for (int t = 0; t < p.T; ++t) {
-          a = fmaf(A1[t * lds + n], __ldg(dR + (long long)t * p.C + c_lo + c), a);
-          a = fmaf(dS[t * lds + n], __ldg(tok + (long long)t * p.C + c_lo + c), a);
-        }
-        dkvt[n * p.CC + c] += a;
-      }
+      contract<kExact>(p.TN, cw, p.T, A1, 1, lds, dR + c_lo, p.C, 1, [&](int n, int c, float v) { dkvt[n * p.CC + c] += v; });
+      contract<kExact>(p.TN, cw, p.T, dS, 1, lds, tok + c_lo, p.C, 1, [&](int n, int c, float v) { dkvt[n * p.CC + c] += v; });
       // dtok[t][c] += sum_n dS[t][n]*kv[n][c]
-      for (int i = threadIdx.x; i < p.T * cw; i += blockDim.x) {
-        const int t = i / cw, c = i - t * cw;
-        float a = 0.f;
-        const float* dsr = dS + t * lds;
-        const float* kc = kvs + c_lo + c;
-        for (int n = 0; n < p.TN; ++n) a = fmaf(dsr[n], kc[n * ld], a);
-        dtk[(ei * p.T + t) * p.CC + c] += a;
-      }
+      contract<kExact>(p.T, cw, p.TN, dS, lds, 1, kvs + c_lo, ld, 1,
+                       [&](int t, int c, float v) { dtk[(ei * p.T + t) * p.CC + c] += v; });
       __syncthreads();
     }
     // write the dkv tile
@@ -256,7 +219,7 @@ __global__ void __launch_bounds__(256) latent_bwd_kernel(const LatentParams p) {
 
 static int plan_latent(LatentParams& p, bool bwd, size_t* smem) {
   // kv tile: keep TN*(C+1) floats under 48 KiB
-  int TN = 12288 / (p.C + 1);
+  int TN = 12288 / (p.C + 4);
   if (TN > 64) TN = 64;
   if (TN >= 32) TN = TN / 32 * 32; else if (TN >= 8) TN = TN / 8 * 8; else TN = TN < 1 ? 1 : TN;
   p.TN = TN;
@@ -277,9 +240,9 @@ static int plan_latent(LatentParams& p, bool bwd, size_t* smem) {
   if (nsplit > 32) nsplit = 32;
   p.tokens_per_split = ((p.Nk + nsplit - 1) / nsplit + TN - 1) / TN * TN;
   p.nsplit = (p.Nk + p.tokens_per_split - 1) / p.tokens_per_split;
-  const size_t lds = TN + 1;
-  if (!bwd) *smem = sizeof(float) * ((size_t)TN * (p.C + 1) + (size_t)p.T * lds + (size_t)p.T * CC + 3 * (size_t)p.T);
-  else *smem = sizeof(float) * ((size_t)TN * (p.C + 1) + 2 * (size_t)p.T * lds + (size_t)TN * CC + (size_t)p.nexp * p.T * CC + (size_t)p.nexp * p.T);
+  const size_t lds = TN + 4;
+  if (!bwd) *smem = sizeof(float) * ((size_t)TN * (p.C + 4) + (size_t)p.T * lds + (size_t)p.T * CC + 3 * (size_t)p.T);
+  else *smem = sizeof(float) * ((size_t)TN * (p.C + 4) + 2 * (size_t)p.T * lds + (size_t)TN * CC + (size_t)p.nexp * p.T * CC + (size_t)p.nexp * p.T);
   return 0;
 }
 
