@@ -24,50 +24,59 @@ static constexpr double kBnEps = 1e-5;
 static constexpr double kBnMomentum = 0.1;
 static constexpr int kThreads = 256;
 
-__device__ __forceinline__ int pow2_group(int tn) { return tn < 32 ? tn : 32; }
+static constexpr int kMaxVLimit = 12;   // float4 vectors per lane per row: C <= 1536 (kernels are instantiated for 1,2,3,6,12)
 
-// sum over groups of `group` consecutive lanes (group is a power of two <= 32)
-__device__ __forceinline__ float group_sum(float v, int group) {
-  for (int o = group >> 1; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-  return v;
+// Row passes: one warp per token row, lane l owns the float4 column groups c = 4*l + 128*k  (k < kMaxV, c < C).
+// No integer divisions, 4 elements per instruction, row reductions by warp shuffles.
+#define ROW_VECS(k, c) _Pragma("unroll") for (int k = 0, c = lane * 4; k < kMaxV; ++k, c += 128) if (c < C)
+
+__device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+__device__ __forceinline__ void st4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
+__device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+__device__ __forceinline__ float hsum(float4 v) { return (v.x + v.y) + (v.z + v.w); }
+__device__ __forceinline__ float4 f4(float a) { return make_float4(a, a, a, a); }
+__device__ __forceinline__ float4 operator+(float4 a, float4 b) { return make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w); }
+__device__ __forceinline__ float4 operator-(float4 a, float4 b) { return make_float4(a.x - b.x, a.y - b.y, a.z - b.z, a.w - b.w); }
+__device__ __forceinline__ float4 operator*(float4 a, float4 b) { return make_float4(a.x * b.x, a.y * b.y, a.z * b.z, a.w * b.w); }
+__device__ __forceinline__ float4 operator*(float a, float4 b) { return make_float4(a * b.x, a * b.y, a * b.z, a * b.w); }
+
+// (scale, shift) or (mean, invstd) pairs are stored interleaved per channel: 4 channels = 2 float4
+__device__ __forceinline__ void ldg_pairs4(const float* p, float4& first, float4& second) {
+  const float4 a = ldg4(p), b = ldg4(p + 4);
+  first = make_float4(a.x, a.z, b.x, b.z);
+  second = make_float4(a.y, a.w, b.y, b.w);
 }
 
 template <typename T>
+__device__ __forceinline__ float4 ldg_act4(const T* p);
+template <>
+__device__ __forceinline__ float4 ldg_act4<float>(const float* p) { return ldg4(p); }
+template <>
+__device__ __forceinline__ float4 ldg_act4<__nv_bfloat16>(const __nv_bfloat16* p) {
+  float v[4];
+  load4<__nv_bfloat16>(p, v);
+  return make_float4(v[0], v[1], v[2], v[3]);
+}
+template <typename T>
+__device__ __forceinline__ void st_act4(T* p, float4 v) {
+  const float a[4] = {v.x, v.y, v.z, v.w};
+  store4<T>(p, a);
+}
+
+// global [rows][C] (storage dtype) -> smem fp32 [rows][ld]; rows >= valid are zero-filled
+template <typename T, int kMaxV>
 __device__ __forceinline__ void load_tile(float* dst, const T* src, int valid_rows, int rows, int C, int ld) {
-  const int C4 = C >> 2;
-  for (int i = threadIdx.x; i < rows * C4; i += blockDim.x) {
-    const int n = i / C4, c4 = i - n * C4;
-    float v[4] = {0.f, 0.f, 0.f, 0.f};
-    if (n < valid_rows) load4<T>(src + (long long)n * C + c4 * 4, v);
-    float* d = dst + n * ld + c4 * 4;
-    d[0] = v[0]; d[1] = v[1]; d[2] = v[2]; d[3] = v[3];
-  }
-}
-
-template <typename T>
-__device__ __forceinline__ void store_tile(T* dst, const float* src, int valid_rows, int C, int ld) {
-  const int C4 = C >> 2;
-  for (int i = threadIdx.x; i < valid_rows * C4; i += blockDim.x) {
-    const int n = i / C4, c4 = i - n * C4;
-    const float* s = src + n * ld + c4 * 4;
-    const float v[4] = {s[0], s[1], s[2], s[3]};
-    store4<T>(dst + (long long)n * C + c4 * 4, v);
-  }
-}
-
-// two-pass mean / rstd of every row (one warp per row)
-__device__ __forceinline__ void row_stats(const float* buf, int rows, int C, int ld, float* mean, float* rstd) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
   for (int r = warp; r < rows; r += nwarps) {
-    const float* row = buf + r * ld;
-    float s = 0.f;
-    for (int c = lane; c < C; c += 32) s += row[c];
-    s = warp_sum(s);
-    const float m = s / C;
-    float ss = 0.f;
-    for (int c = lane; c < C; c += 32) { const float d = row[c] - m; ss = fmaf(d, d, ss); }
-    ss = warp_sum(ss);
-    if (lane == 0) { mean[r] = m; rstd[r] = rsqrtf(ss / C + kLnEps); }
+    ROW_VECS(k, c) st4(dst + r * ld + c, r < valid_rows ? ldg_act4<T>(src + (long long)r * C + c) : f4(0.f));
+  }
+}
+
+template <typename T, int kMaxV>
+__device__ __forceinline__ void store_tile(T* dst, const float* src, int valid_rows, int C, int ld) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  for (int r = warp; r < valid_rows; r += nwarps) {
+    ROW_VECS(k, c) st_act4<T>(dst + (long long)r * C + c, ld4(src + r * ld + c));
   }
 }
 
@@ -85,52 +94,58 @@ __device__ __forceinline__ float block_sum(float v, float* scratch /* >= 32 floa
   return r;  // valid in warp 0
 }
 
-// ---- token <- latent attention on a tile: probabilities into s2 [rows][T+4], xa = x + g * (A2 tok') into ws ----
-template <bool kExact>
-__device__ __forceinline__ void latent_tile_fwd(const float* xs, float* ws, float* s2, const float* tp, float g, int rows, int C, int ld, int T) {
-  const int lt = T + 4;
-  contract<kExact>(rows, T, C, xs, ld, 1, tp, 1, C, [&](int n, int t, float v) { s2[n * lt + t] = v; });
-  __syncthreads();
-  for (int n = threadIdx.x; n < rows; n += blockDim.x) {
-    float* r = s2 + n * lt;
-    float mx = r[0];
-    for (int t = 1; t < T; ++t) mx = fmaxf(mx, r[t]);
+// softmax over the T entries of every row of s2 [rows][lt] (one warp per row, lanes over t)
+__device__ __forceinline__ void row_softmax(float* s2, int rows, int T, int lt) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  for (int r = warp; r < rows; r += nwarps) {
+    float* pr = s2 + r * lt;
+    float mx = -INFINITY;
+    for (int t = lane; t < T; t += 32) mx = fmaxf(mx, pr[t]);
+    mx = warp_max(mx);
     float sum = 0.f;
-    for (int t = 0; t < T; ++t) { const float e = expf(r[t] - mx); r[t] = e; sum += e; }
+    for (int t = lane; t < T; t += 32) { const float e = expf(pr[t] - mx); pr[t] = e; sum += e; }
+    sum = warp_sum(sum);
     const float inv = 1.f / sum;
-    for (int t = 0; t < T; ++t) r[t] *= inv;
+    for (int t = lane; t < T; t += 32) pr[t] *= inv;
   }
-  __syncthreads();
-  contract<kExact>(rows, C, T, s2, lt, 1, tp, C, 1, [&](int n, int c, float v) { ws[n * ld + c] = xs[n * ld + c] + g * v; });
-  __syncthreads();
 }
 
-// builds ws = the tensor ln_before sees for expert `ex` (see AVMOE_PRE_*); leaves latent probabilities in s2
-template <typename T, bool kExact>
-__device__ __forceinline__ void pre_transform(const avmoe_expert& ex, const avmoe_expert_args& p, int b, int n0, int valid, int rows,
-                                              const float* xs, float* ws, float* s2, int ld) {
+// Builds in ws the tensor ln_before sees for expert `ex` (AVMOE_PRE_*), EXCEPT for AVMOE_PRE_NONE where the caller reads xs
+// directly.  Latent experts leave the token<-latent probabilities in s2.  Returns the buffer holding xa.
+template <typename T, bool kExact, int kMaxV>
+__device__ __forceinline__ const float* pre_transform(const avmoe_expert& ex, const avmoe_expert_args& p, int b, int n0, int valid, int rows,
+                                                      const float* xs, float* ws, float* s2, int ld) {
   const int C = p.C;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  if (ex.pre_kind == AVMOE_PRE_NONE) return xs;
   if (ex.pre_kind == AVMOE_PRE_LATENT) {
     const float* tp = p.tokp + ((long long)b * p.nl + ex.latent_slot) * p.T * C;
-    latent_tile_fwd<kExact>(xs, ws, s2, tp, *ex.gate_pre, rows, C, ld, p.T);
-  } else if (ex.pre_kind == AVMOE_PRE_NONE) {
-    for (int i = threadIdx.x; i < rows * C; i += blockDim.x) { const int n = i / C, c = i - n * C; ws[n * ld + c] = xs[n * ld + c]; }
+    const float g = *ex.gate_pre;
+    const int lt = p.T + 4;
+    contract<kExact>(rows, p.T, C, xs, ld, 1, tp, 1, C, [&](int n, int t, float v) { s2[n * lt + t] = v; });
     __syncthreads();
-  } else {
-    const T* aux = reinterpret_cast<const T*>(ex.aux) + ((long long)b * p.N + n0) * C;
-    load_tile<T>(ws, aux, valid, rows, C, ld);
+    row_softmax(s2, rows, p.T, lt);
     __syncthreads();
-    if (ex.pre_kind == AVMOE_PRE_AUX_ADD) {
-      const float g = *ex.gate_pre;
-      for (int i = threadIdx.x; i < rows * C; i += blockDim.x) { const int n = i / C, c = i - n * C; ws[n * ld + c] = xs[n * ld + c] + g * ws[n * ld + c]; }
-      __syncthreads();
+    contract<kExact>(rows, C, p.T, s2, lt, 1, tp, C, 1, [&](int n, int c, float v) { ws[n * ld + c] = xs[n * ld + c] + g * v; });
+    __syncthreads();
+    return ws;
+  }
+  const T* aux = reinterpret_cast<const T*>(ex.aux) + ((long long)b * p.N + n0) * C;
+  const float g = ex.pre_kind == AVMOE_PRE_AUX_ADD ? *ex.gate_pre : 0.f;
+  for (int r = warp; r < rows; r += nwarps) {
+    ROW_VECS(k, c) {
+      float4 a = r < valid ? ldg_act4<T>(aux + (long long)r * C + c) : f4(0.f);
+      if (ex.pre_kind == AVMOE_PRE_AUX_ADD) a = ld4(xs + r * ld + c) + g * a;
+      st4(ws + r * ld + c, a);
     }
   }
+  __syncthreads();
+  return ws;
 }
 
 // ------------------------------------------------------------------------------------------------ front forward
 // grid (ceil(N/TN), BT), block 256
-template <typename T>
+template <typename T, int kMaxV>
 __global__ void __launch_bounds__(kThreads) expert_front_fwd_kernel(const avmoe_expert_args p, int TN) {
   extern __shared__ float sm[];
   constexpr bool kExact = std::is_same<T, float>::value;
@@ -139,25 +154,31 @@ __global__ void __launch_bounds__(kThreads) expert_front_fwd_kernel(const avmoe_
   float* ws = xs + TN * ld;            // [TN][ld]
   float* s2 = ws + TN * ld;            // [TN][T+4]
   float* zt = s2 + TN * (p.T + 4);     // [TN][E*Cr+1]  z tile of all experts
-  float* mean = zt + TN * lz;          // [TN]
-  float* rstd = mean + TN;             // [TN]
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
   const int b = blockIdx.y, n0 = blockIdx.x * TN;
   const int valid = min(TN, p.N - n0);
   const T* xb = reinterpret_cast<const T*>(p.x) + ((long long)b * p.N + n0) * C;
-  load_tile<T>(xs, xb, valid, TN, C, ld);
+  load_tile<T, kMaxV>(xs, xb, valid, TN, C, ld);
   __syncthreads();
   for (int e = 0; e < p.E; ++e) {
     const avmoe_expert& ex = p.ex[e];
-    pre_transform<T, kExact>(ex, p, b, n0, valid, TN, xs, ws, s2, ld);
-    if (ex.ln1_w) {
-      row_stats(ws, TN, C, ld, mean, rstd);
-      __syncthreads();
-      for (int i = threadIdx.x; i < TN * C; i += blockDim.x) {
-        const int n = i / C, c = i - n * C;
-        ws[n * ld + c] = (ws[n * ld + c] - mean[n]) * rstd[n] * __ldg(ex.ln1_w + c) + __ldg(ex.ln1_b + c);
+    const float* xa = pre_transform<T, kExact, kMaxV>(ex, p, b, n0, valid, TN, xs, ws, s2, ld);
+    // ln_before (row pass): ws <- LN(xa) * w + b   (or a plain copy when the variant has no ln_before)
+    for (int r = warp; r < TN; r += nwarps) {
+      float4 v[kMaxV];
+      float sum = 0.f;
+      ROW_VECS(k, c) { v[k] = ld4(xa + r * ld + c); sum += hsum(v[k]); }
+      if (ex.ln1_w) {
+        const float mean = warp_sum(sum) / C;
+        float ss = 0.f;
+        ROW_VECS(k, c) { const float4 d = v[k] - f4(mean); ss += hsum(d * d); }
+        const float rstd = rsqrtf(warp_sum(ss) / C + kLnEps);
+        ROW_VECS(k, c) st4(ws + r * ld + c, (rstd * (v[k] - f4(mean))) * ldg4(ex.ln1_w + c) + ldg4(ex.ln1_b + c));
+      } else if (xa != ws) {
+        ROW_VECS(k, c) st4(ws + r * ld + c, v[k]);
       }
-      __syncthreads();
     }
+    __syncthreads();
     // grouped down projection: z[n][g*Crg+jl] = sum_cl xn[n][g*Cg+cl] * wd[g*Crg+jl][cl]
     for (int g = 0; g < G; ++g)
       contract<kExact>(TN, Crg, Cg, ws + g * Cg, ld, 1, ex.wd + (long long)g * Crg * Cg, 1, Cg,
@@ -166,7 +187,8 @@ __global__ void __launch_bounds__(kThreads) expert_front_fwd_kernel(const avmoe_
   }
   // coalesced store of the z tile [valid][E*Cr] and the bn1 batch sums
   float* zg = p.z + ((long long)b * p.N + n0) * ECr;
-  for (int i = threadIdx.x; i < valid * ECr; i += blockDim.x) { const int n = i / ECr, q = i - n * ECr; zg[i] = zt[n * lz + q]; }
+  for (int n = warp; n < valid; n += nwarps)
+    for (int q = lane; q < ECr; q += 32) zg[(long long)n * ECr + q] = zt[n * lz + q];
   if (p.stats1) {
     for (int q = threadIdx.x; q < ECr; q += blockDim.x) {
       float s1 = 0.f, s2v = 0.f;
@@ -332,16 +354,19 @@ template <bool kExact>
 __device__ __forceinline__ void back_recompute(const avmoe_expert_args& p, const avmoe_expert& ex, int e, int b, int n0, int valid, int TN,
                                                float* as, float* ys, int ld) {
   const int C = p.C, Cr = p.Cr, G = p.G, Cg = C / G, Crg = Cr / G, lda = Cr + 4;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
   const bool bn = p.bn_mode != AVMOE_BN_OFF;
-  for (int i = threadIdx.x; i < TN * Cr; i += blockDim.x) {
-    const int n = i / Cr, j = i - n * Cr;
-    float a = 0.f;
-    if (n < valid) {
-      float zt = p.z[(((long long)b * p.N + n0 + n) * p.E + e) * Cr + j];
-      if (bn) zt = zt * p.aff1[(e * Cr + j) * 2] + p.aff1[(e * Cr + j) * 2 + 1];
-      a = ex.relu ? fmaxf(zt, 0.f) : zt;
+  for (int n = warp; n < TN; n += nwarps) {
+    const float* zr = p.z + (((long long)b * p.N + n0 + n) * p.E + e) * Cr;
+    for (int j = lane; j < Cr; j += 32) {
+      float a = 0.f;
+      if (n < valid) {
+        float zt = zr[j];
+        if (bn) zt = fmaf(zt, __ldg(p.aff1 + (e * Cr + j) * 2), __ldg(p.aff1 + (e * Cr + j) * 2 + 1));
+        a = ex.relu ? fmaxf(zt, 0.f) : zt;
+      }
+      as[n * lda + j] = a;
     }
-    as[n * lda + j] = a;
   }
   __syncthreads();
   for (int g = 0; g < G; ++g)
@@ -351,7 +376,7 @@ __device__ __forceinline__ void back_recompute(const avmoe_expert_args& p, const
 }
 
 // ------------------------------------------------------------------------------------------------ back forward
-template <typename T>
+template <typename T, int kMaxV>
 __global__ void __launch_bounds__(kThreads) expert_back_fwd_kernel(const avmoe_expert_args p, int TN) {
   extern __shared__ float sm[];
   constexpr bool kExact = std::is_same<T, float>::value;
@@ -359,181 +384,175 @@ __global__ void __launch_bounds__(kThreads) expert_back_fwd_kernel(const avmoe_e
   float* ys = sm;                      // [TN][ld]
   float* acc = ys + TN * ld;           // [TN][ld]
   float* as = acc + TN * ld;           // [TN][Cr+4]
-  float* mean = as + TN * (Cr + 4);
-  float* rstd = mean + TN;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
   const int b = blockIdx.y, n0 = blockIdx.x * TN;
   const int valid = min(TN, p.N - n0);
   const bool bn = p.bn_mode != AVMOE_BN_OFF;
-  for (int i = threadIdx.x; i < TN * ld; i += blockDim.x) acc[i] = 0.f;
   for (int e = 0; e < p.E; ++e) {
     const avmoe_expert& ex = p.ex[e];
     back_recompute<kExact>(p, ex, e, b, n0, valid, TN, as, ys, ld);
-    if (bn) {
-      for (int i = threadIdx.x; i < TN * C; i += blockDim.x) {
-        const int n = i / C, c = i - n * C;
-        ys[n * ld + c] = ys[n * ld + c] * p.aff2[(e * C + c) * 2] + p.aff2[(e * C + c) * 2 + 1];
-      }
-      __syncthreads();
-    }
-    if (ex.ln2_w) { row_stats(ys, TN, C, ld, mean, rstd); __syncthreads(); }
     const float scale = p.probs[(long long)b * p.E + e] * (ex.gate ? *ex.gate : 1.f);
-    for (int i = threadIdx.x; i < TN * C; i += blockDim.x) {
-      const int n = i / C, c = i - n * C;
-      float q = ys[n * ld + c];
-      if (ex.ln2_w) q = (q - mean[n]) * rstd[n] * __ldg(ex.ln2_w + c) + __ldg(ex.ln2_b + c);
-      acc[n * ld + c] = fmaf(scale, q, acc[n * ld + c]);
+    // row pass: bn2 affine -> ln_post -> acc += probs*gate*q
+    for (int r = warp; r < valid; r += nwarps) {
+      float4 v[kMaxV];
+      float sum = 0.f;
+      ROW_VECS(k, c) {
+        v[k] = ld4(ys + r * ld + c);
+        if (bn) { float4 sc, sh; ldg_pairs4(p.aff2 + ((long long)e * C + c) * 2, sc, sh); v[k] = v[k] * sc + sh; }
+        sum += hsum(v[k]);
+      }
+      if (ex.ln2_w) {
+        const float mean = warp_sum(sum) / C;
+        float ss = 0.f;
+        ROW_VECS(k, c) { const float4 d = v[k] - f4(mean); ss += hsum(d * d); }
+        const float rstd = rsqrtf(warp_sum(ss) / C + kLnEps);
+        ROW_VECS(k, c) v[k] = (rstd * (v[k] - f4(mean))) * ldg4(ex.ln2_w + c) + ldg4(ex.ln2_b + c);
+      }
+      ROW_VECS(k, c) {
+        float4 o = scale * v[k];
+        if (e > 0) o = o + ld4(acc + r * ld + c);
+        st4(acc + r * ld + c, o);
+      }
     }
     __syncthreads();
   }
   T* ob = reinterpret_cast<T*>(p.out) + ((long long)b * p.N + n0) * C;
-  store_tile<T>(ob, acc, valid, C, ld);
+  store_tile<T, kMaxV>(ob, acc, valid, C, ld);
 }
 
 // ------------------------------------------------------------------------------------------------ back backward
 // kStatsOnly: only the bn2 batch reductions (sum dyt, sum dyt*yhat); otherwise the full backward of the back half.
-template <typename T, bool kStatsOnly>
+template <typename T, bool kStatsOnly, int kMaxV>
 __global__ void __launch_bounds__(kThreads) expert_back_bwd_kernel(const avmoe_expert_args p, int TN) {
   extern __shared__ float sm[];
   constexpr bool kExact = std::is_same<T, float>::value;
   const int C = p.C, Cr = p.Cr, G = p.G, Cg = C / G, Crg = Cr / G, ld = C + 4, lda = Cr + 4;
   float* gs0 = sm;                     // [TN][ld]  dout tile (kept)
   float* ys = gs0 + TN * ld;           // [TN][ld]  y (pre-bn2)
-  float* gs = ys + TN * ld;            // [TN][ld]  working gradient (dq -> dyt -> dy)
-  float* as = gs + TN * ld;            // [TN][Cr+1]
-  float* mean = as + TN * lda;
-  float* rstd = mean + TN;
-  float* m1r = rstd + TN;              // row means of the LN backward
-  float* m2r = m1r + TN;
-  float* scratch = m2r + TN;           // [32]
-  float* dzs = scratch + 32;           // [TN][Cr+4] dzt tile of the current expert
+  float* gs = ys + TN * ld;            // [TN][ld]  dy
+  float* as = gs + TN * ld;            // [TN][Cr+4]
+  float* dzs = as + TN * lda;          // [TN][Cr+4] dzt tile of the current expert
+  float* col = dzs + TN * lda;         // [4][C] column sums: ln_post w/b grads, sum dyt, sum dyt*yhat
+  float* mds = col + 4 * C;            // [2][C] batch means of dyt and dyt*yhat (bn train)
+  float* scratch = mds + 2 * C;        // [32]
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
   const int b = blockIdx.y, n0 = blockIdx.x * TN;
   const int valid = min(TN, p.N - n0);
   const int mode = p.bn_mode;
   const double inv_n = 1.0 / ((double)p.BT * p.N);
   const T* gb = reinterpret_cast<const T*>(p.dout) + ((long long)b * p.N + n0) * C;
-  load_tile<T>(gs0, gb, valid, TN, C, ld);
+  load_tile<T, kMaxV>(gs0, gb, valid, TN, C, ld);
   __syncthreads();
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
   for (int e = 0; e < p.E; ++e) {
     const avmoe_expert& ex = p.ex[e];
-    back_recompute<kExact>(p, ex, e, b, n0, valid, TN, as, ys, ld);
-    const float* aff2 = p.aff2 ? p.aff2 + (long long)e * C * 2 : nullptr;
-    const float* sv2 = p.save2 ? p.save2 + (long long)e * C * 2 : nullptr;
-    // ---- ln_post statistics of yt = bn2(y)
-    if (ex.ln2_w) {
-      if (mode != AVMOE_BN_OFF) {   // row_stats needs yt: materialise into gs temporarily
-        for (int i = threadIdx.x; i < TN * C; i += blockDim.x) {
-          const int n = i / C, c = i - n * C;
-          gs[n * ld + c] = ys[n * ld + c] * aff2[c * 2] + aff2[c * 2 + 1];
-        }
-        __syncthreads();
-        row_stats(gs, TN, C, ld, mean, rstd);
-      } else {
-        row_stats(ys, TN, C, ld, mean, rstd);
+    for (int i = threadIdx.x; i < 4 * C; i += blockDim.x) col[i] = 0.f;
+    if (!kStatsOnly && mode == AVMOE_BN_TRAIN)
+      for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        mds[c] = (float)(p.red2[((long long)e * C + c) * 2] * inv_n);
+        mds[C + c] = (float)(p.red2[((long long)e * C + c) * 2 + 1] * inv_n);
       }
-      __syncthreads();
-    }
+    back_recompute<kExact>(p, ex, e, b, n0, valid, TN, as, ys, ld);   // (syncs)
     const float pe = p.probs[(long long)b * p.E + e];
     const float gate = ex.gate ? *ex.gate : 1.f;
     const float sc = pe * gate;
-    // ---- per element: q, dq; sum(dout*q) for dprobs/dgate; gs = dq*w (dqh) or dq
     float gq = 0.f;
-    for (int i = threadIdx.x; i < TN * C; i += blockDim.x) {
-      const int n = i / C, c = i - n * C;
-      float yt = ys[n * ld + c];
-      if (mode != AVMOE_BN_OFF) yt = yt * aff2[c * 2] + aff2[c * 2 + 1];
-      const float g0 = gs0[n * ld + c];
-      float q = yt, dqh = g0 * sc;
-      if (ex.ln2_w) {
-        const float qh = (yt - mean[n]) * rstd[n];
-        q = qh * __ldg(ex.ln2_w + c) + __ldg(ex.ln2_b + c);
-        dqh *= __ldg(ex.ln2_w + c);
+    // ---- one row pass: yt, ln_post fwd stats, dq, ln_post bwd, bn2 bwd -> dy
+    for (int r = warp; r < TN; r += nwarps) {
+      if (r >= valid) {   // keep the dy tile zero below the valid rows (it feeds the weight-gradient contraction)
+        if (!kStatsOnly) { ROW_VECS(k, c) st4(gs + r * ld + c, f4(0.f)); }
+        continue;
       }
-      gq = fmaf(g0, q, gq);
-      gs[n * ld + c] = dqh;
+      float4 yt[kMaxV], yh[kMaxV], d[kMaxV];
+      float4 s2c[kMaxV];
+      float sum = 0.f;
+      ROW_VECS(k, c) {
+        const float4 y = ld4(ys + r * ld + c);
+        yt[k] = y;
+        if (mode != AVMOE_BN_OFF) {
+          float4 a2s, a2h, mu, is;
+          ldg_pairs4(p.aff2 + ((long long)e * C + c) * 2, a2s, a2h);
+          ldg_pairs4(p.save2 + ((long long)e * C + c) * 2, mu, is);
+          yt[k] = y * a2s + a2h;
+          yh[k] = (y - mu) * is;
+          s2c[k] = a2s;
+        }
+        sum += hsum(yt[k]);
+      }
+      float mean = 0.f, rstd = 1.f;
+      if (ex.ln2_w) {
+        mean = warp_sum(sum) / C;
+        float ss = 0.f;
+        ROW_VECS(k, c) { const float4 t = yt[k] - f4(mean); ss += hsum(t * t); }
+        rstd = rsqrtf(warp_sum(ss) / C + kLnEps);
+      }
+      float s1 = 0.f, s2v = 0.f;
+      ROW_VECS(k, c) {
+        const float4 g0 = ld4(gs0 + r * ld + c);
+        const float4 dq = sc * g0;
+        if (ex.ln2_w) {
+          const float4 w = ldg4(ex.ln2_w + c);
+          const float4 qh = rstd * (yt[k] - f4(mean));
+          const float4 q = qh * w + ldg4(ex.ln2_b + c);
+          gq += hsum(g0 * q);
+          if (!kStatsOnly) {
+            const float4 t = dq * qh;
+            atomicAdd(&col[c], t.x); atomicAdd(&col[c + 1], t.y); atomicAdd(&col[c + 2], t.z); atomicAdd(&col[c + 3], t.w);
+            atomicAdd(&col[C + c], dq.x); atomicAdd(&col[C + c + 1], dq.y); atomicAdd(&col[C + c + 2], dq.z); atomicAdd(&col[C + c + 3], dq.w);
+          }
+          d[k] = dq * w;                         // dqh
+          s1 += hsum(d[k]);
+          s2v += hsum(d[k] * qh);
+          yt[k] = qh;                            // keep qh for the LN backward
+        } else {
+          gq += hsum(g0 * yt[k]);
+          d[k] = dq;
+        }
+      }
+      if (ex.ln2_w) {
+        const float m1 = warp_sum(s1) / C, m2 = warp_sum(s2v) / C;
+        ROW_VECS(k, c) d[k] = rstd * (d[k] - f4(m1) - m2 * yt[k]);      // dyt
+      }
+      if (mode != AVMOE_BN_OFF) {
+        if (kStatsOnly || mode == AVMOE_BN_EVAL) {
+          ROW_VECS(k, c) {
+            const float4 t = d[k] * yh[k];
+            atomicAdd(&col[2 * C + c], d[k].x); atomicAdd(&col[2 * C + c + 1], d[k].y); atomicAdd(&col[2 * C + c + 2], d[k].z); atomicAdd(&col[2 * C + c + 3], d[k].w);
+            atomicAdd(&col[3 * C + c], t.x); atomicAdd(&col[3 * C + c + 1], t.y); atomicAdd(&col[3 * C + c + 2], t.z); atomicAdd(&col[3 * C + c + 3], t.w);
+          }
+        }
+        if (!kStatsOnly) {
+          ROW_VECS(k, c) {
+            if (mode == AVMOE_BN_TRAIN) d[k] = d[k] - ld4(mds + c) - yh[k] * ld4(mds + C + c);
+            d[k] = d[k] * s2c[k];
+          }
+        }
+      }
+      if (!kStatsOnly) { ROW_VECS(k, c) st4(gs + r * ld + c, d[k]); }
     }
-    if (!kStatsOnly) {
+    __syncthreads();
+    // ---- flush the tile's column sums
+    if (kStatsOnly) {
+      for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        atomicAdd(&p.red2[((long long)e * C + c) * 2], (double)col[2 * C + c]);
+        atomicAdd(&p.red2[((long long)e * C + c) * 2 + 1], (double)col[3 * C + c]);
+      }
+      __syncthreads();
+      continue;
+    }
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+      if (ex.ln2_w) { atomicAdd(ex.g_ln2_w + c, col[c]); atomicAdd(ex.g_ln2_b + c, col[C + c]); }
+      if (mode == AVMOE_BN_EVAL) {
+        atomicAdd(&p.red2b[((long long)e * C + c) * 2], (double)col[2 * C + c]);
+        atomicAdd(&p.red2b[((long long)e * C + c) * 2 + 1], (double)col[3 * C + c]);
+      }
+    }
+    {
       const float tot = block_sum(gq, scratch);
       if (threadIdx.x == 0) {
         atomicAdd(&p.dprobs[(long long)b * p.E + e], tot * gate);
         if (ex.g_gate) atomicAdd(ex.g_gate, tot * pe);
       }
     }
-    __syncthreads();
-    if (ex.ln2_w) {
-      // column sums for d ln_post weight/bias (dq = dqh / w is avoided: recompute dq = g0*sc)
-      if (!kStatsOnly) {
-        for (int c = threadIdx.x; c < C; c += blockDim.x) {
-          float sw = 0.f, sb = 0.f;
-          const float a2s = mode != AVMOE_BN_OFF ? aff2[c * 2] : 1.f, a2h = mode != AVMOE_BN_OFF ? aff2[c * 2 + 1] : 0.f;
-          for (int n = 0; n < valid; ++n) {
-            const float yt = ys[n * ld + c] * a2s + a2h;
-            const float qh = (yt - mean[n]) * rstd[n];
-            const float dq = gs0[n * ld + c] * sc;
-            sw = fmaf(dq, qh, sw);
-            sb += dq;
-          }
-          atomicAdd(ex.g_ln2_w + c, sw);
-          atomicAdd(ex.g_ln2_b + c, sb);
-        }
-      }
-      // row means of dqh and dqh*qh
-      for (int r = warp; r < TN; r += nwarps) {
-        float s1 = 0.f, s2v = 0.f;
-        for (int c = lane; c < C; c += 32) {
-          float yt = ys[r * ld + c];
-          if (mode != AVMOE_BN_OFF) yt = yt * aff2[c * 2] + aff2[c * 2 + 1];
-          const float qh = (yt - mean[r]) * rstd[r];
-          const float d = gs[r * ld + c];
-          s1 += d;
-          s2v = fmaf(d, qh, s2v);
-        }
-        s1 = warp_sum(s1); s2v = warp_sum(s2v);
-        if (lane == 0) { m1r[r] = s1 / C; m2r[r] = s2v / C; }
-      }
-      __syncthreads();
-      for (int i = threadIdx.x; i < TN * C; i += blockDim.x) {
-        const int n = i / C, c = i - n * C;
-        float yt = ys[n * ld + c];
-        if (mode != AVMOE_BN_OFF) yt = yt * aff2[c * 2] + aff2[c * 2 + 1];
-        const float qh = (yt - mean[n]) * rstd[n];
-        gs[n * ld + c] = rstd[n] * (gs[n * ld + c] - m1r[n] - qh * m2r[n]);     // dyt
-      }
-      __syncthreads();
-    }
-    // ---- bn2 backward
-    if (mode != AVMOE_BN_OFF) {
-      if (kStatsOnly || mode == AVMOE_BN_EVAL) {
-        double* red = kStatsOnly ? p.red2 : p.red2b;
-        for (int c = threadIdx.x; c < C; c += blockDim.x) {
-          float s1 = 0.f, s2v = 0.f;
-          const float mu = sv2[c * 2], is = sv2[c * 2 + 1];
-          for (int n = 0; n < valid; ++n) {
-            const float d = gs[n * ld + c];
-            s1 += d;
-            s2v = fmaf(d, (ys[n * ld + c] - mu) * is, s2v);
-          }
-          atomicAdd(&red[((long long)e * C + c) * 2], (double)s1);
-          atomicAdd(&red[((long long)e * C + c) * 2 + 1], (double)s2v);
-        }
-        __syncthreads();   // the sums read gs (dyt) before the loop below overwrites it with dy
-      }
-      if (!kStatsOnly) {
-        for (int i = threadIdx.x; i < TN * C; i += blockDim.x) {
-          const int n = i / C, c = i - n * C;
-          float d = gs[n * ld + c];
-          if (mode == AVMOE_BN_TRAIN) {
-            const float md = (float)(p.red2[((long long)e * C + c) * 2] * inv_n);
-            const float mdy = (float)(p.red2[((long long)e * C + c) * 2 + 1] * inv_n);
-            const float yh = (ys[n * ld + c] - sv2[c * 2]) * sv2[c * 2 + 1];
-            d = d - md - yh * mdy;
-          }
-          gs[n * ld + c] = (n < valid) ? d * aff2[c * 2] : 0.f;                   // dy
-        }
-      }
-      __syncthreads();
-    }
-    if (kStatsOnly) continue;
     // ---- d up_sampler.weight[c][jl] += sum_n dy[n][c] * a[n][g*Crg+jl]      (rows >= valid of gs are zero)
     for (int g = 0; g < G; ++g)
       contract<kExact>(Cg, Crg, TN, gs + g * Cg, 1, ld, as + g * Crg, lda, 1,
@@ -543,23 +562,26 @@ __global__ void __launch_bounds__(kThreads) expert_back_bwd_kernel(const avmoe_e
       contract<kExact>(TN, Crg, Cg, gs + g * Cg, ld, 1, ex.wu + (long long)g * Cg * Crg, Crg, 1,
                        [&](int n, int jl, float v) { dzs[n * lda + g * Crg + jl] = v; });
     __syncthreads();
-    // ---- relu mask, store dzt, bn1-backward sums per channel
-    for (int i = threadIdx.x; i < valid * Cr; i += blockDim.x) {
-      const int n = i / Cr, j = i - n * Cr;
-      float d = dzs[n * lda + j];
-      if (ex.relu && !(as[n * lda + j] > 0.f)) d = 0.f;
-      dzs[n * lda + j] = d;
-      p.dzt[(((long long)b * p.N + n0 + n) * p.E + e) * Cr + j] = d;
+    // ---- relu mask, store dzt (coalesced rows of Cr)
+    for (int n = warp; n < valid; n += nwarps) {
+      float* dzr = p.dzt + (((long long)b * p.N + n0 + n) * p.E + e) * Cr;
+      for (int j = lane; j < Cr; j += 32) {
+        float dd = dzs[n * lda + j];
+        if (ex.relu && !(as[n * lda + j] > 0.f)) dd = 0.f;
+        dzs[n * lda + j] = dd;
+        dzr[j] = dd;
+      }
     }
     __syncthreads();
+    // ---- bn1-backward sums per bottleneck channel
     if (mode != AVMOE_BN_OFF) {
       for (int j = threadIdx.x; j < Cr; j += blockDim.x) {
         const float mu = p.save1[(e * Cr + j) * 2], is = p.save1[(e * Cr + j) * 2 + 1];
         float s1 = 0.f, s2v = 0.f;
         for (int n = 0; n < valid; ++n) {
-          const float d = dzs[n * lda + j];
-          s1 += d;
-          s2v = fmaf(d, (p.z[(((long long)b * p.N + n0 + n) * p.E + e) * Cr + j] - mu) * is, s2v);
+          const float dd = dzs[n * lda + j];
+          s1 += dd;
+          s2v = fmaf(dd, (p.z[(((long long)b * p.N + n0 + n) * p.E + e) * Cr + j] - mu) * is, s2v);
         }
         atomicAdd(&p.red1[((long long)e * Cr + j) * 2], (double)s1);
         atomicAdd(&p.red1[((long long)e * Cr + j) * 2 + 1], (double)s2v);
@@ -570,71 +592,77 @@ __global__ void __launch_bounds__(kThreads) expert_back_bwd_kernel(const avmoe_e
 }
 
 // ------------------------------------------------------------------------------------------------ front backward
-template <typename T>
+template <typename T, int kMaxV>
 __global__ void __launch_bounds__(kThreads) expert_front_bwd_kernel(const avmoe_expert_args p, int TN) {
   extern __shared__ float sm[];
   constexpr bool kExact = std::is_same<T, float>::value;
   const int C = p.C, Cr = p.Cr, G = p.G, Cg = C / G, Crg = Cr / G, ld = C + 4, lda = Cr + 4, lt = p.T + 4;
   float* xs = sm;                      // [TN][ld] x tile
   float* ws = xs + TN * ld;            // [TN][ld] xa -> xhat
-  float* t1 = ws + TN * ld;            // [TN][ld] dxn -> dxa
+  float* t1 = ws + TN * ld;            // [TN][ld] xn -> dxn -> dxa
   float* dxs = t1 + TN * ld;           // [TN][ld] accumulated dx
-  float* s2 = dxs + TN * ld;           // [TN][T+1] token<-latent probabilities
-  float* ds2 = s2 + TN * lt;           // [TN][T+1]
-  float* dzs = ds2 + TN * lt;          // [TN][Cr+1]
-  float* mean = dzs + TN * lda;
-  float* rstd = mean + TN;
-  float* m1r = rstd + TN;
-  float* m2r = m1r + TN;
-  float* scratch = m2r + TN;           // [32]
+  float* s2 = dxs + TN * ld;           // [TN][T+4] token<-latent probabilities
+  float* ds2 = s2 + TN * lt;           // [TN][T+4]
+  float* dzs = ds2 + TN * lt;          // [TN][Cr+4]
+  float* rstds = dzs + TN * lda;       // [TN]
+  float* col = rstds + TN;             // [2][C] ln_before weight / bias gradient column sums
+  float* scratch = col + 2 * C;        // [32]
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
   const int b = blockIdx.y, n0 = blockIdx.x * TN;
   const int valid = min(TN, p.N - n0);
   const int mode = p.bn_mode;
   const double inv_n = 1.0 / ((double)p.BT * p.N);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
   const T* xb = reinterpret_cast<const T*>(p.x) + ((long long)b * p.N + n0) * C;
-  load_tile<T>(xs, xb, valid, TN, C, ld);
-  for (int i = threadIdx.x; i < TN * C; i += blockDim.x) {
-    const int n = i / C, c = i - n * C;
-    dxs[n * ld + c] = p.dpool_x ? p.dpool_x[(long long)b * C + c] : 0.f;
+  load_tile<T, kMaxV>(xs, xb, valid, TN, C, ld);
+  for (int r = warp; r < TN; r += nwarps) {
+    ROW_VECS(k, c) st4(dxs + r * ld + c, p.dpool_x ? ldg4(p.dpool_x + (long long)b * C + c) : f4(0.f));
   }
   __syncthreads();
   for (int e = 0; e < p.E; ++e) {
     const avmoe_expert& ex = p.ex[e];
-    // ---- dz = bn1 backward of dzt
-    for (int i = threadIdx.x; i < TN * Cr; i += blockDim.x) {
-      const int n = i / Cr, j = i - n * Cr;
-      float d = 0.f;
-      if (n < valid) {
-        const long long zi = (((long long)b * p.N + n0 + n) * p.E + e) * Cr + j;
-        d = p.dzt[zi];
-        if (mode != AVMOE_BN_OFF) {
-          if (mode == AVMOE_BN_TRAIN) {
-            const float zh = (p.z[zi] - p.save1[(e * Cr + j) * 2]) * p.save1[(e * Cr + j) * 2 + 1];
-            d = d - (float)(p.red1[((long long)e * Cr + j) * 2] * inv_n) - zh * (float)(p.red1[((long long)e * Cr + j) * 2 + 1] * inv_n);
+    for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) col[i] = 0.f;
+    // ---- dz = bn1 backward of dzt (rows of Cr, coalesced)
+    for (int n = warp; n < TN; n += nwarps) {
+      const long long zrow = (((long long)b * p.N + n0 + n) * p.E + e) * Cr;
+      for (int j = lane; j < Cr; j += 32) {
+        float d = 0.f;
+        if (n < valid) {
+          d = p.dzt[zrow + j];
+          if (mode != AVMOE_BN_OFF) {
+            if (mode == AVMOE_BN_TRAIN) {
+              const float zh = (p.z[zrow + j] - p.save1[(e * Cr + j) * 2]) * p.save1[(e * Cr + j) * 2 + 1];
+              d = d - (float)(p.red1[((long long)e * Cr + j) * 2] * inv_n) - zh * (float)(p.red1[((long long)e * Cr + j) * 2 + 1] * inv_n);
+            }
+            d *= p.aff1[(e * Cr + j) * 2];
           }
-          d *= p.aff1[(e * Cr + j) * 2];
         }
+        dzs[n * lda + j] = d;
       }
-      dzs[n * lda + j] = d;
     }
-    // ---- recompute xa and its LN statistics
-    pre_transform<T, kExact>(ex, p, b, n0, valid, TN, xs, ws, s2, ld);
-    if (ex.ln1_w) {
-      row_stats(ws, TN, C, ld, mean, rstd);
-      __syncthreads();
-      for (int i = threadIdx.x; i < TN * C; i += blockDim.x) {
-        const int n = i / C, c = i - n * C;
-        ws[n * ld + c] = (ws[n * ld + c] - mean[n]) * rstd[n];      // xhat
+    // ---- recompute xa; row pass A: LN statistics, ws <- xhat, t1 <- xn
+    const float* xa = pre_transform<T, kExact, kMaxV>(ex, p, b, n0, valid, TN, xs, ws, s2, ld);
+    __syncthreads();
+    for (int r = warp; r < TN; r += nwarps) {
+      float4 v[kMaxV];
+      float sum = 0.f;
+      ROW_VECS(k, c) { v[k] = ld4(xa + r * ld + c); sum += hsum(v[k]); }
+      if (ex.ln1_w) {
+        const float mean = warp_sum(sum) / C;
+        float ss = 0.f;
+        ROW_VECS(k, c) { const float4 d = v[k] - f4(mean); ss += hsum(d * d); }
+        const float rstd = rsqrtf(warp_sum(ss) / C + kLnEps);
+        if (lane == 0) rstds[r] = rstd;
+        ROW_VECS(k, c) {
+          const float4 xh = rstd * (v[k] - f4(mean));
+          st4(ws + r * ld + c, xh);
+          st4(t1 + r * ld + c, xh * ldg4(ex.ln1_w + c) + ldg4(ex.ln1_b + c));
+        }
+      } else {
+        ROW_VECS(k, c) { st4(t1 + r * ld + c, v[k]); }
       }
-      __syncthreads();
-    }
-    // ---- d down_sampler.weight[g*Crg+jl][cl] += sum_n dz[n][g*Crg+jl] * xn[n][g*Cg+cl]   (xn staged in t1; dz rows >= valid are 0)
-    for (int i = threadIdx.x; i < TN * C; i += blockDim.x) {
-      const int n = i / C, c = i - n * C;
-      t1[n * ld + c] = ex.ln1_w ? fmaf(ws[n * ld + c], __ldg(ex.ln1_w + c), __ldg(ex.ln1_b + c)) : ws[n * ld + c];
     }
     __syncthreads();
+    // ---- d down_sampler.weight[g*Crg+jl][cl] += sum_n dz[n][g*Crg+jl] * xn[n][g*Cg+cl]   (dz rows >= valid are 0)
     for (int g = 0; g < G; ++g)
       contract<kExact>(Crg, Cg, TN, dzs + g * Crg, 1, lda, t1 + g * Cg, ld, 1,
                        [&](int jl, int cl, float v) { atomicAdd(ex.g_wd + (long long)(g * Crg + jl) * Cg + cl, v); });
@@ -644,81 +672,74 @@ __global__ void __launch_bounds__(kThreads) expert_front_bwd_kernel(const avmoe_
       contract<kExact>(TN, Cg, Crg, dzs + g * Crg, lda, 1, ex.wd + (long long)g * Crg * Cg, Cg, 1,
                        [&](int n, int cl, float v) { t1[n * ld + g * Cg + cl] = v; });
     __syncthreads();
-    if (ex.ln1_w) {
-      for (int c = threadIdx.x; c < C; c += blockDim.x) {
-        float sw = 0.f, sb = 0.f;
-        for (int n = 0; n < valid; ++n) { const float d = t1[n * ld + c]; sw = fmaf(d, ws[n * ld + c], sw); sb += d; }
-        atomicAdd(ex.g_ln1_w + c, sw);
-        atomicAdd(ex.g_ln1_b + c, sb);
-      }
-      __syncthreads();
-      for (int r = warp; r < TN; r += nwarps) {
-        float s1 = 0.f, s2v = 0.f;
-        for (int c = lane; c < C; c += 32) {
-          const float dh = t1[r * ld + c] * __ldg(ex.ln1_w + c);
-          s1 += dh;
-          s2v = fmaf(dh, ws[r * ld + c], s2v);
+    // ---- row pass B: ln_before backward -> dxa (t1), dx accumulation, aux gradients
+    float dg = 0.f;
+    const T* auxp = ex.aux ? reinterpret_cast<const T*>(ex.aux) + ((long long)b * p.N + n0) * C : nullptr;
+    T* gaux = ex.g_aux ? reinterpret_cast<T*>(ex.g_aux) + ((long long)b * p.N + n0) * C : nullptr;
+    const float gpre = ex.gate_pre ? *ex.gate_pre : 0.f;
+    for (int r = warp; r < TN; r += nwarps) {
+      if (r >= valid) { ROW_VECS(k, c) st4(t1 + r * ld + c, f4(0.f)); continue; }
+      float4 d[kMaxV], xh[kMaxV];
+      float s1 = 0.f, s2v = 0.f;
+      ROW_VECS(k, c) {
+        d[k] = ld4(t1 + r * ld + c);
+        if (ex.ln1_w) {
+          xh[k] = ld4(ws + r * ld + c);
+          const float4 t = d[k] * xh[k];
+          atomicAdd(&col[c], t.x); atomicAdd(&col[c + 1], t.y); atomicAdd(&col[c + 2], t.z); atomicAdd(&col[c + 3], t.w);
+          atomicAdd(&col[C + c], d[k].x); atomicAdd(&col[C + c + 1], d[k].y); atomicAdd(&col[C + c + 2], d[k].z); atomicAdd(&col[C + c + 3], d[k].w);
+          d[k] = d[k] * ldg4(ex.ln1_w + c);
+          s1 += hsum(d[k]);
+          s2v += hsum(d[k] * xh[k]);
         }
-        s1 = warp_sum(s1); s2v = warp_sum(s2v);
-        if (lane == 0) { m1r[r] = s1 / C; m2r[r] = s2v / C; }
       }
-      __syncthreads();
-      for (int i = threadIdx.x; i < TN * C; i += blockDim.x) {
-        const int n = i / C, c = i - n * C;
-        const float dh = t1[n * ld + c] * __ldg(ex.ln1_w + c);
-        t1[n * ld + c] = (n < valid) ? rstd[n] * (dh - m1r[n] - ws[n * ld + c] * m2r[n]) : 0.f;    // dxa
+      if (ex.ln1_w) {
+        const float m1 = warp_sum(s1) / C, m2 = warp_sum(s2v) / C, rstd = rstds[r];
+        ROW_VECS(k, c) d[k] = rstd * (d[k] - f4(m1) - m2 * xh[k]);          // dxa
       }
-      __syncthreads();
+      ROW_VECS(k, c) {
+        st4(t1 + r * ld + c, d[k]);
+        if (ex.pre_kind != AVMOE_PRE_AUX_REPLACE) st4(dxs + r * ld + c, ld4(dxs + r * ld + c) + d[k]);
+        if (ex.pre_kind == AVMOE_PRE_AUX_ADD) {
+          dg += hsum(d[k] * ldg_act4<T>(auxp + (long long)r * C + c));
+          st_act4<T>(gaux + (long long)r * C + c, gpre * d[k]);
+        } else if (ex.pre_kind == AVMOE_PRE_AUX_REPLACE) {
+          st_act4<T>(gaux + (long long)r * C + c, d[k]);
+        }
+      }
     }
-    // ---- route dxa through the pre-transform
-    if (ex.pre_kind == AVMOE_PRE_AUX_REPLACE) {
-      T* ga = reinterpret_cast<T*>(ex.g_aux) + ((long long)b * p.N + n0) * C;
-      store_tile<T>(ga, t1, valid, C, ld);
-      __syncthreads();
-      continue;
-    }
-    for (int i = threadIdx.x; i < TN * C; i += blockDim.x) { const int n = i / C, c = i - n * C; dxs[n * ld + c] += t1[n * ld + c]; }
-    if (ex.pre_kind == AVMOE_PRE_AUX_ADD) {
-      const float g = *ex.gate_pre;
-      const T* aux = reinterpret_cast<const T*>(ex.aux) + ((long long)b * p.N + n0) * C;
-      T* ga = reinterpret_cast<T*>(ex.g_aux) + ((long long)b * p.N + n0) * C;
-      float dg = 0.f;
-      for (int i = threadIdx.x; i < valid * C; i += blockDim.x) {
-        const int n = i / C, c = i - n * C;
-        const float d = t1[n * ld + c];
-        dg = fmaf(d, to_f32(aux[(long long)n * C + c]), dg);
-        ga[(long long)n * C + c] = from_f32<T>(g * d);
-      }
-      const float tot = block_sum(dg, scratch);
-      if (threadIdx.x == 0) atomicAdd(ex.g_gate_pre, tot);
-    } else if (ex.pre_kind == AVMOE_PRE_LATENT) {
-      const float g = *ex.gate_pre;
+    __syncthreads();
+    if (ex.ln1_w)
+      for (int c = threadIdx.x; c < C; c += blockDim.x) { atomicAdd(ex.g_ln1_w + c, col[c]); atomicAdd(ex.g_ln1_b + c, col[C + c]); }
+    if (ex.pre_kind == AVMOE_PRE_LATENT) {
       const float* tp = p.tokp + ((long long)b * p.nl + ex.latent_slot) * p.T * C;
       float* dtp = p.dtokp + ((long long)b * p.nl + ex.latent_slot) * p.T * C;
       // u[n][t] = dxa_n . tok'_t
       contract<kExact>(TN, p.T, C, t1, ld, 1, tp, 1, C, [&](int n, int t, float v) { ds2[n * lt + t] = v; });
       __syncthreads();
-      // d gate_pre = sum A2*u ; dS2 = A2 * (g*u - sum_t A2*g*u)
-      float dg = 0.f;
-      for (int n = threadIdx.x; n < TN; n += blockDim.x) {
+      // d gate_pre = sum A2*u ; dS2 = A2 * g * (u - sum_t A2*u)      (one warp per row, lanes over t)
+      for (int r = warp; r < TN; r += nwarps) {
         float dot = 0.f;
-        for (int t = 0; t < p.T; ++t) dot = fmaf(s2[n * lt + t], ds2[n * lt + t], dot);
-        if (n < valid) dg += dot;
-        for (int t = 0; t < p.T; ++t) ds2[n * lt + t] = (n < valid) ? s2[n * lt + t] * g * (ds2[n * lt + t] - dot) : 0.f;
+        for (int t = lane; t < p.T; t += 32) dot = fmaf(s2[r * lt + t], ds2[r * lt + t], dot);
+        dot = warp_sum(dot);
+        if (r < valid && lane == 0) dg += dot;
+        for (int t = lane; t < p.T; t += 32) ds2[r * lt + t] = (r < valid) ? s2[r * lt + t] * gpre * (ds2[r * lt + t] - dot) : 0.f;
       }
-      const float tot = block_sum(dg, scratch);
-      if (threadIdx.x == 0) atomicAdd(ex.g_gate_pre, tot);
       __syncthreads();
       // dx[n][c] += sum_t dS2[n][t] * tok'[t][c]
       contract<kExact>(TN, C, p.T, ds2, lt, 1, tp, C, 1, [&](int n, int c, float v) { dxs[n * ld + c] += v; });
       // d tok'[t][c] += sum_n A2[n][t]*g*dxa[n][c] + dS2[n][t]*x[n][c]       (rows >= valid of t1 / xs are zero)
-      contract<kExact>(p.T, C, TN, s2, 1, lt, t1, ld, 1, [&](int t, int c, float v) { atomicAdd(dtp + (long long)t * C + c, g * v); });
+      contract<kExact>(p.T, C, TN, s2, 1, lt, t1, ld, 1, [&](int t, int c, float v) { atomicAdd(dtp + (long long)t * C + c, gpre * v); });
       contract<kExact>(p.T, C, TN, ds2, 1, lt, xs, ld, 1, [&](int t, int c, float v) { atomicAdd(dtp + (long long)t * C + c, v); });
+    }
+    if (ex.g_gate_pre) {
+      const float tot = block_sum(dg, scratch);
+      if (threadIdx.x == 0) atomicAdd(ex.g_gate_pre, tot);
     }
     __syncthreads();
   }
   T* dxb = reinterpret_cast<T*>(p.dx) + ((long long)b * p.N + n0) * C;
-  store_tile<T>(dxb, dxs, valid, C, ld);
+  store_tile<T, kMaxV>(dxb, dxs, valid, C, ld);
 }
 
 // ------------------------------------------------------------------------------------------------ host side
@@ -735,6 +756,7 @@ static int check_common(const avmoe_expert_args* a, const char* who) {
   AVMOE_CHECK_ARG(a->E >= 1 && a->E <= AVMOE_MAX_EXPERTS, "%s: E=%d out of range", who, a->E);
   AVMOE_CHECK_ARG(a->BT > 0 && a->N > 0 && a->C > 0 && a->Cr > 0 && a->G > 0, "%s: bad sizes", who);
   AVMOE_CHECK_ARG(a->C % 4 == 0 && a->C % a->G == 0 && a->Cr % a->G == 0, "%s: C must be a multiple of 4 and of G; Cr a multiple of G", who);
+  AVMOE_CHECK_ARG(a->C <= 128 * kMaxVLimit, "%s: C=%d exceeds the supported maximum of %d channels", who, a->C, 128 * kMaxVLimit);
   AVMOE_CHECK_ARG(a->dtype == AVMOE_F32 || a->dtype == AVMOE_BF16, "%s: bad dtype", who);
   AVMOE_CHECK_ARG(a->BT <= 65535, "%s: BT too large for the launch grid", who);
   return 0;
@@ -747,6 +769,18 @@ static int set_smem(K kernel, size_t smem, const char* who) {
   return 0;
 }
 
+
+// instantiate for the smallest per-lane vector count that covers C (register arrays are sized by it)
+#define AVMOE_DISPATCH_V(C_, ...)                                 \
+  do {                                                           \
+    const int _v = ((C_) + 127) / 128;                           \
+    if (_v <= 1) { constexpr int kV = 1; __VA_ARGS__ }           \
+    else if (_v <= 2) { constexpr int kV = 2; __VA_ARGS__ }      \
+    else if (_v <= 3) { constexpr int kV = 3; __VA_ARGS__ }      \
+    else if (_v <= 6) { constexpr int kV = 6; __VA_ARGS__ }      \
+    else { constexpr int kV = 12; __VA_ARGS__ }                  \
+  } while (0)
+
 }  // namespace avmoe
 
 using namespace avmoe;
@@ -756,15 +790,17 @@ extern "C" int avmoe_expert_front_fwd(const avmoe_expert_args* a, avmoe_stream_t
   AVMOE_CHECK_ARG(a->x && a->z, "expert_front_fwd: null tensor");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const int TN = pick_tn(a->C, 12288);
-  const size_t smem = sizeof(float) * (2 * (size_t)TN * (a->C + 4) + (size_t)TN * (a->T + 4) + (size_t)TN * (a->E * a->Cr + 1) + 2 * TN);
+  const size_t smem = sizeof(float) * (2 * (size_t)TN * (a->C + 4) + (size_t)TN * (a->T + 4) + (size_t)TN * (a->E * a->Cr + 1));
   dim3 grid((a->N + TN - 1) / TN, a->BT);
-  if (a->dtype == AVMOE_F32) {
-    if (int rc = set_smem(expert_front_fwd_kernel<float>, smem, "expert_front_fwd")) return rc;
-    expert_front_fwd_kernel<float><<<grid, kThreads, smem, st>>>(*a, TN);
-  } else {
-    if (int rc = set_smem(expert_front_fwd_kernel<__nv_bfloat16>, smem, "expert_front_fwd")) return rc;
-    expert_front_fwd_kernel<__nv_bfloat16><<<grid, kThreads, smem, st>>>(*a, TN);
-  }
+  AVMOE_DISPATCH_V(a->C, {
+    if (a->dtype == AVMOE_F32) {
+      if (int rc = set_smem(expert_front_fwd_kernel<float, kV>, smem, "expert_front_fwd")) return rc;
+      expert_front_fwd_kernel<float, kV><<<grid, kThreads, smem, st>>>(*a, TN);
+    } else {
+      if (int rc = set_smem(expert_front_fwd_kernel<__nv_bfloat16, kV>, smem, "expert_front_fwd")) return rc;
+      expert_front_fwd_kernel<__nv_bfloat16, kV><<<grid, kThreads, smem, st>>>(*a, TN);
+    }
+  });
   AVMOE_LAUNCH_CHECK("expert_front_fwd_kernel");
   return 0;
 }
@@ -821,15 +857,17 @@ extern "C" int avmoe_expert_back_fwd(const avmoe_expert_args* a, avmoe_stream_t 
   AVMOE_CHECK_ARG(a->bn_mode == AVMOE_BN_OFF || (a->aff1 && a->aff2), "expert_back_fwd: batch-norm affine missing");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const int TN = pick_tn(a->C, 12288);
-  const size_t smem = sizeof(float) * (2 * (size_t)TN * (a->C + 4) + (size_t)TN * (a->Cr + 4) + 2 * TN);
+  const size_t smem = sizeof(float) * (2 * (size_t)TN * (a->C + 4) + (size_t)TN * (a->Cr + 4));
   dim3 grid((a->N + TN - 1) / TN, a->BT);
-  if (a->dtype == AVMOE_F32) {
-    if (int rc = set_smem(expert_back_fwd_kernel<float>, smem, "expert_back_fwd")) return rc;
-    expert_back_fwd_kernel<float><<<grid, kThreads, smem, st>>>(*a, TN);
-  } else {
-    if (int rc = set_smem(expert_back_fwd_kernel<__nv_bfloat16>, smem, "expert_back_fwd")) return rc;
-    expert_back_fwd_kernel<__nv_bfloat16><<<grid, kThreads, smem, st>>>(*a, TN);
-  }
+  AVMOE_DISPATCH_V(a->C, {
+    if (a->dtype == AVMOE_F32) {
+      if (int rc = set_smem(expert_back_fwd_kernel<float, kV>, smem, "expert_back_fwd")) return rc;
+      expert_back_fwd_kernel<float, kV><<<grid, kThreads, smem, st>>>(*a, TN);
+    } else {
+      if (int rc = set_smem(expert_back_fwd_kernel<__nv_bfloat16, kV>, smem, "expert_back_fwd")) return rc;
+      expert_back_fwd_kernel<__nv_bfloat16, kV><<<grid, kThreads, smem, st>>>(*a, TN);
+    }
+  });
   AVMOE_LAUNCH_CHECK("expert_back_fwd_kernel");
   return 0;
 }
@@ -847,15 +885,17 @@ static int launch_back_bwd(const avmoe_expert_args* a, cudaStream_t st, const ch
     AVMOE_CHECK_ARG(a->bn_mode == AVMOE_BN_OFF || a->red1, "%s: red1 missing", who);
   }
   const int TN = pick_tn(a->C, 8192);
-  const size_t smem = sizeof(float) * (3 * (size_t)TN * (a->C + 4) + 2 * (size_t)TN * (a->Cr + 4) + 4 * TN + 32);
+  const size_t smem = sizeof(float) * (3 * (size_t)TN * (a->C + 4) + 2 * (size_t)TN * (a->Cr + 4) + 6 * (size_t)a->C + 32);
   dim3 grid((a->N + TN - 1) / TN, a->BT);
-  if (a->dtype == AVMOE_F32) {
-    if (int rc = set_smem(expert_back_bwd_kernel<float, kStatsOnly>, smem, who)) return rc;
-    expert_back_bwd_kernel<float, kStatsOnly><<<grid, kThreads, smem, st>>>(*a, TN);
-  } else {
-    if (int rc = set_smem(expert_back_bwd_kernel<__nv_bfloat16, kStatsOnly>, smem, who)) return rc;
-    expert_back_bwd_kernel<__nv_bfloat16, kStatsOnly><<<grid, kThreads, smem, st>>>(*a, TN);
-  }
+  AVMOE_DISPATCH_V(a->C, {
+    if (a->dtype == AVMOE_F32) {
+      if (int rc = set_smem(expert_back_bwd_kernel<float, kStatsOnly, kV>, smem, who)) return rc;
+      expert_back_bwd_kernel<float, kStatsOnly, kV><<<grid, kThreads, smem, st>>>(*a, TN);
+    } else {
+      if (int rc = set_smem(expert_back_bwd_kernel<__nv_bfloat16, kStatsOnly, kV>, smem, who)) return rc;
+      expert_back_bwd_kernel<__nv_bfloat16, kStatsOnly, kV><<<grid, kThreads, smem, st>>>(*a, TN);
+    }
+  });
   AVMOE_LAUNCH_CHECK("expert_back_bwd_kernel");
   return 0;
 }
@@ -873,15 +913,17 @@ extern "C" int avmoe_expert_front_bwd(const avmoe_expert_args* a, avmoe_stream_t
   AVMOE_CHECK_ARG(a->bn_mode == AVMOE_BN_OFF || (a->aff1 && a->save1 && a->z && a->red1), "expert_front_bwd: batch-norm tensors missing");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const int TN = pick_tn(a->C, 6144);
-  const size_t smem = sizeof(float) * (4 * (size_t)TN * (a->C + 4) + 2 * (size_t)TN * (a->T + 4) + (size_t)TN * (a->Cr + 4) + 4 * TN + 32);
+  const size_t smem = sizeof(float) * (4 * (size_t)TN * (a->C + 4) + 2 * (size_t)TN * (a->T + 4) + (size_t)TN * (a->Cr + 4) + TN + 2 * (size_t)a->C + 32);
   dim3 grid((a->N + TN - 1) / TN, a->BT);
-  if (a->dtype == AVMOE_F32) {
-    if (int rc = set_smem(expert_front_bwd_kernel<float>, smem, "expert_front_bwd")) return rc;
-    expert_front_bwd_kernel<float><<<grid, kThreads, smem, st>>>(*a, TN);
-  } else {
-    if (int rc = set_smem(expert_front_bwd_kernel<__nv_bfloat16>, smem, "expert_front_bwd")) return rc;
-    expert_front_bwd_kernel<__nv_bfloat16><<<grid, kThreads, smem, st>>>(*a, TN);
-  }
+  AVMOE_DISPATCH_V(a->C, {
+    if (a->dtype == AVMOE_F32) {
+      if (int rc = set_smem(expert_front_bwd_kernel<float, kV>, smem, "expert_front_bwd")) return rc;
+      expert_front_bwd_kernel<float, kV><<<grid, kThreads, smem, st>>>(*a, TN);
+    } else {
+      if (int rc = set_smem(expert_front_bwd_kernel<__nv_bfloat16, kV>, smem, "expert_front_bwd")) return rc;
+      expert_front_bwd_kernel<__nv_bfloat16, kV><<<grid, kThreads, smem, st>>>(*a, TN);
+    }
+  });
   AVMOE_LAUNCH_CHECK("expert_front_bwd_kernel");
   return 0;
 }
