@@ -3,8 +3,9 @@
 // their gradients).  These are tiny per token tile (K or N is T<=87, C/r or a token tile), live entirely in shared
 // memory / L1 and never dominate a launch; the dense token-resampler GEMMs run on tcgen05 (gemm.cu).
 //
-// TF32 keeps bf16 activations exact (8-bit mantissa fits in TF32's 10) and rounds fp32 side operands (latent tokens,
-// weights) to 11 significant bits with round-to-nearest, so results stay far inside the bf16 tolerance.
+// TF32 keeps bf16 activations exact (8-bit mantissa fits in TF32's 10); fp32 side operands (latent tokens, weights,
+// probabilities) are fed as raw fp32 bit patterns, of which the tensor core uses the top 10 mantissa bits — an
+// 11-significant-bit truncation, far inside the bf16 tolerance.
 #pragma once
 #include <stdint.h>
 
@@ -32,6 +33,7 @@ __device__ __forceinline__ void block_mma_tf32(int M, int N, int K, const float*
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
   const int g = lane >> 2, t = lane & 3;
   const int tiles_m = (M + 16 * WM - 1) / (16 * WM), tiles_n = (N + 8 * WN - 1) / (8 * WN);
+  const int kfull = K & ~7;
   for (int tile = warp; tile < tiles_m * tiles_n; tile += nwarps) {
     const int m0 = (tile % tiles_m) * 16 * WM, n0 = (tile / tiles_m) * 8 * WN;
     float acc[WM][WN][4];
@@ -39,38 +41,53 @@ __device__ __forceinline__ void block_mma_tf32(int M, int N, int K, const float*
     for (int i = 0; i < WM; ++i)
 #pragma unroll
       for (int j = 0; j < WN; ++j) { acc[i][j][0] = 0.f; acc[i][j][1] = 0.f; acc[i][j][2] = 0.f; acc[i][j][3] = 0.f; }
+    // Row / column indices are CLAMPED instead of predicated: out-of-range fragments read valid (duplicate) data and
+    // their results are simply never handed to epi.  Only the K tail needs zero fill.
     const float* arow[WM][2];
-    bool aval[WM][2];
 #pragma unroll
     for (int i = 0; i < WM; ++i) {
-      const int r0 = m0 + 16 * i + g, r1 = r0 + 8;
-      aval[i][0] = r0 < M; aval[i][1] = r1 < M;
-      arow[i][0] = A + (long long)(aval[i][0] ? r0 : 0) * a_rs;
-      arow[i][1] = A + (long long)(aval[i][1] ? r1 : 0) * a_rs;
+      const int r0 = min(m0 + 16 * i + g, M - 1), r1 = min(m0 + 16 * i + g + 8, M - 1);
+      arow[i][0] = A + (long long)r0 * a_rs + (long long)t * a_cs;
+      arow[i][1] = A + (long long)r1 * a_rs + (long long)t * a_cs;
     }
     const float* bcol[WN];
-    bool bval[WN];
 #pragma unroll
-    for (int j = 0; j < WN; ++j) {
-      const int n = n0 + 8 * j + g;
-      bval[j] = n < N;
-      bcol[j] = B + (long long)(bval[j] ? n : 0) * b_cs;
-    }
-    for (int k0 = 0; k0 < K; k0 += 8) {
-      const int ka = k0 + t, kb = ka + 4;
-      const bool va = ka < K, vb = kb < K;
+    for (int j = 0; j < WN; ++j) bcol[j] = B + (long long)min(n0 + 8 * j + g, N - 1) * b_cs + (long long)t * b_rs;
+    const long long a_k4 = 4ll * a_cs, b_k4 = 4ll * b_rs;
+    long long ao = 0, bo = 0;   // 64-bit: global-memory operands can have row pitches of tens of millions of elements
+    for (int k0 = 0; k0 < kfull; k0 += 8, ao += 8ll * a_cs, bo += 8ll * b_rs) {
       uint32_t af[WM][4], bf[WN][2];
 #pragma unroll
       for (int i = 0; i < WM; ++i) {
-        af[i][0] = to_tf32((aval[i][0] && va) ? arow[i][0][(long long)ka * a_cs] : 0.f);
-        af[i][1] = to_tf32((aval[i][1] && va) ? arow[i][1][(long long)ka * a_cs] : 0.f);
-        af[i][2] = to_tf32((aval[i][0] && vb) ? arow[i][0][(long long)kb * a_cs] : 0.f);
-        af[i][3] = to_tf32((aval[i][1] && vb) ? arow[i][1][(long long)kb * a_cs] : 0.f);
+        af[i][0] = __float_as_uint(arow[i][0][ao]);
+        af[i][1] = __float_as_uint(arow[i][1][ao]);
+        af[i][2] = __float_as_uint(arow[i][0][ao + a_k4]);
+        af[i][3] = __float_as_uint(arow[i][1][ao + a_k4]);
       }
 #pragma unroll
       for (int j = 0; j < WN; ++j) {
-        bf[j][0] = to_tf32((bval[j] && va) ? bcol[j][(long long)ka * b_rs] : 0.f);
-        bf[j][1] = to_tf32((bval[j] && vb) ? bcol[j][(long long)kb * b_rs] : 0.f);
+        bf[j][0] = __float_as_uint(bcol[j][bo]);
+        bf[j][1] = __float_as_uint(bcol[j][bo + b_k4]);
+      }
+#pragma unroll
+      for (int i = 0; i < WM; ++i)
+#pragma unroll
+        for (int j = 0; j < WN; ++j) mma_tf32_16x8x8(acc[i][j], af[i], bf[j]);
+    }
+    if (kfull < K) {   // K tail: zero-fill k >= K
+      const bool va = kfull + t < K, vb = kfull + t + 4 < K;
+      uint32_t af[WM][4], bf[WN][2];
+#pragma unroll
+      for (int i = 0; i < WM; ++i) {
+        af[i][0] = __float_as_uint(va ? arow[i][0][ao] : 0.f);
+        af[i][1] = __float_as_uint(va ? arow[i][1][ao] : 0.f);
+        af[i][2] = __float_as_uint(vb ? arow[i][0][ao + a_k4] : 0.f);
+        af[i][3] = __float_as_uint(vb ? arow[i][1][ao + a_k4] : 0.f);
+      }
+#pragma unroll
+      for (int j = 0; j < WN; ++j) {
+        bf[j][0] = __float_as_uint(va ? bcol[j][bo] : 0.f);
+        bf[j][1] = __float_as_uint(vb ? bcol[j][bo + b_k4] : 0.f);
       }
 #pragma unroll
       for (int i = 0; i < WM; ++i)

@@ -146,7 +146,7 @@ __device__ __forceinline__ const float* pre_transform(const avmoe_expert& ex, co
 // ------------------------------------------------------------------------------------------------ front forward
 // grid (ceil(N/TN), BT), block 256
 template <typename T, int kMaxV>
-__global__ void __launch_bounds__(kThreads) expert_front_fwd_kernel(const avmoe_expert_args p, int TN) {
+__global__ void __launch_bounds__(kThreads, 2) expert_front_fwd_kernel(const avmoe_expert_args p, int TN) {
   extern __shared__ float sm[];
   constexpr bool kExact = std::is_same<T, float>::value;
   const int C = p.C, Cr = p.Cr, G = p.G, Cg = C / G, Crg = Cr / G, ld = C + 4, ECr = p.E * Cr, lz = ECr + 1;
@@ -377,7 +377,7 @@ __device__ __forceinline__ void back_recompute(const avmoe_expert_args& p, const
 
 // ------------------------------------------------------------------------------------------------ back forward
 template <typename T, int kMaxV>
-__global__ void __launch_bounds__(kThreads) expert_back_fwd_kernel(const avmoe_expert_args p, int TN) {
+__global__ void __launch_bounds__(kThreads, 2) expert_back_fwd_kernel(const avmoe_expert_args p, int TN) {
   extern __shared__ float sm[];
   constexpr bool kExact = std::is_same<T, float>::value;
   const int C = p.C, Cr = p.Cr, ld = C + 4;
@@ -423,7 +423,7 @@ __global__ void __launch_bounds__(kThreads) expert_back_fwd_kernel(const avmoe_e
 // ------------------------------------------------------------------------------------------------ back backward
 // kStatsOnly: only the bn2 batch reductions (sum dyt, sum dyt*yhat); otherwise the full backward of the back half.
 template <typename T, bool kStatsOnly, int kMaxV>
-__global__ void __launch_bounds__(kThreads) expert_back_bwd_kernel(const avmoe_expert_args p, int TN) {
+__global__ void __launch_bounds__(kThreads, 2) expert_back_bwd_kernel(const avmoe_expert_args p, int TN) {
   extern __shared__ float sm[];
   constexpr bool kExact = std::is_same<T, float>::value;
   const int C = p.C, Cr = p.Cr, G = p.G, Cg = C / G, Crg = Cr / G, ld = C + 4, lda = Cr + 4;
@@ -593,7 +593,7 @@ __global__ void __launch_bounds__(kThreads) expert_back_bwd_kernel(const avmoe_e
 
 // ------------------------------------------------------------------------------------------------ front backward
 template <typename T, int kMaxV>
-__global__ void __launch_bounds__(kThreads) expert_front_bwd_kernel(const avmoe_expert_args p, int TN) {
+__global__ void __launch_bounds__(kThreads, 2) expert_front_bwd_kernel(const avmoe_expert_args p, int TN) {
   extern __shared__ float sm[];
   constexpr bool kExact = std::is_same<T, float>::value;
   const int C = p.C, Cr = p.Cr, G = p.G, Cg = C / G, Crg = Cr / G, ld = C + 4, lda = Cr + 4, lt = p.T + 4;

@@ -137,6 +137,7 @@ struct GemmParams {
   uint32_t idesc;
   int tmem_cols;       // power of two >= 2*BN
   int tiles_m, tiles_n, splits;
+  int full_batch;      // >1: A, B and D all advance over this many independent problems (third TMA coordinate)
   int k_iters;         // total stages over the whole (batch,K) reduction
   int k_iters_per_batch;  // batched-K: stages per batch element; else k_iters
   int k_iters_per_split;
@@ -199,7 +200,8 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tcgen05_kernel(const __g
   const uint32_t tmem_base = *tmem_ptr_smem;
 
   const int tiles_mn = p.tiles_m * p.tiles_n;
-  const int num_tiles = tiles_mn * p.splits;
+  const int tiles_per_batch = tiles_mn * p.splits;
+  const int num_tiles = tiles_per_batch * p.full_batch;
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -207,8 +209,10 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tcgen05_kernel(const __g
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int split = tile / tiles_mn;
-        const int mn = tile - split * tiles_mn;
+        const int tb = tile / tiles_per_batch;
+        const int trem = tile - tb * tiles_per_batch;
+        const int split = trem / tiles_mn;
+        const int mn = trem - split * tiles_mn;
         const int m0 = (mn % p.tiles_m) * kBM;
         const int n0 = (mn / p.tiles_m) * p.BN;
         const int k_begin = split * p.k_iters_per_split;
@@ -219,20 +223,21 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tcgen05_kernel(const __g
           mbar_expect_tx(fb, stage_bytes);
           const uint32_t sa = smem_u32(smem + (size_t)stage * stage_bytes);
           const uint32_t sb = sa + p.stage_bytes_a;
-          const int kb = kit / p.k_iters_per_batch;
+          int kb = kit / p.k_iters_per_batch;
           const int kc = (kit - kb * p.k_iters_per_batch) * p.BK;
+          if (p.full_batch > 1) kb = tb;
           if (p.a.kmajor) {
             tma_load_3d(sa, &p.tmA, fb, kc, m0, kb);
           } else {
             for (int i = 0; i < p.a.nchunks; ++i)
-              tma_load_3d(sa + i * p.a.chunk_bytes, &p.tmA, fb, m0 + i * p.a.chunk_elems, kc, 0);
+              tma_load_3d(sa + i * p.a.chunk_bytes, &p.tmA, fb, m0 + i * p.a.chunk_elems, kc, tb);
           }
           if (p.b.kmajor) {
             tma_load_3d(sb, &p.tmB, fb, kc, n0, kb);
           } else {
             for (int i = 0; i < p.b.nchunks; ++i) {
               int n = n0 + i * p.b.chunk_elems;
-              int bb = 0;
+              int bb = tb;
               if (p.b.batch_extent) { bb = n / p.b.batch_extent; n -= bb * p.b.batch_extent; }
               tma_load_3d(sb + i * p.b.chunk_bytes, &p.tmB, fb, n, kc, bb);
             }
@@ -248,7 +253,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tcgen05_kernel(const __g
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      const int split = tile / tiles_mn;
+      const int split = (tile % tiles_per_batch) / tiles_mn;
       const int k_begin = split * p.k_iters_per_split;
       const int k_end = min(p.k_iters, k_begin + p.k_iters_per_split);
       mbar_wait(smem_u32(&tmem_empty[acc]), acc_phase ^ 1);
@@ -283,8 +288,10 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tcgen05_kernel(const __g
     uint8_t* my_stage = staging + (warp - 2) * 8192;
     int sbuf = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      const int split = tile / tiles_mn;
-      const int mn = tile - split * tiles_mn;
+      const int tb = tile / tiles_per_batch;
+      const int trem = tile - tb * tiles_per_batch;
+      const int split = trem / tiles_mn;
+      const int mn = trem - split * tiles_mn;
       const int m0 = (mn % p.tiles_m) * kBM;
       const int n0 = (mn / p.tiles_m) * p.BN;
       const int k_begin = split * p.k_iters_per_split;
@@ -301,7 +308,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tcgen05_kernel(const __g
         uint32_t r[32];
         const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * p.BN + g * 32);
         tmem_ld_32x32b_x32(taddr, r);
-        long long bb = 0, c0 = ng;
+        long long bb = tb, c0 = ng;
         if (p.n_batched) { bb = ng / p.Nb; c0 = ng - bb * p.Nb; }
         if (p.tma_store) {
           // ---- fast path: regs -> swizzled smem slab [32 rows][32 cols] -> TMA store / reduce-add ----
@@ -354,7 +361,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tcgen05_kernel(const __g
           for (int v = 0; v < 8; ++v) {
             const long long n = ng + v * 4;
             if (n >= p.N) break;
-            long long b2 = 0, c = n;
+            long long b2 = tb, c = n;
             if (p.n_batched) { b2 = n / p.Nb; c = n - b2 * p.Nb; }
             float o[4];
 #pragma unroll
@@ -407,7 +414,7 @@ struct SimtParams {
   const void* A; const void* B; void* D;
   int bf16, d_bf16;
   long long M, N, K, Nb;
-  int a_kmajor, b_kmajor, a_batch, b_batch, n_batched, b_nbatched;
+  int a_kmajor, b_kmajor, a_batch, b_batch, n_batched, b_nbatched, full_batch;
   long long lda, ldb, ldd, a_bstride, b_bstride, d_bstride;
   float alpha;
   const float* row_bias; const float* col_scale; const float* col_bias;
@@ -421,9 +428,11 @@ __global__ void gemm_simt_kernel(const SimtParams p) {
   if (m >= p.M || n >= p.N) return;
   const T* A = reinterpret_cast<const T*>(p.A);
   const T* B = reinterpret_cast<const T*>(p.B);
-  long long bb = 0, c = n;
+  const long long fbz = p.full_batch > 1 ? blockIdx.z : 0;
+  if (p.full_batch > 1) { A += fbz * p.a_bstride; B += fbz * p.b_bstride; }
+  long long bb = fbz, c = n;
   if (p.n_batched) { bb = n / p.Nb; c = n - bb * p.Nb; }
-  const int kbatches = (p.a_kmajor && p.b_kmajor) ? p.a_batch : 1;
+  const int kbatches = (p.a_kmajor && p.b_kmajor && p.full_batch <= 1) ? p.a_batch : 1;
   float acc = 0.f;
   for (int kb = 0; kb < kbatches; ++kb) {
     for (long long k = 0; k < p.K; ++k) {
@@ -510,8 +519,10 @@ static int launch_simt(const avmoe_gemm_args* a, cudaStream_t st) {
   p.a_bstride = a->a_bstride; p.b_bstride = a->b_bstride; p.d_bstride = a->d_bstride;
   p.alpha = a->alpha; p.row_bias = a->row_bias; p.col_scale = a->col_scale; p.col_bias = a->col_bias;
   p.accumulate = a->accumulate;
+  p.full_batch = a->full_batch > 1 ? a->full_batch : 1;
+  if (p.full_batch > 1) { p.a_batch = p.b_batch = 1; }
   dim3 block(32, 8);
-  dim3 grid((unsigned)((a->N + 31) / 32), (unsigned)((a->M + 7) / 8));
+  dim3 grid((unsigned)((a->N + 31) / 32), (unsigned)((a->M + 7) / 8), (unsigned)p.full_batch);
   if (p.bf16) gemm_simt_kernel<__nv_bfloat16><<<grid, block, 0, st>>>(p);
   else gemm_simt_kernel<float><<<grid, block, 0, st>>>(p);
   AVMOE_LAUNCH_CHECK("gemm_simt_kernel");
@@ -551,6 +562,9 @@ int gemm_dispatch(const avmoe_gemm_args* a, cudaStream_t st) {
   AVMOE_CHECK_ARG(a->M > 0 && a->N > 0 && a->K > 0, "gemm: empty problem M=%lld N=%lld K=%lld", (long long)a->M, (long long)a->N, (long long)a->K);
   AVMOE_CHECK_ARG(a->dtype == AVMOE_F32 || a->dtype == AVMOE_BF16, "gemm: bad dtype");
   AVMOE_CHECK_ARG(a->a_batch >= 1 && a->b_batch >= 1, "gemm: batch counts must be >= 1");
+  const int fbatch = a->full_batch > 1 ? a->full_batch : 1;
+  if (fbatch > 1) AVMOE_CHECK_ARG(a->a_batch == 1 && a->b_batch == 1 && (a->Nb == 0 || a->Nb == a->N) && a->split_k <= 1,
+                                  "gemm: full_batch excludes K-/N-batching and split-K");
   const bool kbatched = a->a_kmajor && a->b_kmajor && a->a_batch > 1;
   if (a->a_kmajor && a->b_kmajor) AVMOE_CHECK_ARG(a->a_batch == a->b_batch, "gemm: K-batched operands need equal batch counts");
   if (!a->a_kmajor) AVMOE_CHECK_ARG(a->a_batch == 1, "gemm: MN-major A cannot be batched");
@@ -573,8 +587,8 @@ int gemm_dispatch(const avmoe_gemm_args* a, cudaStream_t st) {
   if (!plan_operand(a->a_kmajor, bf16, a->a_kmajor ? a->K : a->M, true, &pa)) why = "operand A extent";
   if (!why && !plan_operand(a->b_kmajor, bf16, a->b_kmajor ? a->K : Nb, !b_nbatched, &pb)) why = "operand B per-batch extent";
   if (!why && ((a->lda * es) % 16 || (a->ldb * es) % 16 || ((uintptr_t)a->A % 16) || ((uintptr_t)a->B % 16))) why = "operand alignment";
-  if (!why && (a->a_batch > 1 && (a->a_bstride * es) % 16)) why = "A batch pitch";
-  if (!why && (a->b_batch > 1 && (a->b_bstride * es) % 16)) why = "B batch pitch";
+  if (!why && ((a->a_batch > 1 || fbatch > 1) && (a->a_bstride * es) % 16)) why = "A batch pitch";
+  if (!why && ((a->b_batch > 1 || fbatch > 1) && (a->b_bstride * es) % 16)) why = "B batch pitch";
   if (!why && (a->ldd % 4 || a->d_bstride % 4 || ((uintptr_t)a->D % 16))) why = "D alignment";
   if (!why && n_batched && Nb % 4) why = "per-batch N not a multiple of 4";
   if (why) {
@@ -610,14 +624,14 @@ int gemm_dispatch(const avmoe_gemm_args* a, cudaStream_t st) {
     const int sb = swz_bytes(pa.code);
     p.a.desc_base = make_desc_base(pa.code, a->a_kmajor, BK);
     if (a->a_kmajor) {
-      dims[0] = a->K; dims[1] = a->M; dims[2] = a->a_batch;
-      strides[0] = a->lda * es; strides[1] = (a->a_batch > 1 ? a->a_bstride : a->lda * a->M) * es;
+      dims[0] = a->K; dims[1] = a->M; dims[2] = fbatch > 1 ? fbatch : a->a_batch;
+      strides[0] = a->lda * es; strides[1] = ((a->a_batch > 1 || fbatch > 1) ? a->a_bstride : a->lda * a->M) * es;
       box[0] = BK; box[1] = kBM; box[2] = 1;
       p.a.kmajor = 1; p.a.nchunks = 1; p.a.chunk_bytes = kBM * sb; p.a.k_advance = 32;
       p.stage_bytes_a = kBM * sb;
     } else {
-      dims[0] = a->M; dims[1] = a->K; dims[2] = 1;
-      strides[0] = a->lda * es; strides[1] = a->lda * a->K * es;
+      dims[0] = a->M; dims[1] = a->K; dims[2] = fbatch;
+      strides[0] = a->lda * es; strides[1] = (fbatch > 1 ? a->a_bstride : a->lda * a->K) * es;
       box[0] = pa.chunk; box[1] = BK; box[2] = 1;
       p.a.kmajor = 0; p.a.nchunks = kBM / pa.chunk; p.a.chunk_elems = pa.chunk; p.a.chunk_bytes = BK * sb;
       p.a.k_advance = umma_k * sb;
@@ -632,14 +646,14 @@ int gemm_dispatch(const avmoe_gemm_args* a, cudaStream_t st) {
     const int sb = swz_bytes(pb.code);
     p.b.desc_base = make_desc_base(pb.code, a->b_kmajor, BK);
     if (a->b_kmajor) {
-      dims[0] = a->K; dims[1] = a->N; dims[2] = a->b_batch;
-      strides[0] = a->ldb * es; strides[1] = (a->b_batch > 1 ? a->b_bstride : a->ldb * a->N) * es;
+      dims[0] = a->K; dims[1] = a->N; dims[2] = fbatch > 1 ? fbatch : a->b_batch;
+      strides[0] = a->ldb * es; strides[1] = ((a->b_batch > 1 || fbatch > 1) ? a->b_bstride : a->ldb * a->N) * es;
       box[0] = BK; box[1] = BN; box[2] = 1;
       p.b.kmajor = 1; p.b.nchunks = 1; p.b.chunk_bytes = BN * sb; p.b.k_advance = 32;
       p.stage_bytes_b = BN * sb;
     } else {
-      dims[0] = Nb; dims[1] = a->K; dims[2] = a->b_batch;
-      strides[0] = a->ldb * es; strides[1] = (a->b_batch > 1 ? a->b_bstride : a->ldb * a->K) * es;
+      dims[0] = Nb; dims[1] = a->K; dims[2] = fbatch > 1 ? fbatch : a->b_batch;
+      strides[0] = a->ldb * es; strides[1] = ((a->b_batch > 1 || fbatch > 1) ? a->b_bstride : a->ldb * a->K) * es;
       box[0] = pb.chunk; box[1] = BK; box[2] = 1;
       p.b.kmajor = 0; p.b.nchunks = BN / pb.chunk; p.b.chunk_elems = pb.chunk; p.b.chunk_bytes = BK * sb;
       p.b.batch_extent = b_nbatched ? (int)Nb : 0;
@@ -668,6 +682,7 @@ int gemm_dispatch(const avmoe_gemm_args* a, cudaStream_t st) {
   p.splits = (p.k_iters + p.k_iters_per_split - 1) / p.k_iters_per_split;
   p.tiles_m = (int)((a->M + kBM - 1) / kBM);
   p.tiles_n = (int)((a->N + BN - 1) / BN);
+  p.full_batch = fbatch;
   int tc = 32;
   while (tc < 2 * BN) tc <<= 1;
   p.tmem_cols = tc;
@@ -688,8 +703,8 @@ int gemm_dispatch(const avmoe_gemm_args* a, cudaStream_t st) {
   p.tma_store = (!n_batched || Nb % 32 == 0) ? 1 : 0;
   if (p.tma_store) {
     const int des = p.d_bf16 ? 2 : 4;
-    cuuint64_t dims[3] = {(cuuint64_t)(n_batched ? Nb : a->N), (cuuint64_t)a->M, (cuuint64_t)(n_batched ? a->N / Nb : 1)};
-    cuuint64_t strides[2] = {(cuuint64_t)(a->ldd * des), (cuuint64_t)((n_batched ? a->d_bstride : a->ldd * a->M) * des)};
+    cuuint64_t dims[3] = {(cuuint64_t)(n_batched ? Nb : a->N), (cuuint64_t)a->M, (cuuint64_t)(n_batched ? a->N / Nb : fbatch)};
+    cuuint64_t strides[2] = {(cuuint64_t)(a->ldd * des), (cuuint64_t)(((n_batched || fbatch > 1) ? a->d_bstride : a->ldd * a->M) * des)};
     cuuint32_t box[3] = {32, 32, 1};
     if ((strides[0] % 16) || (strides[1] % 16)) p.tma_store = 0;
     else {
@@ -710,7 +725,7 @@ int gemm_dispatch(const avmoe_gemm_args* a, cudaStream_t st) {
   AVMOE_CHECK_ARG(stages >= 2, "gemm: tile does not fit shared memory");
   p.num_stages = stages;
   const size_t smem_bytes = 1024 + (size_t)stages * stage_bytes + kStagingBytes + 256;
-  const int tiles = p.tiles_m * p.tiles_n * p.splits;
+  const int tiles = p.tiles_m * p.tiles_n * p.splits * p.full_batch;
   int grid = num_sms();
   if (grid > tiles) grid = tiles;
   static std::once_flag attr_once;

@@ -47,7 +47,7 @@ __device__ __forceinline__ void load_kv_tile(float* kvs, const T* kvb, int n0, i
 
 // grid (nsplit*csplit, nexp, BT), block 256
 template <typename T>
-__global__ void __launch_bounds__(256) latent_fwd_kernel(const LatentParams p) {
+__global__ void __launch_bounds__(256, 2) latent_fwd_kernel(const LatentParams p) {
   extern __shared__ float sm[];
   constexpr bool kExact = std::is_same<T, float>::value;
   const int ld = p.C + 4, lds = p.TN + 4;
@@ -140,7 +140,7 @@ __global__ void latent_merge_kernel(const LatentParams p) {
 
 // grid (nsplit*csplit, BT), block 256; loops over the call's experts so dkv is written exactly once
 template <typename T>
-__global__ void __launch_bounds__(256) latent_bwd_kernel(const LatentParams p) {
+__global__ void __launch_bounds__(256, 2) latent_bwd_kernel(const LatentParams p) {
   extern __shared__ float sm[];
   constexpr bool kExact = std::is_same<T, float>::value;
   const int ld = p.C + 4, lds = p.TN + 4;

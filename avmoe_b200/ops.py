@@ -137,6 +137,44 @@ def gemm(A: torch.Tensor, B: torch.Tensor, *, a_kmajor: bool = True, b_kmajor: b
     return out
 
 
+def bgemm(A: torch.Tensor, B: torch.Tensor, *, a_kmajor: bool = True, b_kmajor: bool = True, out_dtype: Optional[torch.dtype] = None,
+          alpha: float = 1.0, col_bias: Optional[torch.Tensor] = None, impl: int = 0) -> torch.Tensor:
+    """Fully batched GEMM: D[b] = alpha * op(A[b]) · op(B[b])ᵀ for independent problems b.
+    A [b,M,K] (a_kmajor) or [b,K,M];  B [b,N,K] (b_kmajor) or [b,K,N];  D [b,M,N]."""
+    _require_cuda(A, B)
+    assert A.dim() == 3 and B.dim() == 3 and A.shape[0] == B.shape[0] and A.dtype == B.dtype
+    assert A.stride(-1) == 1 and B.stride(-1) == 1
+    nb = A.shape[0]
+    M, K = (A.shape[1], A.shape[2]) if a_kmajor else (A.shape[2], A.shape[1])
+    N, Kb = (B.shape[1], B.shape[2]) if b_kmajor else (B.shape[2], B.shape[1])
+    assert K == Kb
+    out = torch.empty((nb, M, N), device=A.device, dtype=out_dtype or A.dtype)
+    a = _lib.GemmArgs()
+    a.dtype, a.d_dtype = _dt(A), _dt(out)
+    a.M, a.N, a.K, a.Nb = M, N, K, 0
+    a.a_kmajor, a.b_kmajor = int(a_kmajor), int(b_kmajor)
+    a.a_batch = a.b_batch = 1
+    a.lda, a.ldb, a.ldd = A.stride(1), B.stride(1), out.stride(1)
+    a.a_bstride, a.b_bstride, a.d_bstride = A.stride(0), B.stride(0), out.stride(0)
+    a.alpha = alpha
+    a.A, a.B, a.D = A.data_ptr(), B.data_ptr(), out.data_ptr()
+    if col_bias is not None:
+        a.col_bias = col_bias.data_ptr()
+    a.split_k, a.accumulate, a.impl, a.full_batch = 1, 0, impl or _GEMM_IMPL_OVERRIDE, nb
+    global LAUNCHES
+    LAUNCHES += 1
+    if GEMM_PROFILE is not None:
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
+        _lib.check(_lib.load().avmoe_gemm(C.byref(a), _stream()), "bgemm")
+        ev1.record()
+        nbytes = A.numel() * A.element_size() + B.numel() * B.element_size() + out.numel() * out.element_size()
+        GEMM_PROFILE.append((ev0, ev1, 2.0 * nb * M * N * K, nbytes, f"b{nb}_M{M}_N{N}_K{K}"))
+        return out
+    _lib.check(_lib.load().avmoe_gemm(C.byref(a), _stream()), "bgemm")
+    return out
+
+
 # ------------------------------------------------------------------------------------------------ layout helpers
 def _lib_call(name, *args):
     global LAUNCHES
@@ -410,17 +448,77 @@ def expert_front_bwd(cfg, x, tokp, dzt, z, bn, bn_mode, red1, packs, dpool_x, dx
 
 
 # ------------------------------------------------------------------------------------------------ variant pre-transforms
+MHA_HEADS = 4
+_NXN_CHUNK_BYTES = 1 << 30   # fp32 scratch budget for the [chunk,N,N] score matrix of the AVVP token self-attention
+
+
+def _nxn_chunk(BT: int, N: int) -> int:
+    return max(1, min(BT, _NXN_CHUNK_BYTES // (4 * N * N)))
+
+
 def selfattn_nxn_fwd(x):
-    raise RuntimeError("avmoe_b200: the AVVP NxN token self-attention kernel is not built yet")
+    """AVVP single-modal pre-transform: aux_j = sum_i softmax_j(x_i·x_·)[j] x_i.  Returns (aux, row log-sum-exps)."""
+    _require_cuda(x)
+    BT, N, Cc = x.shape
+    aux = torch.empty_like(x)
+    lse = torch.empty((BT, N), device=x.device, dtype=torch.float32)
+    bc = _nxn_chunk(BT, N)
+    for b0 in range(0, BT, bc):
+        xc = x[b0:b0 + bc]
+        nb = xc.shape[0]
+        S = bgemm(xc, xc, out_dtype=torch.float32)                                  # [nb,N,N]  x_i . x_j
+        P = torch.empty((nb, N, N), device=x.device, dtype=x.dtype)
+        _lib_call("nxn_softmax_rows", _ptr(S), _ptr(P), _ptr(lse[b0:b0 + bc]), C.c_int64(nb * N), N, _dt(P), _stream())
+        aux[b0:b0 + bc] = bgemm(P, xc, a_kmajor=False, b_kmajor=False)             # sum_i P[i,j] x_i
+    return aux, lse
 
 
-def selfattn_nxn_bwd(x, saved, daux, dx):
-    raise RuntimeError("avmoe_b200: the AVVP NxN token self-attention kernel is not built yet")
+def selfattn_nxn_bwd(x, lse, daux, dx):
+    BT, N, Cc = x.shape
+    bc = _nxn_chunk(BT, N)
+    for b0 in range(0, BT, bc):
+        xc, gc = x[b0:b0 + bc], daux[b0:b0 + bc]
+        nb = xc.shape[0]
+        S = bgemm(xc, xc, out_dtype=torch.float32)
+        dAtt = bgemm(xc, gc, out_dtype=torch.float32)                               # datt[i,j] = x_i . g_j
+        att = torch.empty((nb, N, N), device=x.device, dtype=x.dtype)
+        dS = torch.empty_like(att)
+        _lib_call("nxn_bwd_rows", _ptr(S), _ptr(dAtt), _ptr(lse[b0:b0 + bc]), _ptr(att), _ptr(dS), C.c_int64(nb * N), N, _dt(att), _stream())
+        t1 = bgemm(att, gc, b_kmajor=False)                                         # sum_j att[i,j] g_j
+        t2 = bgemm(dS, xc, b_kmajor=False)                                          # sum_j ds[i,j] x_j
+        t3 = bgemm(dS, xc, a_kmajor=False, b_kmajor=False)                          # sum_i ds[i,j] x_i
+        dxc = dx[b0:b0 + bc]
+        _lib_call("add_into", _ptr(dxc), _ptr(t1), _ptr(t2), _ptr(t3), C.c_int64(dxc.numel()), _dt(dxc), _stream())
 
 
 def mha_fwd(x, mp):
-    raise RuntimeError("avmoe_b200: the AVS-v1 multi-head attention kernel is not built yet")
+    """AVS-v1 single-modal pre-transform: nn.MultiheadAttention(C, 4) over the BT axis of x [BT,N,C]."""
+    _require_cuda(x)
+    w_in, b_in, w_out, b_out = mp
+    L, NB, Cc = x.shape
+    x2 = x.reshape(L * NB, Cc)
+    qkv = gemm(x2, prep_weight(w_in, x.dtype, False), out_dtype=torch.float32, col_bias=b_in.contiguous())      # [L*NB,3C] fp32
+    ctx = torch.empty((L, NB, Cc), device=x.device, dtype=x.dtype)
+    _lib_call("mha_attn_fwd", _ptr(qkv), _ptr(ctx), L, NB, Cc, MHA_HEADS, _dt(x), _stream())
+    out = gemm(ctx.reshape(L * NB, Cc), prep_weight(w_out, x.dtype, False), col_bias=b_out.contiguous()).reshape(L, NB, Cc)
+    return out, (qkv, ctx)
 
 
 def mha_bwd(x, mp, saved, daux, dx):
-    raise RuntimeError("avmoe_b200: the AVS-v1 multi-head attention kernel is not built yet")
+    w_in, b_in, w_out, b_out = mp
+    qkv, ctx = saved
+    L, NB, Cc = x.shape
+    rows = L * NB
+    g2 = daux.reshape(rows, Cc)
+    f32 = torch.float32
+    dw_out = gemm(g2, ctx.reshape(rows, Cc), a_kmajor=False, b_kmajor=False, out_dtype=f32, split_k=split_k_hint(rows, Cc, Cc))   # gᵀ·ctx
+    _, db_out, _ = reduce_bias(daux)
+    dctx = gemm(g2, prep_weight(w_out, x.dtype, True), out_dtype=f32)                                                            # g·W_out   fp32
+    dqkv = torch.empty((L, NB, 3 * Cc), device=x.device, dtype=x.dtype)
+    _lib_call("mha_attn_bwd", _ptr(qkv), _ptr(dctx), _ptr(dqkv), L, NB, Cc, MHA_HEADS, _dt(x), _stream())
+    dq2 = dqkv.reshape(rows, 3 * Cc)
+    dw_in = gemm(dq2, x.reshape(rows, Cc), a_kmajor=False, b_kmajor=False, out_dtype=f32, split_k=split_k_hint(rows, 3 * Cc, Cc))  # dqkvᵀ·x
+    _, db_in, _ = reduce_bias(dqkv)
+    dxa = gemm(dq2, prep_weight(w_in, x.dtype, True))                                                                            # dqkv·W_in
+    _lib_call("add_into", _ptr(dx), _ptr(dxa), None, None, C.c_int64(dx.numel()), _dt(dx), _stream())
+    return [dw_in, db_in, dw_out, db_out]

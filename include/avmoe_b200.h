@@ -95,6 +95,8 @@ typedef struct {
   int32_t split_k;
   int32_t accumulate;         /* 1: D += result (fp32 D only, atomics) */
   int32_t impl;
+  int32_t full_batch;         /* >1: that many independent problems; A, B, D advance by a_bstride/b_bstride/d_bstride
+                                 (a_batch = b_batch = 1, no N-batching, no split-K) */
 } avmoe_gemm_args;
 
 int avmoe_gemm(const avmoe_gemm_args* args, avmoe_stream_t stream);
@@ -213,6 +215,20 @@ typedef struct {
 } avmoe_bn_args;
 int avmoe_bn1_finalize(const avmoe_bn_args* a, avmoe_stream_t stream);
 int avmoe_bn2_finalize(const avmoe_bn_args* a, avmoe_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Variant pre-transforms of the single-modal expert.
+ *   AVVP  N x N token self-attention (AVMOE/AVVP/nets/mgn.py:132-139): the two N x N contractions are avmoe_gemm calls
+ *         with full_batch; these kernels are the row softmax between them and its backward.
+ *   AVS-v1 nn.MultiheadAttention over the BT axis (avs_s4/model/PVT_AVSModel_v2.py:212-215): per (token position, head)
+ *         attention core on the fp32 in_proj output qkv [BT][N][3C]; probabilities are recomputed in the backward.
+ * ------------------------------------------------------------------------------------------ */
+int avmoe_nxn_softmax_rows(const float* S, void* P, float* lse, int64_t rows, int n, int p_dtype, avmoe_stream_t stream);
+int avmoe_nxn_bwd_rows(const float* S, const float* dAtt, const float* lse, void* att, void* dS, int64_t rows, int n, int p_dtype,
+                       avmoe_stream_t stream);
+int avmoe_add_into(void* dst, const void* a, const void* b, const void* c, int64_t n, int dtype, avmoe_stream_t stream);
+int avmoe_mha_attn_fwd(const float* qkv, void* ctx, int L, int NB, int C, int heads, int dtype, avmoe_stream_t stream);
+int avmoe_mha_attn_bwd(const float* qkv, const float* dctx, void* dqkv, int L, int NB, int C, int heads, int dtype, avmoe_stream_t stream);
 
 #ifdef __cplusplus
 }

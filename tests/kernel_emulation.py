@@ -62,6 +62,15 @@ def gemm(A, B, *, a_kmajor=True, b_kmajor=True, out_dtype=None, alpha=1.0, row_b
     return D.to(out_dtype)
 
 
+def bgemm(A, B, *, a_kmajor=True, b_kmajor=True, out_dtype=None, alpha=1.0, col_bias=None, impl=0):
+    Af = A.float() if a_kmajor else A.float().transpose(1, 2)
+    Bf = B.float() if b_kmajor else B.float().transpose(1, 2)
+    D = alpha * (Af @ Bf.transpose(1, 2))
+    if col_bias is not None:
+        D = D + col_bias
+    return D.to(out_dtype or A.dtype)
+
+
 def rowsum(w):
     return w.float().sum(dim=1)
 

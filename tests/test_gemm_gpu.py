@@ -119,6 +119,21 @@ def test_gemm_kmajor_b_nbatched_output(dtype, impl, Nb):
 
 
 @pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32])
+@pytest.mark.parametrize("impl", [0, 1])
+@pytest.mark.parametrize("amaj,bmaj", [(True, True), (True, False), (False, False), (False, True)])
+def test_bgemm_fully_batched(dtype, impl, amaj, bmaj):
+    """independent problems per batch element (AVVP token self-attention, AVS MHA projections)."""
+    from avmoe_b200 import ops
+    nb, M, N, K = 3, 160, 96, 128
+    A = _mk((nb, M, K) if amaj else (nb, K, M), dtype, 1)
+    B = _mk((nb, N, K) if bmaj else (nb, K, N), dtype, 2)
+    D = ops.bgemm(A, B, a_kmajor=amaj, b_kmajor=bmaj, out_dtype=torch.float32, impl=impl, alpha=0.25)
+    Af = A.float() if amaj else A.float().transpose(1, 2)
+    Bf = B.float() if bmaj else B.float().transpose(1, 2)
+    assert util.rel_err(D, 0.25 * Af @ Bf.transpose(1, 2)) < _tol(dtype)
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32])
 def test_hot_shapes_stay_on_tensor_cores(dtype):
     """impl=2 refuses to fall back: the real backbone shapes must be expressible on tcgen05."""
     from avmoe_b200 import ops
