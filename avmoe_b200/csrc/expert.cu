@@ -744,8 +744,11 @@ __global__ void __launch_bounds__(kThreads, 2) expert_front_bwd_kernel(const avm
 
 // ------------------------------------------------------------------------------------------------ host side
 static int pow2_floor(int v) { int p = 1; while (p * 2 <= v) p *= 2; return p; }
-static int pick_tn(int C, int budget_floats) {
-  int tn = budget_floats / (C + 4);
+// rows per token tile: `nbuf` fp32 [TN][C+4] buffers should stay near 100 KiB so two CTAs share an SM; wide channels
+// (stage 3/4) would then get tiles of a few tokens whose per-tile weight traffic dominates, so they may use up to ~190 KiB.
+static int pick_tn(int C, int nbuf) {
+  int tn = ((nbuf >= 4 ? 64 : 100) * 1024 / 4) / (nbuf * (C + 4));
+  if (tn < 16) tn = (190 * 1024 / 4) / (nbuf * (C + 4));
   if (tn < 1) tn = 1;
   if (tn > 64) tn = 64;
   return pow2_floor(tn);
@@ -789,7 +792,7 @@ extern "C" int avmoe_expert_front_fwd(const avmoe_expert_args* a, avmoe_stream_t
   if (int rc = check_common(a, "expert_front_fwd")) return rc;
   AVMOE_CHECK_ARG(a->x && a->z, "expert_front_fwd: null tensor");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  const int TN = pick_tn(a->C, 12288);
+  const int TN = pick_tn(a->C, 2);
   const size_t smem = sizeof(float) * (2 * (size_t)TN * (a->C + 4) + (size_t)TN * (a->T + 4) + (size_t)TN * (a->E * a->Cr + 1));
   dim3 grid((a->N + TN - 1) / TN, a->BT);
   AVMOE_DISPATCH_V(a->C, {
@@ -856,7 +859,7 @@ extern "C" int avmoe_expert_back_fwd(const avmoe_expert_args* a, avmoe_stream_t 
   AVMOE_CHECK_ARG(a->z && a->probs && a->out, "expert_back_fwd: null tensor");
   AVMOE_CHECK_ARG(a->bn_mode == AVMOE_BN_OFF || (a->aff1 && a->aff2), "expert_back_fwd: batch-norm affine missing");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  const int TN = pick_tn(a->C, 12288);
+  const int TN = pick_tn(a->C, 2);
   const size_t smem = sizeof(float) * (2 * (size_t)TN * (a->C + 4) + (size_t)TN * (a->Cr + 4));
   dim3 grid((a->N + TN - 1) / TN, a->BT);
   AVMOE_DISPATCH_V(a->C, {
@@ -884,7 +887,7 @@ static int launch_back_bwd(const avmoe_expert_args* a, cudaStream_t st, const ch
     AVMOE_CHECK_ARG(a->bn_mode != AVMOE_BN_EVAL || a->red2b, "%s: red2b missing", who);
     AVMOE_CHECK_ARG(a->bn_mode == AVMOE_BN_OFF || a->red1, "%s: red1 missing", who);
   }
-  const int TN = pick_tn(a->C, 8192);
+  const int TN = pick_tn(a->C, 3);
   const size_t smem = sizeof(float) * (3 * (size_t)TN * (a->C + 4) + 2 * (size_t)TN * (a->Cr + 4) + 6 * (size_t)a->C + 32);
   dim3 grid((a->N + TN - 1) / TN, a->BT);
   AVMOE_DISPATCH_V(a->C, {
@@ -912,7 +915,7 @@ extern "C" int avmoe_expert_front_bwd(const avmoe_expert_args* a, avmoe_stream_t
   AVMOE_CHECK_ARG(a->x && a->dzt && a->dx, "expert_front_bwd: null tensor");
   AVMOE_CHECK_ARG(a->bn_mode == AVMOE_BN_OFF || (a->aff1 && a->save1 && a->z && a->red1), "expert_front_bwd: batch-norm tensors missing");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  const int TN = pick_tn(a->C, 6144);
+  const int TN = pick_tn(a->C, 4);
   const size_t smem = sizeof(float) * (4 * (size_t)TN * (a->C + 4) + 2 * (size_t)TN * (a->T + 4) + (size_t)TN * (a->Cr + 4) + TN + 2 * (size_t)a->C + 32);
   dim3 grid((a->N + TN - 1) / TN, a->BT);
   AVMOE_DISPATCH_V(a->C, {
