@@ -122,11 +122,11 @@ __device__ __forceinline__ const float* pre_transform(const avmoe_expert& ex, co
     const float* tp = p.tokp + ((long long)b * p.nl + ex.latent_slot) * p.T * C;
     const float g = *ex.gate_pre;
     const int lt = p.T + 4;
-    contract<kExact>(rows, p.T, C, xs, ld, 1, tp, 1, C, [&](int n, int t, float v) { s2[n * lt + t] = v; });
+    contract_to<kExact, Out::Store>(rows, p.T, C, xs, ld, 1, tp, 1, C, s2, lt, 1);
     __syncthreads();
     row_softmax(s2, rows, p.T, lt);
     __syncthreads();
-    contract<kExact>(rows, C, p.T, s2, lt, 1, tp, C, 1, [&](int n, int c, float v) { ws[n * ld + c] = xs[n * ld + c] + g * v; });
+    contract_to<kExact, Out::StorePlusSrc>(rows, C, p.T, s2, lt, 1, tp, C, 1, ws, ld, 1, g, xs);
     __syncthreads();
     return ws;
   }
@@ -181,8 +181,8 @@ __global__ void __launch_bounds__(kThreads, 2) expert_front_fwd_kernel(const avm
     __syncthreads();
     // grouped down projection: z[n][g*Crg+jl] = sum_cl xn[n][g*Cg+cl] * wd[g*Crg+jl][cl]
     for (int g = 0; g < G; ++g)
-      contract<kExact>(TN, Crg, Cg, ws + g * Cg, ld, 1, ex.wd + (long long)g * Crg * Cg, 1, Cg,
-                       [&](int n, int jl, float v) { zt[n * lz + e * Cr + g * Crg + jl] = v; });
+      contract_to<kExact, Out::Store>(TN, Crg, Cg, ws + g * Cg, ld, 1, ex.wd + (long long)g * Crg * Cg, 1, Cg,
+                                      zt + e * Cr + g * Crg, lz, 1);
     __syncthreads();
   }
   // coalesced store of the z tile [valid][E*Cr] and the bn1 batch sums
@@ -370,8 +370,7 @@ __device__ __forceinline__ void back_recompute(const avmoe_expert_args& p, const
   }
   __syncthreads();
   for (int g = 0; g < G; ++g)
-    contract<kExact>(TN, Cg, Crg, as + g * Crg, lda, 1, ex.wu + (long long)g * Cg * Crg, 1, Crg,
-                     [&](int n, int cl, float v) { ys[n * ld + g * Cg + cl] = v; });
+    contract_to<kExact, Out::Store>(TN, Cg, Crg, as + g * Crg, lda, 1, ex.wu + (long long)g * Cg * Crg, 1, Crg, ys + g * Cg, ld, 1);
   __syncthreads();
 }
 
@@ -432,9 +431,10 @@ __global__ void __launch_bounds__(kThreads, 2) expert_back_bwd_kernel(const avmo
   float* gs = ys + TN * ld;            // [TN][ld]  dy
   float* as = gs + TN * ld;            // [TN][Cr+4]
   float* dzs = as + TN * lda;          // [TN][Cr+4] dzt tile of the current expert
-  float* col = dzs + TN * lda;         // [4][C] column sums: ln_post w/b grads, sum dyt, sum dyt*yhat
-  float* mds = col + 4 * C;            // [2][C] batch means of dyt and dyt*yhat (bn train)
-  float* scratch = mds + 2 * C;        // [32]
+  float* mds = dzs + TN * lda;         // [2][C] batch means of dyt and dyt*yhat (bn train)
+  float* rowm = mds + 2 * C;           // [TN] ln_post row means
+  float* rowr = rowm + TN;             // [TN] ln_post row rstd
+  float* scratch = rowr + TN;          // [32]
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
   const int b = blockIdx.y, n0 = blockIdx.x * TN;
   const int valid = min(TN, p.N - n0);
@@ -445,7 +445,6 @@ __global__ void __launch_bounds__(kThreads, 2) expert_back_bwd_kernel(const avmo
   __syncthreads();
   for (int e = 0; e < p.E; ++e) {
     const avmoe_expert& ex = p.ex[e];
-    for (int i = threadIdx.x; i < 4 * C; i += blockDim.x) col[i] = 0.f;
     if (!kStatsOnly && mode == AVMOE_BN_TRAIN)
       for (int c = threadIdx.x; c < C; c += blockDim.x) {
         mds[c] = (float)(p.red2[((long long)e * C + c) * 2] * inv_n);
@@ -456,10 +455,11 @@ __global__ void __launch_bounds__(kThreads, 2) expert_back_bwd_kernel(const avmo
     const float gate = ex.gate ? *ex.gate : 1.f;
     const float sc = pe * gate;
     float gq = 0.f;
-    // ---- one row pass: yt, ln_post fwd stats, dq, ln_post bwd, bn2 bwd -> dy
+    // ---- one row pass: yt, ln_post fwd stats, dq, ln_post bwd, (bn2 bwd) -> gs = dy (bn train / off) or dyt (stats, eval)
     for (int r = warp; r < TN; r += nwarps) {
-      if (r >= valid) {   // keep the dy tile zero below the valid rows (it feeds the weight-gradient contraction)
-        if (!kStatsOnly) { ROW_VECS(k, c) st4(gs + r * ld + c, f4(0.f)); }
+      if (r >= valid) {   // keep the tile zero below the valid rows (it feeds the weight-gradient contraction)
+        ROW_VECS(k, c) st4(gs + r * ld + c, f4(0.f));
+        if (lane == 0) { rowm[r] = 0.f; rowr[r] = 0.f; }
         continue;
       }
       float4 yt[kMaxV], yh[kMaxV], d[kMaxV];
@@ -484,6 +484,7 @@ __global__ void __launch_bounds__(kThreads, 2) expert_back_bwd_kernel(const avmo
         float ss = 0.f;
         ROW_VECS(k, c) { const float4 t = yt[k] - f4(mean); ss += hsum(t * t); }
         rstd = rsqrtf(warp_sum(ss) / C + kLnEps);
+        if (lane == 0) { rowm[r] = mean; rowr[r] = rstd; }
       }
       float s1 = 0.f, s2v = 0.f;
       ROW_VECS(k, c) {
@@ -494,11 +495,6 @@ __global__ void __launch_bounds__(kThreads, 2) expert_back_bwd_kernel(const avmo
           const float4 qh = rstd * (yt[k] - f4(mean));
           const float4 q = qh * w + ldg4(ex.ln2_b + c);
           gq += hsum(g0 * q);
-          if (!kStatsOnly) {
-            const float4 t = dq * qh;
-            atomicAdd(&col[c], t.x); atomicAdd(&col[c + 1], t.y); atomicAdd(&col[c + 2], t.z); atomicAdd(&col[c + 3], t.w);
-            atomicAdd(&col[C + c], dq.x); atomicAdd(&col[C + c + 1], dq.y); atomicAdd(&col[C + c + 2], dq.z); atomicAdd(&col[C + c + 3], dq.w);
-          }
           d[k] = dq * w;                         // dqh
           s1 += hsum(d[k]);
           s2v += hsum(d[k] * qh);
@@ -512,40 +508,43 @@ __global__ void __launch_bounds__(kThreads, 2) expert_back_bwd_kernel(const avmo
         const float m1 = warp_sum(s1) / C, m2 = warp_sum(s2v) / C;
         ROW_VECS(k, c) d[k] = rstd * (d[k] - f4(m1) - m2 * yt[k]);      // dyt
       }
-      if (mode != AVMOE_BN_OFF) {
-        if (kStatsOnly || mode == AVMOE_BN_EVAL) {
-          ROW_VECS(k, c) {
-            const float4 t = d[k] * yh[k];
-            atomicAdd(&col[2 * C + c], d[k].x); atomicAdd(&col[2 * C + c + 1], d[k].y); atomicAdd(&col[2 * C + c + 2], d[k].z); atomicAdd(&col[2 * C + c + 3], d[k].w);
-            atomicAdd(&col[3 * C + c], t.x); atomicAdd(&col[3 * C + c + 1], t.y); atomicAdd(&col[3 * C + c + 2], t.z); atomicAdd(&col[3 * C + c + 3], t.w);
-          }
-        }
-        if (!kStatsOnly) {
-          ROW_VECS(k, c) {
-            if (mode == AVMOE_BN_TRAIN) d[k] = d[k] - ld4(mds + c) - yh[k] * ld4(mds + C + c);
-            d[k] = d[k] * s2c[k];
-          }
-        }
+      if (mode == AVMOE_BN_TRAIN && !kStatsOnly) {
+        ROW_VECS(k, c) d[k] = (d[k] - ld4(mds + c) - yh[k] * ld4(mds + C + c)) * s2c[k];   // dy
       }
-      if (!kStatsOnly) { ROW_VECS(k, c) st4(gs + r * ld + c, d[k]); }
+      ROW_VECS(k, c) st4(gs + r * ld + c, d[k]);
     }
     __syncthreads();
-    // ---- flush the tile's column sums
-    if (kStatsOnly) {
-      for (int c = threadIdx.x; c < C; c += blockDim.x) {
-        atomicAdd(&p.red2[((long long)e * C + c) * 2], (double)col[2 * C + c]);
-        atomicAdd(&p.red2[((long long)e * C + c) * 2 + 1], (double)col[3 * C + c]);
-      }
-      __syncthreads();
-      continue;
-    }
+    // ---- per-channel sums (one thread per channel, rows in order, no shared-memory atomics)
     for (int c = threadIdx.x; c < C; c += blockDim.x) {
-      if (ex.ln2_w) { atomicAdd(ex.g_ln2_w + c, col[c]); atomicAdd(ex.g_ln2_b + c, col[C + c]); }
-      if (mode == AVMOE_BN_EVAL) {
-        atomicAdd(&p.red2b[((long long)e * C + c) * 2], (double)col[2 * C + c]);
-        atomicAdd(&p.red2b[((long long)e * C + c) * 2 + 1], (double)col[3 * C + c]);
+      const bool bn = mode != AVMOE_BN_OFF;
+      const float a2s = bn ? p.aff2[((long long)e * C + c) * 2] : 1.f, a2h = bn ? p.aff2[((long long)e * C + c) * 2 + 1] : 0.f;
+      if (!kStatsOnly && ex.ln2_w) {
+        float sw = 0.f, sb = 0.f;
+        for (int n = 0; n < valid; ++n) {
+          const float qh = (fmaf(ys[n * ld + c], a2s, a2h) - rowm[n]) * rowr[n];
+          const float dq = sc * gs0[n * ld + c];
+          sw = fmaf(dq, qh, sw);
+          sb += dq;
+        }
+        atomicAdd(ex.g_ln2_w + c, sw);
+        atomicAdd(ex.g_ln2_b + c, sb);
+      }
+      if (bn && (kStatsOnly || mode == AVMOE_BN_EVAL)) {
+        const float mu = p.save2[((long long)e * C + c) * 2], is = p.save2[((long long)e * C + c) * 2 + 1];
+        float s1 = 0.f, s2v = 0.f;
+        for (int n = 0; n < valid; ++n) {
+          const float dd = gs[n * ld + c];           // dyt
+          s1 += dd;
+          s2v = fmaf(dd, (ys[n * ld + c] - mu) * is, s2v);
+          if (!kStatsOnly) gs[n * ld + c] = dd * a2s;   // eval mode: dy = scale * dyt
+        }
+        double* red = kStatsOnly ? p.red2 : p.red2b;
+        atomicAdd(&red[((long long)e * C + c) * 2], (double)s1);
+        atomicAdd(&red[((long long)e * C + c) * 2 + 1], (double)s2v);
       }
     }
+    __syncthreads();
+    if (kStatsOnly) continue;
     {
       const float tot = block_sum(gq, scratch);
       if (threadIdx.x == 0) {
@@ -555,12 +554,10 @@ __global__ void __launch_bounds__(kThreads, 2) expert_back_bwd_kernel(const avmo
     }
     // ---- d up_sampler.weight[c][jl] += sum_n dy[n][c] * a[n][g*Crg+jl]      (rows >= valid of gs are zero)
     for (int g = 0; g < G; ++g)
-      contract<kExact>(Cg, Crg, TN, gs + g * Cg, 1, ld, as + g * Crg, lda, 1,
-                       [&](int cl, int jl, float v) { atomicAdd(ex.g_wu + (long long)(g * Cg + cl) * Crg + jl, v); });
+      contract_to<kExact, Out::AtomicAdd>(Cg, Crg, TN, gs + g * Cg, 1, ld, as + g * Crg, lda, 1, ex.g_wu + (long long)g * Cg * Crg, Crg, 1);
     // ---- da[n][g*Crg+jl] = sum_cl dy[n][g*Cg+cl] * wu[g*Cg+cl][jl]
     for (int g = 0; g < G; ++g)
-      contract<kExact>(TN, Crg, Cg, gs + g * Cg, ld, 1, ex.wu + (long long)g * Cg * Crg, Crg, 1,
-                       [&](int n, int jl, float v) { dzs[n * lda + g * Crg + jl] = v; });
+      contract_to<kExact, Out::Store>(TN, Crg, Cg, gs + g * Cg, ld, 1, ex.wu + (long long)g * Cg * Crg, Crg, 1, dzs + g * Crg, lda, 1);
     __syncthreads();
     // ---- relu mask, store dzt (coalesced rows of Cr)
     for (int n = warp; n < valid; n += nwarps) {
@@ -605,8 +602,7 @@ __global__ void __launch_bounds__(kThreads, 2) expert_front_bwd_kernel(const avm
   float* ds2 = s2 + TN * lt;           // [TN][T+4]
   float* dzs = ds2 + TN * lt;          // [TN][Cr+4]
   float* rstds = dzs + TN * lda;       // [TN]
-  float* col = rstds + TN;             // [2][C] ln_before weight / bias gradient column sums
-  float* scratch = col + 2 * C;        // [32]
+  float* scratch = rstds + TN;         // [32]
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
   const int b = blockIdx.y, n0 = blockIdx.x * TN;
   const int valid = min(TN, p.N - n0);
@@ -620,7 +616,6 @@ __global__ void __launch_bounds__(kThreads, 2) expert_front_bwd_kernel(const avm
   __syncthreads();
   for (int e = 0; e < p.E; ++e) {
     const avmoe_expert& ex = p.ex[e];
-    for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) col[i] = 0.f;
     // ---- dz = bn1 backward of dzt (rows of Cr, coalesced)
     for (int n = warp; n < TN; n += nwarps) {
       const long long zrow = (((long long)b * p.N + n0 + n) * p.E + e) * Cr;
@@ -664,14 +659,22 @@ __global__ void __launch_bounds__(kThreads, 2) expert_front_bwd_kernel(const avm
     __syncthreads();
     // ---- d down_sampler.weight[g*Crg+jl][cl] += sum_n dz[n][g*Crg+jl] * xn[n][g*Cg+cl]   (dz rows >= valid are 0)
     for (int g = 0; g < G; ++g)
-      contract<kExact>(Crg, Cg, TN, dzs + g * Crg, 1, lda, t1 + g * Cg, ld, 1,
-                       [&](int jl, int cl, float v) { atomicAdd(ex.g_wd + (long long)(g * Crg + jl) * Cg + cl, v); });
+      contract_to<kExact, Out::AtomicAdd>(Crg, Cg, TN, dzs + g * Crg, 1, lda, t1 + g * Cg, ld, 1, ex.g_wd + (long long)g * Crg * Cg, Cg, 1);
     __syncthreads();
     // ---- dxn[n][g*Cg+cl] = sum_jl dz[n][g*Crg+jl] * wd[g*Crg+jl][cl]
     for (int g = 0; g < G; ++g)
-      contract<kExact>(TN, Cg, Crg, dzs + g * Crg, lda, 1, ex.wd + (long long)g * Crg * Cg, Cg, 1,
-                       [&](int n, int cl, float v) { t1[n * ld + g * Cg + cl] = v; });
+      contract_to<kExact, Out::Store>(TN, Cg, Crg, dzs + g * Crg, lda, 1, ex.wd + (long long)g * Crg * Cg, Cg, 1, t1 + g * Cg, ld, 1);
     __syncthreads();
+    // ---- d ln_before weight / bias: column sums of dxn*xhat and dxn (one thread per channel, no atomics in smem)
+    if (ex.ln1_w) {
+      for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        float sw = 0.f, sb = 0.f;
+        for (int n = 0; n < valid; ++n) { const float d = t1[n * ld + c]; sw = fmaf(d, ws[n * ld + c], sw); sb += d; }
+        atomicAdd(ex.g_ln1_w + c, sw);
+        atomicAdd(ex.g_ln1_b + c, sb);
+      }
+      __syncthreads();
+    }
     // ---- row pass B: ln_before backward -> dxa (t1), dx accumulation, aux gradients
     float dg = 0.f;
     const T* auxp = ex.aux ? reinterpret_cast<const T*>(ex.aux) + ((long long)b * p.N + n0) * C : nullptr;
@@ -685,9 +688,6 @@ __global__ void __launch_bounds__(kThreads, 2) expert_front_bwd_kernel(const avm
         d[k] = ld4(t1 + r * ld + c);
         if (ex.ln1_w) {
           xh[k] = ld4(ws + r * ld + c);
-          const float4 t = d[k] * xh[k];
-          atomicAdd(&col[c], t.x); atomicAdd(&col[c + 1], t.y); atomicAdd(&col[c + 2], t.z); atomicAdd(&col[c + 3], t.w);
-          atomicAdd(&col[C + c], d[k].x); atomicAdd(&col[C + c + 1], d[k].y); atomicAdd(&col[C + c + 2], d[k].z); atomicAdd(&col[C + c + 3], d[k].w);
           d[k] = d[k] * ldg4(ex.ln1_w + c);
           s1 += hsum(d[k]);
           s2v += hsum(d[k] * xh[k]);
@@ -709,13 +709,11 @@ __global__ void __launch_bounds__(kThreads, 2) expert_front_bwd_kernel(const avm
       }
     }
     __syncthreads();
-    if (ex.ln1_w)
-      for (int c = threadIdx.x; c < C; c += blockDim.x) { atomicAdd(ex.g_ln1_w + c, col[c]); atomicAdd(ex.g_ln1_b + c, col[C + c]); }
     if (ex.pre_kind == AVMOE_PRE_LATENT) {
       const float* tp = p.tokp + ((long long)b * p.nl + ex.latent_slot) * p.T * C;
       float* dtp = p.dtokp + ((long long)b * p.nl + ex.latent_slot) * p.T * C;
       // u[n][t] = dxa_n . tok'_t
-      contract<kExact>(TN, p.T, C, t1, ld, 1, tp, 1, C, [&](int n, int t, float v) { ds2[n * lt + t] = v; });
+      contract_to<kExact, Out::Store>(TN, p.T, C, t1, ld, 1, tp, 1, C, ds2, lt, 1);
       __syncthreads();
       // d gate_pre = sum A2*u ; dS2 = A2 * g * (u - sum_t A2*u)      (one warp per row, lanes over t)
       for (int r = warp; r < TN; r += nwarps) {
@@ -727,10 +725,10 @@ __global__ void __launch_bounds__(kThreads, 2) expert_front_bwd_kernel(const avm
       }
       __syncthreads();
       // dx[n][c] += sum_t dS2[n][t] * tok'[t][c]
-      contract<kExact>(TN, C, p.T, ds2, lt, 1, tp, C, 1, [&](int n, int c, float v) { dxs[n * ld + c] += v; });
+      contract_to<kExact, Out::Add>(TN, C, p.T, ds2, lt, 1, tp, C, 1, dxs, ld, 1);
       // d tok'[t][c] += sum_n A2[n][t]*g*dxa[n][c] + dS2[n][t]*x[n][c]       (rows >= valid of t1 / xs are zero)
-      contract<kExact>(p.T, C, TN, s2, 1, lt, t1, ld, 1, [&](int t, int c, float v) { atomicAdd(dtp + (long long)t * C + c, gpre * v); });
-      contract<kExact>(p.T, C, TN, ds2, 1, lt, xs, ld, 1, [&](int t, int c, float v) { atomicAdd(dtp + (long long)t * C + c, v); });
+      contract_to<kExact, Out::AtomicAdd>(p.T, C, TN, s2, 1, lt, t1, ld, 1, dtp, C, 1, gpre);
+      contract_to<kExact, Out::AtomicAdd>(p.T, C, TN, ds2, 1, lt, xs, ld, 1, dtp, C, 1);
     }
     if (ex.g_gate_pre) {
       const float tot = block_sum(dg, scratch);
@@ -888,7 +886,7 @@ static int launch_back_bwd(const avmoe_expert_args* a, cudaStream_t st, const ch
     AVMOE_CHECK_ARG(a->bn_mode == AVMOE_BN_OFF || a->red1, "%s: red1 missing", who);
   }
   const int TN = pick_tn(a->C, 3);
-  const size_t smem = sizeof(float) * (3 * (size_t)TN * (a->C + 4) + 2 * (size_t)TN * (a->Cr + 4) + 6 * (size_t)a->C + 32);
+  const size_t smem = sizeof(float) * (3 * (size_t)TN * (a->C + 4) + 2 * (size_t)TN * (a->Cr + 4) + 2 * (size_t)a->C + 2 * TN + 32);
   dim3 grid((a->N + TN - 1) / TN, a->BT);
   AVMOE_DISPATCH_V(a->C, {
     if (a->dtype == AVMOE_F32) {
@@ -916,7 +914,7 @@ extern "C" int avmoe_expert_front_bwd(const avmoe_expert_args* a, avmoe_stream_t
   AVMOE_CHECK_ARG(a->bn_mode == AVMOE_BN_OFF || (a->aff1 && a->save1 && a->z && a->red1), "expert_front_bwd: batch-norm tensors missing");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const int TN = pick_tn(a->C, 4);
-  const size_t smem = sizeof(float) * (4 * (size_t)TN * (a->C + 4) + 2 * (size_t)TN * (a->T + 4) + (size_t)TN * (a->Cr + 4) + TN + 2 * (size_t)a->C + 32);
+  const size_t smem = sizeof(float) * (4 * (size_t)TN * (a->C + 4) + 2 * (size_t)TN * (a->T + 4) + (size_t)TN * (a->Cr + 4) + TN + 32);
   dim3 grid((a->N + TN - 1) / TN, a->BT);
   AVMOE_DISPATCH_V(a->C, {
     if (a->dtype == AVMOE_F32) {

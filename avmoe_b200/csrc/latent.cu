@@ -72,33 +72,34 @@ __global__ void __launch_bounds__(256, 2) latent_fwd_kernel(const LatentParams p
     load_kv_tile<T>(kvs, kvb, n0, ne, p.TN, p.C, ld);
     __syncthreads();
     // logits S[t][n] = tok_t . kv_n
-    contract<kExact>(p.T, p.TN, p.C, tok, p.C, 1, kvs, 1, ld,
-                     [&](int t, int n, float v) { S[t * lds + n] = (n0 + n < ne) ? v : -INFINITY; });
+    contract_to<kExact, Out::Store>(p.T, p.TN, p.C, tok, p.C, 1, kvs, 1, ld, S, lds, 1);
     __syncthreads();
+    const int nvalid = min(p.TN, ne - n0);   // columns >= nvalid are padding: treated as -inf below
     // online softmax per latent token (one warp per t)
     for (int t = warp; t < p.T; t += nwarps) {
+      const float mold = mrun[t];                 // read by every lane before lane 0 updates it below
       float mx = -INFINITY;
-      for (int n = lane; n < p.TN; n += 32) mx = fmaxf(mx, S[t * lds + n]);
+      for (int n = lane; n < nvalid; n += 32) mx = fmaxf(mx, S[t * lds + n]);
       mx = warp_max(mx);
-      const float mnew = fmaxf(mrun[t], mx);
+      const float mnew = fmaxf(mold, mx);
       float sum = 0.f;
       for (int n = lane; n < p.TN; n += 32) {
-        const float e = expf(S[t * lds + n] - mnew);   // masked entries: exp(-inf) = 0
+        const float e = n < nvalid ? expf(S[t * lds + n] - mnew) : 0.f;
         S[t * lds + n] = e;
         sum += e;
       }
       sum = warp_sum(sum);
+      const float a = expf(mold - mnew);           // first tile: exp(-inf) = 0
       if (lane == 0) {
-        const float a = expf(mrun[t] - mnew);          // first tile: exp(-inf) = 0
-        alpha[t] = a;
         lrun[t] = lrun[t] * a + sum;
         mrun[t] = mnew;
       }
+      // rescale this row of the accumulator for the new running maximum
+      for (int c = lane; c < cw; c += 32) acc[t * p.CC + c] *= a;
     }
     __syncthreads();
     // acc[t][c] = alpha[t]*acc[t][c] + sum_n P[t][n]*kv[n][c]   (this CTA's channel range only)
-    contract<kExact>(p.T, cw, p.TN, S, lds, 1, kvs + c_lo, ld, 1,
-                     [&](int t, int c, float v) { acc[t * p.CC + c] = acc[t * p.CC + c] * alpha[t] + v; });
+    contract_to<kExact, Out::Add>(p.T, cw, p.TN, S, lds, 1, kvs + c_lo, ld, 1, acc, p.CC, 1);
     __syncthreads();
   }
   float* pp = p.part + ((((long long)b * p.nexp + ei) * p.nsplit + split) * p.T) * p.C;
@@ -179,18 +180,26 @@ __global__ void __launch_bounds__(256, 2) latent_bwd_kernel(const LatentParams p
       const long long sbase = ((long long)b * p.nl + p.slot[ei]) * p.T;
       const float* dR = p.dtokp + sbase * p.C;
       // probabilities A1 = exp(tok.kv - lse) and dS = A1 * (dR.kv - D)
-      contract<kExact>(p.T, p.TN, p.C, tok, p.C, 1, kvs, 1, ld,
-                       [&](int t, int n, float v) { A1[t * lds + n] = (n0 + n < ne) ? expf(v - p.lse[sbase + t]) : 0.f; });
+      contract_to<kExact, Out::Store>(p.T, p.TN, p.C, tok, p.C, 1, kvs, 1, ld, A1, lds, 1);
+      contract_to<kExact, Out::Store>(p.T, p.TN, p.C, dR, p.C, 1, kvs, 1, ld, dS, lds, 1);
       __syncthreads();
-      contract<kExact>(p.T, p.TN, p.C, dR, p.C, 1, kvs, 1, ld,
-                       [&](int t, int n, float v) { dS[t * lds + n] = A1[t * lds + n] * (v - Dt[ei * p.T + t]); });
+      {
+        const int nvalid = min(p.TN, ne - n0);
+        for (int t = warp; t < p.T; t += nwarps) {
+          const float l = p.lse[sbase + t], dt = Dt[ei * p.T + t];
+          for (int n = lane; n < p.TN; n += 32) {
+            const float a1 = n < nvalid ? expf(A1[t * lds + n] - l) : 0.f;
+            A1[t * lds + n] = a1;
+            dS[t * lds + n] = a1 * (dS[t * lds + n] - dt);
+          }
+        }
+      }
       __syncthreads();
       // dkv[n][c] += sum_t A1[t][n]*dR[t][c] + dS[t][n]*tok[t][c]
-      contract<kExact>(p.TN, cw, p.T, A1, 1, lds, dR + c_lo, p.C, 1, [&](int n, int c, float v) { dkvt[n * p.CC + c] += v; });
-      contract<kExact>(p.TN, cw, p.T, dS, 1, lds, tok + c_lo, p.C, 1, [&](int n, int c, float v) { dkvt[n * p.CC + c] += v; });
+      contract_to<kExact, Out::Add>(p.TN, cw, p.T, A1, 1, lds, dR + c_lo, p.C, 1, dkvt, p.CC, 1);
+      contract_to<kExact, Out::Add>(p.TN, cw, p.T, dS, 1, lds, tok + c_lo, p.C, 1, dkvt, p.CC, 1);
       // dtok[t][c] += sum_n dS[t][n]*kv[n][c]
-      contract<kExact>(p.T, cw, p.TN, dS, lds, 1, kvs + c_lo, ld, 1,
-                       [&](int t, int c, float v) { dtk[(ei * p.T + t) * p.CC + c] += v; });
+      contract_to<kExact, Out::Add>(p.T, cw, p.TN, dS, lds, 1, kvs + c_lo, ld, 1, dtk + ei * p.T * p.CC, p.CC, 1);
       __syncthreads();
     }
     // write the dkv tile
