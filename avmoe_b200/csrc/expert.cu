@@ -12,6 +12,8 @@
 // Token tiles live in shared memory as fp32 [rows][C+1]; activations are read/written in their storage
 // dtype with 8/16-byte vectors.  Parameter gradients are accumulated with fp32 atomics, BatchNorm sums
 // with fp64 atomics.
+#include <stdlib.h>
+
 #include <type_traits>
 
 #include "block_mma.cuh"
@@ -314,31 +316,38 @@ __global__ void bn1_finalize_kernel(const avmoe_bn_args a) {
 }
 
 __global__ void bn2_finalize_kernel(const avmoe_bn_args a) {
+  // one warp per output channel: the quadratic form wᵀ M2 w over the channel's conv group is spread over the lanes
   const int e = blockIdx.x;
   const int Cg = a.C / a.G, Crg = a.Cr / a.G;
-  for (int c = blockIdx.y * blockDim.x + threadIdx.x; c < a.C; c += gridDim.y * blockDim.x) {
-    double mean, var;
-    if (a.train) {
-      const int g = c / Cg;
-      const float* wr = a.wu[e] + (long long)c * Crg;
-      const double* m1 = a.m1 + e * a.Cr + g * Crg;
-      const double* m2 = a.m2 + ((long long)(e * a.G + g) * Crg) * Crg;
-      double mu = 0.0, ey2 = 0.0;
-      for (int j = 0; j < Crg; ++j) {
-        mu += (double)wr[j] * m1[j];
-        double t = 0.0;
-        for (int k = 0; k < Crg; ++k) t += (double)wr[k] * m2[(long long)j * Crg + k];
-        ey2 += (double)wr[j] * t;
-      }
-      mean = mu / (double)a.n;
-      var = ey2 / (double)a.n - mean * mean;
-      if (var < 0) var = 0;
+  const int lane = threadIdx.x & 31;
+  const int c = blockIdx.y * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (c >= a.C) return;
+  double mean, var;
+  if (a.train) {
+    const int g = c / Cg;
+    const float* wr = a.wu[e] + (long long)c * Crg;
+    const double* m1 = a.m1 + e * a.Cr + g * Crg;
+    const double* m2 = a.m2 + ((long long)(e * a.G + g) * Crg) * Crg;
+    double mu = 0.0, ey2 = 0.0;
+    for (int j = lane; j < Crg; j += 32) {
+      mu += (double)wr[j] * m1[j];
+      double t = 0.0;
+      for (int k = 0; k < Crg; ++k) t += (double)wr[k] * m2[(long long)j * Crg + k];
+      ey2 += (double)wr[j] * t;
+    }
+    for (int o = 16; o > 0; o >>= 1) { mu += __shfl_xor_sync(0xffffffffu, mu, o); ey2 += __shfl_xor_sync(0xffffffffu, ey2, o); }
+    mean = mu / (double)a.n;
+    var = ey2 / (double)a.n - mean * mean;
+    if (var < 0) var = 0;
+    if (lane == 0) {
       const double unbiased = var * ((double)a.n / (double)(a.n > 1 ? a.n - 1 : 1));
       a.rm2[e][c] = (float)((1.0 - kBnMomentum) * a.rm2[e][c] + kBnMomentum * mean);
       a.rv2[e][c] = (float)((1.0 - kBnMomentum) * a.rv2[e][c] + kBnMomentum * unbiased);
-    } else {
-      mean = a.rm2[e][c]; var = a.rv2[e][c];
     }
+  } else {
+    mean = a.rm2[e][c]; var = a.rv2[e][c];
+  }
+  if (lane == 0) {
     const double invstd = 1.0 / sqrt(var + kBnEps);
     const double sc = (double)a.w2[e][c] * invstd;
     a.aff2[(e * a.C + c) * 2] = (float)sc;
@@ -553,6 +562,7 @@ __global__ void __launch_bounds__(kThreads, 2) expert_back_bwd_kernel(const avmo
       }
     }
     // ---- d up_sampler.weight[c][jl] += sum_n dy[n][c] * a[n][g*Crg+jl]      (rows >= valid of gs are zero)
+    if (!(p.ex[0]._pad & 1))
     for (int g = 0; g < G; ++g)
       contract_to<kExact, Out::AtomicAdd>(Cg, Crg, TN, gs + g * Cg, 1, ld, as + g * Crg, lda, 1, ex.g_wu + (long long)g * Cg * Crg, Crg, 1);
     // ---- da[n][g*Crg+jl] = sum_cl dy[n][g*Cg+cl] * wu[g*Cg+cl][jl]
@@ -658,6 +668,7 @@ __global__ void __launch_bounds__(kThreads, 2) expert_front_bwd_kernel(const avm
     }
     __syncthreads();
     // ---- d down_sampler.weight[g*Crg+jl][cl] += sum_n dz[n][g*Crg+jl] * xn[n][g*Cg+cl]   (dz rows >= valid are 0)
+    if (!(p.ex[0]._pad & 1))
     for (int g = 0; g < G; ++g)
       contract_to<kExact, Out::AtomicAdd>(Crg, Cg, TN, dzs + g * Crg, 1, lda, t1 + g * Cg, ld, 1, ex.g_wd + (long long)g * Crg * Cg, Cg, 1);
     __syncthreads();
@@ -750,6 +761,13 @@ static int pick_tn(int C, int nbuf) {
   if (tn < 1) tn = 1;
   if (tn > 64) tn = 64;
   return pow2_floor(tn);
+}
+
+// diagnostics only (AVMOE_DEBUG_SKIP=1): skip the in-kernel weight-gradient contractions to measure their cost
+static int debug_skip() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("AVMOE_DEBUG_SKIP"); v = e ? atoi(e) : 0; }
+  return v;
 }
 
 static int check_common(const avmoe_expert_args* a, const char* who) {
@@ -847,7 +865,7 @@ extern "C" int avmoe_bn1_finalize(const avmoe_bn_args* a, avmoe_stream_t stream)
 extern "C" int avmoe_bn2_finalize(const avmoe_bn_args* a, avmoe_stream_t stream) {
   AVMOE_CHECK_ARG(a && a->E >= 1 && a->E <= AVMOE_MAX_EXPERTS && a->aff2 && a->save2, "bn2_finalize: bad arguments");
   AVMOE_CHECK_ARG(!a->train || (a->m1 && a->m2), "bn2_finalize: training mode needs the moment sums");
-  bn2_finalize_kernel<<<dim3(a->E, (a->C + 127) / 128), 128, 0, reinterpret_cast<cudaStream_t>(stream)>>>(*a);
+  bn2_finalize_kernel<<<dim3(a->E, (a->C + 7) / 8), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(*a);
   AVMOE_LAUNCH_CHECK("bn2_finalize_kernel");
   return 0;
 }
@@ -885,6 +903,9 @@ static int launch_back_bwd(const avmoe_expert_args* a, cudaStream_t st, const ch
     AVMOE_CHECK_ARG(a->bn_mode != AVMOE_BN_EVAL || a->red2b, "%s: red2b missing", who);
     AVMOE_CHECK_ARG(a->bn_mode == AVMOE_BN_OFF || a->red1, "%s: red1 missing", who);
   }
+  avmoe_expert_args dbg = *a;
+  dbg.ex[0]._pad = debug_skip();
+  a = &dbg;
   const int TN = pick_tn(a->C, 3);
   const size_t smem = sizeof(float) * (3 * (size_t)TN * (a->C + 4) + 2 * (size_t)TN * (a->Cr + 4) + 2 * (size_t)a->C + 2 * TN + 32);
   dim3 grid((a->N + TN - 1) / TN, a->BT);
@@ -913,6 +934,9 @@ extern "C" int avmoe_expert_front_bwd(const avmoe_expert_args* a, avmoe_stream_t
   AVMOE_CHECK_ARG(a->x && a->dzt && a->dx, "expert_front_bwd: null tensor");
   AVMOE_CHECK_ARG(a->bn_mode == AVMOE_BN_OFF || (a->aff1 && a->save1 && a->z && a->red1), "expert_front_bwd: batch-norm tensors missing");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  avmoe_expert_args dbg = *a;
+  dbg.ex[0]._pad = debug_skip();
+  a = &dbg;
   const int TN = pick_tn(a->C, 4);
   const size_t smem = sizeof(float) * (4 * (size_t)TN * (a->C + 4) + 2 * (size_t)TN * (a->T + 4) + (size_t)TN * (a->Cr + 4) + TN + 32);
   dim3 grid((a->N + TN - 1) / TN, a->BT);

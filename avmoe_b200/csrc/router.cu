@@ -175,7 +175,7 @@ extern "C" int avmoe_router_fwd(const float* pool_x, const float* pool_v, int ch
   AVMOE_CHECK_ARG(pool_x && pool_v && probs && idx && h1 && h2 && rin && w0 && w2 && w4, "router_fwd: null pointer");
   AVMOE_CHECK_ARG(E >= 1 && E <= AVMOE_MAX_EXPERTS && BT > 0 && C > 0, "router_fwd: bad sizes (E=%d)", E);
   const size_t smem = (2 * (size_t)C + kH1 + kH2 + AVMOE_MAX_EXPERTS) * sizeof(float);
-  router_fwd_kernel<<<BT, 128, smem, reinterpret_cast<cudaStream_t>(stream)>>>(pool_x, pool_v, chunks_x, chunks_v, C, E, inv_n, w0, b0, w2, b2,
+  router_fwd_kernel<<<BT, 512, smem, reinterpret_cast<cudaStream_t>(stream)>>>(pool_x, pool_v, chunks_x, chunks_v, C, E, inv_n, w0, b0, w2, b2,
                                                                                 w4, b4, noise, probs, (long long*)idx, h1, h2, rin);
   AVMOE_LAUNCH_CHECK("router_fwd_kernel");
   return 0;
@@ -191,7 +191,7 @@ extern "C" int avmoe_router_bwd(const float* dprobs, const float* probs, const f
   float* dlg = ws;
   float* dh2 = dlg + (size_t)BT * E;
   float* dh1 = dh2 + (size_t)BT * kH2;
-  router_bwd_sample_kernel<<<BT, 128, 0, st>>>(dprobs, probs, h1, h2, C, E, inv_n, w0, w2, w4, dlg, dh2, dh1, dpool_x, dpool_v);
+  router_bwd_sample_kernel<<<BT, 256, 0, st>>>(dprobs, probs, h1, h2, C, E, inv_n, w0, w2, w4, dlg, dh2, dh1, dpool_x, dpool_v);
   AVMOE_LAUNCH_CHECK("router_bwd_sample_kernel");
   router_wgrad_kernel<<<dim3((2 * C + 127) / 128, kH1), 128, 0, st>>>(dh1, rin, dw0, db0, BT, kH1, 2 * C);
   router_wgrad_kernel<<<dim3(1, kH2), 128, 0, st>>>(dh2, h1, dw2, db2, BT, kH2, kH1);

@@ -186,7 +186,7 @@ def resample_bwd(K, cfg: AdapterConfig, o: torch.Tensor, dv: torch.Tensor, saved
         P = mid
         # bias grads: db_fc[c] = sum dv ; db_tok[n] = sum_c dv*s[c] ; ds[c] = sum_n dv*b_tok[n]  (d rowsum(W_fc))
         db_tok, db_fc, ds = K.reduce_bias(dv, col_weight=s, row_weight=b_tok)
-        dw_tok = K.gemm(dv, P, out_dtype=f32)                                   # sum_b dv[b]·P[b]ᵀ        [N,Nx]
+        dw_tok = K.gemm(dv, P, out_dtype=f32, split_k=K.split_k_hint(BT * C, N, Nx))   # sum_b dv[b]·P[b]ᵀ   [N,Nx]
         dVt = K.transpose(dv)                                                   # [BT,C,N]
         dP = K.gemm(wt_T, dVt.reshape(BT * C, N), d_nbatch=C)                   # W_tokᵀ·dv[b]             [BT,Nx,C]
         dP2 = dP.reshape(BT * Nx, C)
@@ -201,7 +201,7 @@ def resample_bwd(K, cfg: AdapterConfig, o: torch.Tensor, dv: torch.Tensor, saved
                    split_k=K.split_k_hint(BT * N, C, Cx))                        # dvᵀ·U                    [C,Cx]
     dU = K.gemm(dv2, wf_T).reshape(BT, N, Cx)                                    # dv·W_fc                  [BT,N,Cx]
     db_tok, _, _ = K.reduce_bias(dU)
-    dw_tok = K.gemm(dU, o, out_dtype=f32)                                        # sum_b dU[b]·o[b]ᵀ        [N,Nx]
+    dw_tok = K.gemm(dU, o, out_dtype=f32, split_k=K.split_k_hint(BT * Cx, N, Nx))     # sum_b dU[b]·o[b]ᵀ        [N,Nx]
     do = None
     if need_do:
         dUt = K.transpose(dU)                                                    # [BT,Cx,N]
