@@ -127,7 +127,8 @@ struct OperandTile {
 
 struct GemmParams {
   CUtensorMap tmA, tmB, tmD;
-  int tma_store;       // 1: epilogue stages 32x32 slabs in swizzled smem and TMA-stores / TMA-reduces them
+  int tma_store;       // 1: epilogue transposes 32x32 slabs through smem and writes coalesced 16-byte rows (slabs never straddle a batch)
+  int vec_ok;          // D pitches / base allow 16-byte vector stores
   OperandTile a, b;
   int BN;              // tile N (multiple of 32, <= 256)
   int BK;              // K elements per stage
@@ -155,7 +156,7 @@ struct GemmParams {
 
 static constexpr int kGemmThreads = 192;
 static constexpr int kBM = 128;
-static constexpr int kStagingBytes = 4 * 2 * 4096;
+static constexpr int kStagingBytes = 17408;   // 4 epilogue warps x [32][33] fp32 (rounded to 1 KiB)
 
 template <bool kTf32>
 __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tcgen05_kernel(const __grid_constant__ GemmParams p) {
@@ -177,7 +178,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tcgen05_kernel(const __g
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&p.tmA) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&p.tmB) : "memory");
-    if (p.tma_store) asm volatile("prefetch.tensormap [%0];" ::"l"(&p.tmD) : "memory");
+
     for (int s = 0; s < p.num_stages; ++s) {
       mbar_init(smem_u32(&full_bar[s]), 1);
       mbar_init(smem_u32(&empty_bar[s]), 1);
@@ -285,8 +286,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tcgen05_kernel(const __g
     const int quarter = warp & 3;  // TMEM lane quarter this warp may access
     int acc = 0;
     uint32_t acc_phase = 0;
-    uint8_t* my_stage = staging + (warp - 2) * 8192;
-    int sbuf = 0;
+    float* stg = reinterpret_cast<float*>(staging) + (warp - 2) * (32 * 33);   // per-warp [32][33] transpose slab
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int tb = tile / tiles_per_batch;
       const int trem = tile - tb * tiles_per_batch;
@@ -311,50 +311,77 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tcgen05_kernel(const __g
         long long bb = tb, c0 = ng;
         if (p.n_batched) { bb = ng / p.Nb; c0 = ng - bb * p.Nb; }
         if (p.tma_store) {
-          // ---- fast path: regs -> swizzled smem slab [32 rows][32 cols] -> TMA store / reduce-add ----
-          uint8_t* buf = my_stage + sbuf * 4096;
-          tma_store_wait_read<1>();     // the slab issued two steps ago has been read out of this buffer
-          __syncwarp();
-          float o[32];
+          // ---- fast path: registers -> per-warp smem slab [32][33] -> coalesced 16-byte global stores (or fp32 atomics) ----
+          __syncwarp();                                   // the previous slab has been read out
 #pragma unroll
-          for (int e = 0; e < 32; ++e) {
-            float val = has_k ? __uint_as_float(r[e]) * p.alpha : 0.f;
-            if (add_bias) {
-              const long long ce = (c0 + e < p.Nb) ? c0 + e : 0;
-              if (p.row_bias) val += rb * (p.col_scale ? __ldg(p.col_scale + ce) : 1.f);
-              if (p.col_bias) val += __ldg(p.col_bias + ce);
+          for (int e = 0; e < 32; ++e) stg[lane * 33 + e] = has_k ? __uint_as_float(r[e]) * p.alpha : 0.f;
+          __syncwarp();
+          if (p.d_bf16) {
+            const int chunk = lane & 3, rsub = lane >> 2;          // 8 columns per lane, 8 rows per instruction
+            const long long cc = c0 + chunk * 8;
+            const bool cvalid = ng + chunk * 8 < p.N;
+            float cs[8], cb[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const long long ce = cc + j < p.Nb ? cc + j : 0;
+              cs[j] = (add_bias && p.row_bias) ? (p.col_scale ? __ldg(p.col_scale + ce) : 1.f) : 0.f;
+              cb[j] = (add_bias && p.col_bias) ? __ldg(p.col_bias + ce) : 0.f;
             }
-            o[e] = val;
-          }
-          if (p.d_bf16) {   // rows of 64 B, SWIZZLE_64B: 16-byte chunk j of row r lives at chunk j ^ ((r>>1)&3)
-            uint8_t* row = buf + lane * 64;
-            const int x = (lane >> 1) & 3;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const int row = rsub + 8 * k;
+              const long long mm = mrow0 + row;
+              if (mm < p.M && cvalid) {
+                const float rbv = (add_bias && p.row_bias) ? __ldg(p.row_bias + mm) : 0.f;
+                float o[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) o[j] = stg[row * 33 + chunk * 8 + j] + rbv * cs[j] + cb[j];
+                __nv_bfloat16* dp = reinterpret_cast<__nv_bfloat16*>(p.D) + bb * p.d_bstride + mm * p.ldd + cc;
+                const int valid = (int)min((long long)8, p.N - (ng + chunk * 8));
+                if (valid == 8 && p.vec_ok) {
+                  uint4 q;
+                  __nv_bfloat162 h0 = __floats2bfloat162_rn(o[0], o[1]), h1 = __floats2bfloat162_rn(o[2], o[3]);
+                  __nv_bfloat162 h2 = __floats2bfloat162_rn(o[4], o[5]), h3 = __floats2bfloat162_rn(o[6], o[7]);
+                  q.x = *reinterpret_cast<uint32_t*>(&h0); q.y = *reinterpret_cast<uint32_t*>(&h1);
+                  q.z = *reinterpret_cast<uint32_t*>(&h2); q.w = *reinterpret_cast<uint32_t*>(&h3);
+                  *reinterpret_cast<uint4*>(dp) = q;
+                } else {
+                  for (int j = 0; j < valid; ++j) dp[j] = __float2bfloat16_rn(o[j]);
+                }
+              }
+            }
+          } else {
+            const int chunk = lane & 7, rsub = lane >> 3;          // 4 columns per lane, 4 rows per instruction
+            const long long cc = c0 + chunk * 4;
+            const bool cvalid = ng + chunk * 4 < p.N;
+            float cs[4], cb[4];
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-              uint4 q;
-              __nv_bfloat162 h0 = __floats2bfloat162_rn(o[8 * j + 0], o[8 * j + 1]);
-              __nv_bfloat162 h1 = __floats2bfloat162_rn(o[8 * j + 2], o[8 * j + 3]);
-              __nv_bfloat162 h2 = __floats2bfloat162_rn(o[8 * j + 4], o[8 * j + 5]);
-              __nv_bfloat162 h3 = __floats2bfloat162_rn(o[8 * j + 6], o[8 * j + 7]);
-              q.x = *reinterpret_cast<uint32_t*>(&h0); q.y = *reinterpret_cast<uint32_t*>(&h1);
-              q.z = *reinterpret_cast<uint32_t*>(&h2); q.w = *reinterpret_cast<uint32_t*>(&h3);
-              *reinterpret_cast<uint4*>(row + ((j ^ x) << 4)) = q;
+              const long long ce = cc + j < p.Nb ? cc + j : 0;
+              cs[j] = (add_bias && p.row_bias) ? (p.col_scale ? __ldg(p.col_scale + ce) : 1.f) : 0.f;
+              cb[j] = (add_bias && p.col_bias) ? __ldg(p.col_bias + ce) : 0.f;
             }
-          } else {          // rows of 128 B, SWIZZLE_128B: chunk j of row r lives at chunk j ^ (r&7)
-            uint8_t* row = buf + lane * 128;
-            const int x = lane & 7;
 #pragma unroll
-            for (int j = 0; j < 8; ++j)
-              *reinterpret_cast<float4*>(row + ((j ^ x) << 4)) = make_float4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
+            for (int k = 0; k < 8; ++k) {
+              const int row = rsub + 4 * k;
+              const long long mm = mrow0 + row;
+              if (mm < p.M && cvalid) {
+                const float rbv = (add_bias && p.row_bias) ? __ldg(p.row_bias + mm) : 0.f;
+                float o[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) o[j] = stg[row * 33 + chunk * 4 + j] + rbv * cs[j] + cb[j];
+                float* dp = reinterpret_cast<float*>(p.D) + bb * p.d_bstride + mm * p.ldd + cc;
+                const int valid = (int)min((long long)4, p.N - (ng + chunk * 4));
+                if (p.atomic) {
+                  for (int j = 0; j < valid; ++j) atomicAdd(dp + j, o[j]);
+                } else if (valid == 4 && p.vec_ok) {
+                  *reinterpret_cast<float4*>(dp) = make_float4(o[0], o[1], o[2], o[3]);
+                } else {
+                  for (int j = 0; j < valid; ++j) dp[j] = o[j];
+                }
+              }
+            }
           }
-          fence_proxy_async_smem();
-          __syncwarp();
-          if (lane == 0) {
-            if (p.atomic) tma_reduce_add_3d(&p.tmD, smem_u32(buf), (int)c0, mrow0, (int)bb);
-            else tma_store_3d(&p.tmD, smem_u32(buf), (int)c0, mrow0, (int)bb);
-            tma_store_commit();
-          }
-          sbuf ^= 1;
         } else if (m < p.M) {
           // ---- generic path (per-batch N not a multiple of 32): direct 4-wide stores ----
 #pragma unroll
@@ -396,7 +423,6 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tcgen05_kernel(const __g
       if (lane == 0) mbar_arrive(smem_u32(&tmem_empty[acc]));
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
-    if (p.tma_store) tma_store_wait_all();   // smem must outlive the bulk reads; global writes complete before exit
   }
 
   tcgen05_fence_before();
@@ -699,23 +725,11 @@ int gemm_dispatch(const avmoe_gemm_args* a, cudaStream_t st) {
       AVMOE_CUDA(cudaMemset2DAsync(a->D, a->ldd * sizeof(float), 0, a->N * sizeof(float), a->M, st));
     }
   }
-  // ---- D tensor map for the TMA-store epilogue (32x32 slabs; needs slabs that never straddle a batch) ----
+  // ---- epilogue mode: 32x32 slabs must never straddle a batch of an N-batched D ----
   p.tma_store = (!n_batched || Nb % 32 == 0) ? 1 : 0;
-  if (p.tma_store) {
-    const int des = p.d_bf16 ? 2 : 4;
-    cuuint64_t dims[3] = {(cuuint64_t)(n_batched ? Nb : a->N), (cuuint64_t)a->M, (cuuint64_t)(n_batched ? a->N / Nb : fbatch)};
-    cuuint64_t strides[2] = {(cuuint64_t)(a->ldd * des), (cuuint64_t)(((n_batched || fbatch > 1) ? a->d_bstride : a->ldd * a->M) * des)};
-    cuuint32_t box[3] = {32, 32, 1};
-    if ((strides[0] % 16) || (strides[1] % 16)) p.tma_store = 0;
-    else {
-      PFN_encodeTiled fn = get_encode_fn();
-      if (!fn) { set_error("cuTensorMapEncodeTiled not available from the driver"); return AVMOE_E_NODRIVER; }
-      const cuuint32_t estr[3] = {1, 1, 1};
-      CUresult r = fn(&p.tmD, p.d_bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, a->D, dims, strides, box, estr,
-                      CU_TENSOR_MAP_INTERLEAVE_NONE, p.d_bf16 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B,
-                      CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-      if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(D) failed (CUresult %d)", (int)r); return AVMOE_E_BADARG; }
-    }
+  {
+    const int vec = p.d_bf16 ? 8 : 4;
+    p.vec_ok = (a->ldd % vec == 0) && (a->d_bstride % vec == 0) && (((uintptr_t)a->D % 16) == 0) && (!n_batched || Nb % vec == 0);
   }
   // ---- smem / launch --------------------------------------------------------------------------
   const uint32_t stage_bytes = p.stage_bytes_a + p.stage_bytes_b;
