@@ -346,7 +346,8 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tcgen05_kernel(const __g
                   q.z = *reinterpret_cast<uint32_t*>(&h2); q.w = *reinterpret_cast<uint32_t*>(&h3);
                   *reinterpret_cast<uint4*>(dp) = q;
                 } else {
-                  for (int j = 0; j < valid; ++j) dp[j] = __float2bfloat16_rn(o[j]);
+#pragma unroll
+                  for (int j = 0; j < 8; ++j) if (j < valid) dp[j] = __float2bfloat16_rn(o[j]);
                 }
               }
             }
@@ -373,11 +374,13 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tcgen05_kernel(const __g
                 float* dp = reinterpret_cast<float*>(p.D) + bb * p.d_bstride + mm * p.ldd + cc;
                 const int valid = (int)min((long long)4, p.N - (ng + chunk * 4));
                 if (p.atomic) {
-                  for (int j = 0; j < valid; ++j) atomicAdd(dp + j, o[j]);
+#pragma unroll
+                  for (int j = 0; j < 4; ++j) if (j < valid) atomicAdd(dp + j, o[j]);
                 } else if (valid == 4 && p.vec_ok) {
                   *reinterpret_cast<float4*>(dp) = make_float4(o[0], o[1], o[2], o[3]);
                 } else {
-                  for (int j = 0; j < valid; ++j) dp[j] = o[j];
+#pragma unroll
+                  for (int j = 0; j < 4; ++j) if (j < valid) dp[j] = o[j];
                 }
               }
             }
@@ -387,7 +390,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tcgen05_kernel(const __g
 #pragma unroll
           for (int v = 0; v < 8; ++v) {
             const long long n = ng + v * 4;
-            if (n >= p.N) break;
+            if (n >= p.N) continue;        // (no break: keeps r[] statically indexed, i.e. in registers)
             long long b2 = tb, c = n;
             if (p.n_batched) { b2 = n / p.Nb; c = n - b2 * p.Nb; }
             float o[4];
@@ -405,15 +408,22 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tcgen05_kernel(const __g
             const int valid = (int)min((long long)4, p.N - n);
             if (p.atomic) {
               float* dp = reinterpret_cast<float*>(p.D) + off;
-              for (int e = 0; e < valid; ++e) atomicAdd(dp + e, o[e]);
+#pragma unroll
+              for (int e = 0; e < 4; ++e) if (e < valid) atomicAdd(dp + e, o[e]);
             } else if (p.d_bf16) {
               __nv_bfloat16* dp = reinterpret_cast<__nv_bfloat16*>(p.D) + off;
               if (valid == 4) store4<__nv_bfloat16>(dp, o);
-              else for (int e = 0; e < valid; ++e) dp[e] = __float2bfloat16_rn(o[e]);
+              else {
+#pragma unroll
+                for (int e = 0; e < 4; ++e) if (e < valid) dp[e] = __float2bfloat16_rn(o[e]);
+              }
             } else {
               float* dp = reinterpret_cast<float*>(p.D) + off;
               if (valid == 4) store4<float>(dp, o);
-              else for (int e = 0; e < valid; ++e) dp[e] = o[e];
+              else {
+#pragma unroll
+                for (int e = 0; e < 4; ++e) if (e < valid) dp[e] = o[e];
+              }
             }
           }
         }
