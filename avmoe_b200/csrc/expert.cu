@@ -756,7 +756,9 @@ static int pow2_floor(int v) { int p = 1; while (p * 2 <= v) p *= 2; return p; }
 // rows per token tile: `nbuf` fp32 [TN][C+4] buffers should stay near 100 KiB so two CTAs share an SM; wide channels
 // (stage 3/4) would then get tiles of a few tokens whose per-tile weight traffic dominates, so they may use up to ~190 KiB.
 static int pick_tn(int C, int nbuf) {
-  int tn = ((nbuf >= 4 ? 64 : 100) * 1024 / 4) / (nbuf * (C + 4));
+  static int kb_override = -1;   // diagnostics: AVMOE_TILE_KB overrides the shared-memory budget per CTA
+  if (kb_override < 0) { const char* e = getenv("AVMOE_TILE_KB"); kb_override = e ? atoi(e) : 0; }
+  int tn = ((kb_override ? kb_override : (nbuf >= 4 ? 64 : 100)) * 1024 / 4) / (nbuf * (C + 4));
   if (tn < 16) tn = (190 * 1024 / 4) / (nbuf * (C + 4));
   if (tn < 1) tn = 1;
   if (tn > 64) tn = 64;

@@ -3,7 +3,7 @@
 // Product path: a persistent, warp-specialised tcgen05 kernel for sm_100a
 //   warp 0     TMA producer   (cp.async.bulk.tensor 3-D tiles, 128/64/32-byte swizzle, OOB zero fill)
 //   warp 1     MMA issuer     (one elected lane: tcgen05.mma.cta_group::1, M=128, N<=256, fp32 accum in TMEM)
-//   warps 2-5  epilogue       (tcgen05.ld 32x32b -> bias/scale -> vectorised or atomic global stores)
+//   warps 2-9  epilogue       (tcgen05.ld 32x32b -> smem transpose -> bias/scale -> coalesced 16-byte or atomic global stores)
 // with a multi-stage smem ring (full/empty mbarriers) and TWO accumulator stages in TMEM so the
 // epilogue of tile i overlaps the main loop of tile i+1.
 //
@@ -154,9 +154,9 @@ struct GemmParams {
   int atomic;
 };
 
-static constexpr int kGemmThreads = 192;
+static constexpr int kGemmThreads = 320;   // TMA warp, MMA warp, 8 epilogue warps (two per TMEM lane quarter)
 static constexpr int kBM = 128;
-static constexpr int kStagingBytes = 17408;   // 4 epilogue warps x [32][33] fp32 (rounded to 1 KiB)
+static constexpr int kStagingBytes = 34816;   // 8 epilogue warps x [32][33] fp32 (rounded to 1 KiB)
 
 template <bool kTf32>
 __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tcgen05_kernel(const __grid_constant__ GemmParams p) {
@@ -185,7 +185,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tcgen05_kernel(const __g
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(smem_u32(&tmem_full[s]), 1);
-      mbar_init(smem_u32(&tmem_empty[s]), 4);
+      mbar_init(smem_u32(&tmem_empty[s]), 8);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -282,8 +282,9 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tcgen05_kernel(const __g
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
   } else {
-    // ===================== epilogue (warps 2..5) =====================
+    // ===================== epilogue (warps 2..9) =====================
     const int quarter = warp & 3;  // TMEM lane quarter this warp may access
+    const int half = (warp - 2) >> 2;  // the two warps of a quarter take alternate 32-column slabs
     int acc = 0;
     uint32_t acc_phase = 0;
     float* stg = reinterpret_cast<float*>(staging) + (warp - 2) * (32 * 33);   // per-warp [32][33] transpose slab
@@ -302,7 +303,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tcgen05_kernel(const __g
       const long long m = mrow0 + lane;
       const bool add_bias = (split == 0);
       const float rb = (add_bias && p.row_bias && m < p.M) ? p.row_bias[m] : 0.f;
-      for (int g = 0; g < p.BN / 32; ++g) {
+      for (int g = half; g < p.BN / 32; g += 2) {
         const long long ng = (long long)n0 + g * 32;
         if (ng >= p.N || mrow0 >= p.M) break;   // warp-uniform
         uint32_t r[32];

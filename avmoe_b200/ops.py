@@ -176,11 +176,25 @@ def bgemm(A: torch.Tensor, B: torch.Tensor, *, a_kmajor: bool = True, b_kmajor: 
 
 
 # ------------------------------------------------------------------------------------------------ layout helpers
-def _lib_call(name, *args):
+KERNEL_PROFILE = None   # set to a list to collect (name, start_event, end_event, algorithmic_bytes) per C-ABI call
+
+
+def _lib_call(name, *args, _bytes: float = 0.0):
     global LAUNCHES
     LAUNCHES += _KERNELS_PER_CALL.get(name, 1)
     fn = getattr(_lib.load(), "avmoe_" + name)
+    if KERNEL_PROFILE is not None:
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
+        _lib.check(fn(*args), name)
+        ev1.record()
+        KERNEL_PROFILE.append((name, ev0, ev1, float(_bytes)))
+        return
     _lib.check(fn(*args), name)
+
+
+def _nbytes(*ts):
+    return float(sum(t.numel() * t.element_size() for t in ts if t is not None))
 
 
 def transpose(t: torch.Tensor, out_dtype: Optional[torch.dtype] = None) -> torch.Tensor:
@@ -190,7 +204,7 @@ def transpose(t: torch.Tensor, out_dtype: Optional[torch.dtype] = None) -> torch
     b, R, Cc = t.shape
     out = torch.empty((b, Cc, R), device=t.device, dtype=out_dtype or t.dtype)
     _lib_call("transpose", _ptr(t), _ptr(out), b, R, Cc, C.c_int64(Cc), C.c_int64(R * Cc), C.c_int64(R), C.c_int64(R * Cc),
-              _dt(t), _dt(out), _stream())
+              _dt(t), _dt(out), _stream(), _bytes=_nbytes(t, out))
     return out
 
 
@@ -224,7 +238,8 @@ def reduce_bias(d: torch.Tensor, col_weight=None, row_weight=None):
     rows_w = torch.empty(N, **f32)
     cols = torch.empty(Cc, **f32)
     cols_w = torch.empty(Cc, **f32) if row_weight is not None else None
-    _lib_call("reduce_bias", _ptr(d), _ptr(col_weight), _ptr(row_weight), _ptr(rows_w), _ptr(cols), _ptr(cols_w), BT, N, Cc, _dt(d), _stream())
+    _lib_call("reduce_bias", _ptr(d), _ptr(col_weight), _ptr(row_weight), _ptr(rows_w), _ptr(cols), _ptr(cols_w), BT, N, Cc, _dt(d), _stream(),
+              _bytes=_nbytes(d))
     return rows_w, cols, cols_w
 
 
@@ -241,7 +256,7 @@ def pool(x: torch.Tensor) -> torch.Tensor:
     BT, N, Cc = x.shape
     chunks = _lib.load().avmoe_pool_chunks(BT, N)
     part = torch.empty((BT, chunks, Cc), device=x.device, dtype=torch.float32)
-    _lib_call("pool", _ptr(x), _ptr(part), BT, N, Cc, chunks, _dt(x), _stream())
+    _lib_call("pool", _ptr(x), _ptr(part), BT, N, Cc, chunks, _dt(x), _stream(), _bytes=_nbytes(x))
     return part
 
 
@@ -311,7 +326,7 @@ def latent_fwd(kv, tokens, slots, tokp, lse):
     nws = lib.avmoe_latent_fwd_workspace(BT, Nk, Cc, T, len(tokens))
     ws = torch.empty(nws, device=kv.device, dtype=torch.float32)
     _lib_call("latent_fwd", _ptr(kv), _ptr_array(tokens), (C.c_int * len(slots))(*slots), len(tokens), nl, _ptr(tokp), _ptr(lse), _ptr(ws),
-              BT, Nk, Cc, T, _dt(kv), _stream())
+              BT, Nk, Cc, T, _dt(kv), _stream(), _bytes=_nbytes(kv))
 
 
 def latent_bwd(kv, tokens, slots, tokp, lse, dtokp, dpool, dkv, accumulate, dtokens):
@@ -320,7 +335,7 @@ def latent_bwd(kv, tokens, slots, tokp, lse, dtokp, dpool, dkv, accumulate, dtok
     nl = tokp.shape[1]
     tokens = [t.contiguous() for t in tokens]
     _lib_call("latent_bwd", _ptr(kv), _ptr_array(tokens), (C.c_int * len(slots))(*slots), len(tokens), nl, _ptr(tokp), _ptr(lse), _ptr(dtokp),
-              _ptr(dpool), _ptr(dkv), int(bool(accumulate)), _ptr_array(dtokens), BT, Nk, Cc, T, _dt(kv), _stream())
+              _ptr(dpool), _ptr(dkv), int(bool(accumulate)), _ptr_array(dtokens), BT, Nk, Cc, T, _dt(kv), _stream(), _bytes=_nbytes(kv, dkv))
 
 
 # ------------------------------------------------------------------------------------------------ expert kernels
@@ -363,7 +378,7 @@ def expert_front_fwd(cfg, x, tokp, packs, z, stats1):
     _require_cuda(x)
     a, keep = _expert_args(cfg, packs, BT=x.shape[0], dtype=_dt(x), nl=0 if tokp is None else tokp.shape[1])
     _set(a, x=x, tokp=tokp, z=z, stats1=stats1)
-    _lib_call("expert_front_fwd", C.byref(a), _stream())
+    _lib_call("expert_front_fwd", C.byref(a), _stream(), _bytes=_nbytes(x, z))
 
 
 def bn1_finalize(cfg, stats1, n, bn_w, bn_b, train):
@@ -409,7 +424,7 @@ def bn_moments(cfg, z, aff1, packs):
     m2 = torch.empty((cfg.E, cfg.G, crg, crg), device=z.device, dtype=torch.float64)
     a, keep = _expert_args(cfg, packs, BT=z.shape[0], dtype=F32, bn_mode=1)
     _set(a, z=z, aff1=aff1)
-    _lib_call("bn_moments", C.byref(a), _ptr(m1), _ptr(m2), _stream())
+    _lib_call("bn_moments", C.byref(a), _ptr(m1), _ptr(m2), _stream(), _bytes=_nbytes(z))
     return m1, m2
 
 
@@ -423,28 +438,28 @@ def expert_back_fwd(cfg, z, bn, packs, probs, out):
     a, keep = _expert_args(cfg, packs, BT=z.shape[0], dtype=_dt(out), bn_mode=_bn_mode_of(bn))
     _set(a, z=z, probs=probs, out=out)
     _bn_tensors(a, bn)
-    _lib_call("expert_back_fwd", C.byref(a), _stream())
+    _lib_call("expert_back_fwd", C.byref(a), _stream(), _bytes=_nbytes(z, out))
 
 
 def expert_back_bwd_stats(cfg, dout, z, bn, packs, probs, red2):
     a, keep = _expert_args(cfg, packs, BT=z.shape[0], dtype=_dt(dout), bn_mode=1)
     _set(a, z=z, probs=probs, dout=dout, red2=red2)
     _bn_tensors(a, bn)
-    _lib_call("expert_back_bwd_stats", C.byref(a), _stream())
+    _lib_call("expert_back_bwd_stats", C.byref(a), _stream(), _bytes=_nbytes(dout, z))
 
 
 def expert_back_bwd(cfg, dout, z, bn, bn_mode, red2, red2b, packs, probs, dzt, dprobs, red1, egr):
     a, keep = _expert_args(cfg, packs, egr, BT=z.shape[0], dtype=_dt(dout), bn_mode=bn_mode)
     _set(a, z=z, probs=probs, dout=dout, red2=red2, red2b=red2b, red1=red1, dzt=dzt, dprobs=dprobs)
     _bn_tensors(a, bn)
-    _lib_call("expert_back_bwd", C.byref(a), _stream())
+    _lib_call("expert_back_bwd", C.byref(a), _stream(), _bytes=_nbytes(dout, z, dzt))
 
 
 def expert_front_bwd(cfg, x, tokp, dzt, z, bn, bn_mode, red1, packs, dpool_x, dx, dtokp, egr):
     a, keep = _expert_args(cfg, packs, egr, BT=x.shape[0], dtype=_dt(x), bn_mode=bn_mode, nl=0 if tokp is None else tokp.shape[1])
     _set(a, x=x, tokp=tokp, z=z, dzt=dzt, red1=red1, dpool_x=dpool_x, dx=dx, dtokp=dtokp)
     _bn_tensors(a, bn)
-    _lib_call("expert_front_bwd", C.byref(a), _stream())
+    _lib_call("expert_front_bwd", C.byref(a), _stream(), _bytes=_nbytes(x, z, dzt, dx))
 
 
 # ------------------------------------------------------------------------------------------------ variant pre-transforms

@@ -202,32 +202,50 @@ def run_ours(args):
     e2e = {"value": tokens_per_step * world / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d_bytes * world,
            "d2h_bytes_per_step": 4 * world, "ms_per_step": ms_e2e}
 
-    # ---- roofline of the dominant kernel (tcgen05 resampler GEMM), measured live with CUDA events -------------------
+    # ---- roofline: per-kernel CUDA-event timing of one extra (untimed) step, on the launching stream ---------------------
     roofline = None
+    kernel_table = None
     if rank == 0:
-        ops.GEMM_PROFILE = []
+        ops.GEMM_PROFILE, ops.KERNEL_PROFILE = [], []
         step(tokens_dev)
         torch.cuda.synchronize()
-        prof, ops.GEMM_PROFILE = ops.GEMM_PROFILE, None
-        tot_ms = sum(a.elapsed_time(b) for a, b, *_ in prof)
-        tot_flops = sum(p[2] for p in prof)
+        gprof, kprof = ops.GEMM_PROFILE, ops.KERNEL_PROFILE
+        ops.GEMM_PROFILE = ops.KERNEL_PROFILE = None
         peaks = {}
         try:
             peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
         except Exception:
             pass
-        peak = peaks.get("bf16_tflops_sustained") if dtype == torch.bfloat16 else None
-        peak_src = "MEASURED_PEAKS.json bf16_tflops_sustained (kernel timed inside a long step)"
-        if dtype == torch.bfloat16 and peak is None:
-            peak, peak_src = 1400.0, "fallback (B200_PROFILING.md sustained figure)"
-        if dtype == torch.float32:
-            peak = (peaks.get("bf16_tflops_sustained") or 1400.0) / 2.0
-            peak_src = "half of the measured bf16 sustained peak (TF32 runs at half the bf16 rate)"
-        ach = tot_flops / (tot_ms * 1e-3) / 1e12 if tot_ms > 0 else 0.0
-        roofline = {"bound": "tensor", "kernel": "gemm_tcgen05_kernel (token resampler conv_adapter+fc, fwd+dgrad+wgrad)",
-                    "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak if peak else None, "traffic": None,
-                    "launches_per_step": len(prof), "avg_launch_ms": tot_ms / max(len(prof), 1), "gemm_ms_per_step": tot_ms,
-                    "gemm_share_of_step": tot_ms / ms_per_step, "algorithmic_flops_per_step": tot_flops, "peak_source": peak_src}
+        hbm_peak = peaks.get("hbm_gbs", 6650.0)
+        tc_peak = peaks.get("bf16_tflops_sustained", 1400.0) * (1.0 if dtype == torch.bfloat16 else 0.5)
+        peak_src = "MEASURED_PEAKS.json" if peaks else "fallback (B200_PROFILING.md)"
+        agg = {}
+        for name, e0, e1, nbytes in kprof:
+            a = agg.setdefault(name, dict(ms=0.0, n=0, bytes=0.0))
+            a["ms"] += e0.elapsed_time(e1); a["n"] += 1; a["bytes"] += nbytes
+        g_ms = sum(a.elapsed_time(b) for a, b, *_ in gprof)
+        g_fl = sum(p[2] for p in gprof)
+        agg["gemm_tcgen05"] = dict(ms=g_ms, n=len(gprof), bytes=sum(p[3] for p in gprof), flops=g_fl)
+        tot_ms = sum(a["ms"] for a in agg.values())
+        kernel_table = {k: {"launches": v["n"], "ms": round(v["ms"], 3), "share": round(v["ms"] / tot_ms, 4),
+                            **({"GBps": round(v["bytes"] / v["ms"] / 1e6, 1)} if v["bytes"] and k != "gemm_tcgen05" else {}),
+                            **({"TFLOPs": round(v["flops"] / v["ms"] / 1e9, 1)} if "flops" in v else {})}
+                        for k, v in sorted(agg.items(), key=lambda kv: -kv[1]["ms"])}
+        dom = max(agg, key=lambda k: agg[k]["ms"])
+        d = agg[dom]
+        if dom == "gemm_tcgen05":
+            ach = g_fl / (g_ms * 1e-3) / 1e12
+            roofline = {"bound": "tensor", "kernel": "gemm_tcgen05_kernel (token resampler conv_adapter+fc: fwd, dgrad, wgrad)", "achieved": ach,
+                        "peak": tc_peak, "unit": "TFLOP/s", "frac": ach / tc_peak, "traffic": None}
+        else:
+            ach = d["bytes"] / (d["ms"] * 1e-3) / 1e9
+            roofline = {"bound": "hbm", "kernel": f"{dom}_kernel", "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak,
+                        "traffic": None}
+        roofline.update({"launches_per_step": d["n"], "avg_launch_ms": d["ms"] / max(d["n"], 1), "share_of_kernel_time": d["ms"] / tot_ms,
+                         "peak_source": peak_src,
+                         "gemm": {"achieved_TFLOPs": g_fl / (g_ms * 1e-3) / 1e12 if g_ms else None, "peak_TFLOPs": tc_peak,
+                                  "frac": (g_fl / (g_ms * 1e-3) / 1e12) / tc_peak if g_ms else None, "launches_per_step": len(gprof),
+                                  "ms_per_step": g_ms, "algorithmic_flops_per_step": g_fl}})
 
     # ---- CPU baseline (rank 0, N=1 only), bounded sample --------------------------------------------------------------
     cpu = None
@@ -244,7 +262,7 @@ def run_ours(args):
                 "config": {"workload": workload_name(args), "variant": args.variant, "BT_per_gpu": BT, "tokens_per_step_per_gpu": tokens_per_step,
                            "adapter_calls_per_step": 4 * len(model.sites), "parallelism": f"dp{world} (batch-sharded, grad all-reduce)" if world > 1 else "single GPU",
                            "l2": f"inputs+weights per step ({(h2d_bytes + sum(p.numel() * 4 for p in params)) / 1e6:.0f} MB) exceed the 126 MB L2; no explicit flush"},
-                "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "roofline": roofline}
+                "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "kernels": kernel_table}
         if cpu is not None:
             line["cpu_baseline"] = cpu
         print(json.dumps(line), flush=True)
