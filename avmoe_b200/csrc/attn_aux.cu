@@ -1,0 +1,225 @@
+// Softmax / elementwise kernels between the tcgen05 GEMMs of the GEMM-based latent-attention path.
+//
+// The latent cross-attention of a multimodal expert (AVMOE/AVE/nets/net_trans_v3.py:379-390) is four small
+// contractions per direction with T <= 87 latent tokens on one side.  On B200 the batched tcgen05 GEMM runs them at
+// multi-TB/s effective bandwidth, so the path is laid out as   GEMM -> softmax kernel -> GEMM   with token-major
+// logits  S1ᵀ [BT,Nk,T]  (tokens<-kv, softmax over the Nk axis = per COLUMN) and  S2 [BT,N,T]  (token<-latent, softmax
+// over T = per ROW).  These kernels are pure streaming passes over those [rows,T] matrices.
+#include "common.cuh"
+
+namespace avmoe {
+
+// ---- column softmax over the Nk rows of each sample: S [BT][Nk][T] fp32 -> P [BT][Nk][ldp] (first T columns), lse [BT][T]
+// grid BT, block 1024 (32 warps): lanes over t (T <= 128 -> up to 4 columns per lane), warps over rows.
+template <typename TP>
+__global__ void __launch_bounds__(1024) softmax_cols_kernel(const float* __restrict__ S, TP* __restrict__ P, float* __restrict__ lse, int Nk, int T,
+                                                            int lds, int ldp) {
+  __shared__ float smax[32][128];
+  __shared__ float ssum[32][128];
+  __shared__ float flse[128];
+  const int b = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const float* s = S + (long long)b * Nk * lds;
+  float mx[4], sm[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) { mx[k] = -INFINITY; sm[k] = 0.f; }
+  for (int r = warp; r < Nk; r += 32) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int t = lane + 32 * k;
+      if (t < T) {
+        const float v = s[(long long)r * lds + t];
+        const float m2 = fmaxf(mx[k], v);
+        sm[k] = sm[k] * expf(mx[k] - m2) + expf(v - m2);
+        mx[k] = m2;
+      }
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < 4; ++k) { smax[warp][lane + 32 * k] = mx[k]; ssum[warp][lane + 32 * k] = sm[k]; }
+  __syncthreads();
+  if (threadIdx.x < T) {
+    const int t = threadIdx.x;
+    float M = -INFINITY;
+    for (int w = 0; w < 32; ++w) M = fmaxf(M, smax[w][t]);
+    float L = 0.f;
+    for (int w = 0; w < 32; ++w) L += ssum[w][t] * expf(smax[w][t] - M);
+    const float l = M + logf(L);
+    flse[t] = l;
+    lse[(long long)b * T + t] = l;
+  }
+  __syncthreads();
+  TP* p = P + (long long)b * Nk * ldp;
+  for (int r = warp; r < Nk; r += 32) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int t = lane + 32 * k;
+      if (t < T) p[(long long)r * ldp + t] = from_f32<TP>(expf(s[(long long)r * lds + t] - flse[t]));
+    }
+  }
+}
+
+// ---- dS1ᵀ = A1ᵀ * (dA1ᵀ - D[b,t]);  A1ᵀ lives in the first T columns of A12 [BT][Nk][2T], dS1ᵀ is written to the second T
+template <typename TP>
+__global__ void softmax_cols_bwd_kernel(TP* __restrict__ A12, const float* __restrict__ dA, const float* __restrict__ Dt, long long rows, int Nk, int T,
+                                        int ld12, int off2, int ldd) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + warp;
+  if (row >= rows) return;
+  const long long b = row / Nk;
+  TP* a = A12 + row * ld12;
+  const float* d = dA + row * ldd;
+  const float* dt = Dt + b * T;
+  for (int t = lane; t < T; t += 32) a[off2 + t] = from_f32<TP>(to_f32(a[t]) * (d[t] - dt[t]));
+}
+
+// ---- row softmax over T: S [rows][T] fp32 -> A [rows][T]
+template <typename TP>
+__global__ void softmax_rows_kernel(const float* __restrict__ S, TP* __restrict__ A, long long rows, int T, int ld) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + warp;
+  if (row >= rows) return;
+  const float* s = S + row * ld;
+  float mx = -INFINITY;
+  for (int t = lane; t < T; t += 32) mx = fmaxf(mx, s[t]);
+  mx = warp_max(mx);
+  float sum = 0.f;
+  for (int t = lane; t < T; t += 32) sum += expf(s[t] - mx);
+  sum = warp_sum(sum);
+  const float inv = 1.f / sum;
+  for (int t = lane; t < ld; t += 32) A[row * ld + t] = from_f32<TP>(t < T ? expf(s[t] - mx) * inv : 0.f);   // padding columns are zero
+}
+
+// ---- dS = A * (dA - sum_t A*dA)
+template <typename TP>
+__global__ void softmax_rows_bwd_kernel(const TP* __restrict__ A, const float* __restrict__ dA, TP* __restrict__ dS, long long rows, int T, int ld) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + warp;
+  if (row >= rows) return;
+  float r = 0.f;
+  for (int t = lane; t < T; t += 32) r = fmaf(to_f32(A[row * ld + t]), dA[row * ld + t], r);
+  r = warp_sum(r);
+  for (int t = lane; t < ld; t += 32) dS[row * ld + t] = from_f32<TP>(t < T ? to_f32(A[row * ld + t]) * (dA[row * ld + t] - r) : 0.f);
+}
+
+// ---- out[b][i] = in[b][i] + tile[i]  (fp32) and an optional low-precision copy
+template <typename TP>
+__global__ void tile_add_kernel(const float* __restrict__ in, const float* __restrict__ tile, float* __restrict__ out, TP* __restrict__ out_lp,
+                                long long L, long long total) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const float v = in[i] + tile[i % L];
+    out[i] = v;
+    if (out_lp) out_lp[i] = from_f32<TP>(v);
+  }
+}
+
+// ---- Dt[b][t] = sum_c dR[b][t][c] * (tokp[b][t][c] - tok[t][c])   (one warp per (b,t))
+__global__ void latent_dots_kernel(const float* __restrict__ dR, const float* __restrict__ tokp, const float* __restrict__ tok, float* __restrict__ Dt,
+                                   long long rows, int T, int C) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + warp;
+  if (row >= rows) return;
+  const int t = (int)(row % T);
+  float s = 0.f;
+  for (int c = lane; c < C; c += 32) s = fmaf(dR[row * C + c], tokp[row * C + c] - tok[(long long)t * C + c], s);
+  s = warp_sum(s);
+  if (lane == 0) Dt[row] = s;
+}
+
+// ---- d[b][n][c] += vec[b][c]
+template <typename T>
+__global__ void add_rowvec_kernel(T* __restrict__ d, const float* __restrict__ vec, int N, int C) {
+  const int b = blockIdx.y;
+  const long long total = (long long)N * C;
+  T* db = d + (long long)b * total;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x)
+    db[i] = from_f32<T>(to_f32(db[i]) + vec[(long long)b * C + (int)(i % C)]);
+}
+
+// ---- out[i] += sum_b in[b][i]
+__global__ void batch_sum_add_kernel(const float* __restrict__ in, float* __restrict__ out, int BT, long long L) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < L; i += (long long)gridDim.x * blockDim.x) {
+    float s = 0.f;
+    for (int b = 0; b < BT; ++b) s += in[(long long)b * L + i];
+    out[i] += s;
+  }
+}
+
+}  // namespace avmoe
+
+using namespace avmoe;
+
+#define DISPATCH_TP(dt, ...)                                              \
+  if ((dt) == AVMOE_F32) { using TP = float; __VA_ARGS__ }                \
+  else { using TP = __nv_bfloat16; __VA_ARGS__ }
+
+extern "C" int avmoe_softmax_cols(const float* S, void* P, float* lse, int BT, int Nk, int T, int lds, int ldp, int p_dtype, avmoe_stream_t stream) {
+  AVMOE_CHECK_ARG(S && P && lse && BT > 0 && Nk > 0 && T > 0 && T <= 128 && ldp >= T && lds >= T, "softmax_cols: bad arguments (T <= 128)");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  DISPATCH_TP(p_dtype, softmax_cols_kernel<TP><<<BT, 1024, 0, st>>>(S, (TP*)P, lse, Nk, T, lds, ldp);)
+  AVMOE_LAUNCH_CHECK("softmax_cols_kernel");
+  return 0;
+}
+
+extern "C" int avmoe_softmax_cols_bwd(void* A12, const float* dA, const float* Dt, int BT, int Nk, int T, int ld12, int off2, int ldd, int p_dtype,
+                                      avmoe_stream_t stream) {
+  AVMOE_CHECK_ARG(A12 && dA && Dt && BT > 0 && Nk > 0 && T > 0 && off2 >= T && ld12 >= off2 + T && ldd >= T, "softmax_cols_bwd: bad arguments");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const long long rows = (long long)BT * Nk;
+  const unsigned grid = (unsigned)((rows + 7) / 8);
+  DISPATCH_TP(p_dtype, softmax_cols_bwd_kernel<TP><<<grid, 256, 0, st>>>((TP*)A12, dA, Dt, rows, Nk, T, ld12, off2, ldd);)
+  AVMOE_LAUNCH_CHECK("softmax_cols_bwd_kernel");
+  return 0;
+}
+
+extern "C" int avmoe_softmax_rows(const float* S, void* A, int64_t rows, int T, int ld, int p_dtype, avmoe_stream_t stream) {
+  AVMOE_CHECK_ARG(S && A && rows > 0 && T > 0 && ld >= T, "softmax_rows: bad arguments");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const unsigned grid = (unsigned)((rows + 7) / 8);
+  DISPATCH_TP(p_dtype, softmax_rows_kernel<TP><<<grid, 256, 0, st>>>(S, (TP*)A, rows, T, ld);)
+  AVMOE_LAUNCH_CHECK("softmax_rows_kernel");
+  return 0;
+}
+
+extern "C" int avmoe_softmax_rows_bwd(const void* A, const float* dA, void* dS, int64_t rows, int T, int ld, int p_dtype, avmoe_stream_t stream) {
+  AVMOE_CHECK_ARG(A && dA && dS && rows > 0 && T > 0 && ld >= T, "softmax_rows_bwd: bad arguments");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const unsigned grid = (unsigned)((rows + 7) / 8);
+  DISPATCH_TP(p_dtype, softmax_rows_bwd_kernel<TP><<<grid, 256, 0, st>>>((const TP*)A, dA, (TP*)dS, rows, T, ld);)
+  AVMOE_LAUNCH_CHECK("softmax_rows_bwd_kernel");
+  return 0;
+}
+
+extern "C" int avmoe_tile_add(const float* in, const float* tile, float* out, void* out_lp, int64_t L, int64_t total, int lp_dtype, avmoe_stream_t stream) {
+  AVMOE_CHECK_ARG(in && tile && out && L > 0 && total > 0, "tile_add: bad arguments");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const int grid = (int)min((long long)(8 * num_sms()), (long long)((total + 255) / 256));
+  DISPATCH_TP(lp_dtype, tile_add_kernel<TP><<<grid, 256, 0, st>>>(in, tile, out, (TP*)out_lp, L, total);)
+  AVMOE_LAUNCH_CHECK("tile_add_kernel");
+  return 0;
+}
+
+extern "C" int avmoe_latent_dots(const float* dR, const float* tokp, const float* tok, float* Dt, int BT, int T, int C, avmoe_stream_t stream) {
+  AVMOE_CHECK_ARG(dR && tokp && tok && Dt && BT > 0 && T > 0 && C > 0, "latent_dots: bad arguments");
+  const long long rows = (long long)BT * T;
+  latent_dots_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(dR, tokp, tok, Dt, rows, T, C);
+  AVMOE_LAUNCH_CHECK("latent_dots_kernel");
+  return 0;
+}
+
+extern "C" int avmoe_add_rowvec(void* d, const float* vec, int BT, int N, int C, int dtype, avmoe_stream_t stream) {
+  AVMOE_CHECK_ARG(d && vec && BT > 0 && N > 0 && C > 0, "add_rowvec: bad arguments");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  dim3 grid((unsigned)min((long long)64, ((long long)N * C + 255) / 256), BT);
+  if (dtype == AVMOE_F32) add_rowvec_kernel<float><<<grid, 256, 0, st>>>((float*)d, vec, N, C);
+  else add_rowvec_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>((__nv_bfloat16*)d, vec, N, C);
+  AVMOE_LAUNCH_CHECK("add_rowvec_kernel");
+  return 0;
+}
+
+extern "C" int avmoe_batch_sum_add(const float* in, float* out, int BT, int64_t L, avmoe_stream_t stream) {
+  AVMOE_CHECK_ARG(in && out && BT > 0 && L > 0, "batch_sum_add: bad arguments");
+  const int grid = (int)min((long long)(4 * num_sms()), (long long)((L + 255) / 256));
+  batch_sum_add_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(in, out, BT, L);
+  AVMOE_LAUNCH_CHECK("batch_sum_add_kernel");
+  return 0;
+}

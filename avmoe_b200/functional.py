@@ -210,6 +210,72 @@ def resample_bwd(K, cfg: AdapterConfig, o: torch.Tensor, dv: torch.Tensor, saved
 
 
 # -------------------------------------------------------------------------------------------------
+# GEMM-based latent attention (net_trans_v3.py:379-390): every contraction on the tcgen05 GEMM, streaming softmax kernels
+# between them on token-major logits.  [.,T] matrices are stored with a row pitch of Tp = round8(T) (16-byte pitches for TMA).
+# -------------------------------------------------------------------------------------------------
+def gemm_latent_fwd(K, kv: torch.Tensor, tok: torch.Tensor):
+    """tok' = tok + softmax_Nk(tok·kvᵀ)·kv.   kv [BT,Nk,C], tok [T,C] fp32 -> (tok' fp32 [BT,T,C], tok' in kv.dtype, A12)
+    where A12 [BT,Nk,2Tp] holds A1ᵀ (probabilities, token-major) in columns [0,T) and is reused by the backward."""
+    BT, Nk, C = kv.shape
+    T = tok.shape[0]
+    Tp = K.round8(T)
+    dt = kv.dtype
+    S1 = torch.empty((BT * Nk, Tp), device=kv.device, dtype=torch.float32)
+    K.gemm(kv.reshape(BT * Nk, C), K.cast_to(tok, dt), out=S1[:, :T])                    # token-major logits kv_n · tok_t
+    A12, _ = K.softmax_cols(S1.reshape(BT, Nk, Tp), T, dt)
+    R = K.bgemm(A12[:, :, :T], kv, a_kmajor=False, b_kmajor=False, out_dtype=torch.float32)   # A1·kv   [BT,T,C]
+    tokp, tokp_lp = K.tile_add(R, tok, dt)
+    return tokp, tokp_lp, A12
+
+
+def gemm_attn2_fwd(K, x: torch.Tensor, tokp_lp: torch.Tensor, T: int):
+    """x_res = softmax_T(x·tok'ᵀ)·tok'.   Returns (x_res [BT,N,C] in x.dtype, A2 [BT,N,Tp])."""
+    BT, N, C = x.shape
+    Tp = K.round8(T)
+    S2 = torch.empty((BT, N, Tp), device=x.device, dtype=torch.float32)
+    K.bgemm(x, tokp_lp, out=S2[:, :, :T])                                                # x[b]·tok'[b]ᵀ
+    A2 = K.softmax_rows(S2, T, x.dtype)
+    XR = K.bgemm(A2[:, :, :T], tokp_lp, b_kmajor=False)                                  # A2·tok'   [BT,N,C]
+    return XR, A2
+
+
+def gemm_attn2_bwd(K, x, tokp_lp, A2, dXR, T: int, dx):
+    """Backward of gemm_attn2_fwd given dXR [BT,N,C]: adds the gradient through the logits into dx, returns d tok' fp32."""
+    BT, N, C = x.shape
+    Tp = A2.shape[2]
+    f32 = torch.float32
+    dA2 = torch.empty((BT, N, Tp), device=x.device, dtype=f32)
+    K.bgemm(dXR, tokp_lp, out=dA2[:, :, :T])                                             # dXR[b]·tok'[b]ᵀ
+    dS2 = K.softmax_rows_bwd(A2, dA2, T)
+    K.add_into(dx, K.bgemm(dS2[:, :, :T], tokp_lp, b_kmajor=False))                      # dx += dS2·tok'
+    dtokp = K.bgemm(A2[:, :, :T], dXR, a_kmajor=False, b_kmajor=False, out_dtype=f32)    # A2ᵀ·dXR   [BT,T,C]
+    K.add_into(dtokp, K.bgemm(dS2[:, :, :T], x, a_kmajor=False, b_kmajor=False, out_dtype=f32))   # + dS2ᵀ·x
+    return dtokp
+
+
+def gemm_latent_bwd(K, kv, tok, tokp, A12, dtokp, T: int):
+    """Backward of gemm_latent_fwd given d tok' [BT,T,C] fp32.  Returns (dkv [BT,Nk,C] in kv.dtype, d tok [T,C] fp32)."""
+    BT, Nk, C = kv.shape
+    Tp = A12.shape[2] // 2
+    dt = kv.dtype
+    f32 = torch.float32
+    Dt = K.latent_dots(dtokp, tokp, tok)                                                 # sum_c dR·R  [BT,T]
+    dR_lp = K.cast_to(dtokp, dt)
+    dA1 = torch.empty((BT, Nk, Tp), device=kv.device, dtype=f32)
+    K.bgemm(kv, dR_lp, out=dA1[:, :, :T])                                                # kv[b]·dR[b]ᵀ  (token-major)
+    K.softmax_cols_bwd(A12, dA1, Dt, T)                                                  # A12[:, :, Tp:Tp+T] = dS1ᵀ
+    B12 = torch.zeros((BT, 2 * Tp, C), device=kv.device, dtype=dt)                       # [dR ; tok] stacked along K
+    B12[:, :T] = dR_lp
+    B12[:, Tp:Tp + T] = K.cast_to(tok, dt)
+    dkv = K.bgemm(A12, B12, b_kmajor=False)                                              # A1ᵀ·dR + dS1ᵀ·tok   [BT,Nk,C]
+    dS1_flat = A12.reshape(BT * Nk, 2 * Tp)[:, Tp:Tp + T]                                # [K=(b,n), M=T]
+    dtok = K.gemm(dS1_flat, kv.reshape(BT * Nk, C), a_kmajor=False, b_kmajor=False, out_dtype=f32,
+                  split_k=K.split_k_hint(BT * Nk, T, C))                                 # sum_{b,n} dS1ᵀ·kv   [T,C]
+    K.batch_sum_add(dtokp, dtok)                                                         # d tok'/d tok = I
+    return dkv, dtok
+
+
+# -------------------------------------------------------------------------------------------------
 # the fused adapter function
 # -------------------------------------------------------------------------------------------------
 def _bn_mode(cfg: AdapterConfig, training: bool) -> int:
@@ -253,22 +319,39 @@ class MoEAdapterFunction(torch.autograd.Function):
         packs: List[ExpertPack] = []
         latent_tokens, latent_kv_is_x = [], []
         aux_saved = {}
+        aux_kind: Dict[int, str] = {}
+        gate_keys: List[Optional[str]] = []
+        use_gemm_attn = bool(getattr(K, "USE_GEMM_ATTENTION", False))
         for e, (pfx, (pre, relu)) in enumerate(zip(prefixes, kinds)):
             pk = ExpertPack(pre_kind=pre, relu=relu)
             multimodal = e < cfg.Mm
+            gate_key = None
             if pre == PRE_LATENT:
-                pk.latent_slot = len(latent_tokens)
-                latent_tokens.append(P[pfx + "my_tokens"])
-                latent_kv_is_x.append(not multimodal)
-                pk.gate_pre = P[pfx + ("gate_av" if multimodal else "gate_self")]
+                gate_key = "gate_av" if multimodal else "gate_self"
+                pk.gate_pre = P[pfx + gate_key]
+                if use_gemm_attn:   # latent attention on the tensor-core GEMM; the expert kernels see x + gate*x_res as an aux-add
+                    kv = v if multimodal else x
+                    tokp_e, tokp_lp, A12 = gemm_latent_fwd(K, kv, P[pfx + "my_tokens"])
+                    pk.aux, A2 = gemm_attn2_fwd(K, x, tokp_lp, T)
+                    pk.pre_kind = PRE_AUX_ADD
+                    aux_saved[e] = (not multimodal, tokp_e, tokp_lp, A12, A2)
+                    aux_kind[e] = "latent_gemm"
+                else:
+                    pk.latent_slot = len(latent_tokens)
+                    latent_tokens.append(P[pfx + "my_tokens"])
+                    latent_kv_is_x.append(not multimodal)
             elif pre == PRE_AUX_ADD:      # AVVP NxN token self-attention (mgn.py:132-139)
                 pk.aux, lse_rows = K.selfattn_nxn_fwd(x)
                 aux_saved[e] = lse_rows
-                pk.gate_pre = P[pfx + "gate_av"]
+                aux_kind[e] = "nxn"
+                gate_key = "gate_av"
+                pk.gate_pre = P[pfx + gate_key]
             elif pre == PRE_AUX_REPLACE:  # AVS v1 MHA over the BT axis (PVT_AVSModel_v2.py:212-215)
                 mp = [P[pfx + "self_attention." + n] for n in ("in_proj_weight", "in_proj_bias", "out_proj.weight", "out_proj.bias")]
                 pk.aux, mha_saved = K.mha_fwd(x, mp)
                 aux_saved[e] = mha_saved
+                aux_kind[e] = "mha"
+            gate_keys.append(gate_key)
             if cfg.ln_before:
                 pk.ln1_w, pk.ln1_b = P[pfx + "ln_before.weight"], P[pfx + "ln_before.bias"]
             if cfg.ln_post:
@@ -320,6 +403,8 @@ class MoEAdapterFunction(torch.autograd.Function):
         ctx.bn_mode = bn_mode
         ctx.rs_saved = rs_saved
         ctx.aux_saved = aux_saved
+        ctx.aux_kind = aux_kind
+        ctx.gate_keys = gate_keys
         ctx.latent_kv_is_x = latent_kv_is_x
         ctx.packs_meta = [(pk.pre_kind, pk.relu, pk.latent_slot) for pk in packs]
         ctx.bn = bn
@@ -352,10 +437,8 @@ class MoEAdapterFunction(torch.autograd.Function):
             multimodal = e < cfg.Mm
             pk = ExpertPack(pre_kind=pre, relu=relu, latent_slot=slot, aux=ctx.aux[e])
             g = ExpertGrads()
-            if pre == PRE_LATENT:
-                pk.gate_pre = P[pfx + ("gate_av" if multimodal else "gate_self")]
-            elif pre == PRE_AUX_ADD:
-                pk.gate_pre = P[pfx + "gate_av"]
+            if ctx.gate_keys[e] is not None:
+                pk.gate_pre = P[pfx + ctx.gate_keys[e]]
             if pk.gate_pre is not None:
                 g.gate_pre = torch.zeros(1, device=dev, dtype=f32)
             if pre in (PRE_AUX_ADD, PRE_AUX_REPLACE):
@@ -400,17 +483,31 @@ class MoEAdapterFunction(torch.autograd.Function):
         dtokp = torch.zeros((BT, nl, T, C), device=dev, dtype=f32) if nl else None
         dx = torch.empty_like(x)
         K.expert_front_bwd(cfg, x, tokp, dzt, z, ctx.bn, bn_mode, red1, packs, dpool_x, dx, dtokp, egr)
-        # 4. separate pre-transform kernels
+        # 4. separate pre-transform kernels (AVVP NxN attention, AVS-v1 MHA) and the GEMM-based latent attention
+        dv = None
         for e, (pfx, pk) in enumerate(zip(prefixes, packs)):
-            if pk.pre_kind == PRE_AUX_ADD:
+            kind = ctx.aux_kind.get(e)
+            if kind == "nxn":
                 K.selfattn_nxn_bwd(x, ctx.aux_saved[e], egr[e].aux, dx)          # accumulates into dx
-            elif pk.pre_kind == PRE_AUX_REPLACE:
+            elif kind == "mha":
                 mp = [P[pfx + "self_attention." + n] for n in ("in_proj_weight", "in_proj_bias", "out_proj.weight", "out_proj.bias")]
                 dmp = K.mha_bwd(x, mp, ctx.aux_saved[e], egr[e].aux, dx)         # accumulates into dx
                 for n, g in zip(("in_proj_weight", "in_proj_bias", "out_proj.weight", "out_proj.bias"), dmp):
                     grads[pfx + "self_attention." + n] = g
-        # 5. latent attention backward -> dv (and dx for latent-self), d my_tokens
-        dv = None
+            elif kind == "latent_gemm":
+                kv_is_x, tokp_e, tokp_lp, A12, A2 = ctx.aux_saved[e]
+                dtokp_e = gemm_attn2_bwd(K, x, tokp_lp, A2, egr[e].aux, T, dx)   # adds into dx
+                dkv, dtok = gemm_latent_bwd(K, x if kv_is_x else v, P[pfx + "my_tokens"], tokp_e, A12, dtokp_e, T)
+                grads[pfx + "my_tokens"] = dtok
+                if kv_is_x:
+                    K.add_into(dx, dkv)
+                elif dv is None:
+                    dv = dkv
+                else:
+                    K.add_into(dv, dkv)
+        if dv is not None:
+            K.add_rowvec(dv, dpool_v)                                            # router path: d mean_N(v)
+        # 5. fused latent attention backward (when the GEMM path is off) -> dv (and dx for latent-self), d my_tokens
         if nl:
             dtokens = [torch.zeros((T, C), device=dev, dtype=f32) for _ in range(nl)]
             toks = [None] * nl
@@ -446,8 +543,7 @@ class MoEAdapterFunction(torch.autograd.Function):
             if g.gate is not None:
                 grads[pfx + "gate"] = g.gate
             if g.gate_pre is not None:
-                key = "gate_av" if (multimodal or cfg.self_attn == "nxn") else "gate_self"
-                grads[pfx + key] = g.gate_pre
+                grads[pfx + ctx.gate_keys[e]] = g.gate_pre
             grads[pfx + "down_sampler.weight"] = g.wd.reshape(Cr, C // G, 1, 1)
             grads[pfx + "up_sampler.weight"] = g.wu.reshape(C, Cr // G, 1, 1)
             if cfg.ln_before:

@@ -138,7 +138,7 @@ def gemm(A: torch.Tensor, B: torch.Tensor, *, a_kmajor: bool = True, b_kmajor: b
 
 
 def bgemm(A: torch.Tensor, B: torch.Tensor, *, a_kmajor: bool = True, b_kmajor: bool = True, out_dtype: Optional[torch.dtype] = None,
-          alpha: float = 1.0, col_bias: Optional[torch.Tensor] = None, impl: int = 0) -> torch.Tensor:
+          alpha: float = 1.0, col_bias: Optional[torch.Tensor] = None, impl: int = 0, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """Fully batched GEMM: D[b] = alpha * op(A[b]) · op(B[b])ᵀ for independent problems b.
     A [b,M,K] (a_kmajor) or [b,K,M];  B [b,N,K] (b_kmajor) or [b,K,N];  D [b,M,N]."""
     _require_cuda(A, B)
@@ -148,7 +148,9 @@ def bgemm(A: torch.Tensor, B: torch.Tensor, *, a_kmajor: bool = True, b_kmajor: 
     M, K = (A.shape[1], A.shape[2]) if a_kmajor else (A.shape[2], A.shape[1])
     N, Kb = (B.shape[1], B.shape[2]) if b_kmajor else (B.shape[2], B.shape[1])
     assert K == Kb
-    out = torch.empty((nb, M, N), device=A.device, dtype=out_dtype or A.dtype)
+    if out is None:
+        out = torch.empty((nb, M, N), device=A.device, dtype=out_dtype or A.dtype)
+    assert out.stride(-1) == 1 and out.shape[0] == nb
     a = _lib.GemmArgs()
     a.dtype, a.d_dtype = _dt(A), _dt(out)
     a.M, a.N, a.K, a.Nb = M, N, K, 0
@@ -460,6 +462,84 @@ def expert_front_bwd(cfg, x, tokp, dzt, z, bn, bn_mode, red1, packs, dpool_x, dx
     _set(a, x=x, tokp=tokp, z=z, dzt=dzt, red1=red1, dpool_x=dpool_x, dx=dx, dtokp=dtokp)
     _bn_tensors(a, bn)
     _lib_call("expert_front_bwd", C.byref(a), _stream(), _bytes=_nbytes(x, z, dzt, dx))
+
+
+# ------------------------------------------------------------------------------------------------ GEMM-based latent attention helpers
+USE_GEMM_ATTENTION = True   # latent attention through tcgen05 GEMMs + streaming softmax kernels (functional.py "gemm attention")
+
+
+def round8(t: int) -> int:
+    return (t + 7) // 8 * 8
+
+
+def cast_to(t: torch.Tensor, dtype: torch.dtype) -> torch.Tensor:
+    if t.dtype == dtype:
+        return t
+    t = t.contiguous()
+    out = torch.empty(t.shape, device=t.device, dtype=dtype)
+    _lib_call("cast", _ptr(t), _ptr(out), C.c_int64(t.numel()), _dt(t), _dt(out), _stream())
+    return out
+
+
+def softmax_cols(S: torch.Tensor, T: int, dtype: torch.dtype):
+    """S [BT,Nk,Tp] fp32 (first T columns valid) -> A12 [BT,Nk,2*Tp] (A1ᵀ in columns [0,T), rest zero), lse [BT,T]."""
+    BT, Nk, Tp = S.shape
+    A12 = torch.zeros((BT, Nk, 2 * Tp), device=S.device, dtype=dtype)
+    lse = torch.empty((BT, T), device=S.device, dtype=torch.float32)
+    _lib_call("softmax_cols", _ptr(S), _ptr(A12), _ptr(lse), BT, Nk, T, Tp, 2 * Tp, _dt(A12), _stream(), _bytes=_nbytes(S) + _nbytes(A12) / 2)
+    return A12, lse
+
+
+def softmax_cols_bwd(A12: torch.Tensor, dA: torch.Tensor, Dt: torch.Tensor, T: int):
+    BT, Nk, Tp2 = A12.shape
+    _lib_call("softmax_cols_bwd", _ptr(A12), _ptr(dA), _ptr(Dt), BT, Nk, T, Tp2, Tp2 // 2, dA.shape[2], _dt(A12), _stream(),
+              _bytes=_nbytes(dA) + _nbytes(A12))
+
+
+def softmax_rows(S: torch.Tensor, T: int, dtype: torch.dtype) -> torch.Tensor:
+    BT, N, Tp = S.shape
+    A = torch.empty((BT, N, Tp), device=S.device, dtype=dtype)
+    _lib_call("softmax_rows", _ptr(S), _ptr(A), C.c_int64(BT * N), T, Tp, _dt(A), _stream(), _bytes=_nbytes(S, A))
+    return A
+
+
+def softmax_rows_bwd(A: torch.Tensor, dA: torch.Tensor, T: int) -> torch.Tensor:
+    BT, N, Tp = A.shape
+    dS = torch.empty_like(A)
+    _lib_call("softmax_rows_bwd", _ptr(A), _ptr(dA), _ptr(dS), C.c_int64(BT * N), T, Tp, _dt(A), _stream(), _bytes=_nbytes(A, dA, dS))
+    return dS
+
+
+def tile_add(R: torch.Tensor, tile: torch.Tensor, dtype: torch.dtype):
+    out = torch.empty_like(R)
+    out_lp = torch.empty(R.shape, device=R.device, dtype=dtype) if dtype != torch.float32 else None
+    tile = tile.contiguous()
+    _lib_call("tile_add", _ptr(R), _ptr(tile), _ptr(out), _ptr(out_lp), C.c_int64(tile.numel()), C.c_int64(R.numel()),
+              BF16 if out_lp is not None else F32, _stream())
+    return out, (out_lp if out_lp is not None else out)
+
+
+def latent_dots(dR, tokp, tok):
+    BT, T, Cc = dR.shape
+    Dt = torch.empty((BT, T), device=dR.device, dtype=torch.float32)
+    _lib_call("latent_dots", _ptr(dR), _ptr(tokp), _ptr(tok.contiguous()), _ptr(Dt), BT, T, Cc, _stream())
+    return Dt
+
+
+def batch_sum_add(t, out):
+    """out[...] += sum over the leading axis of t (fp32)."""
+    t = t.contiguous()
+    _lib_call("batch_sum_add", _ptr(t), _ptr(out), t.shape[0], C.c_int64(out.numel()), _stream())
+
+
+def add_rowvec(d, vec):
+    BT, N, Cc = d.shape
+    _lib_call("add_rowvec", _ptr(d), _ptr(vec), BT, N, Cc, _dt(d), _stream(), _bytes=2 * _nbytes(d))
+
+
+def add_into(dst, a, b=None, c=None):
+    _lib_call("add_into", _ptr(dst), _ptr(a), _ptr(b), _ptr(c), C.c_int64(dst.numel()), _dt(dst), _stream(),
+              _bytes=2 * _nbytes(dst) + _nbytes(a, b, c))
 
 
 # ------------------------------------------------------------------------------------------------ variant pre-transforms

@@ -230,6 +230,21 @@ int avmoe_add_into(void* dst, const void* a, const void* b, const void* c, int64
 int avmoe_mha_attn_fwd(const float* qkv, void* ctx, int L, int NB, int C, int heads, int dtype, avmoe_stream_t stream);
 int avmoe_mha_attn_bwd(const float* qkv, const float* dctx, void* dqkv, int L, int NB, int C, int heads, int dtype, avmoe_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------
+ * GEMM-based latent attention (the product path for multimodal / latent-self experts; AVMOE/AVE/nets/net_trans_v3.py:379-390):
+ * the contractions are avmoe_gemm calls (flat, fully-batched); these are the streaming softmax passes between them on the
+ * token-major logits S1^T [BT,Nk,T] (softmax over Nk, per column) and S2 [BT,N,T] (softmax over T, per row).
+ * ------------------------------------------------------------------------------------------ */
+int avmoe_softmax_cols(const float* S, void* P, float* lse, int BT, int Nk, int T, int lds, int ldp, int p_dtype, avmoe_stream_t stream);
+int avmoe_softmax_cols_bwd(void* A12 /* [BT,Nk,ld12]: A1^T at column 0, dS1^T written at column off2 */, const float* dA, const float* Dt, int BT,
+                           int Nk, int T, int ld12, int off2, int ldd, int p_dtype, avmoe_stream_t stream);
+int avmoe_softmax_rows(const float* S, void* A, int64_t rows, int T, int ld, int p_dtype, avmoe_stream_t stream);
+int avmoe_softmax_rows_bwd(const void* A, const float* dA, void* dS, int64_t rows, int T, int ld, int p_dtype, avmoe_stream_t stream);
+int avmoe_tile_add(const float* in, const float* tile, float* out, void* out_lp, int64_t L, int64_t total, int lp_dtype, avmoe_stream_t stream);
+int avmoe_latent_dots(const float* dR, const float* tokp, const float* tok, float* Dt, int BT, int T, int C, avmoe_stream_t stream);
+int avmoe_add_rowvec(void* d, const float* vec, int BT, int N, int C, int dtype, avmoe_stream_t stream);
+int avmoe_batch_sum_add(const float* in, float* out /* += */, int BT, int64_t L, avmoe_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

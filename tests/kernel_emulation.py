@@ -62,13 +62,81 @@ def gemm(A, B, *, a_kmajor=True, b_kmajor=True, out_dtype=None, alpha=1.0, row_b
     return D.to(out_dtype)
 
 
-def bgemm(A, B, *, a_kmajor=True, b_kmajor=True, out_dtype=None, alpha=1.0, col_bias=None, impl=0):
+def bgemm(A, B, *, a_kmajor=True, b_kmajor=True, out_dtype=None, alpha=1.0, col_bias=None, impl=0, out=None):
     Af = A.float() if a_kmajor else A.float().transpose(1, 2)
     Bf = B.float() if b_kmajor else B.float().transpose(1, 2)
     D = alpha * (Af @ Bf.transpose(1, 2))
     if col_bias is not None:
         D = D + col_bias
+    if out is not None:
+        out.copy_(D.to(out.dtype))
+        return out
     return D.to(out_dtype or A.dtype)
+
+
+# ------------------------------------------------------------------------------------------------ GEMM-based latent attention helpers
+USE_GEMM_ATTENTION = True
+
+
+def round8(t):
+    return (t + 7) // 8 * 8
+
+
+def cast_to(t, dtype):
+    return t if t.dtype == dtype else t.to(dtype)
+
+
+def softmax_cols(S, T, dtype):
+    BT, Nk, Tp = S.shape
+    A12 = torch.zeros((BT, Nk, 2 * Tp), device=S.device, dtype=dtype)
+    lse = torch.logsumexp(S[:, :, :T], dim=1)
+    A12[:, :, :T] = torch.exp(S[:, :, :T] - lse[:, None, :]).to(dtype)
+    return A12, lse
+
+
+def softmax_cols_bwd(A12, dA, Dt, T):
+    Tp = A12.shape[2] // 2
+    A12[:, :, Tp:Tp + T] = (A12[:, :, :T].float() * (dA[:, :, :T] - Dt[:, None, :])).to(A12.dtype)
+
+
+def softmax_rows(S, T, dtype):
+    A = torch.zeros(S.shape, device=S.device, dtype=dtype)
+    A[:, :, :T] = torch.softmax(S[:, :, :T], dim=-1).to(dtype)
+    return A
+
+
+def softmax_rows_bwd(A, dA, T):
+    a = A[:, :, :T].float()
+    d = dA[:, :, :T]
+    dS = torch.zeros_like(A)
+    dS[:, :, :T] = (a * (d - (a * d).sum(-1, keepdim=True))).to(A.dtype)
+    return dS
+
+
+def tile_add(R, tile, dtype):
+    out = R + tile[None]
+    return out, out.to(dtype)
+
+
+def latent_dots(dR, tokp, tok):
+    return (dR * (tokp - tok[None])).sum(-1)
+
+
+def batch_sum_add(t, out):
+    out += t.sum(0).reshape(out.shape)
+
+
+def add_rowvec(d, vec):
+    d += vec[:, None, :].to(d.dtype)
+
+
+def add_into(dst, a, b=None, c=None):
+    v = dst.float() + a.float()
+    if b is not None:
+        v = v + b.float()
+    if c is not None:
+        v = v + c.float()
+    dst.copy_(v.to(dst.dtype))
 
 
 def rowsum(w):
