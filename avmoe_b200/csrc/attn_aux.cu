@@ -9,11 +9,15 @@
 
 namespace avmoe {
 
+// Logits produced against a bf16 operand that was split into hi + lo halves (ops.split_operand) arrive as two column
+// blocks of the fp32 GEMM output: column t and column off_lo + t.  off_lo == 0 means a single block.
+__device__ __forceinline__ float logit(const float* row, int t, int off_lo) { return off_lo ? row[t] + row[off_lo + t] : row[t]; }
+
 // ---- column softmax over the Nk rows of each sample: S [BT][Nk][T] fp32 -> P [BT][Nk][ldp] (first T columns), lse [BT][T]
 // grid BT, block 1024 (32 warps): lanes over t (T <= 128 -> up to 4 columns per lane), warps over rows.
 template <typename TP>
 __global__ void __launch_bounds__(1024) softmax_cols_kernel(const float* __restrict__ S, TP* __restrict__ P, float* __restrict__ lse, int Nk, int T,
-                                                            int lds, int ldp) {
+                                                            int lds, int ldp, int off_lo, int p_lo) {
   __shared__ float smax[32][128];
   __shared__ float ssum[32][128];
   __shared__ float flse[128];
@@ -27,7 +31,7 @@ __global__ void __launch_bounds__(1024) softmax_cols_kernel(const float* __restr
     for (int k = 0; k < 4; ++k) {
       const int t = lane + 32 * k;
       if (t < T) {
-        const float v = s[(long long)r * lds + t];
+        const float v = logit(s + (long long)r * lds, t, off_lo);
         const float m2 = fmaxf(mx[k], v);
         sm[k] = sm[k] * expf(mx[k] - m2) + expf(v - m2);
         mx[k] = m2;
@@ -53,7 +57,12 @@ __global__ void __launch_bounds__(1024) softmax_cols_kernel(const float* __restr
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
       const int t = lane + 32 * k;
-      if (t < T) p[(long long)r * ldp + t] = from_f32<TP>(expf(s[(long long)r * lds + t] - flse[t]));
+      if (t < T) {
+        const float pv = expf(logit(s + (long long)r * lds, t, off_lo) - flse[t]);
+        const TP hi = from_f32<TP>(pv);
+        p[(long long)r * ldp + t] = hi;
+        if (p_lo) p[(long long)r * ldp + p_lo + t] = from_f32<TP>(pv - to_f32(hi));   // residual: R = (hi + lo)·kv keeps ~16 bits of A1
+      }
     }
   }
 }
@@ -61,7 +70,7 @@ __global__ void __launch_bounds__(1024) softmax_cols_kernel(const float* __restr
 // ---- dS1ᵀ = A1ᵀ * (dA1ᵀ - D[b,t]);  A1ᵀ lives in the first T columns of A12 [BT][Nk][2T], dS1ᵀ is written to the second T
 template <typename TP>
 __global__ void softmax_cols_bwd_kernel(TP* __restrict__ A12, const float* __restrict__ dA, const float* __restrict__ Dt, long long rows, int Nk, int T,
-                                        int ld12, int off2, int ldd) {
+                                        int ld12, int off2, int ldd, int off_lo) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + warp;
   if (row >= rows) return;
@@ -69,46 +78,50 @@ __global__ void softmax_cols_bwd_kernel(TP* __restrict__ A12, const float* __res
   TP* a = A12 + row * ld12;
   const float* d = dA + row * ldd;
   const float* dt = Dt + b * T;
-  for (int t = lane; t < T; t += 32) a[off2 + t] = from_f32<TP>(to_f32(a[t]) * (d[t] - dt[t]));
+  for (int t = lane; t < T; t += 32) a[off2 + t] = from_f32<TP>(to_f32(a[t]) * (logit(d, t, off_lo) - dt[t]));
 }
 
 // ---- row softmax over T: S [rows][T] fp32 -> A [rows][T]
 template <typename TP>
-__global__ void softmax_rows_kernel(const float* __restrict__ S, TP* __restrict__ A, long long rows, int T, int ld) {
+__global__ void softmax_rows_kernel(const float* __restrict__ S, TP* __restrict__ A, long long rows, int T, int lds, int off_lo, int ld) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + warp;
   if (row >= rows) return;
-  const float* s = S + row * ld;
+  const float* s = S + row * lds;
   float mx = -INFINITY;
-  for (int t = lane; t < T; t += 32) mx = fmaxf(mx, s[t]);
+  for (int t = lane; t < T; t += 32) mx = fmaxf(mx, logit(s, t, off_lo));
   mx = warp_max(mx);
   float sum = 0.f;
-  for (int t = lane; t < T; t += 32) sum += expf(s[t] - mx);
+  for (int t = lane; t < T; t += 32) sum += expf(logit(s, t, off_lo) - mx);
   sum = warp_sum(sum);
   const float inv = 1.f / sum;
-  for (int t = lane; t < ld; t += 32) A[row * ld + t] = from_f32<TP>(t < T ? expf(s[t] - mx) * inv : 0.f);   // padding columns are zero
+  for (int t = lane; t < ld; t += 32) A[row * ld + t] = from_f32<TP>(t < T ? expf(logit(s, t, off_lo) - mx) * inv : 0.f);   // padding columns are zero
 }
 
 // ---- dS = A * (dA - sum_t A*dA)
 template <typename TP>
-__global__ void softmax_rows_bwd_kernel(const TP* __restrict__ A, const float* __restrict__ dA, TP* __restrict__ dS, long long rows, int T, int ld) {
+__global__ void softmax_rows_bwd_kernel(const TP* __restrict__ A, const float* __restrict__ dA, TP* __restrict__ dS, long long rows, int T, int ld, int ldd,
+                                        int off_lo) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + warp;
   if (row >= rows) return;
+  const float* d = dA + row * ldd;
   float r = 0.f;
-  for (int t = lane; t < T; t += 32) r = fmaf(to_f32(A[row * ld + t]), dA[row * ld + t], r);
+  for (int t = lane; t < T; t += 32) r = fmaf(to_f32(A[row * ld + t]), logit(d, t, off_lo), r);
   r = warp_sum(r);
-  for (int t = lane; t < ld; t += 32) dS[row * ld + t] = from_f32<TP>(t < T ? to_f32(A[row * ld + t]) * (dA[row * ld + t] - r) : 0.f);
+  for (int t = lane; t < ld; t += 32) dS[row * ld + t] = from_f32<TP>(t < T ? to_f32(A[row * ld + t]) * (logit(d, t, off_lo) - r) : 0.f);
 }
 
-// ---- out[b][i] = in[b][i] + tile[i]  (fp32) and an optional low-precision copy
-template <typename TP>
-__global__ void tile_add_kernel(const float* __restrict__ in, const float* __restrict__ tile, float* __restrict__ out, TP* __restrict__ out_lp,
-                                long long L, long long total) {
+// ---- out[b][t][c] = in[b][t][c] (+ in[b][off_lo + t][c]) + tile[t][c]   (fp32; `in` has `rows` rows per sample)
+__global__ void tile_add_kernel(const float* __restrict__ in, const float* __restrict__ tile, float* __restrict__ out, int T, int C, int rows, int off_lo,
+                                long long total) {
+  const long long L = (long long)T * C;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const float v = in[i] + tile[i % L];
+    const long long b = i / L, r = i - b * L;
+    const float* src = in + b * rows * C + r;
+    float v = src[0] + tile[r];
+    if (off_lo) v += src[(long long)off_lo * C];
     out[i] = v;
-    if (out_lp) out_lp[i] = from_f32<TP>(v);
   }
 }
 
@@ -135,6 +148,21 @@ __global__ void add_rowvec_kernel(T* __restrict__ d, const float* __restrict__ v
     db[i] = from_f32<T>(to_f32(db[i]) + vec[(long long)b * C + (int)(i % C)]);
 }
 
+// ---- fp32 [G][T][C] -> bf16 [G][2*Tp][C]: rows [0,T) hold hi = bf16(v), rows [Tp,Tp+T) hold lo = bf16(v - hi)
+__global__ void cast_split_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ out, long long total, int T, int Tp, int C) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C);
+    const long long gt = i / C;
+    const int t = (int)(gt % T);
+    const long long g = gt / T;
+    const float v = in[i];
+    const __nv_bfloat16 hi = __float2bfloat16(v);
+    const long long o = (g * 2 * Tp + t) * C + c;
+    out[o] = hi;
+    out[o + (long long)Tp * C] = __float2bfloat16(v - __bfloat162float(hi));
+  }
+}
+
 // ---- out[i] += sum_b in[b][i]
 __global__ void batch_sum_add_kernel(const float* __restrict__ in, float* __restrict__ out, int BT, long long L) {
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < L; i += (long long)gridDim.x * blockDim.x) {
@@ -152,48 +180,53 @@ using namespace avmoe;
   if ((dt) == AVMOE_F32) { using TP = float; __VA_ARGS__ }                \
   else { using TP = __nv_bfloat16; __VA_ARGS__ }
 
-extern "C" int avmoe_softmax_cols(const float* S, void* P, float* lse, int BT, int Nk, int T, int lds, int ldp, int p_dtype, avmoe_stream_t stream) {
-  AVMOE_CHECK_ARG(S && P && lse && BT > 0 && Nk > 0 && T > 0 && T <= 128 && ldp >= T && lds >= T, "softmax_cols: bad arguments (T <= 128)");
+extern "C" int avmoe_softmax_cols(const float* S, void* P, float* lse, int BT, int Nk, int T, int lds, int ldp, int off_lo, int p_lo, int p_dtype,
+                              avmoe_stream_t stream) {
+  AVMOE_CHECK_ARG(S && P && lse && BT > 0 && Nk > 0 && T > 0 && T <= 128 && ldp >= T && lds >= T + off_lo && (off_lo == 0 || off_lo >= T) &&
+                      (p_lo == 0 || (p_lo >= T && ldp >= p_lo + T)),
+                  "softmax_cols: bad arguments (T <= 128)");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  DISPATCH_TP(p_dtype, softmax_cols_kernel<TP><<<BT, 1024, 0, st>>>(S, (TP*)P, lse, Nk, T, lds, ldp);)
+  DISPATCH_TP(p_dtype, softmax_cols_kernel<TP><<<BT, 1024, 0, st>>>(S, (TP*)P, lse, Nk, T, lds, ldp, off_lo, p_lo);)
   AVMOE_LAUNCH_CHECK("softmax_cols_kernel");
   return 0;
 }
 
-extern "C" int avmoe_softmax_cols_bwd(void* A12, const float* dA, const float* Dt, int BT, int Nk, int T, int ld12, int off2, int ldd, int p_dtype,
-                                      avmoe_stream_t stream) {
-  AVMOE_CHECK_ARG(A12 && dA && Dt && BT > 0 && Nk > 0 && T > 0 && off2 >= T && ld12 >= off2 + T && ldd >= T, "softmax_cols_bwd: bad arguments");
+extern "C" int avmoe_softmax_cols_bwd(void* A12, const float* dA, const float* Dt, int BT, int Nk, int T, int ld12, int off2, int ldd, int off_lo,
+                                      int p_dtype, avmoe_stream_t stream) {
+  AVMOE_CHECK_ARG(A12 && dA && Dt && BT > 0 && Nk > 0 && T > 0 && off2 >= T && ld12 >= off2 + T && ldd >= T + off_lo && (off_lo == 0 || off_lo >= T),
+                  "softmax_cols_bwd: bad arguments");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const long long rows = (long long)BT * Nk;
   const unsigned grid = (unsigned)((rows + 7) / 8);
-  DISPATCH_TP(p_dtype, softmax_cols_bwd_kernel<TP><<<grid, 256, 0, st>>>((TP*)A12, dA, Dt, rows, Nk, T, ld12, off2, ldd);)
+  DISPATCH_TP(p_dtype, softmax_cols_bwd_kernel<TP><<<grid, 256, 0, st>>>((TP*)A12, dA, Dt, rows, Nk, T, ld12, off2, ldd, off_lo);)
   AVMOE_LAUNCH_CHECK("softmax_cols_bwd_kernel");
   return 0;
 }
 
-extern "C" int avmoe_softmax_rows(const float* S, void* A, int64_t rows, int T, int ld, int p_dtype, avmoe_stream_t stream) {
-  AVMOE_CHECK_ARG(S && A && rows > 0 && T > 0 && ld >= T, "softmax_rows: bad arguments");
+extern "C" int avmoe_softmax_rows(const float* S, void* A, int64_t rows, int T, int lds, int off_lo, int ld, int p_dtype, avmoe_stream_t stream) {
+  AVMOE_CHECK_ARG(S && A && rows > 0 && T > 0 && ld >= T && lds >= T + off_lo && (off_lo == 0 || off_lo >= T), "softmax_rows: bad arguments");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const unsigned grid = (unsigned)((rows + 7) / 8);
-  DISPATCH_TP(p_dtype, softmax_rows_kernel<TP><<<grid, 256, 0, st>>>(S, (TP*)A, rows, T, ld);)
+  DISPATCH_TP(p_dtype, softmax_rows_kernel<TP><<<grid, 256, 0, st>>>(S, (TP*)A, rows, T, lds, off_lo, ld);)
   AVMOE_LAUNCH_CHECK("softmax_rows_kernel");
   return 0;
 }
 
-extern "C" int avmoe_softmax_rows_bwd(const void* A, const float* dA, void* dS, int64_t rows, int T, int ld, int p_dtype, avmoe_stream_t stream) {
-  AVMOE_CHECK_ARG(A && dA && dS && rows > 0 && T > 0 && ld >= T, "softmax_rows_bwd: bad arguments");
+extern "C" int avmoe_softmax_rows_bwd(const void* A, const float* dA, void* dS, int64_t rows, int T, int ld, int ldd, int off_lo, int p_dtype,
+                                      avmoe_stream_t stream) {
+  AVMOE_CHECK_ARG(A && dA && dS && rows > 0 && T > 0 && ld >= T && ldd >= T + off_lo && (off_lo == 0 || off_lo >= T), "softmax_rows_bwd: bad arguments");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const unsigned grid = (unsigned)((rows + 7) / 8);
-  DISPATCH_TP(p_dtype, softmax_rows_bwd_kernel<TP><<<grid, 256, 0, st>>>((const TP*)A, dA, (TP*)dS, rows, T, ld);)
+  DISPATCH_TP(p_dtype, softmax_rows_bwd_kernel<TP><<<grid, 256, 0, st>>>((const TP*)A, dA, (TP*)dS, rows, T, ld, ldd, off_lo);)
   AVMOE_LAUNCH_CHECK("softmax_rows_bwd_kernel");
   return 0;
 }
 
-extern "C" int avmoe_tile_add(const float* in, const float* tile, float* out, void* out_lp, int64_t L, int64_t total, int lp_dtype, avmoe_stream_t stream) {
-  AVMOE_CHECK_ARG(in && tile && out && L > 0 && total > 0, "tile_add: bad arguments");
-  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  const int grid = (int)min((long long)(8 * num_sms()), (long long)((total + 255) / 256));
-  DISPATCH_TP(lp_dtype, tile_add_kernel<TP><<<grid, 256, 0, st>>>(in, tile, out, (TP*)out_lp, L, total);)
+extern "C" int avmoe_tile_add(const float* in, const float* tile, float* out, int BT, int T, int C, int rows, int off_lo, avmoe_stream_t stream) {
+  AVMOE_CHECK_ARG(in && tile && out && BT > 0 && T > 0 && C > 0 && rows >= T + off_lo && (off_lo == 0 || off_lo >= T), "tile_add: bad arguments");
+  const long long total = (long long)BT * T * C;
+  const int grid = (int)min((long long)(8 * num_sms()), (total + 255) / 256);
+  tile_add_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(in, tile, out, T, C, rows, off_lo, total);
   AVMOE_LAUNCH_CHECK("tile_add_kernel");
   return 0;
 }
@@ -221,5 +254,14 @@ extern "C" int avmoe_batch_sum_add(const float* in, float* out, int BT, int64_t 
   const int grid = (int)min((long long)(4 * num_sms()), (long long)((L + 255) / 256));
   batch_sum_add_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(in, out, BT, L);
   AVMOE_LAUNCH_CHECK("batch_sum_add_kernel");
+  return 0;
+}
+
+extern "C" int avmoe_cast_split(const float* in, void* out_bf16, int64_t groups, int T, int Tp, int C, avmoe_stream_t stream) {
+  AVMOE_CHECK_ARG(in && out_bf16 && groups > 0 && T > 0 && Tp >= T && C > 0, "cast_split: bad arguments");
+  const long long total = (long long)groups * T * C;
+  const int grid = (int)min((long long)(8 * num_sms()), (total + 255) / 256);
+  cast_split_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(in, (__nv_bfloat16*)out_bf16, total, T, Tp, C);
+  AVMOE_LAUNCH_CHECK("cast_split_kernel");
   return 0;
 }

@@ -214,39 +214,36 @@ def resample_bwd(K, cfg: AdapterConfig, o: torch.Tensor, dv: torch.Tensor, saved
 # between them on token-major logits.  [.,T] matrices are stored with a row pitch of Tp = round8(T) (16-byte pitches for TMA).
 # -------------------------------------------------------------------------------------------------
 def gemm_latent_fwd(K, kv: torch.Tensor, tok: torch.Tensor):
-    """tok' = tok + softmax_Nk(tok·kvᵀ)·kv.   kv [BT,Nk,C], tok [T,C] fp32 -> (tok' fp32 [BT,T,C], tok' in kv.dtype, A12)
-    where A12 [BT,Nk,2Tp] holds A1ᵀ (probabilities, token-major) in columns [0,T) and is reused by the backward."""
+    """tok' = tok + softmax_Nk(tok·kvᵀ)·kv.   kv [BT,Nk,C], tok [T,C] fp32 -> (tok' fp32 [BT,T,C], K.split_operand(tok'),
+    A12) where A12 [BT,Nk,2Tp] holds A1ᵀ (probabilities, token-major) in columns [0,T) and is reused by the backward.
+    The fp32 latent tokens enter the logits GEMMs as split operands (K.split_operand)."""
     BT, Nk, C = kv.shape
     T = tok.shape[0]
-    Tp = K.round8(T)
     dt = kv.dtype
-    S1 = torch.empty((BT * Nk, Tp), device=kv.device, dtype=torch.float32)
-    K.gemm(kv.reshape(BT * Nk, C), K.cast_to(tok, dt), out=S1[:, :T])                    # token-major logits kv_n · tok_t
-    A12, _ = K.softmax_cols(S1.reshape(BT, Nk, Tp), T, dt)
-    R = K.bgemm(A12[:, :, :T], kv, a_kmajor=False, b_kmajor=False, out_dtype=torch.float32)   # A1·kv   [BT,T,C]
-    tokp, tokp_lp = K.tile_add(R, tok, dt)
-    return tokp, tokp_lp, A12
+    tok_s, off, _ = K.split_operand(tok, dt)                                             # [W,C]
+    S1 = K.gemm(kv.reshape(BT * Nk, C), tok_s, out_dtype=torch.float32)                  # token-major logits kv_n · tok_t  [BT*Nk,W]
+    A12, _, p_lo = K.softmax_cols(S1.reshape(BT, Nk, -1), T, off, dt)
+    A1 = A12 if p_lo else A12[:, :, :T]                                                  # bf16: hi and residual column blocks
+    R = K.bgemm(A1, kv, a_kmajor=False, b_kmajor=False, out_dtype=torch.float32)         # A1·kv   [BT,T (or 2Tp),C]
+    tokp = K.tile_add(R, tok, p_lo)
+    return tokp, K.split_operand(tokp, dt), A12
 
 
-def gemm_attn2_fwd(K, x: torch.Tensor, tokp_lp: torch.Tensor, T: int):
+def gemm_attn2_fwd(K, x: torch.Tensor, tokp_op, T: int):
     """x_res = softmax_T(x·tok'ᵀ)·tok'.   Returns (x_res [BT,N,C] in x.dtype, A2 [BT,N,Tp])."""
-    BT, N, C = x.shape
-    Tp = K.round8(T)
-    S2 = torch.empty((BT, N, Tp), device=x.device, dtype=torch.float32)
-    K.bgemm(x, tokp_lp, out=S2[:, :, :T])                                                # x[b]·tok'[b]ᵀ
-    A2 = K.softmax_rows(S2, T, x.dtype)
+    tokp_s, off, tokp_lp = tokp_op
+    S2 = K.bgemm(x, tokp_s, out_dtype=torch.float32)                                     # x[b]·tok'[b]ᵀ   [BT,N,W]
+    A2 = K.softmax_rows(S2, T, off, x.dtype)
     XR = K.bgemm(A2[:, :, :T], tokp_lp, b_kmajor=False)                                  # A2·tok'   [BT,N,C]
     return XR, A2
 
 
-def gemm_attn2_bwd(K, x, tokp_lp, A2, dXR, T: int, dx):
+def gemm_attn2_bwd(K, x, tokp_op, A2, dXR, T: int, dx):
     """Backward of gemm_attn2_fwd given dXR [BT,N,C]: adds the gradient through the logits into dx, returns d tok' fp32."""
-    BT, N, C = x.shape
-    Tp = A2.shape[2]
     f32 = torch.float32
-    dA2 = torch.empty((BT, N, Tp), device=x.device, dtype=f32)
-    K.bgemm(dXR, tokp_lp, out=dA2[:, :, :T])                                             # dXR[b]·tok'[b]ᵀ
-    dS2 = K.softmax_rows_bwd(A2, dA2, T)
+    tokp_s, off, tokp_lp = tokp_op
+    dA2 = K.bgemm(dXR, tokp_s, out_dtype=f32)                                            # dXR[b]·tok'[b]ᵀ  [BT,N,W]
+    dS2 = K.softmax_rows_bwd(A2, dA2, T, off)
     K.add_into(dx, K.bgemm(dS2[:, :, :T], tokp_lp, b_kmajor=False))                      # dx += dS2·tok'
     dtokp = K.bgemm(A2[:, :, :T], dXR, a_kmajor=False, b_kmajor=False, out_dtype=f32)    # A2ᵀ·dXR   [BT,T,C]
     K.add_into(dtokp, K.bgemm(dS2[:, :, :T], x, a_kmajor=False, b_kmajor=False, out_dtype=f32))   # + dS2ᵀ·x
@@ -260,10 +257,9 @@ def gemm_latent_bwd(K, kv, tok, tokp, A12, dtokp, T: int):
     dt = kv.dtype
     f32 = torch.float32
     Dt = K.latent_dots(dtokp, tokp, tok)                                                 # sum_c dR·R  [BT,T]
-    dR_lp = K.cast_to(dtokp, dt)
-    dA1 = torch.empty((BT, Nk, Tp), device=kv.device, dtype=f32)
-    K.bgemm(kv, dR_lp, out=dA1[:, :, :T])                                                # kv[b]·dR[b]ᵀ  (token-major)
-    K.softmax_cols_bwd(A12, dA1, Dt, T)                                                  # A12[:, :, Tp:Tp+T] = dS1ᵀ
+    dR_s, off, dR_lp = K.split_operand(dtokp, dt)                                              # [BT,W,C]
+    dA1 = K.bgemm(kv, dR_s, out_dtype=f32)                                               # kv[b]·dR[b]ᵀ  (token-major)  [BT,Nk,W]
+    K.softmax_cols_bwd(A12, dA1, Dt, T, off)                                             # A12[:, :, Tp:Tp+T] = dS1ᵀ
     B12 = torch.zeros((BT, 2 * Tp, C), device=kv.device, dtype=dt)                       # [dR ; tok] stacked along K
     B12[:, :T] = dR_lp
     B12[:, Tp:Tp + T] = K.cast_to(tok, dt)
@@ -321,7 +317,11 @@ class MoEAdapterFunction(torch.autograd.Function):
         aux_saved = {}
         aux_kind: Dict[int, str] = {}
         gate_keys: List[Optional[str]] = []
-        use_gemm_attn = bool(getattr(K, "USE_GEMM_ATTENTION", False))
+        # bf16 streams run the latent attention on the tensor-core GEMM.  fp32 streams keep the fused kernels whose
+        # contractions are exact fp32 FMAs, like the reference's torch.bmm (matmul TF32 is off by default in torch);
+        # "always" forces the GEMM path for either dtype (tests).
+        _flag = getattr(K, "USE_GEMM_ATTENTION", False)
+        use_gemm_attn = _flag == "always" or (bool(_flag) and x.dtype == torch.bfloat16)
         for e, (pfx, (pre, relu)) in enumerate(zip(prefixes, kinds)):
             pk = ExpertPack(pre_kind=pre, relu=relu)
             multimodal = e < cfg.Mm
@@ -331,10 +331,10 @@ class MoEAdapterFunction(torch.autograd.Function):
                 pk.gate_pre = P[pfx + gate_key]
                 if use_gemm_attn:   # latent attention on the tensor-core GEMM; the expert kernels see x + gate*x_res as an aux-add
                     kv = v if multimodal else x
-                    tokp_e, tokp_lp, A12 = gemm_latent_fwd(K, kv, P[pfx + "my_tokens"])
-                    pk.aux, A2 = gemm_attn2_fwd(K, x, tokp_lp, T)
+                    tokp_e, tokp_op, A12 = gemm_latent_fwd(K, kv, P[pfx + "my_tokens"])
+                    pk.aux, A2 = gemm_attn2_fwd(K, x, tokp_op, T)
                     pk.pre_kind = PRE_AUX_ADD
-                    aux_saved[e] = (not multimodal, tokp_e, tokp_lp, A12, A2)
+                    aux_saved[e] = (not multimodal, tokp_e, tokp_op, A12, A2)
                     aux_kind[e] = "latent_gemm"
                 else:
                     pk.latent_slot = len(latent_tokens)
@@ -495,8 +495,8 @@ class MoEAdapterFunction(torch.autograd.Function):
                 for n, g in zip(("in_proj_weight", "in_proj_bias", "out_proj.weight", "out_proj.bias"), dmp):
                     grads[pfx + "self_attention." + n] = g
             elif kind == "latent_gemm":
-                kv_is_x, tokp_e, tokp_lp, A12, A2 = ctx.aux_saved[e]
-                dtokp_e = gemm_attn2_bwd(K, x, tokp_lp, A2, egr[e].aux, T, dx)   # adds into dx
+                kv_is_x, tokp_e, tokp_op, A12, A2 = ctx.aux_saved[e]
+                dtokp_e = gemm_attn2_bwd(K, x, tokp_op, A2, egr[e].aux, T, dx)   # adds into dx
                 dkv, dtok = gemm_latent_bwd(K, x if kv_is_x else v, P[pfx + "my_tokens"], tokp_e, A12, dtokp_e, T)
                 grads[pfx + "my_tokens"] = dtok
                 if kv_is_x:

@@ -481,42 +481,70 @@ def cast_to(t: torch.Tensor, dtype: torch.dtype) -> torch.Tensor:
     return out
 
 
-def softmax_cols(S: torch.Tensor, T: int, dtype: torch.dtype):
-    """S [BT,Nk,Tp] fp32 (first T columns valid) -> A12 [BT,Nk,2*Tp] (A1ᵀ in columns [0,T), rest zero), lse [BT,T]."""
-    BT, Nk, Tp = S.shape
+def split_operand(t: torch.Tensor, dtype: torch.dtype):
+    """fp32 [..,T,C] -> (buf [..,W,C] in ``dtype``, off_lo, lp): the small fp32 side of a logits GEMM as a tensor-core operand,
+    plus ``lp`` [..,T,C], t rounded once to ``dtype`` (a view of buf) for the contractions that are not logits.
+    bf16: W = 2*Tp, rows [0,T) = hi = bf16(t), rows [Tp,Tp+T) = lo = bf16(t - hi) -- the GEMM then yields the logits as two
+    column blocks whose sum carries ~16 mantissa bits of t, which the un-scaled softmaxes need (DESIGN.md "numerics").
+    fp32: W = Tp, off_lo = 0 (TF32 operand).  Padding rows are zero."""
+    t = t.contiguous()
+    T, Cc = t.shape[-2], t.shape[-1]
+    Tp = round8(T)
+    lead = t.shape[:-2]
+    if dtype == torch.float32:
+        if Tp == T:
+            return t, 0, t
+        buf = torch.zeros(lead + (Tp, Cc), device=t.device, dtype=dtype)
+        buf[..., :T, :] = t
+        return buf, 0, buf[..., :T, :]
+    assert dtype == torch.bfloat16
+    buf = torch.zeros(lead + (2 * Tp, Cc), device=t.device, dtype=dtype)
+    groups = t.numel() // (T * Cc)
+    _lib_call("cast_split", _ptr(t), _ptr(buf), C.c_int64(groups), T, Tp, Cc, _stream())
+    return buf, Tp, buf[..., :T, :]
+
+
+def softmax_cols(S: torch.Tensor, T: int, off_lo: int, dtype: torch.dtype):
+    """S [BT,Nk,W] fp32 logits (columns [0,T) + columns [off_lo,off_lo+T) when off_lo) -> A12 [BT,Nk,2*Tp] (A1ᵀ in columns
+    [0,T), rest zero), lse [BT,T]."""
+    BT, Nk, W = S.shape
+    Tp = round8(T)
     A12 = torch.zeros((BT, Nk, 2 * Tp), device=S.device, dtype=dtype)
     lse = torch.empty((BT, T), device=S.device, dtype=torch.float32)
-    _lib_call("softmax_cols", _ptr(S), _ptr(A12), _ptr(lse), BT, Nk, T, Tp, 2 * Tp, _dt(A12), _stream(), _bytes=_nbytes(S) + _nbytes(A12) / 2)
-    return A12, lse
+    p_lo = Tp if dtype == torch.bfloat16 else 0      # bf16: rounding residual of A1 in columns [Tp,Tp+T) (until the backward reuses them)
+    _lib_call("softmax_cols", _ptr(S), _ptr(A12), _ptr(lse), BT, Nk, T, W, 2 * Tp, off_lo, p_lo, _dt(A12), _stream(),
+              _bytes=2 * _nbytes(S) + _nbytes(A12) / 2)
+    return A12, lse, p_lo
 
 
-def softmax_cols_bwd(A12: torch.Tensor, dA: torch.Tensor, Dt: torch.Tensor, T: int):
+def softmax_cols_bwd(A12: torch.Tensor, dA: torch.Tensor, Dt: torch.Tensor, T: int, off_lo: int):
     BT, Nk, Tp2 = A12.shape
-    _lib_call("softmax_cols_bwd", _ptr(A12), _ptr(dA), _ptr(Dt), BT, Nk, T, Tp2, Tp2 // 2, dA.shape[2], _dt(A12), _stream(),
+    _lib_call("softmax_cols_bwd", _ptr(A12), _ptr(dA), _ptr(Dt), BT, Nk, T, Tp2, Tp2 // 2, dA.shape[2], off_lo, _dt(A12), _stream(),
               _bytes=_nbytes(dA) + _nbytes(A12))
 
 
-def softmax_rows(S: torch.Tensor, T: int, dtype: torch.dtype) -> torch.Tensor:
-    BT, N, Tp = S.shape
-    A = torch.empty((BT, N, Tp), device=S.device, dtype=dtype)
-    _lib_call("softmax_rows", _ptr(S), _ptr(A), C.c_int64(BT * N), T, Tp, _dt(A), _stream(), _bytes=_nbytes(S, A))
+def softmax_rows(S: torch.Tensor, T: int, off_lo: int, dtype: torch.dtype) -> torch.Tensor:
+    BT, N, W = S.shape
+    A = torch.empty((BT, N, round8(T)), device=S.device, dtype=dtype)
+    _lib_call("softmax_rows", _ptr(S), _ptr(A), C.c_int64(BT * N), T, W, off_lo, A.shape[2], _dt(A), _stream(), _bytes=_nbytes(S, A))
     return A
 
 
-def softmax_rows_bwd(A: torch.Tensor, dA: torch.Tensor, T: int) -> torch.Tensor:
+def softmax_rows_bwd(A: torch.Tensor, dA: torch.Tensor, T: int, off_lo: int) -> torch.Tensor:
     BT, N, Tp = A.shape
     dS = torch.empty_like(A)
-    _lib_call("softmax_rows_bwd", _ptr(A), _ptr(dA), _ptr(dS), C.c_int64(BT * N), T, Tp, _dt(A), _stream(), _bytes=_nbytes(A, dA, dS))
+    _lib_call("softmax_rows_bwd", _ptr(A), _ptr(dA), _ptr(dS), C.c_int64(BT * N), T, Tp, dA.shape[2], off_lo, _dt(A), _stream(),
+              _bytes=_nbytes(A, dA, dS))
     return dS
 
 
-def tile_add(R: torch.Tensor, tile: torch.Tensor, dtype: torch.dtype):
-    out = torch.empty_like(R)
-    out_lp = torch.empty(R.shape, device=R.device, dtype=dtype) if dtype != torch.float32 else None
-    tile = tile.contiguous()
-    _lib_call("tile_add", _ptr(R), _ptr(tile), _ptr(out), _ptr(out_lp), C.c_int64(tile.numel()), C.c_int64(R.numel()),
-              BF16 if out_lp is not None else F32, _stream())
-    return out, (out_lp if out_lp is not None else out)
+def tile_add(R: torch.Tensor, tile: torch.Tensor, off_lo: int = 0) -> torch.Tensor:
+    """R [BT,rows,C] fp32 (rows [0,T) + rows [off_lo,off_lo+T) when off_lo) + tile [T,C] -> [BT,T,C] fp32."""
+    BT, rows, Cc = R.shape
+    T = tile.shape[0]
+    out = torch.empty((BT, T, Cc), device=R.device, dtype=torch.float32)
+    _lib_call("tile_add", _ptr(R), _ptr(tile.contiguous()), _ptr(out), BT, T, Cc, rows, off_lo, _stream())
+    return out
 
 
 def latent_dots(dR, tokp, tok):

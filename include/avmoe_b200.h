@@ -235,12 +235,20 @@ int avmoe_mha_attn_bwd(const float* qkv, const float* dctx, void* dqkv, int L, i
  * the contractions are avmoe_gemm calls (flat, fully-batched); these are the streaming softmax passes between them on the
  * token-major logits S1^T [BT,Nk,T] (softmax over Nk, per column) and S2 [BT,N,T] (softmax over T, per row).
  * ------------------------------------------------------------------------------------------ */
-int avmoe_softmax_cols(const float* S, void* P, float* lse, int BT, int Nk, int T, int lds, int ldp, int p_dtype, avmoe_stream_t stream);
+/* off_lo: logits produced against a bf16 operand split into hi + lo halves (avmoe_cast_split) arrive as two column blocks of
+ * the fp32 GEMM output, columns [0,T) and [off_lo, off_lo+T); the kernels add them on load.  off_lo = 0: one block. */
+/* p_lo > 0 (bf16 P): also write the rounding residual  P - bf16(P)  at column p_lo, so (hi + lo)·kv carries ~16 bits of A1 */
+int avmoe_softmax_cols(const float* S, void* P, float* lse, int BT, int Nk, int T, int lds, int ldp, int off_lo, int p_lo, int p_dtype,
+                       avmoe_stream_t stream);
 int avmoe_softmax_cols_bwd(void* A12 /* [BT,Nk,ld12]: A1^T at column 0, dS1^T written at column off2 */, const float* dA, const float* Dt, int BT,
-                           int Nk, int T, int ld12, int off2, int ldd, int p_dtype, avmoe_stream_t stream);
-int avmoe_softmax_rows(const float* S, void* A, int64_t rows, int T, int ld, int p_dtype, avmoe_stream_t stream);
-int avmoe_softmax_rows_bwd(const void* A, const float* dA, void* dS, int64_t rows, int T, int ld, int p_dtype, avmoe_stream_t stream);
-int avmoe_tile_add(const float* in, const float* tile, float* out, void* out_lp, int64_t L, int64_t total, int lp_dtype, avmoe_stream_t stream);
+                           int Nk, int T, int ld12, int off2, int ldd, int off_lo, int p_dtype, avmoe_stream_t stream);
+int avmoe_softmax_rows(const float* S, void* A, int64_t rows, int T, int lds, int off_lo, int ld, int p_dtype, avmoe_stream_t stream);
+int avmoe_softmax_rows_bwd(const void* A, const float* dA, void* dS, int64_t rows, int T, int ld, int ldd, int off_lo, int p_dtype,
+                           avmoe_stream_t stream);
+/* fp32 [groups][T][C] -> bf16 [groups][2*Tp][C]: rows [0,T) = hi = bf16(v), rows [Tp,Tp+T) = lo = bf16(v - hi); padding rows untouched */
+int avmoe_cast_split(const float* in, void* out_bf16, int64_t groups, int T, int Tp, int C, avmoe_stream_t stream);
+/* out[b][t][c] = in[b][t][c] (+ in[b][off_lo+t][c]) + tile[t][c], fp32; `in` has `rows` rows per sample */
+int avmoe_tile_add(const float* in, const float* tile, float* out, int BT, int T, int C, int rows, int off_lo, avmoe_stream_t stream);
 int avmoe_latent_dots(const float* dR, const float* tokp, const float* tok, float* Dt, int BT, int T, int C, avmoe_stream_t stream);
 int avmoe_add_rowvec(void* d, const float* vec, int BT, int N, int C, int dtype, avmoe_stream_t stream);
 int avmoe_batch_sum_add(const float* in, float* out /* += */, int BT, int64_t L, avmoe_stream_t stream);

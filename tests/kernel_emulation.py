@@ -86,36 +86,59 @@ def cast_to(t, dtype):
     return t if t.dtype == dtype else t.to(dtype)
 
 
-def softmax_cols(S, T, dtype):
-    BT, Nk, Tp = S.shape
+EMULATE_SPLIT = True   # model the hi/lo operand split (with an exact, lopsided split) so the off_lo plumbing is exercised on CPU
+
+
+def split_operand(t, dtype):
+    T, Cc = t.shape[-2], t.shape[-1]
+    Tp = round8(T)
+    if not EMULATE_SPLIT:
+        buf = torch.zeros(t.shape[:-2] + (Tp, Cc), dtype=t.dtype)
+        buf[..., :T, :] = t
+        return buf, 0, t
+    buf = torch.zeros(t.shape[:-2] + (2 * Tp, Cc), dtype=t.dtype)
+    buf[..., :T, :] = 0.75 * t          # exact in binary; a consumer that drops or mis-addresses the lo block is off by 25 %
+    buf[..., Tp:Tp + T, :] = 0.25 * t
+    return buf, Tp, t
+
+
+def _logits(S, T, off_lo):
+    return S[:, :, :T] + S[:, :, off_lo:off_lo + T] if off_lo else S[:, :, :T]
+
+
+def softmax_cols(S, T, off_lo, dtype):
+    BT, Nk, _ = S.shape
+    Tp = round8(T)
     A12 = torch.zeros((BT, Nk, 2 * Tp), device=S.device, dtype=dtype)
-    lse = torch.logsumexp(S[:, :, :T], dim=1)
-    A12[:, :, :T] = torch.exp(S[:, :, :T] - lse[:, None, :]).to(dtype)
-    return A12, lse
+    L = _logits(S, T, off_lo)
+    lse = torch.logsumexp(L, dim=1)
+    A12[:, :, :T] = torch.exp(L - lse[:, None, :]).to(dtype)
+    # the product's bf16 path stores the rounding residual of A1 at column p_lo = Tp; here the residual is exactly zero
+    return A12, lse, (Tp if EMULATE_SPLIT else 0)
 
 
-def softmax_cols_bwd(A12, dA, Dt, T):
+def softmax_cols_bwd(A12, dA, Dt, T, off_lo):
     Tp = A12.shape[2] // 2
-    A12[:, :, Tp:Tp + T] = (A12[:, :, :T].float() * (dA[:, :, :T] - Dt[:, None, :])).to(A12.dtype)
+    A12[:, :, Tp:Tp + T] = (A12[:, :, :T].float() * (_logits(dA, T, off_lo) - Dt[:, None, :])).to(A12.dtype)
 
 
-def softmax_rows(S, T, dtype):
-    A = torch.zeros(S.shape, device=S.device, dtype=dtype)
-    A[:, :, :T] = torch.softmax(S[:, :, :T], dim=-1).to(dtype)
+def softmax_rows(S, T, off_lo, dtype):
+    A = torch.zeros(S.shape[:2] + (round8(T),), device=S.device, dtype=dtype)
+    A[:, :, :T] = torch.softmax(_logits(S, T, off_lo), dim=-1).to(dtype)
     return A
 
 
-def softmax_rows_bwd(A, dA, T):
+def softmax_rows_bwd(A, dA, T, off_lo):
     a = A[:, :, :T].float()
-    d = dA[:, :, :T]
+    d = _logits(dA, T, off_lo)
     dS = torch.zeros_like(A)
     dS[:, :, :T] = (a * (d - (a * d).sum(-1, keepdim=True))).to(A.dtype)
     return dS
 
 
-def tile_add(R, tile, dtype):
-    out = R + tile[None]
-    return out, out.to(dtype)
+def tile_add(R, tile, off_lo=0):
+    T = tile.shape[0]
+    return R[:, :T] + (R[:, off_lo:off_lo + T] if off_lo else 0) + tile[None]
 
 
 def latent_dots(dR, tokp, tok):

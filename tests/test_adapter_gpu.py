@@ -31,6 +31,18 @@ def test_cuda_matches_reference_golden_fp32(name):
     compare_to_fixture(got, fx, TOL_F32, gtol=10 * TOL_F32, tensor_core=True)
 
 
+@pytest.mark.parametrize("name", util.golden_names())
+def test_gemm_attention_forced_on_fp32_golden(name, monkeypatch):
+    """fp32 streams default to the fused exact latent kernels; forcing the tcgen05 path (TF32 operands) must still
+    track the reference -- outputs at 2x the fp32 bound, gradients at the tensor-core gradient bound."""
+    from avmoe_b200 import ops
+    monkeypatch.setattr(ops, "USE_GEMM_ATTENTION", "always")
+    fx = util.load_golden(name)
+    mod = build_module(fx["spec"], fx["state_dict"], kernels=None)
+    got = run_module_on_fixture(mod, fx, device="cuda")
+    compare_to_fixture(got, fx, 2 * TOL_F32, gtol=GTOL_F32, tensor_core=True)
+
+
 def _oracle_run(spec, sd, x, o, gout, training=True):
     sdg = {k: (v.clone().requires_grad_() if v.is_floating_point() else v.clone()) for k, v in sd.items()}
     x, o = x.clone().requires_grad_(), o.clone().requires_grad_()

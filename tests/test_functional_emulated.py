@@ -96,7 +96,7 @@ def compare_to_fixture(got, fx, tol, gtol=None, tensor_core=False):
 @pytest.mark.parametrize("name", util.golden_names())
 def test_emulated_pipeline_matches_reference_golden(name, gemm_attention, monkeypatch):
     """both latent-attention orchestrations: through the batched GEMM (product default) and the fused latent kernels"""
-    monkeypatch.setattr(KE, "USE_GEMM_ATTENTION", gemm_attention)
+    monkeypatch.setattr(KE, "USE_GEMM_ATTENTION", "always" if gemm_attention else False)
     fx = util.load_golden(name)
     mod = build_module(fx["spec"], fx["state_dict"])
     got = run_module_on_fixture(mod, fx)

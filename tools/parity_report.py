@@ -8,6 +8,11 @@ from tests.test_adapter_gpu import _oracle_run, _cuda_run
 
 def main():
     cases = [("ave", 3, "audio"), ("ave", 3, "visual"), ("ave", 1, "audio"), ("ave", 1, "visual"), ("avqa", 3, "audio"), ("ms3", 3, "audio")]
+    if os.environ.get("AVMOE_PARITY_CASES"):
+        cases = [tuple(int(t) if t.isdigit() else t for t in c.split("-")) for c in os.environ["AVMOE_PARITY_CASES"].split(",")]
+    if os.environ.get("AVMOE_GEMM_ATTENTION"):
+        from avmoe_b200 import ops
+        ops.USE_GEMM_ATTENTION = {"0": False, "1": True}.get(os.environ["AVMOE_GEMM_ATTENTION"], "always")
     rows = []
     for variant, stage, modality in cases:
         for dtype in (torch.float32, torch.bfloat16):
