@@ -98,6 +98,23 @@ class ExpertArgs(C.Structure):
 _PtrArr = C.c_void_p * MAX_EXPERTS
 
 
+class XgArgs(C.Structure):
+    """avmoe_xg_args: the GEMM-based expert path's row kernels."""
+    _fields_ = [
+        ("BT", C.c_int32), ("N", C.c_int32), ("C", C.c_int32), ("Cr", C.c_int32), ("Crp", C.c_int32), ("G", C.c_int32),
+        ("E", C.c_int32), ("dtype", C.c_int32), ("bn_mode", C.c_int32), ("_pad", C.c_int32),
+        ("ex", Expert * MAX_EXPERTS),
+        ("bn2_w", _PtrArr), ("bn2_b", _PtrArr),
+        ("x", C.c_void_p), ("xl", C.c_void_p), ("ln1_stats", C.c_void_p),
+        ("z", C.c_void_p), ("a", C.c_void_p), ("yd", C.c_void_p), ("ln2_stats", C.c_void_p),
+        ("aff1", C.c_void_p), ("save1", C.c_void_p), ("save2", C.c_void_p),
+        ("probs", C.c_void_p), ("out", C.c_void_p), ("dout", C.c_void_p),
+        ("stats1", C.c_void_p), ("red1", C.c_void_p), ("red2", C.c_void_p),
+        ("da", C.c_void_p), ("dz", C.c_void_p), ("dxl", C.c_void_p),
+        ("dprobs", C.c_void_p), ("dpool_x", C.c_void_p), ("dx", C.c_void_p),
+    ]
+
+
 class BnArgs(C.Structure):
     _fields_ = [
         ("E", C.c_int32), ("C", C.c_int32), ("Cr", C.c_int32), ("G", C.c_int32), ("train", C.c_int32), ("_pad", C.c_int32),

@@ -271,6 +271,114 @@ def gemm_latent_bwd(K, kv, tok, tokp, A12, dtokp, T: int):
     return dkv, dtok
 
 
+def _bn_params(P, bufs, prefixes):
+    bn_w = [[P[p + f"bn{i}.{w}"] for i in (1, 2) for w in ("weight", "bias")] for p in prefixes]
+    bn_b = [[bufs[p + f"bn{i}.{w}"] for i in (1, 2) for w in ("running_mean", "running_var")] for p in prefixes]
+    return bn_w, bn_b
+
+
+def fused_experts_fwd(K, cfg, x, tokp, packs, probs, P, bufs, prefixes, bn_mode):
+    """Experts through the fused tile kernels (csrc/expert.cu): returns (out, z, bn)."""
+    BT, N, C = x.shape
+    E, Cr = cfg.E, cfg.Cr
+    dev, f32 = x.device, torch.float32
+    # 5. expert front: pre-transform, ln_before, grouped down projection -> z (pre-BN), BN1 batch sums
+    z = torch.empty((BT, N, E, Cr), device=dev, dtype=f32)
+    stats1 = torch.zeros((E, Cr, 2), device=dev, dtype=torch.float64) if bn_mode == BN_TRAIN else None
+    K.expert_front_fwd(cfg, x, tokp, packs, z, stats1)
+    # 6. BatchNorm statistics -> per-channel affine + (mean, invstd) for both norms
+    bn = None
+    if bn_mode != BN_OFF:
+        bn_w = [[P[p + f"bn{i}.{w}"] for i in (1, 2) for w in ("weight", "bias")] for p in prefixes]
+        bn_b = [[bufs[p + f"bn{i}.{w}"] for i in (1, 2) for w in ("running_mean", "running_var")] for p in prefixes]
+        moments = None
+        if bn_mode == BN_TRAIN:
+            aff1, save1 = K.bn1_finalize(cfg, stats1, BT * N, bn_w, bn_b, True)
+            moments = K.bn_moments(cfg, z, aff1, packs)                       # sums of a and a aᵀ per group (float64)
+        else:
+            aff1, save1 = K.bn1_finalize(cfg, None, BT * N, bn_w, bn_b, False)
+        aff2, save2 = K.bn2_finalize(cfg, moments, BT * N, packs, bn_w, bn_b, bn_mode == BN_TRAIN)
+        if bn_mode == BN_TRAIN:
+            for p in prefixes:
+                bufs[p + "bn1.num_batches_tracked"] += 1
+                bufs[p + "bn2.num_batches_tracked"] += 1
+        bn = (aff1, save1, aff2, save2)
+    # 7. expert back: activation, up projection, bn2, ln_post, gate, probability-weighted combine
+    out = torch.empty_like(x)
+    K.expert_back_fwd(cfg, z, bn, packs, probs, out)
+    return out, z, bn
+
+
+def gemm_experts_fwd(K, cfg, x, packs, probs, P, bufs, prefixes, bn_mode):
+    """Experts with every channel contraction on the tcgen05 GEMM (block-diagonal dense weights) and streaming row kernels
+    in between (csrc/expert_rows.cu).  Returns (out, z, bn, saved-for-backward)."""
+    BT, N, C = x.shape
+    E, Cr = cfg.E, cfg.Cr
+    rows = BT * N
+    dev, f32, dt = x.device, torch.float32, x.dtype
+    wdd, wdt = K.xg_prep_weights(cfg, packs, dt)                                  # [E,Cr,C], [E,C,Crp]
+    xl, ln1s = K.xg_ln_pre_fwd(cfg, x, packs)                                     # [E,rows,C]
+    z = torch.empty((BT, N, E, Cr), device=dev, dtype=f32)
+    zf = z.view(rows, E * Cr)
+    for e in range(E):
+        K.gemm(xl[e], wdd[e], out=zf[:, e * Cr:(e + 1) * Cr])                     # down projection
+    bn = bn2_wb = suma = None
+    if bn_mode != BN_OFF:
+        bn_w, bn_b = _bn_params(P, bufs, prefixes)
+        moments = None
+        if bn_mode == BN_TRAIN:
+            stats1 = K.xg_z_stats(cfg, z)
+            aff1, save1 = K.bn1_finalize(cfg, stats1, rows, bn_w, bn_b, True)
+            moments = K.bn_moments(cfg, z, aff1, packs)
+            suma = moments[0]
+        else:
+            aff1, save1 = K.bn1_finalize(cfg, None, rows, bn_w, bn_b, False)
+        aff2, save2 = K.bn2_finalize(cfg, moments, rows, packs, bn_w, bn_b, bn_mode == BN_TRAIN)
+        if bn_mode == BN_TRAIN:
+            for p in prefixes:
+                bufs[p + "bn1.num_batches_tracked"] += 1
+                bufs[p + "bn2.num_batches_tracked"] += 1
+        bn = (aff1, save1, aff2, save2)
+        bn2_wb = [(P[p + "bn2.weight"], P[p + "bn2.bias"]) for p in prefixes]
+    act = K.xg_bn_act(cfg, z, bn[0] if bn else None, packs, dt, bn_mode)          # [E,rows,Crp]
+    wud, ybi = K.xg_prep_up(cfg, packs, bn[3] if bn else None, bn_mode, dt)       # bn2 normalisation folded into the operand
+    yd = torch.empty((E, rows, 2 * C), device=dev, dtype=dt)
+    for e in range(E):
+        K.gemm(act[e], wud[e], out=yd[e][:, :C], col_bias=ybi[e])                 # up projection -> normalised y
+    out = torch.empty_like(x)
+    ln2s = K.xg_post_fwd(cfg, yd, bn2_wb, packs, probs, out)
+    return out, z, bn, (xl, ln1s, act, yd, ln2s, wdt, suma)
+
+
+def gemm_experts_bwd(K, cfg, x, dout, z, bn, bn_mode, packs, egr, probs, P, prefixes, saved):
+    """Backward of gemm_experts_fwd up to the ln_before input: returns (dprobs, red1, red2, dxl, ln1s)."""
+    BT, N, C = x.shape
+    E, Cr = cfg.E, cfg.Cr
+    Crp = K.round8(Cr)
+    rows = BT * N
+    dev, f32, dt = x.device, torch.float32, x.dtype
+    xl, ln1s, act, yd, ln2s, wdt, suma = saved
+    bn2_wb = [(P[p + "bn2.weight"], P[p + "bn2.bias"]) for p in prefixes] if bn_mode != BN_OFF else None
+    red2 = torch.zeros((E, C, 2), device=dev, dtype=torch.float64) if bn_mode != BN_OFF else None
+    red1 = torch.zeros((E, Cr, 2), device=dev, dtype=torch.float64) if bn_mode != BN_OFF else None
+    dprobs = torch.zeros((BT, E), device=dev, dtype=f32)
+    K.xg_post_bwd(cfg, dout, yd, ln2s, bn2_wb, bn_mode, packs, probs, dprobs, red2, egr)   # yd[:, :, C:] = d(bn2 output)
+    w2, bias2 = K.xg_prep_bwd(cfg, packs, bn2_wb, bn, bn_mode, red2, BT, dt)               # bn2 backward folded into the operand
+    da = torch.empty((E, rows, Crp), device=dev, dtype=f32)
+    pwu = torch.empty((E, 2 * C, Crp), device=dev, dtype=f32)
+    for e in range(E):
+        K.gemm(yd[e], w2[e], out=da[e], col_bias=bias2[e])                                 # d a = dy · Wu
+        K.gemm(yd[e], act[e], a_kmajor=False, b_kmajor=False, out=pwu[e], split_k=K.split_k_hint(rows, 2 * C, Crp))
+    dz = K.xg_bn1_bwd(cfg, da, z, bn, bn_mode, packs, red1, dt)                            # relu mask + bn1 backward
+    dxl = torch.empty((E, rows, C), device=dev, dtype=dt)
+    pwd = torch.empty((E, Crp, C), device=dev, dtype=f32)
+    for e in range(E):
+        K.gemm(dz[e], wdt[e], out=dxl[e])                                                  # d xl = dz · Wd
+        K.gemm(dz[e], xl[e], a_kmajor=False, b_kmajor=False, out=pwd[e], split_k=K.split_k_hint(rows, Crp, C))
+    K.xg_finish_wgrads(cfg, packs, egr, bn2_wb, bn, bn_mode, red2, BT, pwd, pwu, suma)
+    return dprobs, red1, red2, dxl, ln1s
+
+
 # -------------------------------------------------------------------------------------------------
 # the fused adapter function
 # -------------------------------------------------------------------------------------------------
@@ -371,30 +479,15 @@ class MoEAdapterFunction(torch.autograd.Function):
                 slots = [i for i in range(nl) if latent_kv_is_x[i] == kv_is_x]
                 if slots:
                     K.latent_fwd(x if kv_is_x else v, [latent_tokens[i] for i in slots], slots, tokp, lse)
-        # 5. expert front: pre-transform, ln_before, grouped down projection -> z (pre-BN), BN1 batch sums
-        z = torch.empty((BT, N, E, Cr), device=dev, dtype=f32)
-        stats1 = torch.zeros((E, Cr, 2), device=dev, dtype=torch.float64) if bn_mode == BN_TRAIN else None
-        K.expert_front_fwd(cfg, x, tokp, packs, z, stats1)
-        # 6. BatchNorm statistics -> per-channel affine + (mean, invstd) for both norms
-        bn = None
-        if bn_mode != BN_OFF:
-            bn_w = [[P[p + f"bn{i}.{w}"] for i in (1, 2) for w in ("weight", "bias")] for p in prefixes]
-            bn_b = [[bufs[p + f"bn{i}.{w}"] for i in (1, 2) for w in ("running_mean", "running_var")] for p in prefixes]
-            moments = None
-            if bn_mode == BN_TRAIN:
-                aff1, save1 = K.bn1_finalize(cfg, stats1, BT * N, bn_w, bn_b, True)
-                moments = K.bn_moments(cfg, z, aff1, packs)                       # sums of a and a aᵀ per group (float64)
-            else:
-                aff1, save1 = K.bn1_finalize(cfg, None, BT * N, bn_w, bn_b, False)
-            aff2, save2 = K.bn2_finalize(cfg, moments, BT * N, packs, bn_w, bn_b, bn_mode == BN_TRAIN)
-            if bn_mode == BN_TRAIN:
-                for p in prefixes:
-                    bufs[p + "bn1.num_batches_tracked"] += 1
-                    bufs[p + "bn2.num_batches_tracked"] += 1
-            bn = (aff1, save1, aff2, save2)
-        # 7. expert back: activation, up projection, bn2, ln_post, gate, probability-weighted combine
-        out = torch.empty_like(x)
-        K.expert_back_fwd(cfg, z, bn, packs, probs, out)
+        # bf16 streams run the expert projections on the tensor-core GEMM with streaming row kernels in between
+        # ("gemm experts"); fp32 streams keep the fused kernels (exact fp32 contractions).  "always" forces it (tests).
+        _xflag = getattr(K, "USE_GEMM_EXPERTS", False)
+        use_xg = (_xflag == "always" or (bool(_xflag) and x.dtype == torch.bfloat16)) and all(pk.pre_kind != PRE_LATENT for pk in packs)
+        xg_saved = None
+        if use_xg:
+            out, z, bn, xg_saved = gemm_experts_fwd(K, cfg, x, packs, probs, P, bufs, prefixes, bn_mode)
+        else:
+            out, z, bn = fused_experts_fwd(K, cfg, x, tokp, packs, probs, P, bufs, prefixes, bn_mode)
         lb = K.lb_loss_fwd(probs) if cfg.lb_loss else torch.zeros((), device=dev, dtype=f32)
 
         state["idx"] = idx
@@ -408,6 +501,7 @@ class MoEAdapterFunction(torch.autograd.Function):
         ctx.latent_kv_is_x = latent_kv_is_x
         ctx.packs_meta = [(pk.pre_kind, pk.relu, pk.latent_slot) for pk in packs]
         ctx.bn = bn
+        ctx.xg_saved = xg_saved
         ctx.aux = [pk.aux for pk in packs]
         ctx.save_for_backward(x, o, v, rin, probs, h1, h2, tokp, lse, z, *params)
         ctx.mark_non_differentiable(idx)
@@ -460,15 +554,20 @@ class MoEAdapterFunction(torch.autograd.Function):
             egr.append(g)
 
         # 1. expert back (BN2 batch reductions first when training with BN)
-        red2 = None
-        if bn_mode == BN_TRAIN:
-            red2 = torch.zeros((E, C, 2), device=dev, dtype=torch.float64)
-            K.expert_back_bwd_stats(cfg, dout, z, ctx.bn, packs, probs, red2)
-        dzt = torch.empty((BT, N, E, Cr), device=dev, dtype=f32)
-        dprobs = torch.zeros((BT, E), device=dev, dtype=f32)
-        red1 = torch.zeros((E, Cr, 2), device=dev, dtype=torch.float64) if bn_mode != BN_OFF else None
-        red2b = torch.zeros((E, C, 2), device=dev, dtype=torch.float64) if bn_mode == BN_EVAL else red2
-        K.expert_back_bwd(cfg, dout, z, ctx.bn, bn_mode, red2, red2b, packs, probs, dzt, dprobs, red1, egr)
+        use_xg = ctx.xg_saved is not None
+        if use_xg:
+            dprobs, red1, red2, dxl, ln1s = gemm_experts_bwd(K, cfg, x, dout, z, ctx.bn, bn_mode, packs, egr, probs, P, prefixes, ctx.xg_saved)
+            red2b = red2
+        else:
+            red2 = None
+            if bn_mode == BN_TRAIN:
+                red2 = torch.zeros((E, C, 2), device=dev, dtype=torch.float64)
+                K.expert_back_bwd_stats(cfg, dout, z, ctx.bn, packs, probs, red2)
+            dzt = torch.empty((BT, N, E, Cr), device=dev, dtype=f32)
+            dprobs = torch.zeros((BT, E), device=dev, dtype=f32)
+            red1 = torch.zeros((E, Cr, 2), device=dev, dtype=torch.float64) if bn_mode != BN_OFF else None
+            red2b = torch.zeros((E, C, 2), device=dev, dtype=torch.float64) if bn_mode == BN_EVAL else red2
+            K.expert_back_bwd(cfg, dout, z, ctx.bn, bn_mode, red2, red2b, packs, probs, dzt, dprobs, red1, egr)
         # 2. router backward (dprobs from the combine + external grads on gating_probs + lb-loss)
         if dprobs_ext is not None:
             dprobs = dprobs + dprobs_ext.to(f32)
@@ -482,7 +581,10 @@ class MoEAdapterFunction(torch.autograd.Function):
         nl = 0 if tokp is None else tokp.shape[1]
         dtokp = torch.zeros((BT, nl, T, C), device=dev, dtype=f32) if nl else None
         dx = torch.empty_like(x)
-        K.expert_front_bwd(cfg, x, tokp, dzt, z, ctx.bn, bn_mode, red1, packs, dpool_x, dx, dtokp, egr)
+        if use_xg:
+            K.xg_ln_pre_bwd(cfg, x, dxl, ln1s, packs, dpool_x, dx, egr)
+        else:
+            K.expert_front_bwd(cfg, x, tokp, dzt, z, ctx.bn, bn_mode, red1, packs, dpool_x, dx, dtokp, egr)
         # 4. separate pre-transform kernels (AVVP NxN attention, AVS-v1 MHA) and the GEMM-based latent attention
         dv = None
         for e, (pfx, pk) in enumerate(zip(prefixes, packs)):

@@ -26,7 +26,7 @@ _KERNELS_PER_CALL = {"transpose": 1, "cast": 1, "pool": 1, "reduce_bias": 1, "ro
                      "router_bwd": 4, "lb_loss_fwd": 1, "lb_loss_bwd": 1, "latent_fwd": 2, "latent_bwd": 1, "expert_front_fwd": 1,
                      "bn1_finalize": 1, "bn2_finalize": 1, "bn_moments": 1, "expert_back_fwd": 1, "expert_back_bwd_stats": 1,
                      "expert_back_bwd": 1, "expert_front_bwd": 1, "selfattn_nxn_fwd": 2, "selfattn_nxn_bwd": 2, "mha_attn_fwd": 1,
-                     "mha_attn_bwd": 1}
+                     "mha_attn_bwd": 1, "xg_bn1_bwd": 2}
 
 
 def _dt(t: torch.Tensor) -> int:
@@ -568,6 +568,149 @@ def add_rowvec(d, vec):
 def add_into(dst, a, b=None, c=None):
     _lib_call("add_into", _ptr(dst), _ptr(a), _ptr(b), _ptr(c), C.c_int64(dst.numel()), _dt(dst), _stream(),
               _bytes=2 * _nbytes(dst) + _nbytes(a, b, c))
+
+
+# ------------------------------------------------------------------------------------------------ GEMM-based expert path
+USE_GEMM_EXPERTS = True   # bf16 streams: expert projections on the tcgen05 GEMM + streaming row kernels (functional.py "gemm experts")
+
+
+def _xg_args(cfg, packs, egr=None, *, BT, dtype, bn_mode=0, bn2_wb=None):
+    a = _lib.XgArgs()
+    a.BT, a.N, a.C, a.Cr, a.Crp, a.G, a.E = BT, cfg.N, cfg.C, cfg.Cr, round8(cfg.Cr), cfg.G, cfg.E
+    a.dtype, a.bn_mode = dtype, bn_mode
+    keep = []
+    for e, pk in enumerate(packs):
+        ex = a.ex[e]
+        ex.pre_kind, ex.relu = pk.pre_kind, int(pk.relu)
+        for name in ("gate_pre", "aux", "ln1_w", "ln1_b", "wd", "wu", "ln2_w", "ln2_b", "gate"):
+            t = getattr(pk, name)
+            if t is not None:
+                t = t.contiguous()
+                keep.append(t)
+                setattr(ex, name, t.data_ptr())
+        if egr is not None:
+            g = egr[e]
+            for name in ("gate_pre", "aux", "ln1_w", "ln1_b", "wd", "wu", "ln2_w", "ln2_b", "gate"):
+                t = getattr(g, name)
+                if t is not None:
+                    assert t.is_contiguous()
+                    setattr(ex, "g_" + name, t.data_ptr())
+        if bn2_wb is not None:
+            w, b = bn2_wb[e]
+            w, b = w.contiguous(), b.contiguous()
+            keep += [w, b]
+            a.bn2_w[e], a.bn2_b[e] = w.data_ptr(), b.data_ptr()
+    return a, keep
+
+
+def xg_prep_weights(cfg, packs, dtype):
+    dev = packs[0].wd.device
+    Crp = round8(cfg.Cr)
+    wdd = torch.empty((cfg.E, cfg.Cr, cfg.C), device=dev, dtype=dtype)
+    wdt = torch.empty((cfg.E, cfg.C, Crp), device=dev, dtype=dtype)
+    a, keep = _xg_args(cfg, packs, BT=1, dtype=_dt(wdd))
+    _lib_call("xg_prep_weights", C.byref(a), _ptr(wdd), _ptr(wdt), _stream())
+    return wdd, wdt
+
+
+def xg_prep_up(cfg, packs, save2, bn_mode, dtype):
+    dev = packs[0].wu.device
+    wud = torch.empty((cfg.E, cfg.C, round8(cfg.Cr)), device=dev, dtype=dtype)
+    ybi = torch.empty((cfg.E, cfg.C), device=dev, dtype=torch.float32)
+    a, keep = _xg_args(cfg, packs, BT=1, dtype=_dt(wud), bn_mode=bn_mode)
+    _set(a, save2=save2)
+    _lib_call("xg_prep_up", C.byref(a), _ptr(wud), _ptr(ybi), _stream())
+    return wud, ybi
+
+
+def xg_ln_pre_fwd(cfg, x, packs):
+    """-> xl [E,BT*N,C] (x.dtype), ln1_stats [E,BT*N,2] fp32 (None without ln_before)"""
+    _require_cuda(x)
+    BT, N, Cc = x.shape
+    xl = torch.empty((cfg.E, BT * N, Cc), device=x.device, dtype=x.dtype)
+    st = torch.empty((cfg.E, BT * N, 2), device=x.device, dtype=torch.float32) if packs[0].ln1_w is not None else None
+    a, keep = _xg_args(cfg, packs, BT=BT, dtype=_dt(x))
+    _set(a, x=x, xl=xl, ln1_stats=st)
+    aux_bytes = sum(_nbytes(pk.aux) for pk in packs)
+    _lib_call("xg_ln_pre_fwd", C.byref(a), _stream(), _bytes=_nbytes(x, xl) + aux_bytes)
+    return xl, st
+
+
+def xg_z_stats(cfg, z):
+    stats1 = torch.zeros((cfg.E, cfg.Cr, 2), device=z.device, dtype=torch.float64)
+    a = _lib.XgArgs()
+    a.BT, a.N, a.C, a.Cr, a.Crp, a.G, a.E, a.dtype = z.shape[0], cfg.N, cfg.C, cfg.Cr, round8(cfg.Cr), cfg.G, cfg.E, F32
+    _set(a, z=z, stats1=stats1)
+    _lib_call("xg_z_stats", C.byref(a), _stream(), _bytes=_nbytes(z))
+    return stats1
+
+
+def xg_bn_act(cfg, z, aff1, packs, dtype, bn_mode):
+    """-> a [E,BT*N,Crp] = act(bn1(z)) in ``dtype`` (padding columns zero)"""
+    BT, N = z.shape[0], z.shape[1]
+    act = torch.empty((cfg.E, BT * N, round8(cfg.Cr)), device=z.device, dtype=dtype)
+    a, keep = _xg_args(cfg, packs, BT=BT, dtype=_dt(act), bn_mode=bn_mode)
+    _set(a, z=z, aff1=aff1)
+    a.a = act.data_ptr()
+    _lib_call("xg_bn_act", C.byref(a), _stream(), _bytes=_nbytes(z, act))
+    return act
+
+
+def xg_post_fwd(cfg, yd, bn2_wb, packs, probs, out):
+    BT, N = out.shape[0], out.shape[1]
+    st = torch.empty((cfg.E, BT * N, 2), device=out.device, dtype=torch.float32) if packs[0].ln2_w is not None else None
+    a, keep = _xg_args(cfg, packs, BT=BT, dtype=_dt(out), bn_mode=int(bn2_wb is not None), bn2_wb=bn2_wb)
+    _set(a, yd=yd, ln2_stats=st, probs=probs, out=out)
+    _lib_call("xg_post_fwd", C.byref(a), _stream(), _bytes=_nbytes(yd) / 2 + _nbytes(out))
+    return st
+
+
+def xg_post_bwd(cfg, dout, yd, ln2_stats, bn2_wb, bn_mode, packs, probs, dprobs, red2, egr):
+    BT = dout.shape[0]
+    a, keep = _xg_args(cfg, packs, egr, BT=BT, dtype=_dt(dout), bn_mode=bn_mode, bn2_wb=bn2_wb)
+    _set(a, yd=yd, ln2_stats=ln2_stats, probs=probs, dout=dout, dprobs=dprobs, red2=red2)
+    _lib_call("xg_post_bwd", C.byref(a), _stream(), _bytes=cfg.E * _nbytes(dout) + _nbytes(yd))
+    return None
+
+
+def xg_bn1_bwd(cfg, da, z, bn, bn_mode, packs, red1, dtype):
+    """-> dz [E,BT*N,Crp] in ``dtype``; red1 [E,Cr,2] += (sum dh, sum dh*zhat)"""
+    BT = z.shape[0]
+    dz = torch.empty(da.shape, device=da.device, dtype=dtype)
+    a, keep = _xg_args(cfg, packs, BT=BT, dtype=_dt(dz), bn_mode=bn_mode)
+    _set(a, z=z, da=da, dz=dz, red1=red1)
+    if bn is not None:
+        _set(a, aff1=bn[0], save1=bn[1])
+    _lib_call("xg_bn1_bwd", C.byref(a), _stream(), _bytes=2 * _nbytes(da) + 2 * _nbytes(z) + _nbytes(dz))
+    return dz
+
+
+def xg_ln_pre_bwd(cfg, x, dxl, ln1_stats, packs, dpool_x, dx, egr):
+    a, keep = _xg_args(cfg, packs, egr, BT=x.shape[0], dtype=_dt(x))
+    _set(a, x=x, dxl=dxl, ln1_stats=ln1_stats, dpool_x=dpool_x, dx=dx)
+    aux_bytes = sum(2 * _nbytes(pk.aux) for pk in packs)
+    _lib_call("xg_ln_pre_bwd", C.byref(a), _stream(), _bytes=_nbytes(dxl) + (cfg.E + 1) * _nbytes(x) + aux_bytes)
+
+
+def xg_prep_bwd(cfg, packs, bn2_wb, bn, bn_mode, red2, BT, dtype):
+    dev = packs[0].wu.device
+    Crp = round8(cfg.Cr)
+    w2 = torch.empty((cfg.E, Crp, 2 * cfg.C), device=dev, dtype=dtype)
+    bias = torch.empty((cfg.E, Crp), device=dev, dtype=torch.float32)
+    a, keep = _xg_args(cfg, packs, BT=BT, dtype=_dt(w2), bn_mode=bn_mode, bn2_wb=bn2_wb)
+    _set(a, red2=red2)
+    if bn is not None:
+        _set(a, save2=bn[3])
+    _lib_call("xg_prep_bwd", C.byref(a), _ptr(w2), _ptr(bias), _stream())
+    return w2, bias
+
+
+def xg_finish_wgrads(cfg, packs, egr, bn2_wb, bn, bn_mode, red2, BT, pwd, pwu, suma):
+    a, keep = _xg_args(cfg, packs, egr, BT=BT, dtype=F32, bn_mode=bn_mode, bn2_wb=bn2_wb)
+    _set(a, red2=red2)
+    if bn is not None:
+        _set(a, save2=bn[3])
+    _lib_call("xg_finish_wgrads", C.byref(a), _ptr(pwd), _ptr(pwu), _ptr(suma), _stream())
 
 
 # ------------------------------------------------------------------------------------------------ variant pre-transforms

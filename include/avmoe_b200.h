@@ -231,6 +231,53 @@ int avmoe_mha_attn_fwd(const float* qkv, void* ctx, int L, int NB, int C, int he
 int avmoe_mha_attn_bwd(const float* qkv, const float* dctx, void* dqkv, int L, int NB, int C, int heads, int dtype, avmoe_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
+ * GEMM-based expert path (bf16 streams).  The grouped 1x1 down/up projections of an expert (net_trans_v3.py:393-401, "down_sampler" /
+ * "up_sampler") and their backward run as avmoe_gemm calls against block-diagonal dense weights; these entry points are the streaming
+ * row passes between the GEMMs (pre-transform + ln_before, bn1 + activation, bn2 affine + ln_post + gate + probability-weighted
+ * combine, and the hand-derived backward of each).  rows = BT*N.  Buffers (caller-owned, activation dtype unless noted):
+ *   xl [E,rows,C]  ln_before output            z [rows,E,Cr] fp32  bottleneck before bn1      a [E,rows,Crp]  act(bn1(z)), zero padded
+ *   yd [E,rows,2C] columns [0,C) = bn2-normalised up projection (written by the GEMM epilogue), columns [C,2C) = gradient at the bn2
+ *                  output (written by avmoe_xg_post_bwd): one K-concatenated operand for  da = yd·W2^T  and  [2C,Crp] = yd^T·a
+ *   da [E,rows,Crp] fp32   dz [E,rows,Crp]   dxl [E,rows,C]   ln1_stats / ln2_stats [E,rows,2] fp32 (mean, rstd)
+ * avmoe_expert.pre_kind must be NONE / AUX_ADD / AUX_REPLACE (latent attention arrives as an aux-add).
+ * ------------------------------------------------------------------------------------------ */
+typedef struct {
+  int32_t BT, N, C, Cr, Crp, G, E, dtype, bn_mode, _pad;
+  avmoe_expert ex[AVMOE_MAX_EXPERTS];
+  const float* bn2_w[AVMOE_MAX_EXPERTS]; const float* bn2_b[AVMOE_MAX_EXPERTS];   /* bn2 weight / bias (NULL: no BatchNorm) */
+  const void* x; void* xl; float* ln1_stats;
+  float* z; void* a; void* yd; float* ln2_stats;
+  const float* aff1; const float* save1; const float* save2;   /* [E,Cr,2] (scale,shift), [E,Cr,2] / [E,C,2] (mean,invstd) */
+  const float* probs; void* out; const void* dout;
+  double* stats1;          /* [E,Cr,2] sum z, sum z^2 */
+  double* red1;            /* [E,Cr,2] sum dh, sum dh*zhat  (dh = relu-masked da) */
+  double* red2;            /* [E,C,2]  sum dy2, sum dy2*yhat */
+  const float* da; void* dz; const void* dxl;
+  float* dprobs;           /* [BT,E] += */
+  const float* dpool_x;    /* [BT,C] router-path gradient per token (already /N), or NULL */
+  void* dx;                /* [rows,C] */
+} avmoe_xg_args;
+
+int avmoe_xg_ln_pre_fwd(const avmoe_xg_args* a, avmoe_stream_t stream);     /* x, ex[].aux -> xl, ln1_stats */
+int avmoe_xg_z_stats(const avmoe_xg_args* a, avmoe_stream_t stream);        /* z -> stats1 (+=) */
+int avmoe_xg_bn_act(const avmoe_xg_args* a, avmoe_stream_t stream);         /* z, aff1 -> a */
+int avmoe_xg_post_fwd(const avmoe_xg_args* a, avmoe_stream_t stream);       /* yd[:, :C], probs -> out, ln2_stats */
+/* dout, yd[:, :C], ln2_stats, probs -> yd[:, C:], red2 (+=), dprobs (+=), ex[].g_ln2_w / g_ln2_b / g_gate (+=) */
+int avmoe_xg_post_bwd(const avmoe_xg_args* a, avmoe_stream_t stream);
+int avmoe_xg_bn1_bwd(const avmoe_xg_args* a, avmoe_stream_t stream);        /* da, z -> red1 (+=), dz */
+/* dxl, x, ex[].aux, ln1_stats, dpool_x -> dx, ex[].g_aux, ex[].g_gate_pre / g_ln1_w / g_ln1_b (+=) */
+int avmoe_xg_ln_pre_bwd(const avmoe_xg_args* a, avmoe_stream_t stream);
+/* dense block-diagonal operands of the down projection from ex[].wd [Cr,C/G]:  wdd [E,Cr,C] (forward), wdt [E,C,Crp] (dgrad) */
+int avmoe_xg_prep_weights(const avmoe_xg_args* a, void* wdd, void* wdt, avmoe_stream_t stream);
+/* up-projection operand with bn2's normalisation folded in (yhat = a·wud^T + ybi):  wud [E,C,Crp] = invstd_c * dense(ex[].wu),
+ * ybi [E,C] = -mean_c*invstd_c from save2; bn off: plain dense weight, zero bias */
+int avmoe_xg_prep_up(const avmoe_xg_args* a, void* wud, float* ybi, avmoe_stream_t stream);
+/* bn2 backward folded into the operand of  da = yd·W2^T + bias:  w2 [E,Crp,2C] (activation dtype), bias [E,Crp] fp32 */
+int avmoe_xg_prep_bwd(const avmoe_xg_args* a, void* w2, float* bias, avmoe_stream_t stream);
+/* pwd [E,Crp,C] = dz^T·xl, pwu [E,2C,Crp] = yd^T·a, suma [E,Cr] fp64 column sums of a (bn train)  ->  ex[].g_wd, ex[].g_wu (=) */
+int avmoe_xg_finish_wgrads(const avmoe_xg_args* a, const float* pwd, const float* pwu, const double* suma, avmoe_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
  * GEMM-based latent attention (the product path for multimodal / latent-self experts; AVMOE/AVE/nets/net_trans_v3.py:379-390):
  * the contractions are avmoe_gemm calls (flat, fully-batched); these are the streaming softmax passes between them on the
  * token-major logits S1^T [BT,Nk,T] (softmax over Nk, per column) and S2 [BT,N,T] (softmax over T, per row).

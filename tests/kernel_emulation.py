@@ -582,3 +582,221 @@ def expert_front_bwd(cfg, x, tokp, dzt, z, bn, bn_mode, red1, packs, dpool_x, dx
         else:
             gr.aux.copy_(dxa.to(gr.aux.dtype))
     dx.copy_(dxa_total.to(dx.dtype))
+
+
+# ------------------------------------------------------------------------------------------------ GEMM-based expert path (csrc/expert_rows.cu)
+USE_GEMM_EXPERTS = True
+
+
+def _dense_wd(wd, cfg):
+    """grouped [Cr, C/G] -> block-diagonal dense [Cr, C]"""
+    Cr, C, G = cfg.Cr, cfg.C, cfg.G
+    out = torch.zeros((Cr, C), dtype=torch.float32)
+    for g in range(G):
+        out[g * (Cr // G):(g + 1) * (Cr // G), g * (C // G):(g + 1) * (C // G)] = wd[g * (Cr // G):(g + 1) * (Cr // G)]
+    return out
+
+
+def _dense_wu(wu, cfg):
+    """grouped [C, Cr/G] -> block-diagonal dense [C, Crp] (zero padded)"""
+    Cr, C, G = cfg.Cr, cfg.C, cfg.G
+    out = torch.zeros((C, round8(Cr)), dtype=torch.float32)
+    for g in range(G):
+        out[g * (C // G):(g + 1) * (C // G), g * (Cr // G):(g + 1) * (Cr // G)] = wu[g * (C // G):(g + 1) * (C // G)]
+    return out
+
+
+def xg_prep_weights(cfg, packs, dtype):
+    Crp = round8(cfg.Cr)
+    wdd = torch.stack([_dense_wd(pk.wd, cfg) for pk in packs]).to(dtype)
+    wdt = torch.zeros((cfg.E, cfg.C, Crp), dtype=dtype)
+    wdt[:, :, :cfg.Cr] = wdd.transpose(1, 2)
+    return wdd, wdt
+
+
+def xg_prep_up(cfg, packs, save2, bn_mode, dtype):
+    wud = torch.stack([_dense_wu(pk.wu, cfg) for pk in packs])
+    ybi = torch.zeros((cfg.E, cfg.C), dtype=torch.float32)
+    if bn_mode != BN_OFF:
+        wud = wud * save2[:, :, 1, None]
+        ybi = -save2[:, :, 0] * save2[:, :, 1]
+    return wud.to(dtype), ybi
+
+
+def _xg_xa(x, pk):
+    xf = x.float()
+    if pk.pre_kind == PRE_NONE:
+        return xf
+    assert pk.pre_kind != PRE_LATENT, "the GEMM expert path takes latent attention as an aux-add"
+    if pk.pre_kind == PRE_AUX_ADD:
+        return xf + pk.gate_pre * pk.aux.float()
+    return pk.aux.float()
+
+
+def xg_ln_pre_fwd(cfg, x, packs):
+    BT, N, C = x.shape
+    xl = torch.empty((cfg.E, BT * N, C), dtype=x.dtype)
+    st = torch.empty((cfg.E, BT * N, 2), dtype=torch.float32) if packs[0].ln1_w is not None else None
+    for e, pk in enumerate(packs):
+        xa = _xg_xa(x, pk).reshape(BT * N, C)
+        if pk.ln1_w is not None:
+            mean, rstd = _ln_stats(xa)
+            st[e, :, 0], st[e, :, 1] = mean[:, 0], rstd[:, 0]
+            xa = (xa - mean) * rstd * pk.ln1_w + pk.ln1_b
+        xl[e] = xa.to(x.dtype)
+    return xl, st
+
+
+def xg_z_stats(cfg, z):
+    zz = z.double().reshape(-1, cfg.E, cfg.Cr)
+    return torch.stack([zz.sum(0), (zz * zz).sum(0)], dim=-1)
+
+
+def xg_bn_act(cfg, z, aff1, packs, dtype, bn_mode):
+    BT, N = z.shape[0], z.shape[1]
+    act = torch.zeros((cfg.E, BT * N, round8(cfg.Cr)), dtype=dtype)
+    for e, pk in enumerate(packs):
+        zt = z[:, :, e, :].reshape(BT * N, cfg.Cr)
+        if bn_mode != BN_OFF:
+            zt = zt * aff1[e, :, 0] + aff1[e, :, 1]
+        act[e, :, :cfg.Cr] = _act(zt, pk.relu).to(dtype)
+    return act
+
+
+def _xg_post_t(cfg, yd, bn2_wb, pk, e):
+    """bn2 affine applied to the normalised up projection: the tensor ln_post sees"""
+    yh = yd[e, :, :cfg.C].float()
+    return yh, (yh * bn2_wb[e][0] + bn2_wb[e][1] if bn2_wb is not None else yh)
+
+
+def xg_post_fwd(cfg, yd, bn2_wb, packs, probs, out):
+    BT, N, C = out.shape
+    st = torch.empty((cfg.E, BT * N, 2), dtype=torch.float32) if packs[0].ln2_w is not None else None
+    acc = torch.zeros((BT, N, C), dtype=torch.float32)
+    for e, pk in enumerate(packs):
+        _, t = _xg_post_t(cfg, yd, bn2_wb, pk, e)
+        if pk.ln2_w is not None:
+            mean, rstd = _ln_stats(t)
+            st[e, :, 0], st[e, :, 1] = mean[:, 0], rstd[:, 0]
+            t = (t - mean) * rstd * pk.ln2_w + pk.ln2_b
+        if pk.gate is not None:
+            t = t * pk.gate
+        acc = acc + probs[:, e, None, None] * t.reshape(BT, N, C)
+    out.copy_(acc.to(out.dtype))
+    return st
+
+
+def xg_post_bwd(cfg, dout, yd, ln2_stats, bn2_wb, bn_mode, packs, probs, dprobs, red2, egr):
+    BT, N, C = dout.shape
+    g = dout.float().reshape(BT * N, C)
+    for e, (pk, gr) in enumerate(zip(packs, egr)):
+        yh, t = _xg_post_t(cfg, yd, bn2_wb, pk, e)
+        if pk.ln2_w is not None:
+            mean, rstd = ln2_stats[e, :, 0:1], ln2_stats[e, :, 1:2]
+            qhat = (t - mean) * rstd
+            q = qhat * pk.ln2_w + pk.ln2_b
+        else:
+            qhat, q = None, t
+        gate = pk.gate if pk.gate is not None else 1.0
+        gq = (g * q).reshape(BT, N * C).sum(1)
+        dprobs[:, e] += gq * gate
+        if gr.gate is not None:
+            gr.gate += (gq * probs[:, e]).sum()
+        dq = g * (probs[:, e].repeat_interleave(N)[:, None] * gate)
+        if pk.ln2_w is not None:
+            gr.ln2_w += (dq * qhat).sum(0)
+            gr.ln2_b += dq.sum(0)
+            dqh = dq * pk.ln2_w
+            dy2 = rstd * (dqh - dqh.mean(-1, keepdim=True) - qhat * (dqh * qhat).mean(-1, keepdim=True))
+        else:
+            dy2 = dq
+        if bn_mode != BN_OFF:
+            red2[e, :, 0] += dy2.double().sum(0)
+            red2[e, :, 1] += (dy2 * yh).double().sum(0)
+        yd[e, :, C:] = dy2.to(yd.dtype)
+
+
+def xg_bn1_bwd(cfg, da, z, bn, bn_mode, packs, red1, dtype):
+    rows = da.shape[1]
+    Cr = cfg.Cr
+    dz = torch.zeros(da.shape, dtype=dtype)
+    for e, pk in enumerate(packs):
+        ze = z[:, :, e, :].reshape(rows, Cr)
+        d = da[e, :, :Cr]
+        zt = ze * bn[0][e, :, 0] + bn[0][e, :, 1] if bn_mode != BN_OFF else ze
+        if pk.relu:
+            d = d * (zt > 0)
+        if bn_mode != BN_OFF:
+            aff1, save1 = bn[0], bn[1]
+            zhat = (ze - save1[e, :, 0]) * save1[e, :, 1]
+            red1[e, :, 0] += d.double().sum(0)
+            red1[e, :, 1] += (d * zhat).double().sum(0)
+            if bn_mode == BN_TRAIN:
+                d = aff1[e, :, 0] * (d - (red1[e, :, 0] / rows).float() - zhat * (red1[e, :, 1] / rows).float())
+            else:
+                d = aff1[e, :, 0] * d
+        dz[e, :, :Cr] = d.to(dtype)
+    return dz
+
+
+def xg_ln_pre_bwd(cfg, x, dxl, ln1_stats, packs, dpool_x, dx, egr):
+    BT, N, C = x.shape
+    total = dpool_x[:, None, :].expand(BT, N, C).reshape(BT * N, C).clone() if dpool_x is not None else torch.zeros((BT * N, C))
+    for e, (pk, gr) in enumerate(zip(packs, egr)):
+        g = dxl[e].float()
+        if pk.ln1_w is not None:
+            xa = _xg_xa(x, pk).reshape(BT * N, C)
+            mean, rstd = ln1_stats[e, :, 0:1], ln1_stats[e, :, 1:2]
+            xhat = (xa - mean) * rstd
+            gr.ln1_w += (g * xhat).sum(0)
+            gr.ln1_b += g.sum(0)
+            dh = g * pk.ln1_w
+            g = rstd * (dh - dh.mean(-1, keepdim=True) - xhat * (dh * xhat).mean(-1, keepdim=True))
+        if pk.pre_kind == PRE_AUX_ADD:
+            gr.gate_pre += (g * pk.aux.float().reshape(BT * N, C)).sum()
+            gr.aux.copy_((pk.gate_pre * g).reshape(BT, N, C).to(gr.aux.dtype))
+            total = total + g
+        elif pk.pre_kind == PRE_AUX_REPLACE:
+            gr.aux.copy_(g.reshape(BT, N, C).to(gr.aux.dtype))
+        else:
+            total = total + g
+    dx.copy_(total.reshape(BT, N, C).to(dx.dtype))
+
+
+def _xg_bn2_coeffs(cfg, bn2_wb, bn, bn_mode, red2, rows, e):
+    C = cfg.C
+    alpha, beta, gamma = torch.ones(C), torch.zeros(C), torch.zeros(C)
+    if bn_mode != BN_OFF:
+        alpha = bn[3][e, :, 1] * bn2_wb[e][0]
+        if bn_mode == BN_TRAIN:
+            gamma = -alpha * (red2[e, :, 0] / rows).float()
+            beta = -alpha * (red2[e, :, 1] / rows).float()
+    return alpha, beta, gamma
+
+
+def xg_prep_bwd(cfg, packs, bn2_wb, bn, bn_mode, red2, BT, dtype):
+    rows = BT * cfg.N
+    Crp, C = round8(cfg.Cr), cfg.C
+    w2 = torch.zeros((cfg.E, Crp, 2 * C), dtype=torch.float32)
+    bias = torch.zeros((cfg.E, Crp), dtype=torch.float32)
+    for e, pk in enumerate(packs):
+        alpha, beta, gamma = _xg_bn2_coeffs(cfg, bn2_wb, bn, bn_mode, red2, rows, e)
+        wu = _dense_wu(pk.wu, cfg)                       # [C, Crp]
+        w2[e, :, :C] = (beta[:, None] * wu).t()
+        w2[e, :, C:] = (alpha[:, None] * wu).t()
+        bias[e] = (gamma[:, None] * wu).sum(0)
+    return w2.to(dtype), bias
+
+
+def xg_finish_wgrads(cfg, packs, egr, bn2_wb, bn, bn_mode, red2, BT, pwd, pwu, suma):
+    rows = BT * cfg.N
+    C, Cr, G = cfg.C, cfg.Cr, cfg.G
+    Cg, Crg = C // G, Cr // G
+    for e, (pk, gr) in enumerate(zip(packs, egr)):
+        alpha, beta, gamma = _xg_bn2_coeffs(cfg, bn2_wb, bn, bn_mode, red2, rows, e)
+        dense = alpha[:, None] * pwu[e, C:, :Cr]
+        if bn_mode == BN_TRAIN:
+            dense = dense + beta[:, None] * pwu[e, :C, :Cr] + gamma[:, None] * suma[e].float()[None, :]
+        for g in range(G):
+            gr.wd[g * Crg:(g + 1) * Crg] = pwd[e, g * Crg:(g + 1) * Crg, g * Cg:(g + 1) * Cg]
+            gr.wu[g * Cg:(g + 1) * Cg] = dense[g * Cg:(g + 1) * Cg, g * Crg:(g + 1) * Crg]

@@ -33,14 +33,30 @@ def test_cuda_matches_reference_golden_fp32(name):
 
 @pytest.mark.parametrize("name", util.golden_names())
 def test_gemm_attention_forced_on_fp32_golden(name, monkeypatch):
-    """fp32 streams default to the fused exact latent kernels; forcing the tcgen05 path (TF32 operands) must still
-    track the reference -- outputs at 2x the fp32 bound, gradients at the tensor-core gradient bound."""
+    """fp32 streams default to the fused exact latent kernels; forcing the tcgen05 latent-attention path (TF32 operands) must
+    still track the reference -- outputs at 2x the fp32 bound, gradients at the tensor-core gradient bound."""
     from avmoe_b200 import ops
     monkeypatch.setattr(ops, "USE_GEMM_ATTENTION", "always")
+    monkeypatch.setattr(ops, "USE_GEMM_EXPERTS", False)
     fx = util.load_golden(name)
     mod = build_module(fx["spec"], fx["state_dict"], kernels=None)
     got = run_module_on_fixture(mod, fx, device="cuda")
     compare_to_fixture(got, fx, 2 * TOL_F32, gtol=GTOL_F32, tensor_core=True)
+
+
+@pytest.mark.parametrize("name", util.golden_names())
+def test_gemm_orchestration_exact_on_fp32_golden(name, monkeypatch):
+    """The bf16 product orchestration (latent attention AND expert projections as GEMMs with streaming row kernels between
+    them) forced onto the fp32 golden fixtures with exact fp32 GEMMs (impl=1): every row kernel, operand-folding and
+    weight-gradient step is then pinned against the reference at the strict fp32 bound, free of tensor-core rounding."""
+    from avmoe_b200 import ops
+    monkeypatch.setattr(ops, "USE_GEMM_ATTENTION", "always")
+    monkeypatch.setattr(ops, "USE_GEMM_EXPERTS", "always")
+    monkeypatch.setattr(ops, "_GEMM_IMPL_OVERRIDE", 1)
+    fx = util.load_golden(name)
+    mod = build_module(fx["spec"], fx["state_dict"], kernels=None)
+    got = run_module_on_fixture(mod, fx, device="cuda")
+    compare_to_fixture(got, fx, TOL_F32, gtol=10 * TOL_F32, tensor_core=False)
 
 
 def _oracle_run(spec, sd, x, o, gout, training=True):

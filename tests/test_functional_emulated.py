@@ -92,11 +92,13 @@ def compare_to_fixture(got, fx, tol, gtol=None, tensor_core=False):
             assert util.rel_err(got["buffers"][k].float(), v.float(), floor=1e-6) < tol, k
 
 
-@pytest.mark.parametrize("gemm_attention", [True, False])
+@pytest.mark.parametrize("gemm_attention,gemm_experts", [(True, True), (True, False), (False, False)])
 @pytest.mark.parametrize("name", util.golden_names())
-def test_emulated_pipeline_matches_reference_golden(name, gemm_attention, monkeypatch):
-    """both latent-attention orchestrations: through the batched GEMM (product default) and the fused latent kernels"""
+def test_emulated_pipeline_matches_reference_golden(name, gemm_attention, gemm_experts, monkeypatch):
+    """all orchestrations: latent attention + expert projections through the tensor-core GEMM (the bf16 product default),
+    GEMM attention with the fused expert kernels, and the fully fused kernels (the fp32 default)"""
     monkeypatch.setattr(KE, "USE_GEMM_ATTENTION", "always" if gemm_attention else False)
+    monkeypatch.setattr(KE, "USE_GEMM_EXPERTS", "always" if gemm_experts else False)
     fx = util.load_golden(name)
     mod = build_module(fx["spec"], fx["state_dict"])
     got = run_module_on_fixture(mod, fx)
