@@ -41,6 +41,39 @@ __device__ __forceinline__ float4 ld_act4(const T* p) {
   return make_float4(v[0], v[1], v[2], v[3]);
 }
 
+// Packed 4-element loads kept in their storage form (2 registers for bf16): the next row's operands are requested before the
+// current row is processed, so every warp keeps two rows of loads in flight (the kernels are latency-, not bandwidth-limited
+// at one row per warp).
+template <typename T> struct Raw4;
+template <> struct Raw4<float> { float4 v; };
+template <> struct Raw4<__nv_bfloat16> { uint2 v; };
+__device__ __forceinline__ Raw4<float> ldg_raw(const float* p, bool pred) {
+  Raw4<float> r;
+  r.v = pred ? __ldg(reinterpret_cast<const float4*>(p)) : make_float4(0.f, 0.f, 0.f, 0.f);
+  return r;
+}
+__device__ __forceinline__ Raw4<__nv_bfloat16> ldg_raw(const __nv_bfloat16* p, bool pred) {
+  Raw4<__nv_bfloat16> r;
+  r.v = pred ? __ldg(reinterpret_cast<const uint2*>(p)) : make_uint2(0u, 0u);
+  return r;
+}
+__device__ __forceinline__ Raw4<float> ld_raw(const float* p, bool pred) {   // coherent variant
+  Raw4<float> r;
+  r.v = pred ? *reinterpret_cast<const float4*>(p) : make_float4(0.f, 0.f, 0.f, 0.f);
+  return r;
+}
+__device__ __forceinline__ Raw4<__nv_bfloat16> ld_raw(const __nv_bfloat16* p, bool pred) {
+  Raw4<__nv_bfloat16> r;
+  r.v = pred ? *reinterpret_cast<const uint2*>(p) : make_uint2(0u, 0u);
+  return r;
+}
+__device__ __forceinline__ float4 cvt(const Raw4<float>& r) { return r.v; }
+__device__ __forceinline__ float4 cvt(const Raw4<__nv_bfloat16>& r) {
+  const __nv_bfloat162 a = *reinterpret_cast<const __nv_bfloat162*>(&r.v.x);
+  const __nv_bfloat162 b = *reinterpret_cast<const __nv_bfloat162*>(&r.v.y);
+  return make_float4(__low2float(a), __high2float(a), __low2float(b), __high2float(b));
+}
+
 #define TEAM_VECS(k, c) _Pragma("unroll") for (int k = 0, c = tm.tlane * 4; k < kMaxV; ++k, c += 128 * kTeam) if (c < C)
 
 // sum of up to four values over the lanes of a team.  kTeam > 1 goes through shared memory with ONE __syncthreads per call
@@ -189,21 +222,32 @@ __global__ void __launch_bounds__(256) xg_post_bwd_kernel(const avmoe_xg_args p,
     TEAM_VECS(k, c) a_lw[k] = a_lb[k] = a_r0[k] = a_r1[k] = f4(0.f);
     float a_gate = 0.f, dp_acc = 0.f;
     long long dp_b = -1;
+    const T* dout = static_cast<const T*>(p.dout);
+    T* yde = static_cast<T*>(p.yd) + (long long)e * rows * 2 * C;
+    Raw4<T> nd[kMaxV], ny[kMaxV];
+    float2 nst = make_float2(0.f, 0.f);
+    {
+      const long long row = r0 + tm.team;
+      const bool act = row < r1;
+      TEAM_VECS(k, c) { nd[k] = ldg_raw(dout + row * C + c, act); ny[k] = ldg_raw(yde + row * 2 * C + c, act); }
+      if (ex.ln2_w && act) nst = __ldg(reinterpret_cast<const float2*>(p.ln2_stats) + (long long)e * rows + row);
+    }
     for (long long rb = r0; rb < r1; rb += kTeams) {
       const long long row = rb + tm.team;
       const bool act = row < r1;
       const long long b = act ? row / p.N : 0;
-      T* ydr = static_cast<T*>(p.yd) + ((long long)e * rows + row) * 2 * C;
+      T* ydr = yde + row * 2 * C;
       float4 d[kMaxV], yh[kMaxV], xh[kMaxV];
-      float mean = 0.f, rstd = 0.f;
-      if (ex.ln2_w && act) {
-        const float* st = p.ln2_stats + ((long long)e * rows + row) * 2;
-        mean = st[0]; rstd = st[1];
+      TEAM_VECS(k, c) { d[k] = cvt(nd[k]); yh[k] = cvt(ny[k]); }
+      const float mean = nst.x, rstd = nst.y;
+      {   // request the next row of this team
+        const long long nrow = row + kTeams;
+        const bool nact = nrow < r1;
+        TEAM_VECS(k, c) { nd[k] = ldg_raw(dout + nrow * C + c, nact); ny[k] = ldg_raw(yde + nrow * 2 * C + c, nact); }
+        nst = (ex.ln2_w && nact) ? __ldg(reinterpret_cast<const float2*>(p.ln2_stats) + (long long)e * rows + nrow) : make_float2(0.f, 0.f);
       }
       float dot = 0.f, s1 = 0.f, s2 = 0.f;
       TEAM_VECS(k, c) {
-        d[k] = act ? ldg_act4<T>(static_cast<const T*>(p.dout) + row * C + c) : f4(0.f);
-        yh[k] = act ? ldg_act4<T>(ydr + c) : f4(0.f);
         float4 t = yh[k];
         if (has_bn) t = t * ldg4(p.bn2_w[e] + c) + ldg4(p.bn2_b[e] + c);
         if (ex.ln2_w) {
@@ -284,30 +328,49 @@ __global__ void __launch_bounds__(256) xg_ln_pre_bwd_kernel(const avmoe_xg_args 
     float4 a_w[kMaxV], a_b[kMaxV];
     TEAM_VECS(k, c) a_w[k] = a_b[k] = f4(0.f);
     float a_gp = 0.f;
+    const T* dxl = static_cast<const T*>(p.dxl) + (long long)e * rows * C;
+    const T* xin = static_cast<const T*>(p.x);
+    const T* auxp = kind == AVMOE_PRE_NONE ? nullptr : static_cast<const T*>(ex.aux);
+    T* dxo = static_cast<T*>(p.dx);
+    const bool need_x = ex.ln1_w && kind != AVMOE_PRE_AUX_REPLACE;
+    const bool need_prev = e > 0 && kind != AVMOE_PRE_AUX_REPLACE;     // dx already holds the earlier experts' sum
+    Raw4<T> ng[kMaxV], nx[kMaxV], na[kMaxV], np[kMaxV];
+    float2 nst = make_float2(0.f, 0.f);
+    {
+      const long long row = r0 + tm.team;
+      const bool act = row < r1;
+      TEAM_VECS(k, c) {
+        ng[k] = ldg_raw(dxl + row * C + c, act);
+        nx[k] = ldg_raw(xin + row * C + c, act && need_x);
+        na[k] = ldg_raw(auxp + row * C + c, act && auxp);
+        np[k] = ld_raw(dxo + row * C + c, act && need_prev);
+      }
+      if (ex.ln1_w && act) nst = __ldg(reinterpret_cast<const float2*>(p.ln1_stats) + (long long)e * rows + row);
+    }
     for (long long rb = r0; rb < r1; rb += kTeams) {
       const long long row = rb + tm.team;
       const bool act = row < r1;
       const long long b = act ? row / p.N : 0;
-      const T* gr = static_cast<const T*>(p.dxl) + ((long long)e * rows + row) * C;
-      const T* xr = static_cast<const T*>(p.x) + row * C;
-      const T* aux = kind == AVMOE_PRE_NONE ? nullptr : static_cast<const T*>(ex.aux) + row * C;
-      float4 g[kMaxV], xh[kMaxV], av[kMaxV];
-      float mean = 0.f, rstd = 0.f;
-      if (ex.ln1_w && act) {
-        const float* st = p.ln1_stats + ((long long)e * rows + row) * 2;
-        mean = st[0]; rstd = st[1];
+      float4 g[kMaxV], xh[kMaxV], av[kMaxV], prev[kMaxV];
+      TEAM_VECS(k, c) { g[k] = cvt(ng[k]); xh[k] = cvt(nx[k]); av[k] = cvt(na[k]); prev[k] = cvt(np[k]); }
+      const float mean = nst.x, rstd = nst.y;
+      {   // request the next row of this team (its dx was stored by this same thread while processing the previous expert)
+        const long long nrow = row + kTeams;
+        const bool nact = nrow < r1;
+        TEAM_VECS(k, c) {
+          ng[k] = ldg_raw(dxl + nrow * C + c, nact);
+          nx[k] = ldg_raw(xin + nrow * C + c, nact && need_x);
+          na[k] = ldg_raw(auxp + nrow * C + c, nact && auxp);
+          np[k] = ld_raw(dxo + nrow * C + c, nact && need_prev);
+        }
+        nst = (ex.ln1_w && nact) ? __ldg(reinterpret_cast<const float2*>(p.ln1_stats) + (long long)e * rows + nrow) : make_float2(0.f, 0.f);
       }
-      float s1 = 0.f, s2 = 0.f;
-      TEAM_VECS(k, c) {
-        g[k] = act ? ldg_act4<T>(gr + c) : f4(0.f);
-        if (kind != AVMOE_PRE_NONE) av[k] = act ? ldg_act4<T>(aux + c) : f4(0.f);
-        if (ex.ln1_w) {
-          float4 xa;
+      if (ex.ln1_w) {
+        float s1 = 0.f, s2 = 0.f;
+        TEAM_VECS(k, c) {
+          float4 xa = xh[k];                                   // x (or unused for aux-replace)
           if (kind == AVMOE_PRE_AUX_REPLACE) xa = av[k];
-          else {
-            xa = act ? ldg_act4<T>(xr + c) : f4(0.f);
-            if (kind == AVMOE_PRE_AUX_ADD) xa = xa + gp * av[k];
-          }
+          else if (kind == AVMOE_PRE_AUX_ADD) xa = xa + gp * av[k];
           xh[k] = rstd * (xa - f4(mean));
           a_w[k] = a_w[k] + g[k] * xh[k];
           a_b[k] = a_b[k] + g[k];
@@ -315,22 +378,17 @@ __global__ void __launch_bounds__(256) xg_ln_pre_bwd_kernel(const avmoe_xg_args 
           s1 += hsum(g[k]);
           s2 += hsum(g[k] * xh[k]);
         }
-      }
-      if (ex.ln1_w) {
         const float4 sums = team_sum<kTeam>(make_float4(s1, s2, 0.f, 0.f), red, par, tm);
         const float m1 = sums.x * invC, m2 = sums.y * invC;
         TEAM_VECS(k, c) g[k] = rstd * (g[k] - f4(m1) - m2 * xh[k]);   // d xa
       }
-      T* dxr = static_cast<T*>(p.dx) + row * C;
       TEAM_VECS(k, c) {
         if (kind == AVMOE_PRE_AUX_ADD) a_gp += hsum(g[k] * av[k]);
         if (!act) continue;
         if (kind != AVMOE_PRE_NONE) st_act4<T>(static_cast<T*>(ex.g_aux) + row * C + c, kind == AVMOE_PRE_AUX_ADD ? gp * g[k] : g[k]);
-        float4 base;
-        if (e == 0) base = p.dpool_x ? ldg4(p.dpool_x + b * C + c) : f4(0.f);
-        else base = ld_act4<T>(dxr + c);           // this thread's own store of the previous expert
+        float4 base = e == 0 ? (p.dpool_x ? ldg4(p.dpool_x + b * C + c) : f4(0.f)) : prev[k];
         if (kind != AVMOE_PRE_AUX_REPLACE) base = base + g[k];
-        if (e == 0 || kind != AVMOE_PRE_AUX_REPLACE) st_act4<T>(dxr + c, base);
+        if (e == 0 || kind != AVMOE_PRE_AUX_REPLACE) st_act4<T>(dxo + row * C + c, base);
       }
     }
     if (ex.ln1_w) {

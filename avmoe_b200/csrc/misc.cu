@@ -5,6 +5,7 @@
 //                      replaces modal.mean(dim=1), AVMOE/AVE/nets/net_trans_v3.py:474-475)
 //   reduce_bias        row / column sums of a gradient tensor (autograd of the conv/linear biases)
 #include "common.cuh"
+#include "row_pass.cuh"
 
 namespace avmoe {
 
@@ -110,6 +111,51 @@ __global__ void reduce_bias_kernel(const T* __restrict__ d, const float* __restr
   }
 }
 
+// vectorised single pass (C % 4 == 0): one warp per token row, 4 channels per lane per load; column partials stay in registers
+// over the CTA's chunk, the row dot product is reduced by shuffles in the same pass
+template <typename T, int kMaxV>
+__global__ void reduce_bias_vec_kernel(const T* __restrict__ d, const float* __restrict__ colw, const float* __restrict__ roww,
+                                       float* __restrict__ rows_w, float* __restrict__ cols, float* __restrict__ cols_w, int N, int C,
+                                       int tokens_per_chunk) {
+  extern __shared__ float sm[];  // [2][C] column partials
+  float* scol = sm;
+  float* scolw = sm + C;
+  const int b = blockIdx.y;
+  const int n0 = blockIdx.x * tokens_per_chunk;
+  const int n1 = min(N, n0 + tokens_per_chunk);
+  for (int c = threadIdx.x; c < 2 * C; c += blockDim.x) sm[c] = 0.f;
+  __syncthreads();
+  const T* db = d + (long long)b * N * C;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  float4 acc[kMaxV], accw[kMaxV];
+  ROW_VECS(k, c) acc[k] = accw[k] = f4(0.f);
+  for (int n = n0 + warp; n < n1; n += nwarps) {
+    const float rw = roww ? __ldg(roww + n) : 0.f;
+    float racc = 0.f;
+    ROW_VECS(k, c) {
+      const float4 v = ldg_act4<T>(db + (long long)n * C + c);
+      acc[k] = acc[k] + v;
+      accw[k] = accw[k] + rw * v;
+      if (rows_w) racc += hsum(colw ? v * ldg4(colw + c) : v);
+    }
+    if (rows_w) {
+      racc = warp_sum(racc);
+      if (lane == 0) atomicAdd(&rows_w[n], racc);
+    }
+  }
+  ROW_VECS(k, c) {
+    atomicAdd(&scol[c], acc[k].x); atomicAdd(&scol[c + 1], acc[k].y); atomicAdd(&scol[c + 2], acc[k].z); atomicAdd(&scol[c + 3], acc[k].w);
+    if (roww) {
+      atomicAdd(&scolw[c], accw[k].x); atomicAdd(&scolw[c + 1], accw[k].y); atomicAdd(&scolw[c + 2], accw[k].z); atomicAdd(&scolw[c + 3], accw[k].w);
+    }
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    if (cols) atomicAdd(&cols[c], scol[c]);
+    if (cols_w) atomicAdd(&cols_w[c], scolw[c]);
+  }
+}
+
 __global__ void rowsum_kernel(const float* __restrict__ w, float* __restrict__ out, int rows, int cols) {
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
@@ -197,7 +243,14 @@ extern "C" int avmoe_reduce_bias(const void* d, const float* col_weight, const f
   const int tpc = (N + chunks - 1) / chunks;
   dim3 grid(chunks, BT);
   const size_t smem = 2 * (size_t)C * sizeof(float);
-  if (dtype == AVMOE_F32) reduce_bias_kernel<float><<<grid, 256, smem, st>>>((const float*)d, col_weight, row_weight, rows_w, cols, cols_w, N, C, tpc);
+  if (C % 4 == 0 && C <= 128 * kMaxVLimit) {
+    AVMOE_DISPATCH_V(C, {
+      if (dtype == AVMOE_F32)
+        reduce_bias_vec_kernel<float, kV><<<grid, 256, smem, st>>>((const float*)d, col_weight, row_weight, rows_w, cols, cols_w, N, C, tpc);
+      else
+        reduce_bias_vec_kernel<__nv_bfloat16, kV><<<grid, 256, smem, st>>>((const __nv_bfloat16*)d, col_weight, row_weight, rows_w, cols, cols_w, N, C, tpc);
+    });
+  } else if (dtype == AVMOE_F32) reduce_bias_kernel<float><<<grid, 256, smem, st>>>((const float*)d, col_weight, row_weight, rows_w, cols, cols_w, N, C, tpc);
   else reduce_bias_kernel<__nv_bfloat16><<<grid, 256, smem, st>>>((const __nv_bfloat16*)d, col_weight, row_weight, rows_w, cols, cols_w, N, C, tpc);
   AVMOE_LAUNCH_CHECK("reduce_bias_kernel");
   return 0;

@@ -118,20 +118,33 @@ __global__ void router_bwd_sample_kernel(const float* __restrict__ dprobs, const
   }
 }
 
-// dW[j][i] = sum_b dy[b][j] * xin[b][i],  db[j] = sum_b dy[b][j]   (deterministic; BT is small)
+// dW[j][i] = sum_b dy[b][j] * xin[b][i],  db[j] = sum_b dy[b][j]   (deterministic: fixed 8-way split of b + ordered combine)
+// grid (ceil(I/32), J), block (32, 8): x -> input column i, y -> slice of the batch
 __global__ void router_wgrad_kernel(const float* __restrict__ dy, const float* __restrict__ xin, float* __restrict__ dw,
                                     float* __restrict__ db, int BT, int J, int I) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  __shared__ float red[8][33];
+  const int i = blockIdx.x * 32 + threadIdx.x;
   const int j = blockIdx.y;
-  if (i < I) {
-    float s = 0.f;
-    for (int b = 0; b < BT; ++b) s = fmaf(dy[(long long)b * J + j], xin[(long long)b * I + i], s);
-    dw[(long long)j * I + i] = s;
+  float s = 0.f, sb = 0.f;
+  for (int b = threadIdx.y; b < BT; b += 8) {
+    const float d = dy[(long long)b * J + j];
+    sb += d;
+    if (i < I) s = fmaf(d, xin[(long long)b * I + i], s);
   }
-  if (blockIdx.x == 0 && threadIdx.x == 0) {
-    float s = 0.f;
-    for (int b = 0; b < BT; ++b) s += dy[(long long)b * J + j];
-    db[j] = s;
+  red[threadIdx.y][threadIdx.x] = s;
+  if (threadIdx.x == 0) red[threadIdx.y][32] = sb;
+  __syncthreads();
+  if (threadIdx.y == 0) {
+    float t = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) t += red[k][threadIdx.x];
+    if (i < I) dw[(long long)j * I + i] = t;
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+      float u = 0.f;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) u += red[k][32];
+      db[j] = u;
+    }
   }
 }
 
@@ -193,9 +206,10 @@ extern "C" int avmoe_router_bwd(const float* dprobs, const float* probs, const f
   float* dh1 = dh2 + (size_t)BT * kH2;
   router_bwd_sample_kernel<<<BT, 256, 0, st>>>(dprobs, probs, h1, h2, C, E, inv_n, w0, w2, w4, dlg, dh2, dh1, dpool_x, dpool_v);
   AVMOE_LAUNCH_CHECK("router_bwd_sample_kernel");
-  router_wgrad_kernel<<<dim3((2 * C + 127) / 128, kH1), 128, 0, st>>>(dh1, rin, dw0, db0, BT, kH1, 2 * C);
-  router_wgrad_kernel<<<dim3(1, kH2), 128, 0, st>>>(dh2, h1, dw2, db2, BT, kH2, kH1);
-  router_wgrad_kernel<<<dim3(1, E), 32, 0, st>>>(dlg, h2, dw4, db4, BT, E, kH2);
+  const dim3 wblock(32, 8);
+  router_wgrad_kernel<<<dim3((2 * C + 31) / 32, kH1), wblock, 0, st>>>(dh1, rin, dw0, db0, BT, kH1, 2 * C);
+  router_wgrad_kernel<<<dim3((kH1 + 31) / 32, kH2), wblock, 0, st>>>(dh2, h1, dw2, db2, BT, kH2, kH1);
+  router_wgrad_kernel<<<dim3((kH2 + 31) / 32, E), wblock, 0, st>>>(dlg, h2, dw4, db4, BT, E, kH2);
   AVMOE_LAUNCH_CHECK("router_wgrad_kernel");
   return 0;
 }
