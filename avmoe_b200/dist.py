@@ -51,10 +51,9 @@ class GradientAllReducer:
             off = 0
             views = []
             for g in grads:
-                v = flat[off:off + g.numel()]
-                v.copy_(g.reshape(-1))
-                views.append(v)
+                views.append(flat[off:off + g.numel()].view_as(g))
                 off += g.numel()
+            torch._foreach_copy_(views, grads)          # multi-tensor pack: a handful of launches for ~1e3 small gradients
             w = dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
             works.append((w, bucket, views))
         if async_op:
@@ -64,12 +63,13 @@ class GradientAllReducer:
 
     def finish(self, works):
         inv = 1.0 / self.world
-        for w, bucket, views in works:
+        for (w, bucket, views), flat in zip(works, self._flat):
             w.wait()
-            for p, v in zip(bucket, views):
+            flat.mul_(inv)
+            for p in bucket:
                 if p.grad is None:
                     p.grad = torch.empty_like(p)
-                p.grad.copy_(v.view_as(p)).mul_(inv)
+            torch._foreach_copy_([p.grad for p in bucket], views)
 
 
 def shard_batch(total: int, rank: int, world: int):
