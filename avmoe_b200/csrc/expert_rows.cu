@@ -116,11 +116,25 @@ __global__ void __launch_bounds__(256) xg_ln_pre_fwd_kernel(const avmoe_xg_args 
   const int C = p.C;
   const float invC = 1.f / C;
   const long long r0 = blockIdx.x * (long long)rpb, r1 = min(rows, r0 + rpb);
+  // next-row prefetch of x and of the first expert's aux stream (the common case: one aux-carrying expert)
+  const T* xin = static_cast<const T*>(p.x);
+  const T* aux0 = p.ex[0].pre_kind == AVMOE_PRE_NONE ? nullptr : static_cast<const T*>(p.ex[0].aux);
+  Raw4<T> nx[kMaxV], na[kMaxV];
+  {
+    const long long row = r0 + tm.team;
+    const bool act = row < r1;
+    TEAM_VECS(k, c) { nx[k] = ldg_raw(xin + row * C + c, act); na[k] = ldg_raw(aux0 + row * C + c, act && aux0); }
+  }
   for (long long rb = r0; rb < r1; rb += kTeams) {
     const long long row = rb + tm.team;
     const bool act = row < r1;
-    float4 xv[kMaxV];
-    TEAM_VECS(k, c) xv[k] = act ? ldg_act4<T>(static_cast<const T*>(p.x) + row * C + c) : f4(0.f);
+    float4 xv[kMaxV], a0[kMaxV];
+    TEAM_VECS(k, c) { xv[k] = cvt(nx[k]); a0[k] = cvt(na[k]); }
+    {
+      const long long nrow = row + kTeams;
+      const bool nact = nrow < r1;
+      TEAM_VECS(k, c) { nx[k] = ldg_raw(xin + nrow * C + c, nact); na[k] = ldg_raw(aux0 + nrow * C + c, nact && aux0); }
+    }
     for (int e = 0; e < p.E; ++e) {
       const avmoe_expert& ex = p.ex[e];
       float4 v[kMaxV];
@@ -130,7 +144,7 @@ __global__ void __launch_bounds__(256) xg_ln_pre_fwd_kernel(const avmoe_xg_args 
         const T* aux = static_cast<const T*>(ex.aux) + row * C;
         const float g = ex.pre_kind == AVMOE_PRE_AUX_ADD ? __ldg(ex.gate_pre) : 1.f;
         TEAM_VECS(k, c) {
-          const float4 a = act ? ldg_act4<T>(aux + c) : f4(0.f);
+          const float4 a = e == 0 ? a0[k] : (act ? ldg_act4<T>(aux + c) : f4(0.f));
           v[k] = ex.pre_kind == AVMOE_PRE_AUX_ADD ? xv[k] + g * a : a;
         }
       }
@@ -171,12 +185,19 @@ __global__ void __launch_bounds__(256) xg_post_fwd_kernel(const avmoe_xg_args p,
     const long long b = act ? row / p.N : 0;
     float4 acc[kMaxV];
     TEAM_VECS(k, c) acc[k] = f4(0.f);
+    // all experts' rows are requested up front (independent loads in flight), then reduced one expert at a time
+    Raw4<T> ry[2][kMaxV];
+#pragma unroll
+    for (int e = 0; e < 2; ++e)
+      TEAM_VECS(k, c) ry[e][k] = ldg_raw(static_cast<const T*>(p.yd) + ((long long)e * rows + row) * 2 * C + c, act && e < p.E);
     for (int e = 0; e < p.E; ++e) {
       const avmoe_expert& ex = p.ex[e];
       const T* yh = static_cast<const T*>(p.yd) + ((long long)e * rows + row) * 2 * C;
       float4 t[kMaxV];
       TEAM_VECS(k, c) {
-        t[k] = act ? ldg_act4<T>(yh + c) : f4(0.f);
+        if (e == 0) t[k] = cvt(ry[0][k]);
+        else if (e == 1) t[k] = cvt(ry[1][k]);
+        else t[k] = act ? ldg_act4<T>(yh + c) : f4(0.f);
         if (p.bn2_w[e]) t[k] = t[k] * ldg4(p.bn2_w[e] + c) + ldg4(p.bn2_b[e] + c);
       }
       if (ex.ln2_w) {
