@@ -290,8 +290,16 @@ def run_ours(args):
         else:
             ach = d["bytes"] / (d["ms"] * 1e-3) / 1e9
             name = "gemm_tcgen05_kernel (skinny expert-projection / latent-attention GEMMs)" if dom == HB else f"{dom}_kernel"
+            traffic = traffic_src = None
+            if dom == HB:   # ncu --set full DRAM bytes vs algorithmic bytes of the same launches (profiles/r01_traffic_gemm.json)
+                try:
+                    tr = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic_gemm.json")))
+                    traffic = tr["dram_to_algorithmic_ratio"] * d["bytes"] / max(d["n"], 1)
+                    traffic_src = "profiles/r01_traffic_gemm.json: measured dram/algorithmic ratio x algorithmic bytes per launch"
+                except Exception:
+                    pass
             roofline = {"bound": "hbm", "kernel": name, "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak,
-                        "traffic": None}
+                        "traffic": traffic, "traffic_source": traffic_src, "algorithmic_bytes_per_launch": d["bytes"] / max(d["n"], 1)}
         gt = agg.get(TB)
         roofline.update({"launches_per_step": d["n"], "avg_launch_ms": d["ms"] / max(d["n"], 1), "share_of_kernel_time": d["ms"] / tot_ms,
                          "peak_source": peak_src, "ridge_flop_per_byte": ridge,
