@@ -112,6 +112,15 @@ __device__ __forceinline__ void tmem_ld_32x32b_x32(uint32_t taddr, uint32_t (&r)
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+// explicit shared-space accesses for the epilogue staging slabs (the dynamic-smem carve-up hides the address space from the
+// compiler, which otherwise emits generic LD.E/ST.E with their longer latency)
+__device__ __forceinline__ void sts_f32(uint32_t addr, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory"); }
+__device__ __forceinline__ float lds_f32(uint32_t addr) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr) : "memory");
+  return v;
+}
+
 // ------------------------------------------------------------------------------------------------
 // kernel parameters
 // ------------------------------------------------------------------------------------------------
@@ -287,7 +296,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tcgen05_kernel(const __g
     const int half = (warp - 2) >> 2;  // the two warps of a quarter take alternate 32-column slabs
     int acc = 0;
     uint32_t acc_phase = 0;
-    float* stg = reinterpret_cast<float*>(staging) + (warp - 2) * (32 * 33);   // per-warp [32][33] transpose slab
+    const uint32_t stg = smem_u32(staging) + (uint32_t)((warp - 2) * (32 * 33) * 4);   // per-warp [32][33] fp32 transpose slab (shared address)
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int tb = tile / tiles_per_batch;
       const int trem = tile - tb * tiles_per_batch;
@@ -314,10 +323,36 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tcgen05_kernel(const __g
         if (p.tma_store) {
           // ---- fast path: registers -> per-warp smem slab [32][33] -> coalesced 16-byte global stores (or fp32 atomics) ----
           __syncwarp();                                   // the previous slab has been read out
+          if (has_k) {
 #pragma unroll
-          for (int e = 0; e < 32; ++e) stg[lane * 33 + e] = has_k ? __uint_as_float(r[e]) * p.alpha : 0.f;
+            for (int e = 0; e < 32; ++e) sts_f32(stg + (uint32_t)((lane * 33 + e) * 4), __uint_as_float(r[e]) * p.alpha);
+          } else {
+#pragma unroll
+            for (int e = 0; e < 32; ++e) sts_f32(stg + (uint32_t)((lane * 33 + e) * 4), 0.f);
+          }
           __syncwarp();
-          if (p.d_bf16) {
+          if (p.d_bf16 && p.vec_ok && !p.row_bias && mrow0 + 32 <= p.M && ng + 32 <= p.N) {
+            // ---- interior bf16 slab: no predicates, one 64-bit address per lane, 4 x (8 LDS + pack + 16-byte store) ----
+            const int chunk = lane & 3, rsub = lane >> 2;
+            float cb[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) cb[j] = (add_bias && p.col_bias) ? __ldg(p.col_bias + c0 + chunk * 8 + j) : 0.f;
+            __nv_bfloat16* dp = reinterpret_cast<__nv_bfloat16*>(p.D) + bb * p.d_bstride + (long long)(mrow0 + rsub) * p.ldd + c0 + chunk * 8;
+            const uint32_t sp = stg + (uint32_t)((rsub * 33 + chunk * 8) * 4);
+            const long long step = 8 * p.ldd;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              float o[8];
+#pragma unroll
+              for (int j = 0; j < 8; ++j) o[j] = lds_f32(sp + (uint32_t)((k * (8 * 33) + j) * 4)) + cb[j];
+              uint4 q;
+              __nv_bfloat162 h0 = __floats2bfloat162_rn(o[0], o[1]), h1 = __floats2bfloat162_rn(o[2], o[3]);
+              __nv_bfloat162 h2 = __floats2bfloat162_rn(o[4], o[5]), h3 = __floats2bfloat162_rn(o[6], o[7]);
+              q.x = *reinterpret_cast<uint32_t*>(&h0); q.y = *reinterpret_cast<uint32_t*>(&h1);
+              q.z = *reinterpret_cast<uint32_t*>(&h2); q.w = *reinterpret_cast<uint32_t*>(&h3);
+              *reinterpret_cast<uint4*>(dp + k * step) = q;
+            }
+          } else if (p.d_bf16) {
             const int chunk = lane & 3, rsub = lane >> 2;          // 8 columns per lane, 8 rows per instruction
             const long long cc = c0 + chunk * 8;
             const bool cvalid = ng + chunk * 8 < p.N;
@@ -336,7 +371,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tcgen05_kernel(const __g
                 const float rbv = (add_bias && p.row_bias) ? __ldg(p.row_bias + mm) : 0.f;
                 float o[8];
 #pragma unroll
-                for (int j = 0; j < 8; ++j) o[j] = stg[row * 33 + chunk * 8 + j] + rbv * cs[j] + cb[j];
+                for (int j = 0; j < 8; ++j) o[j] = lds_f32(stg + (uint32_t)((row * 33 + chunk * 8 + j) * 4)) + rbv * cs[j] + cb[j];
                 __nv_bfloat16* dp = reinterpret_cast<__nv_bfloat16*>(p.D) + bb * p.d_bstride + mm * p.ldd + cc;
                 const int valid = (int)min((long long)8, p.N - (ng + chunk * 8));
                 if (valid == 8 && p.vec_ok) {
@@ -371,7 +406,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tcgen05_kernel(const __g
                 const float rbv = (add_bias && p.row_bias) ? __ldg(p.row_bias + mm) : 0.f;
                 float o[4];
 #pragma unroll
-                for (int j = 0; j < 4; ++j) o[j] = stg[row * 33 + chunk * 4 + j] + rbv * cs[j] + cb[j];
+                for (int j = 0; j < 4; ++j) o[j] = lds_f32(stg + (uint32_t)((row * 33 + chunk * 4 + j) * 4)) + rbv * cs[j] + cb[j];
                 float* dp = reinterpret_cast<float*>(p.D) + bb * p.d_bstride + mm * p.ldd + cc;
                 const int valid = (int)min((long long)4, p.N - (ng + chunk * 4));
                 if (p.atomic) {

@@ -98,6 +98,14 @@ class AdapterStack(nn.Module):
                 if isinstance(m, nn.MultiheadAttention):
                     m.dropout = 0.0
 
+    parallel_modalities = True
+    _side = None
+
+    def _side_stream(self, device):
+        if self._side is None or self._side.device != device:
+            object.__setattr__(self, "_side", torch.cuda.Stream(device=device))
+        return self._side
+
     def stages(self):
         return [s for s, _ in VARIANT_SITES[self.variant]]
 
@@ -117,8 +125,23 @@ class AdapterStack(nn.Module):
             f_a, f_v = cur[stage]
             for pa, pv in ((self.audio_moe_adapter_blocks_p1, self.vis_moe_adapter_blocks_p1),
                            (self.audio_moe_adapter_blocks_p2, self.vis_moe_adapter_blocks_p2)):
-                ra, la = self._call(pa[i], f_a, f_v)
-                rv, lv = self._call(pv[i], f_v, f_a)
+                # The audio-side and visual-side adapters of a block read the same pre-update features and are independent
+                # (net_trans_v3.py:695-705), so on a GPU they run on two streams: the small stage-3/4 kernels of one fill the
+                # SMs the other leaves idle.  Autograd replays each node on its forward stream, so the backward overlaps too.
+                if self.parallel_modalities and f_a.is_cuda:
+                    main = torch.cuda.current_stream()
+                    side = self._side_stream(f_a.device)
+                    side.wait_stream(main)
+                    with torch.cuda.stream(side):
+                        rv, lv = self._call(pv[i], f_v, f_a)
+                    ra, la = self._call(pa[i], f_a, f_v)
+                    main.wait_stream(side)
+                    rv.record_stream(main)
+                    if lv is not None:
+                        lv.record_stream(main)
+                else:
+                    ra, la = self._call(pa[i], f_a, f_v)
+                    rv, lv = self._call(pv[i], f_v, f_a)
                 f_v = f_v + rv
                 f_a = f_a + ra
                 for l in (la, lv):
