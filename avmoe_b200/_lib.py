@@ -25,6 +25,7 @@ class GemmArgs(C.Structure):
         ("alpha", C.c_float),
         ("row_bias", C.c_void_p), ("col_scale", C.c_void_p), ("col_bias", C.c_void_p),
         ("split_k", C.c_int32), ("accumulate", C.c_int32), ("impl", C.c_int32), ("full_batch", C.c_int32),
+        ("col_bias_bstride", C.c_int64),
     ]
 
 

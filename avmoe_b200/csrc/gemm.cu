@@ -160,6 +160,7 @@ struct GemmParams {
   const float* row_bias;
   const float* col_scale;
   const float* col_bias;
+  long long cb_bstride;   // full_batch: col_bias advances by this many floats per problem (0 = shared)
   int atomic;
 };
 
@@ -311,6 +312,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tcgen05_kernel(const __g
       const int mrow0 = m0 + quarter * 32;
       const long long m = mrow0 + lane;
       const bool add_bias = (split == 0);
+      const float* cbias = p.col_bias ? p.col_bias + (long long)tb * p.cb_bstride : nullptr;
       const float rb = (add_bias && p.row_bias && m < p.M) ? p.row_bias[m] : 0.f;
       for (int g = half; g < p.BN / 32; g += 2) {
         const long long ng = (long long)n0 + g * 32;
@@ -336,7 +338,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tcgen05_kernel(const __g
             const int chunk = lane & 3, rsub = lane >> 2;
             float cb[8];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) cb[j] = (add_bias && p.col_bias) ? __ldg(p.col_bias + c0 + chunk * 8 + j) : 0.f;
+            for (int j = 0; j < 8; ++j) cb[j] = (add_bias && cbias) ? __ldg(cbias + c0 + chunk * 8 + j) : 0.f;
             __nv_bfloat16* dp = reinterpret_cast<__nv_bfloat16*>(p.D) + bb * p.d_bstride + (long long)(mrow0 + rsub) * p.ldd + c0 + chunk * 8;
             const uint32_t sp = stg + (uint32_t)((rsub * 33 + chunk * 8) * 4);
             const long long step = 8 * p.ldd;
@@ -361,7 +363,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tcgen05_kernel(const __g
             for (int j = 0; j < 8; ++j) {
               const long long ce = cc + j < p.Nb ? cc + j : 0;
               cs[j] = (add_bias && p.row_bias) ? (p.col_scale ? __ldg(p.col_scale + ce) : 1.f) : 0.f;
-              cb[j] = (add_bias && p.col_bias) ? __ldg(p.col_bias + ce) : 0.f;
+              cb[j] = (add_bias && cbias) ? __ldg(cbias + ce) : 0.f;
             }
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
@@ -396,7 +398,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tcgen05_kernel(const __g
             for (int j = 0; j < 4; ++j) {
               const long long ce = cc + j < p.Nb ? cc + j : 0;
               cs[j] = (add_bias && p.row_bias) ? (p.col_scale ? __ldg(p.col_scale + ce) : 1.f) : 0.f;
-              cb[j] = (add_bias && p.col_bias) ? __ldg(p.col_bias + ce) : 0.f;
+              cb[j] = (add_bias && cbias) ? __ldg(cbias + ce) : 0.f;
             }
 #pragma unroll
             for (int k = 0; k < 8; ++k) {
@@ -436,7 +438,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tcgen05_kernel(const __g
               if (add_bias) {
                 const long long ce = c + e;
                 if (p.row_bias) val += rb * (p.col_scale ? p.col_scale[ce < p.Nb ? ce : 0] : 1.f);
-                if (p.col_bias) val += p.col_bias[ce < p.Nb ? ce : 0];
+                if (cbias) val += cbias[ce < p.Nb ? ce : 0];
               }
               o[e] = val;
             }
@@ -489,7 +491,7 @@ struct SimtParams {
   int a_kmajor, b_kmajor, a_batch, b_batch, n_batched, b_nbatched, full_batch;
   long long lda, ldb, ldd, a_bstride, b_bstride, d_bstride;
   float alpha;
-  const float* row_bias; const float* col_scale; const float* col_bias;
+  const float* row_bias; const float* col_scale; const float* col_bias; long long cb_bstride;
   int accumulate;
 };
 
@@ -516,7 +518,7 @@ __global__ void gemm_simt_kernel(const SimtParams p) {
   }
   float val = acc * p.alpha;
   if (p.row_bias) val += p.row_bias[m] * (p.col_scale ? p.col_scale[c] : 1.f);
-  if (p.col_bias) val += p.col_bias[c];
+  if (p.col_bias) val += p.col_bias[fbz * p.cb_bstride + c];
   const long long off = bb * p.d_bstride + m * p.ldd + c;
   if (p.d_bf16) reinterpret_cast<__nv_bfloat16*>(p.D)[off] = __float2bfloat16_rn(val);
   else if (p.accumulate) reinterpret_cast<float*>(p.D)[off] += val;
@@ -590,6 +592,7 @@ static int launch_simt(const avmoe_gemm_args* a, cudaStream_t st) {
   p.lda = a->lda; p.ldb = a->ldb; p.ldd = a->ldd;
   p.a_bstride = a->a_bstride; p.b_bstride = a->b_bstride; p.d_bstride = a->d_bstride;
   p.alpha = a->alpha; p.row_bias = a->row_bias; p.col_scale = a->col_scale; p.col_bias = a->col_bias;
+  p.cb_bstride = a->full_batch > 1 ? a->col_bias_bstride : 0;
   p.accumulate = a->accumulate;
   p.full_batch = a->full_batch > 1 ? a->full_batch : 1;
   if (p.full_batch > 1) { p.a_batch = p.b_batch = 1; }
@@ -762,6 +765,7 @@ int gemm_dispatch(const avmoe_gemm_args* a, cudaStream_t st) {
   p.D = a->D; p.d_bf16 = a->d_dtype == AVMOE_BF16;
   p.M = a->M; p.N = a->N; p.Nb = Nb; p.ldd = a->ldd; p.d_bstride = a->d_bstride; p.n_batched = n_batched;
   p.alpha = a->alpha; p.row_bias = a->row_bias; p.col_scale = a->col_scale; p.col_bias = a->col_bias;
+  p.cb_bstride = a->full_batch > 1 ? a->col_bias_bstride : 0;
   p.atomic = atomic;
   if (p.splits > 1 && !a->accumulate) {
     if (n_batched) {

@@ -250,8 +250,9 @@ def gemm_attn2_bwd(K, x, tokp_op, A2, dXR, T: int, dx):
     return dtokp
 
 
-def gemm_latent_bwd(K, kv, tok, tokp, A12, dtokp, T: int):
-    """Backward of gemm_latent_fwd given d tok' [BT,T,C] fp32.  Returns (dkv [BT,Nk,C] in kv.dtype, d tok [T,C] fp32)."""
+def gemm_latent_bwd(K, kv, tok, tokp, A12, dtokp, T: int, dkv_bias=None):
+    """Backward of gemm_latent_fwd given d tok' [BT,T,C] fp32.  Returns (dkv [BT,Nk,C] in kv.dtype, d tok [T,C] fp32).
+    dkv_bias [BT,C] fp32 (the router-path gradient of mean_N(kv)) is added to every row of dkv in the GEMM epilogue."""
     BT, Nk, C = kv.shape
     Tp = A12.shape[2] // 2
     dt = kv.dtype
@@ -263,7 +264,7 @@ def gemm_latent_bwd(K, kv, tok, tokp, A12, dtokp, T: int):
     B12 = torch.zeros((BT, 2 * Tp, C), device=kv.device, dtype=dt)                       # [dR ; tok] stacked along K
     B12[:, :T] = dR_lp
     B12[:, Tp:Tp + T] = K.cast_to(tok, dt)
-    dkv = K.bgemm(A12, B12, b_kmajor=False)                                              # A1ᵀ·dR + dS1ᵀ·tok   [BT,Nk,C]
+    dkv = K.bgemm(A12, B12, b_kmajor=False, col_bias=dkv_bias)                           # A1ᵀ·dR + dS1ᵀ·tok (+ bias)  [BT,Nk,C]
     dS1_flat = A12.reshape(BT * Nk, 2 * Tp)[:, Tp:Tp + T]                                # [K=(b,n), M=T]
     dtok = K.gemm(dS1_flat, kv.reshape(BT * Nk, C), a_kmajor=False, b_kmajor=False, out_dtype=f32,
                   split_k=K.split_k_hint(BT * Nk, T, C))                                 # sum_{b,n} dS1ᵀ·kv   [T,C]
@@ -319,9 +320,7 @@ def gemm_experts_fwd(K, cfg, x, packs, probs, P, bufs, prefixes, bn_mode):
     wdd, wdt = K.xg_prep_weights(cfg, packs, dt)                                  # [E,Cr,C], [E,C,Crp]
     xl, ln1s = K.xg_ln_pre_fwd(cfg, x, packs)                                     # [E,rows,C]
     z = torch.empty((BT, N, E, Cr), device=dev, dtype=f32)
-    zf = z.view(rows, E * Cr)
-    for e in range(E):
-        K.gemm(xl[e], wdd[e], out=zf[:, e * Cr:(e + 1) * Cr])                     # down projection
+    K.bgemm(xl, wdd, out=z.view(rows, E, Cr).permute(1, 0, 2))                    # down projection, all experts in one launch
     bn = bn2_wb = suma = None
     if bn_mode != BN_OFF:
         bn_w, bn_b = _bn_params(P, bufs, prefixes)
@@ -343,8 +342,7 @@ def gemm_experts_fwd(K, cfg, x, packs, probs, P, bufs, prefixes, bn_mode):
     act = K.xg_bn_act(cfg, z, bn[0] if bn else None, packs, dt, bn_mode)          # [E,rows,Crp]
     wud, ybi = K.xg_prep_up(cfg, packs, bn[3] if bn else None, bn_mode, dt)       # bn2 normalisation folded into the operand
     yd = torch.empty((E, rows, 2 * C), device=dev, dtype=dt)
-    for e in range(E):
-        K.gemm(act[e], wud[e], out=yd[e][:, :C], col_bias=ybi[e])                 # up projection -> normalised y
+    K.bgemm(act, wud, out=yd[:, :, :C], col_bias=ybi)                             # up projection -> normalised y (per-expert bias)
     out = torch.empty_like(x)
     ln2s = K.xg_post_fwd(cfg, yd, bn2_wb, packs, probs, out)
     return out, z, bn, (xl, ln1s, act, yd, ln2s, wdt, suma)
@@ -366,14 +364,14 @@ def gemm_experts_bwd(K, cfg, x, dout, z, bn, bn_mode, packs, egr, probs, P, pref
     w2, bias2 = K.xg_prep_bwd(cfg, packs, bn2_wb, bn, bn_mode, red2, BT, dt)               # bn2 backward folded into the operand
     da = torch.empty((E, rows, Crp), device=dev, dtype=f32)
     pwu = torch.empty((E, 2 * C, Crp), device=dev, dtype=f32)
+    K.bgemm(yd, w2, out=da, col_bias=bias2)                                                # d a = dy · Wu   (all experts)
     for e in range(E):
-        K.gemm(yd[e], w2[e], out=da[e], col_bias=bias2[e])                                 # d a = dy · Wu
         K.gemm(yd[e], act[e], a_kmajor=False, b_kmajor=False, out=pwu[e], split_k=K.split_k_hint(rows, 2 * C, Crp))
     dz = K.xg_bn1_bwd(cfg, da, z, bn, bn_mode, packs, red1, dt)                            # relu mask + bn1 backward
     dxl = torch.empty((E, rows, C), device=dev, dtype=dt)
     pwd = torch.empty((E, Crp, C), device=dev, dtype=f32)
+    K.bgemm(dz, wdt, out=dxl)                                                              # d xl = dz · Wd  (all experts)
     for e in range(E):
-        K.gemm(dz[e], wdt[e], out=dxl[e])                                                  # d xl = dz · Wd
         K.gemm(dz[e], xl[e], a_kmajor=False, b_kmajor=False, out=pwd[e], split_k=K.split_k_hint(rows, Crp, C))
     K.xg_finish_wgrads(cfg, packs, egr, bn2_wb, bn, bn_mode, red2, BT, pwd, pwu, suma)
     return dprobs, red1, red2, dxl, ln1s
@@ -599,7 +597,9 @@ class MoEAdapterFunction(torch.autograd.Function):
             elif kind == "latent_gemm":
                 kv_is_x, tokp_e, tokp_op, A12, A2 = ctx.aux_saved[e]
                 dtokp_e = gemm_attn2_bwd(K, x, tokp_op, A2, egr[e].aux, T, dx)   # adds into dx
-                dkv, dtok = gemm_latent_bwd(K, x if kv_is_x else v, P[pfx + "my_tokens"], tokp_e, A12, dtokp_e, T)
+                fold_pool = not kv_is_x and dv is None                           # router path d mean_N(v): once, in the epilogue
+                dkv, dtok = gemm_latent_bwd(K, x if kv_is_x else v, P[pfx + "my_tokens"], tokp_e, A12, dtokp_e, T,
+                                            dkv_bias=dpool_v if fold_pool else None)
                 grads[pfx + "my_tokens"] = dtok
                 if kv_is_x:
                     K.add_into(dx, dkv)
@@ -607,8 +607,6 @@ class MoEAdapterFunction(torch.autograd.Function):
                     dv = dkv
                 else:
                     K.add_into(dv, dkv)
-        if dv is not None:
-            K.add_rowvec(dv, dpool_v)                                            # router path: d mean_N(v)
         # 5. fused latent attention backward (when the GEMM path is off) -> dv (and dx for latent-self), d my_tokens
         if nl:
             dtokens = [torch.zeros((T, C), device=dev, dtype=f32) for _ in range(nl)]

@@ -160,8 +160,10 @@ def bgemm(A: torch.Tensor, B: torch.Tensor, *, a_kmajor: bool = True, b_kmajor: 
     a.a_bstride, a.b_bstride, a.d_bstride = A.stride(0), B.stride(0), out.stride(0)
     a.alpha = alpha
     a.A, a.B, a.D = A.data_ptr(), B.data_ptr(), out.data_ptr()
-    if col_bias is not None:
+    if col_bias is not None:          # [N] shared by every problem, or [b,N] one bias per problem
+        assert col_bias.dtype == torch.float32 and col_bias.stride(-1) == 1 and col_bias.shape[-1] == N
         a.col_bias = col_bias.data_ptr()
+        a.col_bias_bstride = col_bias.stride(0) if col_bias.dim() == 2 else 0
     a.split_k, a.accumulate, a.impl, a.full_batch = 1, 0, impl or _GEMM_IMPL_OVERRIDE, nb
     global LAUNCHES
     LAUNCHES += 1

@@ -97,6 +97,7 @@ typedef struct {
   int32_t impl;
   int32_t full_batch;         /* >1: that many independent problems; A, B, D advance by a_bstride/b_bstride/d_bstride
                                  (a_batch = b_batch = 1, no N-batching, no split-K) */
+  int64_t col_bias_bstride;   /* full_batch: col_bias advances by this many floats per problem (0 = one bias shared by all) */
 } avmoe_gemm_args;
 
 int avmoe_gemm(const avmoe_gemm_args* args, avmoe_stream_t stream);

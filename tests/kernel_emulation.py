@@ -67,7 +67,7 @@ def bgemm(A, B, *, a_kmajor=True, b_kmajor=True, out_dtype=None, alpha=1.0, col_
     Bf = B.float() if b_kmajor else B.float().transpose(1, 2)
     D = alpha * (Af @ Bf.transpose(1, 2))
     if col_bias is not None:
-        D = D + col_bias
+        D = D + (col_bias[:, None, :] if col_bias.dim() == 2 else col_bias)
     if out is not None:
         out.copy_(D.to(out.dtype))
         return out

@@ -154,3 +154,25 @@ def test_gemm_resampler_shape_bf16():
     D = ops.gemm(W, P, b_kmajor=False)
     ref = torch.einsum("mk,bkn->bmn", W.float(), P.float())
     assert util.rel_err(D, ref) < 1e-2
+
+
+@pytest.mark.parametrize("impl", [0, 1])
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32])
+def test_bgemm_per_problem_bias_and_strided_outputs(dtype, impl):
+    """the expert-path forms: one launch for E experts with a per-expert column bias, output written through a strided view
+    ([rows,E,Cr] bottleneck buffer / first half of the [rows,2C] yd buffer)."""
+    from avmoe_b200 import ops
+    E, rows, C, Cr = 2, 300, 192, 24
+    xl, wdd = _mk((E, rows, C), dtype, 1), _mk((E, Cr, C), dtype, 2)
+    z = torch.zeros((rows, E, Cr), device="cuda", dtype=torch.float32)
+    ops.bgemm(xl, wdd, out=z.permute(1, 0, 2), impl=impl)
+    assert util.rel_err(z.permute(1, 0, 2), xl.float() @ wdd.float().transpose(1, 2)) < _tol(dtype)
+    act, wud = _mk((E, rows, Cr), dtype, 3), _mk((E, C, Cr), dtype, 4)
+    bias = _mk((E, C), torch.float32, 5)
+    yd = torch.full((E, rows, 2 * C), 7.0, device="cuda", dtype=dtype)
+    ops.bgemm(act, wud, out=yd[:, :, :C], col_bias=bias, impl=impl)
+    want = act.float() @ wud.float().transpose(1, 2) + bias[:, None, :]
+    assert util.rel_err(yd[:, :, :C].float(), want) < (2e-2 if dtype == torch.bfloat16 else _tol(dtype))
+    assert torch.all(yd[:, :, C:] == 7.0), "the second half of the buffer must be untouched"
+    shared = ops.bgemm(act, wud, out_dtype=torch.float32, col_bias=bias[0].contiguous(), impl=impl)
+    assert util.rel_err(shared, act.float() @ wud.float().transpose(1, 2) + bias[0]) < _tol(dtype)
