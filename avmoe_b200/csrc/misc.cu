@@ -29,6 +29,37 @@ __global__ void transpose_kernel(const TIn* __restrict__ in, TOut* __restrict__ 
   }
 }
 
+// bf16 -> bf16 with 64x64 tiles and 4-byte accesses on both sides (full 128-byte rows per warp instruction); needs even R, C,
+// pitches and 4-byte aligned bases
+__global__ void __launch_bounds__(256) transpose_bf16_x2_kernel(const __nv_bfloat16* __restrict__ in, __nv_bfloat16* __restrict__ out, int R, int C,
+                                                                long long in_ld, long long in_bs, long long out_ld, long long out_bs) {
+  __shared__ __nv_bfloat16 tile[64][66];
+  const int b = blockIdx.z;
+  const int c0 = blockIdx.x * 64, r0 = blockIdx.y * 64;
+  const __nv_bfloat16* ip = in + (long long)b * in_bs;
+  __nv_bfloat16* op = out + (long long)b * out_bs;
+  const int tx = threadIdx.x, ty = threadIdx.y;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int r = r0 + ty + 8 * i, c = c0 + 2 * tx;
+    __nv_bfloat162 v = __floats2bfloat162_rn(0.f, 0.f);
+    if (r < R && c < C) v = *reinterpret_cast<const __nv_bfloat162*>(ip + (long long)r * in_ld + c);
+    *reinterpret_cast<__nv_bfloat162*>(&tile[ty + 8 * i][2 * tx]) = v;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int cl = ty + 8 * i;                 // input column -> output row
+    const int c = c0 + cl, r = r0 + 2 * tx;    // output columns r, r+1
+    if (c < C && r < R) {
+      __nv_bfloat162 v;
+      v.x = tile[2 * tx][cl];
+      v.y = tile[2 * tx + 1][cl];
+      *reinterpret_cast<__nv_bfloat162*>(op + (long long)c * out_ld + r) = v;
+    }
+  }
+}
+
 template <typename TIn, typename TOut>
 __global__ void cast_kernel(const TIn* __restrict__ in, TOut* __restrict__ out, long long n) {
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
@@ -197,6 +228,10 @@ extern "C" int avmoe_transpose(const void* in, void* out, int batch, int R, int 
     transpose_kernel<float, float><<<grid, block, 0, st>>>((const float*)in, (float*)out, R, C, in_ld, in_bstride, out_ld, out_bstride);
   else if (in_dtype == AVMOE_F32 && out_dtype == AVMOE_BF16)
     transpose_kernel<float, __nv_bfloat16><<<grid, block, 0, st>>>((const float*)in, (__nv_bfloat16*)out, R, C, in_ld, in_bstride, out_ld, out_bstride);
+  else if (in_dtype == AVMOE_BF16 && out_dtype == AVMOE_BF16 && R % 2 == 0 && C % 2 == 0 && in_ld % 2 == 0 && in_bstride % 2 == 0 && out_ld % 2 == 0 &&
+           out_bstride % 2 == 0 && (uintptr_t)in % 4 == 0 && (uintptr_t)out % 4 == 0 && (R + 63) / 64 <= 65535)
+    transpose_bf16_x2_kernel<<<dim3((C + 63) / 64, (R + 63) / 64, batch), block, 0, st>>>((const __nv_bfloat16*)in, (__nv_bfloat16*)out, R, C, in_ld, in_bstride,
+                                                                                       out_ld, out_bstride);
   else if (in_dtype == AVMOE_BF16 && out_dtype == AVMOE_BF16)
     transpose_kernel<__nv_bfloat16, __nv_bfloat16><<<grid, block, 0, st>>>((const __nv_bfloat16*)in, (__nv_bfloat16*)out, R, C, in_ld, in_bstride, out_ld, out_bstride);
   else { set_error("transpose: unsupported dtype pair"); return AVMOE_E_UNSUPPORTED; }

@@ -113,3 +113,14 @@ def test_split_operand_tile_add_dots_and_sums(T, C):
         want = (d.float() + vec[:, None, :]).to(dt)
         ops.add_rowvec(d, vec)
         assert torch.allclose(d.float(), want.float(), atol=1e-2 if dt == torch.bfloat16 else 1e-6)
+
+
+@pytest.mark.parametrize("shape", [(3, 144, 384), (2, 2304, 96), (2, 37, 50), (1, 36, 1536), (2, 65, 130)])
+def test_transpose_layout_helper(shape):
+    """[b,R,C] -> [b,C,R]: the 64x64 bf16 fast path (even sizes), the generic path (odd sizes) and the casting forms are exact."""
+    ops = _ops()
+    t = _rand(*shape, seed=13).cuda()
+    tb = t.bfloat16()
+    assert torch.equal(ops.transpose(tb), tb.transpose(1, 2).contiguous())
+    assert torch.equal(ops.transpose(t), t.transpose(1, 2).contiguous())
+    assert torch.equal(ops.transpose(t, torch.bfloat16), t.transpose(1, 2).contiguous().bfloat16())
