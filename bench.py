@@ -236,8 +236,41 @@ def run_ours(args):
         loss = run_step(tokens_host)       # pinned host -> device copies of this step's tokens, then the step
         return float(loss.item())          # device -> host read of the step's result
 
-    e2e_step()
-    ms_e2e = timed(e2e_step, args.steps) / args.steps
+    if graph is None:
+        e2e_step()
+        ms_e2e = timed(e2e_step, args.steps) / args.steps
+    else:
+        # Pipelined: step i+1's tokens stream host -> device (copy stream, staging buffers) while step i computes; a
+        # device-to-device copy moves them into the graph's static inputs.  Every step's H2D copy and loss read-back is
+        # inside the timed region (K copies for K steps).
+        copy_stream = torch.cuda.Stream()
+        staging = {s: (torch.empty_like(a), torch.empty_like(v)) for s, (a, v) in tokens_dev.items()}
+        landed, consumed = torch.cuda.Event(), torch.cuda.Event()
+
+        def issue_h2d():
+            with torch.cuda.stream(copy_stream):
+                for s, (a, v) in tokens_host.items():
+                    staging[s][0].copy_(a, non_blocking=True)
+                    staging[s][1].copy_(v, non_blocking=True)
+                landed.record(copy_stream)
+
+        def e2e_loop(n):
+            main = torch.cuda.current_stream()
+            issue_h2d()
+            for i in range(n):
+                main.wait_event(landed)
+                for s in tokens_dev:
+                    tokens_dev[s][0].copy_(staging[s][0], non_blocking=True)
+                    tokens_dev[s][1].copy_(staging[s][1], non_blocking=True)
+                consumed.record(main)
+                if i + 1 < n:
+                    copy_stream.wait_event(consumed)
+                    issue_h2d()
+                loss = run_step()
+                float(loss.item())
+
+        e2e_loop(2)
+        ms_e2e = timed(lambda: e2e_loop(args.steps), 1) / args.steps
     e2e = {"value": tokens_per_step * world / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d_bytes * world,
            "d2h_bytes_per_step": 4 * world, "ms_per_step": ms_e2e}
 
