@@ -522,9 +522,21 @@ class MoEAdapterFunction(torch.autograd.Function):
         grads: Dict[str, Optional[torch.Tensor]] = {n: None for n in names}
         dout = dout.contiguous()
 
-        # rebuild packs (parameters come from saved tensors)
+        # rebuild packs (parameters come from saved tensors); the small fp32 gradient accumulators of all experts are views of
+        # ONE zero-filled arena (a single fill instead of ~9 per expert)
         packs: List[ExpertPack] = []
         egr: List[ExpertGrads] = []
+        arena_req = []          # (ExpertGrads, field, shape, offset)
+        arena_len = 0
+
+        def want(g, field, shape):
+            nonlocal arena_len
+            n = 1
+            for d in shape:
+                n *= d
+            arena_req.append((g, field, shape, arena_len, n))
+            arena_len += (n + 3) // 4 * 4
+
         for e, (pfx, (pre, relu, slot)) in enumerate(zip(prefixes, ctx.packs_meta)):
             multimodal = e < cfg.Mm
             pk = ExpertPack(pre_kind=pre, relu=relu, latent_slot=slot, aux=ctx.aux[e])
@@ -532,24 +544,26 @@ class MoEAdapterFunction(torch.autograd.Function):
             if ctx.gate_keys[e] is not None:
                 pk.gate_pre = P[pfx + ctx.gate_keys[e]]
             if pk.gate_pre is not None:
-                g.gate_pre = torch.zeros(1, device=dev, dtype=f32)
+                want(g, "gate_pre", (1,))
             if pre in (PRE_AUX_ADD, PRE_AUX_REPLACE):
                 g.aux = torch.empty((BT, N, C), device=dev, dtype=x.dtype)
             if cfg.ln_before:
                 pk.ln1_w, pk.ln1_b = P[pfx + "ln_before.weight"], P[pfx + "ln_before.bias"]
-                g.ln1_w, g.ln1_b = torch.zeros(C, device=dev, dtype=f32), torch.zeros(C, device=dev, dtype=f32)
+                want(g, "ln1_w", (C,)); want(g, "ln1_b", (C,))
             if cfg.ln_post:
                 pk.ln2_w, pk.ln2_b = P[pfx + "ln_post.weight"], P[pfx + "ln_post.bias"]
-                g.ln2_w, g.ln2_b = torch.zeros(C, device=dev, dtype=f32), torch.zeros(C, device=dev, dtype=f32)
+                want(g, "ln2_w", (C,)); want(g, "ln2_b", (C,))
             pk.wd = P[pfx + "down_sampler.weight"].reshape(Cr, C // G)
             pk.wu = P[pfx + "up_sampler.weight"].reshape(C, Cr // G)
-            g.wd = torch.zeros((Cr, C // G), device=dev, dtype=f32)
-            g.wu = torch.zeros((C, Cr // G), device=dev, dtype=f32)
+            want(g, "wd", (Cr, C // G)); want(g, "wu", (C, Cr // G))
             if cfg.use_gate:
                 pk.gate = P[pfx + "gate"]
-                g.gate = torch.zeros(1, device=dev, dtype=f32)
+                want(g, "gate", (1,))
             packs.append(pk)
             egr.append(g)
+        arena = torch.zeros(arena_len, device=dev, dtype=f32)
+        for g, field, shape, off, n in arena_req:
+            setattr(g, field, arena[off:off + n].view(shape))
 
         # 1. expert back (BN2 batch reductions first when training with BN)
         use_xg = ctx.xg_saved is not None
