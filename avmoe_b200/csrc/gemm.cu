@@ -161,6 +161,7 @@ struct GemmParams {
   const float* col_scale;
   const float* col_bias;
   long long cb_bstride;   // full_batch: col_bias advances by this many floats per problem (0 = shared)
+  int acc_bf16;           // bf16 D, accumulate: D = D + result (read-modify-write in the epilogue, one rounding)
   int atomic;
 };
 
@@ -347,6 +348,12 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tcgen05_kernel(const __g
               float o[8];
 #pragma unroll
               for (int j = 0; j < 8; ++j) o[j] = lds_f32(sp + (uint32_t)((k * (8 * 33) + j) * 4)) + cb[j];
+              if (p.acc_bf16) {
+                const uint4 old = *reinterpret_cast<const uint4*>(dp + k * step);
+                const __nv_bfloat162* oh = reinterpret_cast<const __nv_bfloat162*>(&old);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) { o[2 * j] += __low2float(oh[j]); o[2 * j + 1] += __high2float(oh[j]); }
+              }
               uint4 q;
               __nv_bfloat162 h0 = __floats2bfloat162_rn(o[0], o[1]), h1 = __floats2bfloat162_rn(o[2], o[3]);
               __nv_bfloat162 h2 = __floats2bfloat162_rn(o[4], o[5]), h3 = __floats2bfloat162_rn(o[6], o[7]);
@@ -376,6 +383,10 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tcgen05_kernel(const __g
                 for (int j = 0; j < 8; ++j) o[j] = lds_f32(stg + (uint32_t)((row * 33 + chunk * 8 + j) * 4)) + rbv * cs[j] + cb[j];
                 __nv_bfloat16* dp = reinterpret_cast<__nv_bfloat16*>(p.D) + bb * p.d_bstride + mm * p.ldd + cc;
                 const int valid = (int)min((long long)8, p.N - (ng + chunk * 8));
+                if (p.acc_bf16) {
+#pragma unroll
+                  for (int j = 0; j < 8; ++j) if (j < valid) o[j] += __bfloat162float(dp[j]);
+                }
                 if (valid == 8 && p.vec_ok) {
                   uint4 q;
                   __nv_bfloat162 h0 = __floats2bfloat162_rn(o[0], o[1]), h1 = __floats2bfloat162_rn(o[2], o[3]);
@@ -450,6 +461,10 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tcgen05_kernel(const __g
               for (int e = 0; e < 4; ++e) if (e < valid) atomicAdd(dp + e, o[e]);
             } else if (p.d_bf16) {
               __nv_bfloat16* dp = reinterpret_cast<__nv_bfloat16*>(p.D) + off;
+              if (p.acc_bf16) {
+#pragma unroll
+                for (int e = 0; e < 4; ++e) if (e < valid) o[e] += __bfloat162float(dp[e]);
+              }
               if (valid == 4) store4<__nv_bfloat16>(dp, o);
               else {
 #pragma unroll
@@ -520,7 +535,10 @@ __global__ void gemm_simt_kernel(const SimtParams p) {
   if (p.row_bias) val += p.row_bias[m] * (p.col_scale ? p.col_scale[c] : 1.f);
   if (p.col_bias) val += p.col_bias[fbz * p.cb_bstride + c];
   const long long off = bb * p.d_bstride + m * p.ldd + c;
-  if (p.d_bf16) reinterpret_cast<__nv_bfloat16*>(p.D)[off] = __float2bfloat16_rn(val);
+  if (p.d_bf16) {
+    __nv_bfloat16* dp = reinterpret_cast<__nv_bfloat16*>(p.D) + off;
+    *dp = __float2bfloat16_rn(p.accumulate ? val + __bfloat162float(*dp) : val);
+  }
   else if (p.accumulate) reinterpret_cast<float*>(p.D)[off] += val;
   else reinterpret_cast<float*>(p.D)[off] = val;
 }
@@ -649,8 +667,10 @@ int gemm_dispatch(const avmoe_gemm_args* a, cudaStream_t st) {
   const long long Nb = n_batched ? a->Nb : a->N;
   if (n_batched) AVMOE_CHECK_ARG(Nb > 0 && a->N % Nb == 0, "gemm: N must be a multiple of Nb");
   if (b_nbatched) AVMOE_CHECK_ARG(Nb * a->b_batch == a->N, "gemm: N must equal b_batch*Nb");
-  const bool atomic = a->split_k > 1 || a->accumulate;
-  if (atomic) AVMOE_CHECK_ARG(a->d_dtype == AVMOE_F32, "gemm: split-K / accumulate need an fp32 D");
+  const bool acc_bf16 = a->accumulate && a->d_dtype == AVMOE_BF16;     // plain read-modify-write in the epilogue
+  if (acc_bf16) AVMOE_CHECK_ARG(a->split_k <= 1, "gemm: accumulate into a bf16 D excludes split-K");
+  const bool atomic = a->split_k > 1 || (a->accumulate && !acc_bf16);
+  if (atomic) AVMOE_CHECK_ARG(a->d_dtype == AVMOE_F32, "gemm: split-K needs an fp32 D");
   if (a->impl == 1) return launch_simt(a, st);
 
   const bool bf16 = a->dtype == AVMOE_BF16;
@@ -767,6 +787,7 @@ int gemm_dispatch(const avmoe_gemm_args* a, cudaStream_t st) {
   p.alpha = a->alpha; p.row_bias = a->row_bias; p.col_scale = a->col_scale; p.col_bias = a->col_bias;
   p.cb_bstride = a->full_batch > 1 ? a->col_bias_bstride : 0;
   p.atomic = atomic;
+  p.acc_bf16 = acc_bf16 ? 1 : 0;
   if (p.splits > 1 && !a->accumulate) {
     if (n_batched) {
       AVMOE_CHECK_ARG(a->d_bstride == a->M * a->ldd && a->ldd == Nb, "gemm: split-K needs a dense D");

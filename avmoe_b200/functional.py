@@ -244,7 +244,7 @@ def gemm_attn2_bwd(K, x, tokp_op, A2, dXR, T: int, dx):
     tokp_s, off, tokp_lp = tokp_op
     dA2 = K.bgemm(dXR, tokp_s, out_dtype=f32)                                            # dXR[b]·tok'[b]ᵀ  [BT,N,W]
     dS2 = K.softmax_rows_bwd(A2, dA2, T, off)
-    K.add_into(dx, K.bgemm(dS2[:, :, :T], tokp_lp, b_kmajor=False))                      # dx += dS2·tok'
+    K.bgemm(dS2[:, :, :T], tokp_lp, b_kmajor=False, out=dx, accumulate=True)             # dx += dS2·tok'  (in the epilogue)
     dtokp = K.bgemm(A2[:, :, :T], dXR, a_kmajor=False, b_kmajor=False, out_dtype=f32)    # A2ᵀ·dXR   [BT,T,C]
     K.add_into(dtokp, K.bgemm(dS2[:, :, :T], x, a_kmajor=False, b_kmajor=False, out_dtype=f32))   # + dS2ᵀ·x
     return dtokp

@@ -138,8 +138,9 @@ def gemm(A: torch.Tensor, B: torch.Tensor, *, a_kmajor: bool = True, b_kmajor: b
 
 
 def bgemm(A: torch.Tensor, B: torch.Tensor, *, a_kmajor: bool = True, b_kmajor: bool = True, out_dtype: Optional[torch.dtype] = None,
-          alpha: float = 1.0, col_bias: Optional[torch.Tensor] = None, impl: int = 0, out: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """Fully batched GEMM: D[b] = alpha * op(A[b]) · op(B[b])ᵀ for independent problems b.
+          alpha: float = 1.0, col_bias: Optional[torch.Tensor] = None, impl: int = 0, out: Optional[torch.Tensor] = None,
+          accumulate: bool = False) -> torch.Tensor:
+    """Fully batched GEMM: D[b] = alpha * op(A[b]) · op(B[b])ᵀ for independent problems b (accumulate: added to ``out``).
     A [b,M,K] (a_kmajor) or [b,K,M];  B [b,N,K] (b_kmajor) or [b,K,N];  D [b,M,N]."""
     _require_cuda(A, B)
     assert A.dim() == 3 and B.dim() == 3 and A.shape[0] == B.shape[0] and A.dtype == B.dtype
@@ -164,7 +165,8 @@ def bgemm(A: torch.Tensor, B: torch.Tensor, *, a_kmajor: bool = True, b_kmajor: 
         assert col_bias.dtype == torch.float32 and col_bias.stride(-1) == 1 and col_bias.shape[-1] == N
         a.col_bias = col_bias.data_ptr()
         a.col_bias_bstride = col_bias.stride(0) if col_bias.dim() == 2 else 0
-    a.split_k, a.accumulate, a.impl, a.full_batch = 1, 0, impl or _GEMM_IMPL_OVERRIDE, nb
+    assert not accumulate or out is not None
+    a.split_k, a.accumulate, a.impl, a.full_batch = 1, int(accumulate), impl or _GEMM_IMPL_OVERRIDE, nb
     global LAUNCHES
     LAUNCHES += 1
     if GEMM_PROFILE is not None:

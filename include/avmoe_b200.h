@@ -93,7 +93,7 @@ typedef struct {
   const float* col_scale;     /* [Nb] or NULL (=1) ; multiplies row_bias */
   const float* col_bias;      /* [Nb] or NULL */
   int32_t split_k;
-  int32_t accumulate;         /* 1: D += result (fp32 D only, atomics) */
+  int32_t accumulate;         /* 1: D += result (fp32 D: atomics; bf16 D: read-modify-write in the epilogue, no split-K) */
   int32_t impl;
   int32_t full_batch;         /* >1: that many independent problems; A, B, D advance by a_bstride/b_bstride/d_bstride
                                  (a_batch = b_batch = 1, no N-batching, no split-K) */

@@ -62,14 +62,14 @@ def gemm(A, B, *, a_kmajor=True, b_kmajor=True, out_dtype=None, alpha=1.0, row_b
     return D.to(out_dtype)
 
 
-def bgemm(A, B, *, a_kmajor=True, b_kmajor=True, out_dtype=None, alpha=1.0, col_bias=None, impl=0, out=None):
+def bgemm(A, B, *, a_kmajor=True, b_kmajor=True, out_dtype=None, alpha=1.0, col_bias=None, impl=0, out=None, accumulate=False):
     Af = A.float() if a_kmajor else A.float().transpose(1, 2)
     Bf = B.float() if b_kmajor else B.float().transpose(1, 2)
     D = alpha * (Af @ Bf.transpose(1, 2))
     if col_bias is not None:
         D = D + (col_bias[:, None, :] if col_bias.dim() == 2 else col_bias)
     if out is not None:
-        out.copy_(D.to(out.dtype))
+        out.copy_((out.float() + D if accumulate else D).to(out.dtype))
         return out
     return D.to(out_dtype or A.dtype)
 

@@ -176,3 +176,17 @@ def test_bgemm_per_problem_bias_and_strided_outputs(dtype, impl):
     assert torch.all(yd[:, :, C:] == 7.0), "the second half of the buffer must be untouched"
     shared = ops.bgemm(act, wud, out_dtype=torch.float32, col_bias=bias[0].contiguous(), impl=impl)
     assert util.rel_err(shared, act.float() @ wud.float().transpose(1, 2) + bias[0]) < _tol(dtype)
+
+
+@pytest.mark.parametrize("impl", [0, 1])
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32])
+def test_bgemm_accumulates_into_existing_output(dtype, impl):
+    """dx += dS2·tok' in the epilogue (bf16: read-modify-write with one rounding; fp32: atomics), interior and edge tiles"""
+    from avmoe_b200 import ops
+    nb, M, N, K = 3, 200, 104, 32
+    A, B = _mk((nb, M, K), dtype, 1), _mk((nb, K, N), dtype, 2)
+    D0 = _mk((nb, M, N), dtype, 3)
+    D = D0.clone()
+    ops.bgemm(A, B, b_kmajor=False, out=D, accumulate=True, impl=impl)
+    want = D0.float() + A.float() @ B.float()
+    assert util.rel_err(D.float(), want) < (1e-2 if dtype == torch.bfloat16 else _tol(dtype))
