@@ -211,8 +211,8 @@ extern "C" int avmoe_mha_attn_fwd(const float* qkv, void* ctx, int L, int NB, in
   const int hd = C / heads;
   const size_t base = sizeof(float) * (size_t)L * (L + 4);
   const size_t full = base + sizeof(float) * 3 * (size_t)L * (hd + 4);
-  AVMOE_CHECK_ARG(base <= 200 * 1024, "mha_attn_fwd: attended axis BT=%d too long for one CTA", L);
-  const int staged = full <= 200 * 1024;
+  AVMOE_CHECK_ARG(base <= 226 * 1024, "mha_attn_fwd: attended axis BT=%d too long for one CTA", L);
+  const int staged = full <= 226 * 1024;
   const size_t smem = staged ? full : base;
   const float scale = 1.f / sqrtf((float)hd);
   dim3 grid(NB, heads);
@@ -233,8 +233,8 @@ extern "C" int avmoe_mha_attn_bwd(const float* qkv, const float* dctx, void* dqk
   const int hd = C / heads;
   const size_t base = sizeof(float) * 2 * (size_t)L * (L + 4);
   const size_t full = base + sizeof(float) * 4 * (size_t)L * (hd + 4);
-  AVMOE_CHECK_ARG(base <= 200 * 1024, "mha_attn_bwd: attended axis BT=%d too long for one CTA", L);
-  const int staged = full <= 200 * 1024;
+  AVMOE_CHECK_ARG(base <= 226 * 1024, "mha_attn_bwd: attended axis BT=%d too long for one CTA", L);
+  const int staged = full <= 226 * 1024;
   const size_t smem = staged ? full : base;
   const float scale = 1.f / sqrtf((float)hd);
   dim3 grid(NB, heads);
