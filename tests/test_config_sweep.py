@@ -122,3 +122,17 @@ def test_flag_sweep_cuda(variant, overrides, dtype):
     # (C=64, 72 rows) average the bf16 rounding noise of the un-normalised (no-BN) chains over far fewer terms
     tol, gtol = (1e-3, 6e-2) if dtype == torch.float32 else (2e-2, 3e-1)
     _compare(spec, ref, got, tol, gtol)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("variant,BT", [("ave", 1), ("avqa", 1), ("ms3", 1), ("avvp", 2), ("s4", 2), ("s4", 7)])
+def test_tiny_batches_cuda(variant, BT, dtype):
+    """single-segment batches (BatchNorm statistics over N rows only, one CTA per sample kernels with a 1-long grid axis)"""
+    spec, sd, x, o, gout = _case(variant, {}, seed=5, BT=BT)
+    if dtype == torch.bfloat16:
+        x, o = x.bfloat16().float(), o.bfloat16().float()
+    ref = _run_oracle(spec, sd, x, o, gout, True)
+    got = _run_module(build_module(spec, sd, kernels=None), spec, x, o, gout, True, "cuda", dtype)
+    tol, gtol = (1e-3, 6e-2) if dtype == torch.float32 else (2e-2, 3e-1)
+    _compare(spec, ref, got, tol, gtol)
