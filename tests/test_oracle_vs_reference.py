@@ -70,3 +70,35 @@ def test_reference_bn_backward_bug_is_torch_not_oracle():
     for c in (0, 7):
         fd = (loss_with(1e-6, c) - loss_with(-1e-6, c)) / 2e-6
         assert abs(fd - sdg[key].grad[c].item()) < 1e-5 * max(1.0, abs(fd))
+
+
+@pytest.mark.parametrize("variant", ["ave", "avqa", "avvp", "s4", "ms3"])
+def test_patch_reference_module_swaps_in_the_drop_ins(variant):
+    """after patch_reference_module() the reference model module constructs the CUDA drop-ins from the
+    same constructor call, and their state dict has the reference's keys and shapes (checkpoints stay loadable)."""
+    import sys
+    from avmoe_b200 import adapters
+    Expert, MoE = ref_loader.load_variant(variant)
+    module = sys.modules[MoE.__module__]
+    spec = O.spec_for(variant, 3, "audio")
+    ref_sd = H.build_reference(spec).state_dict()
+    saved = (module.MoEAdapter, module.ExpertAdapter)
+    try:
+        adapters.patch_reference_module(module, variant)
+        assert module.MoEAdapter is adapters.VARIANTS[variant] and module.ExpertAdapter is adapters.ExpertAdapter
+        opt = H.make_opt(spec)
+        common = dict(input_dim=spec.C, output_dim=spec.C, adapter_kind="bottleneck", dim_list=None, layer_idx=0, opt=opt,
+                      conv_dim_in=spec.Nx, conv_dim_out=spec.N, linear_in=spec.Cx, linear_out=spec.C)
+        if variant == "avvp":
+            mod = module.MoEAdapter(**common)
+        elif variant == "avqa":
+            mod = module.MoEAdapter(reduction_factor=spec.r, use_bn=spec.use_bn, use_gate=spec.use_gate, **common)
+        else:
+            mod = module.MoEAdapter(reduction_factor=spec.r, use_bn=spec.use_bn, use_gate=spec.use_gate, num_tk=spec.T, **common)
+        ours = mod.state_dict()
+        assert set(ours) == set(ref_sd), set(ours) ^ set(ref_sd)
+        for k, v in ref_sd.items():
+            assert tuple(ours[k].shape) == tuple(v.shape), k
+        mod.load_state_dict(ref_sd, strict=True)
+    finally:
+        module.MoEAdapter, module.ExpertAdapter = saved
