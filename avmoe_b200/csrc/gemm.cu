@@ -121,6 +121,17 @@ __device__ __forceinline__ float lds_f32(uint32_t addr) {
   return v;
 }
 
+__device__ __forceinline__ void sts_u32(uint32_t addr, uint32_t v) { asm volatile("st.shared.b32 [%0], %1;" ::"r"(addr), "r"(v) : "memory"); }
+__device__ __forceinline__ uint32_t lds_u32(uint32_t addr) {
+  uint32_t v;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+  const __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<const uint32_t*>(&h);
+}
+
 // ------------------------------------------------------------------------------------------------
 // kernel parameters
 // ------------------------------------------------------------------------------------------------
@@ -318,12 +329,57 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tcgen05_kernel(const __g
       for (int g = half; g < p.BN / 32; g += 2) {
         const long long ng = (long long)n0 + g * 32;
         if (ng >= p.N || mrow0 >= p.M) break;   // warp-uniform
+        long long bb = tb, c0 = ng;
+        if (p.n_batched) { bb = ng / p.Nb; c0 = ng - bb * p.Nb; }
+        // interior bf16 slab: the 8 bias values this lane adds are requested BEFORE the TMEM load so their latency hides under it
+        const bool interior = p.tma_store && p.d_bf16 && p.vec_ok && !p.row_bias && mrow0 + 32 <= p.M && ng + 32 <= p.N;
+        const bool packed = interior && !p.acc_bf16;        // convert to bf16 BEFORE the transpose: half the smem traffic, no re-pack
+        float cbv[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) cbv[j] = (interior && !packed && add_bias && cbias) ? __ldg(cbias + c0 + (lane & 3) * 8 + j) : 0.f;
+        const bool pbias = packed && add_bias && cbias;
+        const float cbl = pbias ? __ldg(cbias + c0 + lane) : 0.f;   // lane e holds the bias of column e (broadcast by shuffles below)
         uint32_t r[32];
         const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * p.BN + g * 32);
         tmem_ld_32x32b_x32(taddr, r);
-        long long bb = tb, c0 = ng;
-        if (p.n_batched) { bb = ng / p.Nb; c0 = ng - bb * p.Nb; }
-        if (p.tma_store) {
+        if (packed) {
+          // ---- interior bf16 slab, packed: lane = row holds 32 columns -> 16 bf16x2 words -> per-warp [32][17]-word slab ->
+          //      each lane reads 4 consecutive words (8 columns) of 4 rows -> 16-byte global stores ----
+          const float al = has_k ? p.alpha : 0.f;
+          uint32_t pk[16];
+          if (pbias) {
+#pragma unroll
+            for (int e2 = 0; e2 < 16; ++e2) {
+              const float b0 = __shfl_sync(0xffffffffu, cbl, 2 * e2), b1 = __shfl_sync(0xffffffffu, cbl, 2 * e2 + 1);
+              const float v0 = has_k ? fmaf(__uint_as_float(r[2 * e2]), al, b0) : b0;
+              const float v1 = has_k ? fmaf(__uint_as_float(r[2 * e2 + 1]), al, b1) : b1;
+              pk[e2] = pack_bf16x2(v0, v1);
+            }
+          } else if (has_k) {
+#pragma unroll
+            for (int e2 = 0; e2 < 16; ++e2) pk[e2] = pack_bf16x2(__uint_as_float(r[2 * e2]) * al, __uint_as_float(r[2 * e2 + 1]) * al);
+          } else {
+#pragma unroll
+            for (int e2 = 0; e2 < 16; ++e2) pk[e2] = 0u;
+          }
+          __syncwarp();                                   // the previous slab has been read out
+#pragma unroll
+          for (int e2 = 0; e2 < 16; ++e2) sts_u32(stg + (uint32_t)((lane * 17 + e2) * 4), pk[e2]);
+          __syncwarp();
+          const int chunk = lane & 3, rsub = lane >> 2;
+          __nv_bfloat16* dp = reinterpret_cast<__nv_bfloat16*>(p.D) + bb * p.d_bstride + (long long)(mrow0 + rsub) * p.ldd + c0 + chunk * 8;
+          const uint32_t sp = stg + (uint32_t)((rsub * 17 + chunk * 4) * 4);
+          const long long step = 8 * p.ldd;
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            uint4 q;
+            q.x = lds_u32(sp + (uint32_t)((k * (8 * 17) + 0) * 4));
+            q.y = lds_u32(sp + (uint32_t)((k * (8 * 17) + 1) * 4));
+            q.z = lds_u32(sp + (uint32_t)((k * (8 * 17) + 2) * 4));
+            q.w = lds_u32(sp + (uint32_t)((k * (8 * 17) + 3) * 4));
+            *reinterpret_cast<uint4*>(dp + k * step) = q;
+          }
+        } else if (p.tma_store) {
           // ---- fast path: registers -> per-warp smem slab [32][33] -> coalesced 16-byte global stores (or fp32 atomics) ----
           __syncwarp();                                   // the previous slab has been read out
           if (has_k) {
@@ -334,12 +390,10 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tcgen05_kernel(const __g
             for (int e = 0; e < 32; ++e) sts_f32(stg + (uint32_t)((lane * 33 + e) * 4), 0.f);
           }
           __syncwarp();
-          if (p.d_bf16 && p.vec_ok && !p.row_bias && mrow0 + 32 <= p.M && ng + 32 <= p.N) {
+          if (interior) {
             // ---- interior bf16 slab: no predicates, one 64-bit address per lane, 4 x (8 LDS + pack + 16-byte store) ----
             const int chunk = lane & 3, rsub = lane >> 2;
-            float cb[8];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) cb[j] = (add_bias && cbias) ? __ldg(cbias + c0 + chunk * 8 + j) : 0.f;
+            const float (&cb)[8] = cbv;
             __nv_bfloat16* dp = reinterpret_cast<__nv_bfloat16*>(p.D) + bb * p.d_bstride + (long long)(mrow0 + rsub) * p.ldd + c0 + chunk * 8;
             const uint32_t sp = stg + (uint32_t)((rsub * 33 + chunk * 8) * 4);
             const long long step = 8 * p.ldd;
