@@ -176,9 +176,10 @@ struct GemmParams {
   int atomic;
 };
 
-static constexpr int kGemmThreads = 320;   // TMA warp, MMA warp, 8 epilogue warps (two per TMEM lane quarter)
+static constexpr int kEpiWarps = 16;        // epilogue warps: kEpiWarps/4 per TMEM lane quarter, taking interleaved 32-column slabs
+static constexpr int kGemmThreads = 64 + 32 * kEpiWarps;   // TMA warp, MMA warp, epilogue warps
 static constexpr int kBM = 128;
-static constexpr int kStagingBytes = 34816;   // 8 epilogue warps x [32][33] fp32 (rounded to 1 KiB)
+static constexpr int kStagingBytes = ((kEpiWarps * 32 * 33 * 4 + 1023) / 1024) * 1024;   // per-warp [32][33] fp32 slabs
 
 template <bool kTf32>
 __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tcgen05_kernel(const __grid_constant__ GemmParams p) {
@@ -207,7 +208,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tcgen05_kernel(const __g
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(smem_u32(&tmem_full[s]), 1);
-      mbar_init(smem_u32(&tmem_empty[s]), 8);
+      mbar_init(smem_u32(&tmem_empty[s]), kEpiWarps);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -306,7 +307,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tcgen05_kernel(const __g
   } else {
     // ===================== epilogue (warps 2..9) =====================
     const int quarter = warp & 3;  // TMEM lane quarter this warp may access
-    const int half = (warp - 2) >> 2;  // the two warps of a quarter take alternate 32-column slabs
+    const int half = (warp - 2) >> 2;  // the warps of a quarter take interleaved 32-column slabs
     int acc = 0;
     uint32_t acc_phase = 0;
     const uint32_t stg = smem_u32(staging) + (uint32_t)((warp - 2) * (32 * 33) * 4);   // per-warp [32][33] fp32 transpose slab (shared address)
@@ -326,7 +327,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tcgen05_kernel(const __g
       const bool add_bias = (split == 0);
       const float* cbias = p.col_bias ? p.col_bias + (long long)tb * p.cb_bstride : nullptr;
       const float rb = (add_bias && p.row_bias && m < p.M) ? p.row_bias[m] : 0.f;
-      for (int g = half; g < p.BN / 32; g += 2) {
+      for (int g = half; g < p.BN / 32; g += kEpiWarps / 4) {
         const long long ng = (long long)n0 + g * 32;
         if (ng >= p.N || mrow0 >= p.M) break;   // warp-uniform
         long long bb = tb, c0 = ng;

@@ -352,7 +352,7 @@ def gemm_experts_bwd(K, cfg, x, dout, z, bn, bn_mode, packs, egr, probs, P, pref
     """Backward of gemm_experts_fwd up to the ln_before input: returns (dprobs, red1, red2, dxl, ln1s)."""
     BT, N, C = x.shape
     E, Cr = cfg.E, cfg.Cr
-    Crp = K.round8(Cr)
+    Crp = K.pad_bottleneck(Cr)
     rows = BT * N
     dev, f32, dt = x.device, torch.float32, x.dtype
     xl, ln1s, act, yd, ln2s, wdt, suma = saved

@@ -476,6 +476,13 @@ def round8(t: int) -> int:
     return (t + 7) // 8 * 8
 
 
+def pad_bottleneck(cr: int) -> int:
+    """Row length of the bottleneck-sized GEMM operands (a, dz, da): C/r rounded up to 32 elements, i.e. 64-byte bf16 rows.
+    TMA fetches an operand row by row; with 48-byte rows (C/r = 24) the K=24 GEMMs ran SLOWER than K=64 ones
+    (profiles/r01_summary.md), so the padding columns (zeros) pay for themselves."""
+    return (cr + 31) // 32 * 32
+
+
 def cast_to(t: torch.Tensor, dtype: torch.dtype) -> torch.Tensor:
     if t.dtype == dtype:
         return t
@@ -580,7 +587,7 @@ USE_GEMM_EXPERTS = True   # bf16 streams: expert projections on the tcgen05 GEMM
 
 def _xg_args(cfg, packs, egr=None, *, BT, dtype, bn_mode=0, bn2_wb=None):
     a = _lib.XgArgs()
-    a.BT, a.N, a.C, a.Cr, a.Crp, a.G, a.E = BT, cfg.N, cfg.C, cfg.Cr, round8(cfg.Cr), cfg.G, cfg.E
+    a.BT, a.N, a.C, a.Cr, a.Crp, a.G, a.E = BT, cfg.N, cfg.C, cfg.Cr, pad_bottleneck(cfg.Cr), cfg.G, cfg.E
     a.dtype, a.bn_mode = dtype, bn_mode
     keep = []
     for e, pk in enumerate(packs):
@@ -609,7 +616,7 @@ def _xg_args(cfg, packs, egr=None, *, BT, dtype, bn_mode=0, bn2_wb=None):
 
 def xg_prep_weights(cfg, packs, dtype):
     dev = packs[0].wd.device
-    Crp = round8(cfg.Cr)
+    Crp = pad_bottleneck(cfg.Cr)
     wdd = torch.empty((cfg.E, cfg.Cr, cfg.C), device=dev, dtype=dtype)
     wdt = torch.empty((cfg.E, cfg.C, Crp), device=dev, dtype=dtype)
     a, keep = _xg_args(cfg, packs, BT=1, dtype=_dt(wdd))
@@ -619,7 +626,7 @@ def xg_prep_weights(cfg, packs, dtype):
 
 def xg_prep_up(cfg, packs, save2, bn_mode, dtype):
     dev = packs[0].wu.device
-    wud = torch.empty((cfg.E, cfg.C, round8(cfg.Cr)), device=dev, dtype=dtype)
+    wud = torch.empty((cfg.E, cfg.C, pad_bottleneck(cfg.Cr)), device=dev, dtype=dtype)
     ybi = torch.empty((cfg.E, cfg.C), device=dev, dtype=torch.float32)
     a, keep = _xg_args(cfg, packs, BT=1, dtype=_dt(wud), bn_mode=bn_mode)
     _set(a, save2=save2)
@@ -643,7 +650,7 @@ def xg_ln_pre_fwd(cfg, x, packs):
 def xg_z_stats(cfg, z):
     stats1 = torch.zeros((cfg.E, cfg.Cr, 2), device=z.device, dtype=torch.float64)
     a = _lib.XgArgs()
-    a.BT, a.N, a.C, a.Cr, a.Crp, a.G, a.E, a.dtype = z.shape[0], cfg.N, cfg.C, cfg.Cr, round8(cfg.Cr), cfg.G, cfg.E, F32
+    a.BT, a.N, a.C, a.Cr, a.Crp, a.G, a.E, a.dtype = z.shape[0], cfg.N, cfg.C, cfg.Cr, pad_bottleneck(cfg.Cr), cfg.G, cfg.E, F32
     _set(a, z=z, stats1=stats1)
     _lib_call("xg_z_stats", C.byref(a), _stream(), _bytes=_nbytes(z))
     return stats1
@@ -652,7 +659,7 @@ def xg_z_stats(cfg, z):
 def xg_bn_act(cfg, z, aff1, packs, dtype, bn_mode):
     """-> a [E,BT*N,Crp] = act(bn1(z)) in ``dtype`` (padding columns zero)"""
     BT, N = z.shape[0], z.shape[1]
-    act = torch.empty((cfg.E, BT * N, round8(cfg.Cr)), device=z.device, dtype=dtype)
+    act = torch.empty((cfg.E, BT * N, pad_bottleneck(cfg.Cr)), device=z.device, dtype=dtype)
     a, keep = _xg_args(cfg, packs, BT=BT, dtype=_dt(act), bn_mode=bn_mode)
     _set(a, z=z, aff1=aff1)
     a.a = act.data_ptr()
@@ -698,7 +705,7 @@ def xg_ln_pre_bwd(cfg, x, dxl, ln1_stats, packs, dpool_x, dx, egr):
 
 def xg_prep_bwd(cfg, packs, bn2_wb, bn, bn_mode, red2, BT, dtype):
     dev = packs[0].wu.device
-    Crp = round8(cfg.Cr)
+    Crp = pad_bottleneck(cfg.Cr)
     w2 = torch.empty((cfg.E, Crp, 2 * cfg.C), device=dev, dtype=dtype)
     bias = torch.empty((cfg.E, Crp), device=dev, dtype=torch.float32)
     a, keep = _xg_args(cfg, packs, BT=BT, dtype=_dt(w2), bn_mode=bn_mode, bn2_wb=bn2_wb)

@@ -82,6 +82,10 @@ def round8(t):
     return (t + 7) // 8 * 8
 
 
+def pad_bottleneck(cr):
+    return (cr + 31) // 32 * 32
+
+
 def cast_to(t, dtype):
     return t if t.dtype == dtype else t.to(dtype)
 
@@ -600,14 +604,14 @@ def _dense_wd(wd, cfg):
 def _dense_wu(wu, cfg):
     """grouped [C, Cr/G] -> block-diagonal dense [C, Crp] (zero padded)"""
     Cr, C, G = cfg.Cr, cfg.C, cfg.G
-    out = torch.zeros((C, round8(Cr)), dtype=torch.float32)
+    out = torch.zeros((C, pad_bottleneck(Cr)), dtype=torch.float32)
     for g in range(G):
         out[g * (C // G):(g + 1) * (C // G), g * (Cr // G):(g + 1) * (Cr // G)] = wu[g * (C // G):(g + 1) * (C // G)]
     return out
 
 
 def xg_prep_weights(cfg, packs, dtype):
-    Crp = round8(cfg.Cr)
+    Crp = pad_bottleneck(cfg.Cr)
     wdd = torch.stack([_dense_wd(pk.wd, cfg) for pk in packs]).to(dtype)
     wdt = torch.zeros((cfg.E, cfg.C, Crp), dtype=dtype)
     wdt[:, :, :cfg.Cr] = wdd.transpose(1, 2)
@@ -654,7 +658,7 @@ def xg_z_stats(cfg, z):
 
 def xg_bn_act(cfg, z, aff1, packs, dtype, bn_mode):
     BT, N = z.shape[0], z.shape[1]
-    act = torch.zeros((cfg.E, BT * N, round8(cfg.Cr)), dtype=dtype)
+    act = torch.zeros((cfg.E, BT * N, pad_bottleneck(cfg.Cr)), dtype=dtype)
     for e, pk in enumerate(packs):
         zt = z[:, :, e, :].reshape(BT * N, cfg.Cr)
         if bn_mode != BN_OFF:
@@ -776,7 +780,7 @@ def _xg_bn2_coeffs(cfg, bn2_wb, bn, bn_mode, red2, rows, e):
 
 def xg_prep_bwd(cfg, packs, bn2_wb, bn, bn_mode, red2, BT, dtype):
     rows = BT * cfg.N
-    Crp, C = round8(cfg.Cr), cfg.C
+    Crp, C = pad_bottleneck(cfg.Cr), cfg.C
     w2 = torch.zeros((cfg.E, Crp, 2 * C), dtype=torch.float32)
     bias = torch.zeros((cfg.E, Crp), dtype=torch.float32)
     for e, pk in enumerate(packs):

@@ -101,7 +101,7 @@ def test_row_kernels_match_emulation_fp32(geom, bn_mode):
     from avmoe_b200 import ops
     BT, N, C, r, G, kinds = geom
     cfg, x, packs, probs, g = _make(BT, N, C, r, G, kinds)
-    E, Cr, Crp, rows = cfg.E, cfg.Cr, KE.round8(cfg.Cr), BT * N
+    E, Cr, Crp, rows = cfg.E, cfg.Cr, KE.pad_bottleneck(cfg.Cr), BT * N
     cpk = _to_cuda(packs)
     f32 = torch.float32
     # ---- weights
