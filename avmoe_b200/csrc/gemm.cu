@@ -308,6 +308,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tcgen05_kernel(const __g
     // ===================== epilogue (warps 2..9) =====================
     const int quarter = warp & 3;  // TMEM lane quarter this warp may access
     const int half = (warp - 2) >> 2;  // the warps of a quarter take interleaved 32-column slabs
+    int tseq = 0;
     int acc = 0;
     uint32_t acc_phase = 0;
     const uint32_t stg = smem_u32(staging) + (uint32_t)((warp - 2) * (32 * 33) * 4);   // per-warp [32][33] fp32 transpose slab (shared address)
@@ -327,7 +328,12 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tcgen05_kernel(const __g
       const bool add_bias = (split == 0);
       const float* cbias = p.col_bias ? p.col_bias + (long long)tb * p.cb_bstride : nullptr;
       const float rb = (add_bias && p.row_bias && m < p.M) ? p.row_bias[m] : 0.f;
-      for (int g = half; g < p.BN / 32; g += kEpiWarps / 4) {
+      // slab g of this CTA's tseq-th tile goes to warp group (g + tseq) % groups: consecutive narrow tiles are drained by
+      // different warps, so their epilogues overlap (two accumulator stages in flight) instead of queueing on one group
+      constexpr int kGroups = kEpiWarps / 4;
+      const int gstart = (half + kGroups - (tseq % kGroups)) % kGroups;
+      ++tseq;
+      for (int g = gstart; g < p.BN / 32; g += kGroups) {
         const long long ng = (long long)n0 + g * 32;
         if (ng >= p.N || mrow0 >= p.M) break;   // warp-uniform
         long long bb = tb, c0 = ng;
