@@ -156,7 +156,8 @@ struct GemmParams {
   int num_stages;
   uint32_t stage_bytes_a, stage_bytes_b;
   uint32_t idesc;
-  int tmem_cols;       // power of two >= 2*BN
+  int tmem_cols;       // power of two >= nacc*BN
+  int nacc;            // accumulator stages in TMEM: 4 when BN <= 128 (narrow tiles: epilogues of consecutive tiles overlap), else 2
   int tiles_m, tiles_n, splits;
   int full_batch;      // >1: A, B and D all advance over this many independent problems (third TMA coordinate)
   int k_iters;         // total stages over the whole (batch,K) reduction
@@ -176,6 +177,7 @@ struct GemmParams {
   int atomic;
 };
 
+static constexpr int kMaxAcc = 4;
 static constexpr int kEpiWarps = 16;        // epilogue warps: kEpiWarps/4 per TMEM lane quarter, taking interleaved 32-column slabs
 static constexpr int kGemmThreads = 64 + 32 * kEpiWarps;   // TMA warp, MMA warp, epilogue warps
 static constexpr int kBM = 128;
@@ -191,9 +193,9 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tcgen05_kernel(const __g
   uint64_t* bars = reinterpret_cast<uint64_t*>(staging + kStagingBytes);
   uint64_t* full_bar = bars;                       // [num_stages]
   uint64_t* empty_bar = bars + p.num_stages;       // [num_stages]
-  uint64_t* tmem_full = bars + 2 * p.num_stages;   // [2]
-  uint64_t* tmem_empty = tmem_full + 2;            // [2]
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  uint64_t* tmem_full = bars + 2 * p.num_stages;   // [kMaxAcc]
+  uint64_t* tmem_empty = tmem_full + kMaxAcc;      // [kMaxAcc]
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_empty + kMaxAcc);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -206,7 +208,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tcgen05_kernel(const __g
       mbar_init(smem_u32(&full_bar[s]), 1);
       mbar_init(smem_u32(&empty_bar[s]), 1);
     }
-    for (int s = 0; s < 2; ++s) {
+    for (int s = 0; s < p.nacc; ++s) {
       mbar_init(smem_u32(&tmem_full[s]), 1);
       mbar_init(smem_u32(&tmem_empty[s]), kEpiWarps);
     }
@@ -302,7 +304,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tcgen05_kernel(const __g
       }
       if (k_end <= k_begin && lane == 0) tcgen05_commit(smem_u32(&tmem_full[acc]));  // empty split: still signal
       __syncwarp();
-      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      if (++acc == p.nacc) { acc = 0; acc_phase ^= 1; }
     }
   } else {
     // ===================== epilogue (warps 2..9) =====================
@@ -545,7 +547,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tcgen05_kernel(const __g
       tcgen05_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(smem_u32(&tmem_empty[acc]));
-      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      if (++acc == p.nacc) { acc = 0; acc_phase ^= 1; }
     }
   }
 
@@ -839,8 +841,9 @@ int gemm_dispatch(const avmoe_gemm_args* a, cudaStream_t st) {
   p.tiles_m = (int)((a->M + kBM - 1) / kBM);
   p.tiles_n = (int)((a->N + BN - 1) / BN);
   p.full_batch = fbatch;
+  p.nacc = BN <= 128 ? kMaxAcc : 2;
   int tc = 32;
-  while (tc < 2 * BN) tc <<= 1;
+  while (tc < p.nacc * BN) tc <<= 1;
   p.tmem_cols = tc;
   // ---- epilogue -------------------------------------------------------------------------------
   p.D = a->D; p.d_bf16 = a->d_dtype == AVMOE_BF16;
@@ -866,11 +869,11 @@ int gemm_dispatch(const avmoe_gemm_args* a, cudaStream_t st) {
   // ---- smem / launch --------------------------------------------------------------------------
   const uint32_t stage_bytes = p.stage_bytes_a + p.stage_bytes_b;
   const int max_smem = 227 * 1024;
-  int stages = (max_smem - 1024 /*align slack*/ - 256 /*barriers*/ - kStagingBytes) / (int)stage_bytes;
+  int stages = (max_smem - 1024 /*align slack*/ - 512 /*barriers*/ - kStagingBytes) / (int)stage_bytes;
   if (stages > 8) stages = 8;
   AVMOE_CHECK_ARG(stages >= 2, "gemm: tile does not fit shared memory");
   p.num_stages = stages;
-  const size_t smem_bytes = 1024 + (size_t)stages * stage_bytes + kStagingBytes + 256;
+  const size_t smem_bytes = 1024 + (size_t)stages * stage_bytes + kStagingBytes + 512;
   const int tiles = p.tiles_m * p.tiles_n * p.splits * p.full_batch;
   int grid = num_sms();
   if (grid > tiles) grid = tiles;
