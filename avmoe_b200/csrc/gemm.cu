@@ -61,23 +61,6 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map
       "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
       : "memory");
 }
-__device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, uint32_t src, int c0, int c1, int c2) {
-  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.tile.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(map), "r"(src),
-               "r"(c0), "r"(c1), "r"(c2)
-               : "memory");
-}
-__device__ __forceinline__ void tma_reduce_add_3d(const CUtensorMap* map, uint32_t src, int c0, int c1, int c2) {
-  asm volatile("cp.reduce.async.bulk.tensor.3d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(map),
-               "r"(src), "r"(c0), "r"(c1), "r"(c2)
-               : "memory");
-}
-__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
-template <int kPending>
-__device__ __forceinline__ void tma_store_wait_read() {
-  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(kPending) : "memory");
-}
-__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
-__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tcgen05_commit(uint32_t bar) {
@@ -146,8 +129,8 @@ struct OperandTile {
 };
 
 struct GemmParams {
-  CUtensorMap tmA, tmB, tmD;
-  int tma_store;       // 1: epilogue transposes 32x32 slabs through smem and writes coalesced 16-byte rows (slabs never straddle a batch)
+  CUtensorMap tmA, tmB;
+  int slab_path;       // 1: epilogue transposes 32x32 slabs through smem and writes coalesced 16-byte rows (slabs never straddle a batch)
   int vec_ok;          // D pitches / base allow 16-byte vector stores
   OperandTile a, b;
   int BN;              // tile N (multiple of 32, <= 256)
@@ -341,7 +324,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tcgen05_kernel(const __g
         long long bb = tb, c0 = ng;
         if (p.n_batched) { bb = ng / p.Nb; c0 = ng - bb * p.Nb; }
         // interior bf16 slab: the 8 bias values this lane adds are requested BEFORE the TMEM load so their latency hides under it
-        const bool interior = p.tma_store && p.d_bf16 && p.vec_ok && !p.row_bias && mrow0 + 32 <= p.M && ng + 32 <= p.N;
+        const bool interior = p.slab_path && p.d_bf16 && p.vec_ok && !p.row_bias && mrow0 + 32 <= p.M && ng + 32 <= p.N;
         const bool packed = interior && !p.acc_bf16;        // convert to bf16 BEFORE the transpose: half the smem traffic, no re-pack
         float cbv[8];
 #pragma unroll
@@ -388,7 +371,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tcgen05_kernel(const __g
             q.w = lds_u32(sp + (uint32_t)((k * (8 * 17) + 3) * 4));
             *reinterpret_cast<uint4*>(dp + k * step) = q;
           }
-        } else if (p.tma_store) {
+        } else if (p.slab_path) {
           // ---- fast path: registers -> per-warp smem slab [32][33] -> coalesced 16-byte global stores (or fp32 atomics) ----
           __syncwarp();                                   // the previous slab has been read out
           if (has_k) {
@@ -861,7 +844,7 @@ int gemm_dispatch(const avmoe_gemm_args* a, cudaStream_t st) {
     }
   }
   // ---- epilogue mode: 32x32 slabs must never straddle a batch of an N-batched D ----
-  p.tma_store = (!n_batched || Nb % 32 == 0) ? 1 : 0;
+  p.slab_path = (!n_batched || Nb % 32 == 0) ? 1 : 0;
   {
     const int vec = p.d_bf16 ? 8 : 4;
     p.vec_ok = (a->ldd % vec == 0) && (a->d_bstride % vec == 0) && (((uintptr_t)a->D % 16) == 0) && (!n_batched || Nb % vec == 0);
