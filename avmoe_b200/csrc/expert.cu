@@ -519,7 +519,6 @@ __global__ void __launch_bounds__(kThreads, 2) expert_back_bwd_kernel(const avmo
       }
     }
     // ---- d up_sampler.weight[c][jl] += sum_n dy[n][c] * a[n][g*Crg+jl]      (rows >= valid of gs are zero)
-    if (!(p.ex[0]._pad & 1))
     for (int g = 0; g < G; ++g)
       contract_to<kExact, Out::AtomicAdd>(Cg, Crg, TN, gs + g * Cg, 1, ld, as + g * Crg, lda, 1, ex.g_wu + (long long)g * Cg * Crg, Crg, 1);
     // ---- da[n][g*Crg+jl] = sum_cl dy[n][g*Cg+cl] * wu[g*Cg+cl][jl]
@@ -625,7 +624,6 @@ __global__ void __launch_bounds__(kThreads, 2) expert_front_bwd_kernel(const avm
     }
     __syncthreads();
     // ---- d down_sampler.weight[g*Crg+jl][cl] += sum_n dz[n][g*Crg+jl] * xn[n][g*Cg+cl]   (dz rows >= valid are 0)
-    if (!(p.ex[0]._pad & 1))
     for (int g = 0; g < G; ++g)
       contract_to<kExact, Out::AtomicAdd>(Crg, Cg, TN, dzs + g * Crg, 1, lda, t1 + g * Cg, ld, 1, ex.g_wd + (long long)g * Crg * Cg, Cg, 1);
     __syncthreads();
@@ -720,13 +718,6 @@ static int pick_tn(int C, int nbuf) {
   if (tn < 1) tn = 1;
   if (tn > 64) tn = 64;
   return pow2_floor(tn);
-}
-
-// diagnostics only (AVMOE_DEBUG_SKIP=1): skip the in-kernel weight-gradient contractions to measure their cost
-static int debug_skip() {
-  static int v = -1;
-  if (v < 0) { const char* e = getenv("AVMOE_DEBUG_SKIP"); v = e ? atoi(e) : 0; }
-  return v;
 }
 
 static int check_common(const avmoe_expert_args* a, const char* who) {
@@ -851,9 +842,6 @@ static int launch_back_bwd(const avmoe_expert_args* a, cudaStream_t st, const ch
     AVMOE_CHECK_ARG(a->bn_mode != AVMOE_BN_EVAL || a->red2b, "%s: red2b missing", who);
     AVMOE_CHECK_ARG(a->bn_mode == AVMOE_BN_OFF || a->red1, "%s: red1 missing", who);
   }
-  avmoe_expert_args dbg = *a;
-  dbg.ex[0]._pad = debug_skip();
-  a = &dbg;
   const int TN = pick_tn(a->C, 3);
   const size_t smem = sizeof(float) * (3 * (size_t)TN * (a->C + 4) + 2 * (size_t)TN * (a->Cr + 4) + 2 * (size_t)a->C + 2 * TN + 32);
   dim3 grid((a->N + TN - 1) / TN, a->BT);
@@ -882,9 +870,6 @@ extern "C" int avmoe_expert_front_bwd(const avmoe_expert_args* a, avmoe_stream_t
   AVMOE_CHECK_ARG(a->x && a->dzt && a->dx, "expert_front_bwd: null tensor");
   AVMOE_CHECK_ARG(a->bn_mode == AVMOE_BN_OFF || (a->aff1 && a->save1 && a->z && a->red1), "expert_front_bwd: batch-norm tensors missing");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  avmoe_expert_args dbg = *a;
-  dbg.ex[0]._pad = debug_skip();
-  a = &dbg;
   const int TN = pick_tn(a->C, 4);
   const size_t smem = sizeof(float) * (4 * (size_t)TN * (a->C + 4) + 2 * (size_t)TN * (a->T + 4) + (size_t)TN * (a->Cr + 4) + TN + 32);
   dim3 grid((a->N + TN - 1) / TN, a->BT);
