@@ -220,6 +220,132 @@ __global__ void __launch_bounds__(kThreads) bn_moments_kernel(const avmoe_expert
   }
 }
 
+// Register-blocked form: a thread owns groups of kB consecutive outputs (one a_j broadcast feeds kB products, kB independent
+// FMA chains), index arithmetic hoisted out of the tile loop.  Same sums, same fp32-per-tile / fp64-across-tiles accumulation.
+template <int kB>
+__global__ void __launch_bounds__(kThreads) bn_moments_blk_kernel(const avmoe_expert_args p, double* m1, double* m2, int TN, long long rows_total) {
+  extern __shared__ float sm[];
+  constexpr int kGroups = kMomPerThread / kB;
+  const int Cr = p.Cr, G = p.G, Crg = Cr / G, E = p.E;
+  const int ECr = E * Cr;
+  float* as = sm;  // [TN][ECr+1]
+  const int lda = ECr + 1;
+  float* colp = sm + (size_t)TN * lda;   // [3][ECr]: bn1 scale, shift, relu flag per bottleneck column (column q = e*Cr + j)
+  for (int q = threadIdx.x; q < ECr; q += blockDim.x) {
+    colp[q] = p.aff1[q * 2];
+    colp[ECr + q] = p.aff1[q * 2 + 1];
+    colp[2 * ECr + q] = p.ex[q / Cr].relu ? 1.f : 0.f;
+  }
+  __syncthreads();
+  const int kq = Crg / kB;
+  const int n_m1g = ECr / kB, n_m2g = E * G * Crg * kq;
+  const int n_groups = n_m1g + n_m2g;
+  float accv[kGroups][kB];
+  int cjv[kGroups], ckv[kGroups];      // smem columns: a_j (or -1 for first-moment groups) and the first of the kB partner columns
+  long long outv[kGroups];             // linear output index (m1: column, m2: offset by ECr)
+#pragma unroll
+  for (int t = 0; t < kGroups; ++t) {
+#pragma unroll
+    for (int b = 0; b < kB; ++b) accv[t][b] = 0.f;
+    const int gi = threadIdx.x + t * kThreads;
+    cjv[t] = -2; ckv[t] = 0; outv[t] = 0;
+    if (gi < n_m1g) {
+      cjv[t] = -1; ckv[t] = gi * kB; outv[t] = gi * kB;
+    } else if (gi < n_groups) {
+      const int q = gi - n_m1g;
+      const int e = q / (G * Crg * kq);
+      const int r = q - e * G * Crg * kq;
+      const int g = r / (Crg * kq);
+      const int jk = r - g * Crg * kq;
+      const int j = jk / kq, kb0 = (jk - j * kq) * kB;
+      cjv[t] = e * Cr + g * Crg + j;
+      ckv[t] = e * Cr + g * Crg + kb0;
+      outv[t] = (long long)ECr + (((long long)(e * G + g) * Crg + j) * Crg + kb0);
+    }
+  }
+  const long long tiles = (rows_total + TN - 1) / TN;
+  for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+    const long long r0 = tile * TN;
+    const int valid = (int)min((long long)TN, rows_total - r0);
+    {   // the tile of z is one contiguous chunk: flat coalesced 16-byte loads (ECr % 4 == 0 for kB = 4, else scalar), up to
+        // kDepth requests in flight per thread, (row, column) tracked incrementally -- the fill is latency-bound otherwise
+      const float* zt = p.z + r0 * ECr;
+      const int total = valid * ECr, cap = TN * ECr;
+      constexpr int kV = kB == 4 ? 4 : 1;          // elements per load
+      constexpr int kDepth = 8;
+      const int stride = kV * kThreads;
+      const int sq = stride % ECr, sn = stride / ECr;
+      int q = (kV * threadIdx.x) % ECr, n = (kV * threadIdx.x) / ECr;
+      for (int i = kV * threadIdx.x; i < cap; i += kDepth * stride) {
+        float zv[kDepth][kV];
+        int qq[kDepth], nn[kDepth];
+#pragma unroll
+        for (int u = 0; u < kDepth; ++u) {
+          const int ii = i + u * stride;
+          qq[u] = q; nn[u] = n;
+          if (kV == 4) {
+            const float4 t = ii < total ? *reinterpret_cast<const float4*>(zt + ii) : make_float4(0.f, 0.f, 0.f, 0.f);
+            zv[u][0] = t.x; zv[u][kV > 1 ? 1 : 0] = t.y; zv[u][kV > 2 ? 2 : 0] = t.z; zv[u][kV > 3 ? 3 : 0] = t.w;
+          } else {
+            zv[u][0] = ii < total ? zt[ii] : 0.f;
+          }
+          q += sq; n += sn;
+          if (q >= ECr) { q -= ECr; ++n; }
+        }
+#pragma unroll
+        for (int u = 0; u < kDepth; ++u) {
+          const int ii = i + u * stride;
+          if (ii < cap) {
+#pragma unroll
+            for (int v = 0; v < kV; ++v) {
+              float a = 0.f;
+              if (ii < total) {
+                a = fmaf(zv[u][v], colp[qq[u] + v], colp[ECr + qq[u] + v]);
+                if (colp[2 * ECr + qq[u] + v] != 0.f) a = fmaxf(a, 0.f);
+              }
+              as[ii + v + nn[u]] = a;      // n * (ECr + 1) + q
+            }
+          }
+        }
+      }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int t = 0; t < kGroups; ++t) {
+      if (cjv[t] == -2) continue;
+      float s[kB];
+#pragma unroll
+      for (int b = 0; b < kB; ++b) s[b] = 0.f;
+      const float* pk = as + ckv[t];
+      if (cjv[t] < 0) {
+        for (int n = 0; n < valid; ++n) {
+#pragma unroll
+          for (int b = 0; b < kB; ++b) s[b] += pk[n * lda + b];
+        }
+      } else {
+        const float* pj = as + cjv[t];
+        for (int n = 0; n < valid; ++n) {
+          const float aj = pj[n * lda];
+#pragma unroll
+          for (int b = 0; b < kB; ++b) s[b] = fmaf(aj, pk[n * lda + b], s[b]);
+        }
+      }
+#pragma unroll
+      for (int b = 0; b < kB; ++b) accv[t][b] += s[b];
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int t = 0; t < kGroups; ++t) {
+    if (cjv[t] == -2) continue;
+#pragma unroll
+    for (int b = 0; b < kB; ++b) {
+      if (cjv[t] < 0) atomicAdd(&m1[outv[t] + b], (double)accv[t][b]);
+      else atomicAdd(&m2[outv[t] - ECr + b], (double)accv[t][b]);
+    }
+  }
+}
+
 // generic (slow) variant when the moment matrix has more entries than kMomPerThread*256: one output per thread, grid-stride
 __global__ void bn_moments_big_kernel(const avmoe_expert_args p, double* m1, double* m2, long long rows_total, long long rows_per_cta) {
   const int Cr = p.Cr, G = p.G, Crg = Cr / G, E = p.E, ECr = E * Cr;
@@ -777,11 +903,19 @@ extern "C" int avmoe_bn_moments(const avmoe_expert_args* a, double* m1, double* 
     int TN = 8192 / (ECr + 1);
     if (TN > 128) TN = 128;
     if (TN < 1) TN = 1;
-    const size_t smem = sizeof(float) * (size_t)TN * (ECr + 1);
+    const size_t smem = sizeof(float) * ((size_t)TN * (ECr + 1) + 3 * (size_t)ECr);
     long long tiles = (rows + TN - 1) / TN;
     int grid = (int)(tiles < 2LL * num_sms() ? tiles : 2LL * num_sms());
     if (int rc = set_smem(bn_moments_kernel, smem, "bn_moments")) return rc;
-    bn_moments_kernel<<<grid, kThreads, smem, st>>>(*a, m1, m2, TN, rows);
+    if (Crg % 4 == 0 && ECr % 4 == 0) {
+      if (int rc = set_smem(bn_moments_blk_kernel<4>, smem, "bn_moments")) return rc;
+      bn_moments_blk_kernel<4><<<grid, kThreads, smem, st>>>(*a, m1, m2, TN, rows);
+    } else if (Crg % 2 == 0 && ECr % 2 == 0) {
+      if (int rc = set_smem(bn_moments_blk_kernel<2>, smem, "bn_moments")) return rc;
+      bn_moments_blk_kernel<2><<<grid, kThreads, smem, st>>>(*a, m1, m2, TN, rows);
+    } else {
+      bn_moments_kernel<<<grid, kThreads, smem, st>>>(*a, m1, m2, TN, rows);
+    }
   } else {
     const int gx = (int)((n_out + 255) / 256 < 64 ? (n_out + 255) / 256 : 64);
     int gy = (2 * num_sms() + gx - 1) / gx;
