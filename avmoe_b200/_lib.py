@@ -112,7 +112,7 @@ class XgArgs(C.Structure):
         ("probs", C.c_void_p), ("out", C.c_void_p), ("dout", C.c_void_p),
         ("stats1", C.c_void_p), ("red1", C.c_void_p), ("red2", C.c_void_p),
         ("da", C.c_void_p), ("dz", C.c_void_p), ("dxl", C.c_void_p),
-        ("dprobs", C.c_void_p), ("dpool_x", C.c_void_p), ("dx", C.c_void_p),
+        ("dprobs", C.c_void_p), ("dpool_x", C.c_void_p), ("dx", C.c_void_p), ("res", C.c_void_p),
     ]
 
 

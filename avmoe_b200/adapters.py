@@ -115,8 +115,15 @@ class _MoEAdapterBase(nn.Module):
         return self._kernels
 
     def _flat_params(self):
-        d = dict(self.named_parameters())
-        return [d[n] for n in self._names]
+        # resolved by attribute walk, not named_parameters(): nn.DataParallel replicas (AVMOE/AVVP/main.py:420-421) hold
+        # their weights as plain (non-leaf) tensor attributes, which named_parameters() does not list
+        out = []
+        for n in self._names:
+            obj = self
+            for part in n.split("."):
+                obj = getattr(obj, part)
+            out.append(obj)
+        return out
 
     def _bn_buffers(self):
         return {k: v for k, v in self.named_buffers()}
@@ -127,7 +134,7 @@ class _MoEAdapterBase(nn.Module):
         assert t.dim() == 4 and t.shape[-1] == 1, "expected [BT, C, N, 1]"
         return t.squeeze(-1).permute(0, 2, 1).contiguous()
 
-    def _run(self, x, vis_token, noise: Optional[torch.Tensor] = None):
+    def _run(self, x, vis_token, noise: Optional[torch.Tensor] = None, residual: Optional[torch.Tensor] = None):
         K = self._kernel_namespace()
         if K.__name__.endswith(".ops") and not x.is_cuda:
             raise RuntimeError("avmoe_b200 has no CPU path: move the module and its inputs to a CUDA device")
@@ -138,7 +145,8 @@ class _MoEAdapterBase(nn.Module):
                     raise RuntimeError("attention dropout inside the AVS-v1 MultiheadAttention is RNG-dependent; set "
                                        "self_attention.dropout = 0 or call .eval() (SURVEY.md §8c caveat 3)")
         state = {"cfg": self.cfg, "K": K, "training": self.training, "buffers": self._bn_buffers(), "noise": noise}
-        out, probs, lb, idx = Fn.MoEAdapterFunction.apply(state, xt, ot, *self._flat_params())
+        rt = None if residual is None else self._token_major(residual).to(xt.dtype)
+        out, probs, lb, idx = Fn.MoEAdapterFunction.apply(state, xt, ot, rt, *self._flat_params())
         return out.permute(0, 2, 1).unsqueeze(-1), idx.unsqueeze(-1), probs.unsqueeze(1), lb
 
 
@@ -153,8 +161,11 @@ class MoEAdapterAVE(_MoEAdapterBase):
         self._build(input_dim, output_dim, adapter_kind, reduction_factor, opt, use_bn, use_gate, num_tk,
                     conv_dim_in, conv_dim_out, linear_in, linear_out, sa, False)
 
-    def forward(self, x, vis_token=None):
-        out, idx, _, _ = self._run(x, vis_token)
+    def forward(self, x, vis_token=None, residual=None):
+        """``residual`` (optional, same layout as ``x``): the stream the call site adds the adapter output to
+        (net_trans_v3.py:703,706,718,720); when given, the add is folded into the combine epilogue and ``out`` is the
+        updated stream."""
+        out, idx, _, _ = self._run(x, vis_token, residual=residual)
         return out, idx
 
 
@@ -169,8 +180,8 @@ class MoEAdapterAVQA(_MoEAdapterBase):
         self._build(input_dim, output_dim, adapter_kind, reduction_factor, opt, use_bn, use_gate, opt.num_tokens,
                     conv_dim_in, conv_dim_out, linear_in, linear_out, sa, False)
 
-    def forward(self, x, vis_token=None):
-        out, idx, _, _ = self._run(x, vis_token)
+    def forward(self, x, vis_token=None, residual=None):
+        out, idx, _, _ = self._run(x, vis_token, residual=residual)
         return out, idx
 
 
@@ -184,8 +195,8 @@ class MoEAdapterAVVP(_MoEAdapterBase):
         self._build(input_dim, output_dim, adapter_kind, opt.Adapter_downsample, opt, opt.is_bn, opt.is_gate, opt.num_tokens,
                     conv_dim_in, conv_dim_out, linear_in, linear_out, "nxn", opt.use_load_balacing_loss == 1)
 
-    def forward(self, x, vis_token=None):
-        out, _, _, lb = self._run(x, vis_token)
+    def forward(self, x, vis_token=None, residual=None):
+        out, _, _, lb = self._run(x, vis_token, residual=residual)
         return out, (lb if self.cfg.lb_loss else 0.)
 
 
@@ -203,14 +214,14 @@ class MoEAdapterAVS(_MoEAdapterBase):
                     conv_dim_in, conv_dim_out, linear_in, linear_out, sa, _opt_get(opt, "use_load_balacing_loss", 0) == 1)
         self.noise_std = 0.01   # PVT_AVSModel_v2.py:295
 
-    def forward(self, x, vis_token=None, is_training=True, noise: Optional[torch.Tensor] = None):
+    def forward(self, x, vis_token=None, is_training=True, noise: Optional[torch.Tensor] = None, residual=None):
         """``noise`` ([BT,E], optional) lets a caller inject the router noise tensor for reproducible parity runs;
         by default it is drawn with torch.randn exactly where the reference draws it."""
         if is_training and noise is None:
             noise = torch.randn((x.shape[0], self.cfg.E), device=x.device, dtype=torch.float32) * self.noise_std
         if not is_training:
             noise = None
-        out, idx, probs, lb = self._run(x, vis_token, noise)
+        out, idx, probs, lb = self._run(x, vis_token, noise, residual=residual)
         return out, idx, probs, (lb if self.cfg.lb_loss else 0.)
 
 

@@ -218,6 +218,10 @@ __global__ void __launch_bounds__(256) xg_post_fwd_kernel(const avmoe_xg_args p,
     }
     if (act) {
       T* dst = static_cast<T*>(p.out) + row * C;
+      if (p.res) {   // residual stream folded into the combine epilogue (row a9)
+        const T* rs = static_cast<const T*>(p.res) + row * C;
+        TEAM_VECS(k, c) acc[k] = acc[k] + ldg_act4<T>(rs + c);
+      }
       TEAM_VECS(k, c) st_act4<T>(dst + c, acc[k]);
     }
   }

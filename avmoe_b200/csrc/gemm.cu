@@ -13,6 +13,7 @@
 //
 // Replaces: nn.Conv2d(Nx->N,1x1) over the token axis + nn.Linear(Cx->C)
 //           (AVMOE/AVE/nets/net_trans_v3.py:445-446,469-471) and their autograd.
+#include <atomic>
 #include <mutex>
 
 #include "common.cuh"
@@ -860,14 +861,18 @@ int gemm_dispatch(const avmoe_gemm_args* a, cudaStream_t st) {
   const int tiles = p.tiles_m * p.tiles_n * p.splits * p.full_batch;
   int grid = num_sms();
   if (grid > tiles) grid = tiles;
-  static std::once_flag attr_once;
-  static cudaError_t attr_err = cudaSuccess;
-  std::call_once(attr_once, [&] {
-    attr_err = cudaFuncSetAttribute(gemm_tcgen05_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
-    if (attr_err == cudaSuccess)
-      attr_err = cudaFuncSetAttribute(gemm_tcgen05_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
-  });
-  AVMOE_CUDA(attr_err);
+  // The dynamic-shared-memory opt-in is a per-device (per-context) function attribute: a single-process multi-GPU host
+  // (nn.DataParallel, AVMOE/AVVP/main.py:420-421) needs it set once on EVERY device it launches on.
+  {
+    static std::atomic<unsigned char> attr_done[64];
+    int dev = 0;
+    AVMOE_CUDA(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64 || !attr_done[dev].load(std::memory_order_acquire)) {
+      AVMOE_CUDA(cudaFuncSetAttribute(gemm_tcgen05_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+      AVMOE_CUDA(cudaFuncSetAttribute(gemm_tcgen05_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+      if (dev >= 0 && dev < 64) attr_done[dev].store(1, std::memory_order_release);
+    }
+  }
   if (bf16) gemm_tcgen05_kernel<false><<<grid, kGemmThreads, smem_bytes, st>>>(p);
   else gemm_tcgen05_kernel<true><<<grid, kGemmThreads, smem_bytes, st>>>(p);
   AVMOE_LAUNCH_CHECK("gemm_tcgen05_kernel");

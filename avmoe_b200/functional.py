@@ -310,7 +310,7 @@ def fused_experts_fwd(K, cfg, x, tokp, packs, probs, P, bufs, prefixes, bn_mode)
     return out, z, bn
 
 
-def gemm_experts_fwd(K, cfg, x, packs, probs, P, bufs, prefixes, bn_mode):
+def gemm_experts_fwd(K, cfg, x, packs, probs, P, bufs, prefixes, bn_mode, res=None):
     """Experts with every channel contraction on the tcgen05 GEMM (block-diagonal dense weights) and streaming row kernels
     in between (csrc/expert_rows.cu).  Returns (out, z, bn, saved-for-backward)."""
     BT, N, C = x.shape
@@ -344,7 +344,7 @@ def gemm_experts_fwd(K, cfg, x, packs, probs, P, bufs, prefixes, bn_mode):
     yd = torch.empty((E, rows, 2 * C), device=dev, dtype=dt)
     K.bgemm(act, wud, out=yd[:, :, :C], col_bias=ybi)                             # up projection -> normalised y (per-expert bias)
     out = torch.empty_like(x)
-    ln2s = K.xg_post_fwd(cfg, yd, bn2_wb, packs, probs, out)
+    ln2s = K.xg_post_fwd(cfg, yd, bn2_wb, packs, probs, out, res)                    # residual add folded in (row a9)
     return out, z, bn, (xl, ln1s, act, yd, ln2s, wdt, suma)
 
 
@@ -393,7 +393,14 @@ class MoEAdapterFunction(torch.autograd.Function):
     place in training mode, exactly like nn.BatchNorm2d), the optional router noise tensor, and receives ``idx``."""
 
     @staticmethod
-    def forward(ctx, state: dict, x: torch.Tensor, o: torch.Tensor, *params: torch.Tensor):
+    def forward(ctx, state: dict, x: torch.Tensor, o: torch.Tensor, res: Optional[torch.Tensor], *params: torch.Tensor):
+        # launch on the device that owns the tensors (nn.DataParallel replicas, AVMOE/AVVP/main.py:420-421, call this from one
+        # thread per GPU; autograd engine threads likewise)
+        with torch.cuda.device_of(x):
+            return MoEAdapterFunction._forward(ctx, state, x, o, res, *params)
+
+    @staticmethod
+    def _forward(ctx, state: dict, x: torch.Tensor, o: torch.Tensor, res: Optional[torch.Tensor], *params: torch.Tensor):
         cfg: AdapterConfig = state["cfg"]
         K = state["K"]
         training: bool = state["training"]
@@ -404,6 +411,7 @@ class MoEAdapterFunction(torch.autograd.Function):
         BT, N, C = x.shape
         assert (N, C) == (cfg.N, cfg.C) and o.shape[1:] == (cfg.Nx, cfg.Cx), "token shapes do not match the adapter"
         assert x.is_contiguous() and o.is_contiguous()
+        assert res is None or (res.shape == x.shape and res.is_contiguous() and res.dtype == x.dtype)
         E, Cr, G, T = cfg.E, cfg.Cr, cfg.G, cfg.T
         bn_mode = _bn_mode(cfg, training)
         f32 = torch.float32
@@ -483,9 +491,11 @@ class MoEAdapterFunction(torch.autograd.Function):
         use_xg = (_xflag == "always" or (bool(_xflag) and x.dtype == torch.bfloat16)) and all(pk.pre_kind != PRE_LATENT for pk in packs)
         xg_saved = None
         if use_xg:
-            out, z, bn, xg_saved = gemm_experts_fwd(K, cfg, x, packs, probs, P, bufs, prefixes, bn_mode)
+            out, z, bn, xg_saved = gemm_experts_fwd(K, cfg, x, packs, probs, P, bufs, prefixes, bn_mode, res)
         else:
             out, z, bn = fused_experts_fwd(K, cfg, x, tokp, packs, probs, P, bufs, prefixes, bn_mode)
+            if res is not None:
+                K.add_into(out, res)
         lb = K.lb_loss_fwd(probs) if cfg.lb_loss else torch.zeros((), device=dev, dtype=f32)
 
         state["idx"] = idx
@@ -507,6 +517,15 @@ class MoEAdapterFunction(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, dout, dprobs_ext, dlb, _didx):
+        with torch.cuda.device_of(dout):
+            grads = MoEAdapterFunction._backward(ctx, dout, dprobs_ext, dlb, _didx)
+        # the large forward intermediates must not outlive the backward (a training loop that keeps `loss` alive into the
+        # next forward would otherwise hold two steps of activations)
+        ctx.rs_saved = ctx.aux_saved = ctx.xg_saved = ctx.bn = ctx.aux = None
+        return grads
+
+    @staticmethod
+    def _backward(ctx, dout, dprobs_ext, dlb, _didx):
         state = ctx.state
         cfg: AdapterConfig = state["cfg"]
         K = state["K"]
@@ -667,4 +686,5 @@ class MoEAdapterFunction(torch.autograd.Function):
             if bn_mode != BN_OFF:
                 grads[pfx + "bn1.weight"], grads[pfx + "bn1.bias"] = r1[e, :, 1], r1[e, :, 0]
                 grads[pfx + "bn2.weight"], grads[pfx + "bn2.bias"] = r2[e, :, 1], r2[e, :, 0]
-        return (None, dx, do) + tuple(grads[n] for n in names)
+        dres = dout if ctx.needs_input_grad[3] else None                      # residual passes the gradient through
+        return (None, dx, do, dres) + tuple(grads[n] for n in names)

@@ -667,12 +667,13 @@ def xg_bn_act(cfg, z, aff1, packs, dtype, bn_mode):
     return act
 
 
-def xg_post_fwd(cfg, yd, bn2_wb, packs, probs, out):
+def xg_post_fwd(cfg, yd, bn2_wb, packs, probs, out, res=None):
+    """res [BT,N,C] (optional): the residual stream, folded into the combine epilogue (out = res + sum_e ...)."""
     BT, N = out.shape[0], out.shape[1]
     st = torch.empty((cfg.E, BT * N, 2), device=out.device, dtype=torch.float32) if packs[0].ln2_w is not None else None
     a, keep = _xg_args(cfg, packs, BT=BT, dtype=_dt(out), bn_mode=int(bn2_wb is not None), bn2_wb=bn2_wb)
-    _set(a, yd=yd, ln2_stats=st, probs=probs, out=out)
-    _lib_call("xg_post_fwd", C.byref(a), _stream(), _bytes=_nbytes(yd) / 2 + _nbytes(out))
+    _set(a, yd=yd, ln2_stats=st, probs=probs, out=out, res=res)
+    _lib_call("xg_post_fwd", C.byref(a), _stream(), _bytes=_nbytes(yd) / 2 + _nbytes(out, res))
     return st
 
 

@@ -109,9 +109,13 @@ class AdapterStack(nn.Module):
     def stages(self):
         return [s for s, _ in VARIANT_SITES[self.variant]]
 
+    fuse_residual = True   # fold the call-site add f = f + adapter(f, other) into the adapter's combine epilogue
+
     def _call(self, mod, x_tok, o_tok):
         """reference call-site convention: permuted [BT,C,N,1] views in, residual in the same layout out."""
-        res = mod(x_tok.permute(0, 2, 1).unsqueeze(-1), o_tok.permute(0, 2, 1).unsqueeze(-1))
+        xv = x_tok.permute(0, 2, 1).unsqueeze(-1)
+        kw = {"residual": xv} if self.fuse_residual else {}
+        res = mod(xv, o_tok.permute(0, 2, 1).unsqueeze(-1), **kw)
         out = res[0].squeeze(-1).permute(0, 2, 1)
         aux = res[-1] if self.variant in ("avvp", "s4", "ms3") and torch.is_tensor(res[-1]) else None
         return out, aux
@@ -142,8 +146,11 @@ class AdapterStack(nn.Module):
                 else:
                     ra, la = self._call(pa[i], f_a, f_v)
                     rv, lv = self._call(pv[i], f_v, f_a)
-                f_v = f_v + rv
-                f_a = f_a + ra
+                if self.fuse_residual:     # the adapters returned the updated streams
+                    f_v, f_a = rv, ra
+                else:
+                    f_v = f_v + rv
+                    f_a = f_a + ra
                 for l in (la, lv):
                     if l is not None:
                         lb_sum = l if lb_sum is None else lb_sum + l

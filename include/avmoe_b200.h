@@ -257,6 +257,8 @@ typedef struct {
   float* dprobs;           /* [BT,E] += */
   const float* dpool_x;    /* [BT,C] router-path gradient per token (already /N), or NULL */
   void* dx;                /* [rows,C] */
+  const void* res;         /* [rows,C] or NULL: residual stream folded into the combine epilogue, out = res + sum_e ... (the call-site add
+                            * f = f + adapter(...), AVMOE/AVE/nets/net_trans_v3.py:703,706,718,720 -- SURVEY.md §8 row a9) */
 } avmoe_xg_args;
 
 int avmoe_xg_ln_pre_fwd(const avmoe_xg_args* a, avmoe_stream_t stream);     /* x, ex[].aux -> xl, ln1_stats */

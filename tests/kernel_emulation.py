@@ -673,7 +673,7 @@ def _xg_post_t(cfg, yd, bn2_wb, pk, e):
     return yh, (yh * bn2_wb[e][0] + bn2_wb[e][1] if bn2_wb is not None else yh)
 
 
-def xg_post_fwd(cfg, yd, bn2_wb, packs, probs, out):
+def xg_post_fwd(cfg, yd, bn2_wb, packs, probs, out, res=None):
     BT, N, C = out.shape
     st = torch.empty((cfg.E, BT * N, 2), dtype=torch.float32) if packs[0].ln2_w is not None else None
     acc = torch.zeros((BT, N, C), dtype=torch.float32)
@@ -686,6 +686,8 @@ def xg_post_fwd(cfg, yd, bn2_wb, packs, probs, out):
         if pk.gate is not None:
             t = t * pk.gate
         acc = acc + probs[:, e, None, None] * t.reshape(BT, N, C)
+    if res is not None:
+        acc = acc + res.float()
     out.copy_(acc.to(out.dtype))
     return st
 

@@ -96,7 +96,13 @@ def _cuda_run(spec, sd, x, o, gout, dtype, training=True):
 
 STAGE_CASES = [("ave", 3, "audio"), ("ave", 3, "visual"), ("ave", 1, "audio"), ("ave", 1, "visual"),
                ("avqa", 3, "audio"), ("avqa", 4, "visual"), ("ms3", 3, "audio"), ("ms3", 1, "visual"),
-               ("avvp", 3, "audio"), ("s4", 3, "visual")]
+               ("avvp", 3, "audio"), ("s4", 3, "visual"),
+               # round 2: every stage of the 12-site variants, both modalities where the shapes differ in kind -- stage 2, stage 4
+               # (N = 64 / 36 tokens), and the stage-1 hot spots of the variant self-attentions (AVVP 4096 x 4096 token
+               # self-attention, mgn.py:132-139; AVS-v1 attention over the BT axis at 4096 positions)
+               ("avqa", 2, "audio"), ("avqa", 2, "visual"), ("avqa", 4, "audio"), ("avvp", 1, "audio"), ("avvp", 2, "visual"),
+               ("avvp", 4, "audio"), ("avvp", 4, "visual"), ("s4", 1, "audio"), ("s4", 2, "audio"), ("s4", 4, "visual"),
+               ("ms3", 1, "audio")]
 
 
 @pytest.mark.parametrize("variant,stage,modality", STAGE_CASES)
