@@ -37,8 +37,9 @@ def parse_args():
     ap.add_argument("--clips", type=int, default=16, help="clips per GPU (x10 segments = BT)")
     ap.add_argument("--segments", type=int, default=10)
     ap.add_argument("--dtype", default="bf16", choices=["bf16", "f32"])
-    ap.add_argument("--cpu-sample-clips", type=int, default=1, help="clips in the bounded CPU-baseline sample")
+    ap.add_argument("--cpu-sample-clips", type=int, default=2, help="clips in the bounded CPU-baseline sample (2 x 10 = the reference's own batch, AVMOE/AVE/train.sh:32-33)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-gpu-eager", action="store_true", help="skip the reported GPU comparator (reference modules in PyTorch eager on the same GPU)")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel from Python each step instead of replaying a CUDA graph")
     return ap.parse_args()
 
@@ -73,6 +74,45 @@ def run_reference_arm(args):
             "data": "synthetic", "config": {"workload": workload_name(args), "sample": base["sample"]},
             "cpu_baseline": base, "e2e": {"value": base["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
+
+
+def gpu_eager_baseline(args, BT):
+    """COMPARATOR, reported only: the reference's own adapter modules (staged copies under oracle/_ref or /root/reference; else
+    the oracle port) in PyTorch eager on this GPU, same stack / tokens-per-step definition, fp32 (the reference's training
+    precision) and under bf16 autocast.  This is what `model.cuda()` gives a reference user."""
+    import torch
+    from oracle import ref_loader, stack_oracle
+    use_ref = ref_loader.available()
+    out = {"kind": "reference" if use_ref else "port", "BT": BT, "unit": UNIT}
+    for name, ac in (("f32", None), ("bf16_autocast", torch.bfloat16)):
+        try:
+            tps, ms = stack_oracle.time_gpu_eager(args.variant, BT, 3, 2, use_reference=use_ref, autocast_dtype=ac)
+            out[name] = {"value": tps, "ms_per_step": ms}
+        except Exception as ex:   # e.g. out of memory for the materialised N x N variants
+            out[name] = {"value": None, "error": str(ex)[:200]}
+        torch.cuda.empty_cache()
+    return out
+
+
+def stack_roofline(variant, BT, elem_bytes, n_params, tc_peak_tflops, hbm_peak_gbs):
+    """SURVEY.md §8(d) stack-level roofline of one step (fwd+bwd) on one GPU:
+       algorithmic HBM bytes  = sum over MoEAdapter calls of (5·N·C + 3·Nx·Cx)·s per sample  +  parameters read (4 B) and
+                                their gradients written (4 B) once per step;
+       resampler FLOPs        = 3 x [2·N·Nx·min(C,Cx) + 2·C·Cx·(Nx if Cx > C else N)] per sample and call (tensor-bound);
+       roofline_time          = resampler FLOPs / measured tensor peak  +  algorithmic bytes / measured HBM peak."""
+    from avmoe_b200 import stack as S
+    nbytes = 0.0
+    flops = 0.0
+    for stage, blocks in S.VARIANT_SITES[variant]:
+        Cv, Nv, Ca, Na = S.STAGE_SHAPES[stage]
+        for (C, N, Cx, Nx) in ((Ca, Na, Cv, Nv), (Cv, Nv, Ca, Na)):
+            calls = 2 * blocks
+            nbytes += calls * BT * (5 * N * C + 3 * Nx * Cx) * elem_bytes
+            flops += calls * BT * 3 * (2 * N * Nx * min(C, Cx) + 2 * C * Cx * (Nx if Cx > C else N))
+    nbytes += 8.0 * n_params
+    t_ms = flops / (tc_peak_tflops * 1e12) * 1e3 + nbytes / (hbm_peak_gbs * 1e9) * 1e3
+    return {"algorithmic_bytes_per_step": nbytes, "resampler_flops_per_step": flops, "roofline_time_ms": t_ms,
+            "hbm_ms": nbytes / (hbm_peak_gbs * 1e9) * 1e3, "tensor_ms": flops / (tc_peak_tflops * 1e12) * 1e3}
 
 
 # ------------------------------------------------------------------------------------------------ clocks
@@ -334,6 +374,19 @@ def run_ours(args):
             roofline = {"bound": "hbm", "kernel": name, "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak,
                         "traffic": traffic, "traffic_source": traffic_src, "algorithmic_bytes_per_launch": d["bytes"] / max(d["n"], 1)}
         gt = agg.get(TB)
+        st = stack_roofline(args.variant, BT, 2 if dtype == torch.bfloat16 else 4, sum(p.numel() for p in params), tc_peak, hbm_peak)
+        st["achieved"] = st["roofline_time_ms"] / ms_per_step          # fraction of the stack-level roofline (north-star bar: 0.60)
+        st["kernel_moved_bytes_per_step"] = sum(a["bytes"] for a in agg.values())   # bytes the kernels' own operands add up to
+        st["moved_over_algorithmic"] = st["kernel_moved_bytes_per_step"] / st["algorithmic_bytes_per_step"]
+        try:    # whole-step DRAM traffic from an ncu pass of the same command (tools/dram_step.py), when one is committed
+            dr = json.load(open(os.path.join(ROOT, "profiles", "r02_dram_step.json")))
+            if dr.get("variant") == args.variant and dr.get("BT") == BT:
+                st["dram_bytes_per_step_ncu"] = dr["dram_bytes"]
+                st["dram_over_algorithmic"] = dr["dram_bytes"] / st["algorithmic_bytes_per_step"]
+                st["dram_source"] = "profiles/r02_dram_step.json"
+        except Exception:
+            pass
+        roofline["stack"] = st
         roofline.update({"launches_per_step": d["n"], "avg_launch_ms": d["ms"] / max(d["n"], 1), "share_of_kernel_time": d["ms"] / tot_ms,
                          "peak_source": peak_src, "ridge_flop_per_byte": ridge,
                          "gemm_tensor_bound": None if not gt else {
@@ -349,16 +402,29 @@ def run_ours(args):
         except Exception as ex:  # the baseline is a report, never a dependency of the product path
             cpu = {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "port", "sample": f"failed: {ex}"}
 
+    launch_mode = "cuda-graph replay" if graph is not None else "eager python launches"
+    gpu_eager = None
+    if rank == 0 and world == 1 and not args.no_gpu_eager:
+        graph = graph_loss = None
+        model.zero_grad(set_to_none=True)
+        torch.cuda.empty_cache()
+        try:
+            gpu_eager = gpu_eager_baseline(args, BT)
+        except Exception as ex:
+            gpu_eager = {"error": str(ex)[:200]}
+
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
                 "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "bf16" if dtype == torch.bfloat16 else "f32", "data": "synthetic",
                 "config": {"workload": workload_name(args), "variant": args.variant, "BT_per_gpu": BT, "tokens_per_step_per_gpu": tokens_per_step,
-                           "adapter_calls_per_step": 4 * len(model.sites), "launch": "cuda-graph replay" if graph is not None else "eager python launches", "parallelism": f"dp{world} (batch-sharded, grad all-reduce)" if world > 1 else "single GPU",
+                           "adapter_calls_per_step": 4 * len(model.sites), "launch": launch_mode, "parallelism": f"dp{world} (batch-sharded, grad all-reduce)" if world > 1 else "single GPU",
                            "l2": f"inputs+weights per step ({(h2d_bytes + sum(p.numel() * 4 for p in params)) / 1e6:.0f} MB) exceed the 126 MB L2; no explicit flush"},
                 "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "kernels": kernel_table}
         if cpu is not None:
             line["cpu_baseline"] = cpu
+        if gpu_eager is not None:
+            line["gpu_eager_baseline"] = gpu_eager
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()

@@ -24,7 +24,17 @@ import os
 import sys
 import types
 
-REFERENCE_ROOT = os.environ.get("AVMOE_REFERENCE_ROOT", "/root/reference")
+def _reference_root() -> str:
+    """/root/reference in the build container; on the GPU box the unmodified copies staged by oracle/stage_reference.py"""
+    env = os.environ.get("AVMOE_REFERENCE_ROOT")
+    if env:
+        return env
+    if os.path.isdir("/root/reference/AVMOE"):
+        return "/root/reference"
+    return os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref")
+
+
+REFERENCE_ROOT = _reference_root()
 
 _VARIANTS = {
     "ave": ("AVMOE/AVE", "nets.net_trans_v3"),

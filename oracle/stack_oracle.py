@@ -26,9 +26,10 @@ def tokens_per_segment(variant: str) -> int:
 
 
 class OracleStack:
-    def __init__(self, variant: str = "ave", seed: int = 0, use_reference: bool = False):
+    def __init__(self, variant: str = "ave", seed: int = 0, use_reference: bool = False, device=None):
         self.variant = variant
         self.use_reference = use_reference
+        self.device = device
         self.sites: List[Tuple[int, int]] = []
         self.adapters = []   # per site: dict(name -> (spec, state_dict or module))
         k = 0
@@ -46,8 +47,12 @@ class OracleStack:
                             if isinstance(m, torch.nn.MultiheadAttention):
                                 m.dropout = 0.0
                         H.make_bn_grads_contiguous(mod)
+                        if device is not None:
+                            mod = mod.to(device)
                         entry[name] = (spec, mod)
                     else:
+                        if device is not None:
+                            sd = {kk: v.to(device) for kk, v in sd.items()}
                         sd = {kk: (v.clone().requires_grad_() if v.is_floating_point() and "running" not in kk else v.clone())
                               for kk, v in sd.items()}
                         entry[name] = (spec, sd)
@@ -101,13 +106,15 @@ class OracleStack:
         return float(loss.detach())
 
 
-def make_stage_tokens(variant: str, BT: int, seed: int = 1234):
+def make_stage_tokens(variant: str, BT: int, seed: int = 1234, device=None):
     out = {}
     for stage, _ in O.VARIANT_SITES[variant]:
         Cv, Nv, Ca, Na = STAGE_SHAPES[stage]
         g = torch.Generator().manual_seed(seed + 97 * stage)
         f_a = torch.randn((BT, Na, Ca), generator=g) + torch.randn((BT, 1, Ca), generator=g)
         f_v = torch.randn((BT, Nv, Cv), generator=g) + torch.randn((BT, 1, Cv), generator=g)
+        if device is not None:
+            f_a, f_v = f_a.to(device), f_v.to(device)
         out[stage] = (f_a.requires_grad_(), f_v.requires_grad_())
     return out
 
@@ -131,3 +138,34 @@ def time_cpu(variant: str, BT: int, steps: int, warmup: int, use_reference: bool
             times.append(dt)
     med = sorted(times)[len(times) // 2]
     return tokens_per_segment(variant) * BT / med, times, torch.get_num_threads()
+
+
+def time_gpu_eager(variant: str, BT: int, steps: int, warmup: int, use_reference: bool = False, autocast_dtype=None, device="cuda"):
+    """COMPARATOR, not a product path: the reference's (or the oracle port's) eager PyTorch modules on the GPU — what a
+    reference user gets from ``model.cuda()`` ("the thing to beat on the same box").  fp32 parameters and
+    tokens; ``autocast_dtype=torch.bfloat16`` wraps the forward in torch.autocast.  Returns (tokens/s, ms per step)."""
+    stack = OracleStack(variant, use_reference=use_reference, device=device)
+    toks = make_stage_tokens(variant, BT, device=device)
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+
+    def one():
+        stack.zero_grad()
+        for s in toks:
+            for t in toks[s]:
+                t.grad = None
+        if autocast_dtype is not None:
+            with torch.autocast("cuda", dtype=autocast_dtype):
+                stack.step(toks)
+        else:
+            stack.step(toks)
+
+    for _ in range(warmup):
+        one()
+    torch.cuda.synchronize()
+    ev[0].record()
+    for _ in range(steps):
+        one()
+    ev[1].record()
+    torch.cuda.synchronize()
+    ms = ev[0].elapsed_time(ev[1]) / steps
+    return tokens_per_segment(variant) * BT / (ms * 1e-3), ms
