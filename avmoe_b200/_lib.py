@@ -116,6 +116,19 @@ class XgArgs(C.Structure):
     ]
 
 
+class RfBackArgs(C.Structure):
+    """avmoe_rf_back_args: the row-fused back pass (bn1 affine .. combine) and its backward."""
+    _fields_ = [
+        ("BT", C.c_int32), ("N", C.c_int32), ("C", C.c_int32), ("Cr", C.c_int32), ("Crp", C.c_int32), ("G", C.c_int32),
+        ("E", C.c_int32), ("bn_mode", C.c_int32),
+        ("ex", Expert * MAX_EXPERTS),
+        ("bn2_w", _PtrArr), ("bn2_b", _PtrArr),
+        ("z", C.c_void_p), ("aff1", C.c_void_p), ("wu_pack", C.c_void_p), ("ybi", C.c_void_p), ("probs", C.c_void_p),
+        ("res", C.c_void_p), ("out", C.c_void_p), ("dout", C.c_void_p), ("yd", C.c_void_p), ("act", C.c_void_p),
+        ("dprobs", C.c_void_p), ("red2", C.c_void_p),
+    ]
+
+
 class BnArgs(C.Structure):
     _fields_ = [
         ("E", C.c_int32), ("C", C.c_int32), ("Cr", C.c_int32), ("G", C.c_int32), ("train", C.c_int32), ("_pad", C.c_int32),

@@ -339,13 +339,20 @@ def gemm_experts_fwd(K, cfg, x, packs, probs, P, bufs, prefixes, bn_mode, res=No
                 bufs[p + "bn2.num_batches_tracked"] += 1
         bn = (aff1, save1, aff2, save2)
         bn2_wb = [(P[p + "bn2.weight"], P[p + "bn2.bias"]) for p in prefixes]
+    if bool(getattr(K, "USE_ROWFUSED", False)) and K.rf_supported(cfg, dt):
+        # row-fused back pass: bn1 affine, activation, up projection, bn2, ln_post, gate, combine (+ residual) on one 16-row tile
+        # per warp; nothing is materialised -- the backward recomputes from z
+        wu_pack, ybi = K.rf_prep_up(cfg, packs, bn[3] if bn else None, bn_mode)
+        out = torch.empty_like(x)
+        K.rf_back_fwd(cfg, z, bn[0] if bn else None, wu_pack, ybi, bn2_wb, bn_mode, packs, probs, out, res)
+        return out, z, bn, (xl, ln1s, None, None, None, wdt, suma, (wu_pack, ybi))
     act = K.xg_bn_act(cfg, z, bn[0] if bn else None, packs, dt, bn_mode)          # [E,rows,Crp]
     wud, ybi = K.xg_prep_up(cfg, packs, bn[3] if bn else None, bn_mode, dt)       # bn2 normalisation folded into the operand
     yd = torch.empty((E, rows, 2 * C), device=dev, dtype=dt)
     K.bgemm(act, wud, out=yd[:, :, :C], col_bias=ybi)                             # up projection -> normalised y (per-expert bias)
     out = torch.empty_like(x)
     ln2s = K.xg_post_fwd(cfg, yd, bn2_wb, packs, probs, out, res)                    # residual add folded in (row a9)
-    return out, z, bn, (xl, ln1s, act, yd, ln2s, wdt, suma)
+    return out, z, bn, (xl, ln1s, act, yd, ln2s, wdt, suma, None)
 
 
 def gemm_experts_bwd(K, cfg, x, dout, z, bn, bn_mode, packs, egr, probs, P, prefixes, saved):
@@ -355,12 +362,15 @@ def gemm_experts_bwd(K, cfg, x, dout, z, bn, bn_mode, packs, egr, probs, P, pref
     Crp = K.pad_bottleneck(Cr)
     rows = BT * N
     dev, f32, dt = x.device, torch.float32, x.dtype
-    xl, ln1s, act, yd, ln2s, wdt, suma = saved
+    xl, ln1s, act, yd, ln2s, wdt, suma, rf = saved
     bn2_wb = [(P[p + "bn2.weight"], P[p + "bn2.bias"]) for p in prefixes] if bn_mode != BN_OFF else None
     red2 = torch.zeros((E, C, 2), device=dev, dtype=torch.float64) if bn_mode != BN_OFF else None
     red1 = torch.zeros((E, Cr, 2), device=dev, dtype=torch.float64) if bn_mode != BN_OFF else None
     dprobs = torch.zeros((BT, E), device=dev, dtype=f32)
-    K.xg_post_bwd(cfg, dout, yd, ln2s, bn2_wb, bn_mode, packs, probs, dprobs, red2, egr)   # yd[:, :, C:] = d(bn2 output)
+    if rf is not None:     # recompute yhat / a from z (row-fused): yd = [yhat | d(bn2 output)], a
+        yd, act = K.rf_back_bwd(cfg, dout, z, bn[0] if bn else None, rf[0], rf[1], bn2_wb, bn_mode, packs, probs, dprobs, red2, egr)
+    else:
+        K.xg_post_bwd(cfg, dout, yd, ln2s, bn2_wb, bn_mode, packs, probs, dprobs, red2, egr)   # yd[:, :, C:] = d(bn2 output)
     w2, bias2 = K.xg_prep_bwd(cfg, packs, bn2_wb, bn, bn_mode, red2, BT, dt)               # bn2 backward folded into the operand
     da = torch.empty((E, rows, Crp), device=dev, dtype=f32)
     pwu = torch.empty((E, 2 * C, Crp), device=dev, dtype=f32)

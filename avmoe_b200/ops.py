@@ -725,6 +725,106 @@ def xg_finish_wgrads(cfg, packs, egr, bn2_wb, bn, bn_mode, red2, BT, pwd, pwu, s
     _lib_call("xg_finish_wgrads", C.byref(a), _ptr(pwd), _ptr(pwu), _ptr(suma), _stream())
 
 
+# ------------------------------------------------------------------------------------------------ row-fused expert passes
+USE_ROWFUSED = True   # bf16 streams: fused per-row expert passes on warp-level tensor-core tiles (csrc/rowfused.cu) where supported
+
+
+def rf_supported(cfg, dtype) -> bool:
+    """geometry check of the row-fused passes (C % 16 == 0, C/r <= 96, 2 <= E <= 4, T <= 96); bf16 streams only"""
+    return dtype == torch.bfloat16 and bool(_lib.load().avmoe_rf_supported(cfg.C, cfg.Cr, cfg.E, cfg.T))
+
+
+def rf_pack_bytes(nb: int, Nn: int, K: int, hi_lo: bool = False) -> int:
+    lib = _lib.load()
+    lib.avmoe_rf_pack_b_bytes.restype = C.c_int64
+    return int(lib.avmoe_rf_pack_b_bytes(nb, Nn, K, int(hi_lo)))
+
+
+def rf_pack_b(src: torch.Tensor, *, nb: int, bstride: int, stride_n: int, stride_k: int, Nn: int, K: int, groups: int = 1,
+              group_local_k: bool = True, scale_n: Optional[torch.Tensor] = None, scale_k: Optional[torch.Tensor] = None, hi_lo: bool = False,
+              out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """fp32 matrix -> packed tensor-core B operand B[k][n] (mma fragment order, bf16; include/avmoe_b200.h avmoe_rf_pack_b).
+    Returns a uint8 tensor; ``out`` may be a slice of a larger arena."""
+    _require_cuda(src)
+    assert src.dtype == torch.float32
+    nbytes = rf_pack_bytes(nb, Nn, K, hi_lo)
+    if out is None:
+        out = torch.empty(nbytes, device=src.device, dtype=torch.uint8)
+    assert out.numel() == nbytes and out.is_contiguous() and out.data_ptr() % 16 == 0
+    for sc in (scale_n, scale_k):
+        assert sc is None or sc.dtype == torch.float32
+    _lib_call("rf_pack_b", _ptr(src), C.c_int64(bstride), C.c_int64(stride_n), C.c_int64(stride_k), nb, Nn, K, groups, int(group_local_k),
+              _ptr(scale_n), 0 if scale_n is None else scale_n.stride(-1), _ptr(scale_k), 0 if scale_k is None else scale_k.stride(-1),
+              int(hi_lo), _ptr(out), _stream())
+    return out
+
+
+def rf_prep_up(cfg, packs, save2, bn_mode):
+    """Up-projection operand of the row-fused back pass: per expert the packed B[k=j][n=c] = invstd2_c * dense(up_sampler)[c][j]
+    (bn2's normalisation folded in, like xg_prep_up) and ybi [E,C] = -mean2_c * invstd2_c (zeros without BatchNorm)."""
+    dev = packs[0].wu.device
+    one = rf_pack_bytes(1, cfg.C, cfg.Cr)
+    pack = torch.empty(cfg.E * one, device=dev, dtype=torch.uint8)
+    crg = cfg.Cr // cfg.G
+    for e, pk in enumerate(packs):
+        wu = pk.wu.contiguous()
+        rf_pack_b(wu, nb=1, bstride=0, stride_n=crg, stride_k=1, Nn=cfg.C, K=cfg.Cr, groups=cfg.G, group_local_k=True,
+                  scale_n=save2[e, :, 1] if bn_mode != 0 else None, out=pack[e * one:(e + 1) * one])
+    if bn_mode != 0:
+        ybi = -(save2[:, :, 0] * save2[:, :, 1])
+    else:
+        ybi = torch.zeros((cfg.E, cfg.C), device=dev, dtype=torch.float32)
+    return pack, ybi.contiguous()
+
+
+def _rf_back_args(cfg, packs, egr, *, BT, bn_mode, bn2_wb):
+    a = _lib.RfBackArgs()
+    a.BT, a.N, a.C, a.Cr, a.Crp, a.G, a.E, a.bn_mode = BT, cfg.N, cfg.C, cfg.Cr, pad_bottleneck(cfg.Cr), cfg.G, cfg.E, bn_mode
+    keep = []
+    for e, pk in enumerate(packs):
+        ex = a.ex[e]
+        ex.pre_kind, ex.relu = pk.pre_kind, int(pk.relu)
+        for name in ("ln2_w", "ln2_b", "gate"):
+            t = getattr(pk, name)
+            if t is not None:
+                t = t.contiguous()
+                keep.append(t)
+                setattr(ex, name, t.data_ptr())
+        if egr is not None:
+            for name in ("ln2_w", "ln2_b", "gate"):
+                t = getattr(egr[e], name)
+                if t is not None:
+                    assert t.is_contiguous()
+                    setattr(ex, "g_" + name, t.data_ptr())
+        if bn2_wb is not None:
+            w, b = bn2_wb[e]
+            w, b = w.contiguous(), b.contiguous()
+            keep += [w, b]
+            a.bn2_w[e], a.bn2_b[e] = w.data_ptr(), b.data_ptr()
+    return a, keep
+
+
+def rf_back_fwd(cfg, z, aff1, wu_pack, ybi, bn2_wb, bn_mode, packs, probs, out, res=None):
+    """z -> out = (res +) sum_e probs*gate * ln_post(bn2(up(act(bn1(z)))))   in one pass (replaces xg_bn_act + up GEMM + xg_post_fwd)"""
+    _require_cuda(z, out)
+    a, keep = _rf_back_args(cfg, packs, None, BT=z.shape[0], bn_mode=bn_mode, bn2_wb=bn2_wb)
+    _set(a, z=z, aff1=aff1, wu_pack=wu_pack, ybi=ybi, probs=probs, res=res, out=out)
+    _lib_call("rf_back_fwd", C.byref(a), _stream(), _bytes=_nbytes(z, out, res))
+
+
+def rf_back_bwd(cfg, dout, z, aff1, wu_pack, ybi, bn2_wb, bn_mode, packs, probs, dprobs, red2, egr):
+    """dout, z -> yd [E,rows,2C] = [yhat | dy2], a [E,rows,Crp]; d ln_post / d gate / d probs / bn2 reductions accumulated
+    (replaces xg_post_bwd and the yd / a tensors the forward used to save)."""
+    BT, N, Cc = dout.shape
+    rows = BT * N
+    yd = torch.empty((cfg.E, rows, 2 * Cc), device=dout.device, dtype=dout.dtype)
+    act = torch.empty((cfg.E, rows, pad_bottleneck(cfg.Cr)), device=dout.device, dtype=dout.dtype)
+    a, keep = _rf_back_args(cfg, packs, egr, BT=BT, bn_mode=bn_mode, bn2_wb=bn2_wb)
+    _set(a, z=z, aff1=aff1, wu_pack=wu_pack, ybi=ybi, probs=probs, dout=dout, yd=yd, act=act, dprobs=dprobs, red2=red2)
+    _lib_call("rf_back_bwd", C.byref(a), _stream(), _bytes=_nbytes(dout, z, yd, act))
+    return yd, act
+
+
 # ------------------------------------------------------------------------------------------------ variant pre-transforms
 MHA_HEADS = 4
 _NXN_CHUNK_BYTES = 1 << 30   # fp32 scratch budget for the [chunk,N,N] score matrix of the AVVP token self-attention

@@ -303,6 +303,58 @@ int avmoe_latent_dots(const float* dR, const float* tokp, const float* tok, floa
 int avmoe_add_rowvec(void* d, const float* vec, int BT, int N, int C, int dtype, avmoe_stream_t stream);
 int avmoe_batch_sum_add(const float* in, float* out /* += */, int BT, int64_t L, avmoe_stream_t stream);
 
+
+/* ------------------------------------------------------------------------------------------
+ * Row-fused expert passes (bf16 streams; csrc/rowfused.cu).  One warp owns 16 token rows and keeps every intermediate of
+ * those rows in registers / its shared-memory tile; the skinny contractions (K or N = T latent tokens, C/r bottleneck
+ * channels) run on warp-level bf16 tensor-core tiles against "packed B" weight operands (mma fragment order, see
+ * csrc/mma_tile.cuh), so only the row's inputs and outputs touch HBM.  They replace chains of GEMM + row-kernel launches:
+ *
+ *   avmoe_rf_front_fwd   x (+aux), tok' -> [softmax_T(x tok'^T) tok', gate_pre residual, ln_before, grouped down projection] -> z
+ *                        (net_trans_v3.py:386-395; replaces S2 GEMM + softmax_rows + A2.tok' GEMM + xg_ln_pre_fwd + down GEMM)
+ *   avmoe_rf_back_fwd    z -> [bn1 affine, act, grouped up projection, bn2, ln_post, gate, probability-weighted combine over
+ *                        experts, + residual stream] -> out      (net_trans_v3.py:398-403,430-434,481-486 and the call-site add
+ *                        :703-720; replaces xg_bn_act + up GEMM + xg_post_fwd)
+ *   avmoe_rf_back_bwd    dout, z -> recompute of the above, yd = [yhat | dy2], a, d ln_post / d gate / d probs, bn2 batch reductions
+ *                        (replaces xg_post_bwd and the saved yd / a tensors)
+ *   avmoe_rf_front_bwd   dz, x, tok' -> recompute of the front pass, dx, xl (for the weight-gradient GEMM), d aux / dXR,
+ *                        A2 | dS2 (for the d tok' GEMMs), d ln_before, d gate_pre
+ *                        (replaces dxl GEMM + xg_ln_pre_bwd + dA2 GEMM + softmax_rows_bwd + dS2.tok' GEMM)
+ * ------------------------------------------------------------------------------------------ */
+/* fp32 weight matrix -> packed B operand.  Logical operand B[k][n], k < K, n < Nn, zero padded to KS = ceil(K/16) k-steps and
+ * NP = ceil(Nn/16) n-tile pairs; dst holds nb * NP * KS * 32 uint4.  Source element of B[k][n] for batch b:
+ *   src[b*bstride + n*stride_n + k*stride_k]                              (groups == 1), or the block-diagonal operand of a grouped
+ *   1x1 convolution (groups > 1): non-zero only where n and k fall in the same group (n / (Nn/groups) == k / (K/groups));
+ *   group_local = 1: the k index (0: the n index) is taken relative to its group start, as conv weights are stored.
+ * scale_n [nb,Nn] / scale_k [nb,K] (optional, fp32, element stride scale_*_stride) multiply the element.  hi_lo = 1: n-tile pairs hold (hi, lo) halves of ONE
+ * n-tile each (NP = ceil(Nn/8)). */
+int avmoe_rf_pack_b(const float* src, int64_t bstride, int64_t stride_n, int64_t stride_k, int nb, int Nn, int K, int groups,
+                    int group_local_k, const float* scale_n, int scale_n_stride, const float* scale_k, int scale_k_stride, int hi_lo,
+                    void* dst, avmoe_stream_t stream);
+int64_t avmoe_rf_pack_b_bytes(int nb, int Nn, int K, int hi_lo);
+
+typedef struct {
+  int32_t BT, N, C, Cr, Crp, G, E, bn_mode;
+  avmoe_expert ex[AVMOE_MAX_EXPERTS];                    /* relu, ln2_w/ln2_b, gate (+ g_ln2_w, g_ln2_b, g_gate in the backward) */
+  const float* bn2_w[AVMOE_MAX_EXPERTS]; const float* bn2_b[AVMOE_MAX_EXPERTS];   /* NULL: no BatchNorm */
+  const float* z;            /* [rows,E,Cr] fp32 bottleneck before bn1 */
+  const float* aff1;         /* [E,Cr,2] bn1 (scale, shift) or NULL */
+  const void* wu_pack;       /* E packed operands B[k=j][n=c] = invstd2_c * up_sampler (block diagonal), K = Cr, Nn = C */
+  const float* ybi;          /* [E,C] -mean2_c * invstd2_c (zeros without BatchNorm) */
+  const float* probs;        /* [BT,E] */
+  const void* res;           /* [rows,C] residual stream or NULL */
+  void* out;                 /* [rows,C] */
+  const void* dout;          /* [rows,C]  (backward) */
+  void* yd;                  /* [E,rows,2C]: columns [0,C) = yhat, [C,2C) = gradient at the bn2 output (backward) */
+  void* act;                 /* [E,rows,Crp] a = act(bn1(z)), zero padded (backward) */
+  float* dprobs;             /* [BT,E] += */
+  double* red2;              /* [E,C,2] += sum dy2, sum dy2*yhat (BatchNorm only) */
+} avmoe_rf_back_args;
+int avmoe_rf_back_fwd(const avmoe_rf_back_args* a, avmoe_stream_t stream);
+int avmoe_rf_back_bwd(const avmoe_rf_back_args* a, avmoe_stream_t stream);
+/* 1 when the row-fused passes support this geometry (C % 16 == 0, C/r <= 96, E <= 4, T <= 96), else 0 (callers use the GEMM path) */
+int avmoe_rf_supported(int C, int Cr, int E, int T);
+
 #ifdef __cplusplus
 }
 #endif

@@ -769,6 +769,46 @@ def xg_ln_pre_bwd(cfg, x, dxl, ln1_stats, packs, dpool_x, dx, egr):
     dx.copy_(total.reshape(BT, N, C).to(dx.dtype))
 
 
+# ------------------------------------------------------------------------------------------------ row-fused passes (csrc/rowfused.cu)
+USE_ROWFUSED = True
+
+
+def rf_supported(cfg, dtype) -> bool:
+    crk = (cfg.Cr + 15) // 16
+    return cfg.C % 16 == 0 and cfg.Cr % 2 == 0 and crk in (1, 2, 3, 6) and 2 <= cfg.E <= 4 and cfg.T <= 96
+
+
+def rf_prep_up(cfg, packs, save2, bn_mode):
+    """emulated "packed operand": the dense fp32 [E,C,Crp] matrix itself"""
+    wud, ybi = xg_prep_up(cfg, packs, save2, bn_mode, torch.float32)
+    return wud, ybi
+
+
+def _rf_yhat(cfg, z, aff1, wud, ybi, packs, bn_mode):
+    act = xg_bn_act(cfg, z, aff1, packs, torch.float32, bn_mode)                  # [E,rows,Crp]
+    return act, torch.einsum("erk,eck->erc", act, wud) + ybi[:, None, :]
+
+
+def rf_back_fwd(cfg, z, aff1, wu_pack, ybi, bn2_wb, bn_mode, packs, probs, out, res=None):
+    _, yh = _rf_yhat(cfg, z, aff1, wu_pack, ybi, packs, bn_mode)
+    yd = torch.cat([yh, torch.zeros_like(yh)], dim=-1)
+    xg_post_fwd(cfg, yd, bn2_wb, packs, probs, out, res)
+
+
+def rf_back_bwd(cfg, dout, z, aff1, wu_pack, ybi, bn2_wb, bn_mode, packs, probs, dprobs, red2, egr):
+    act, yh = _rf_yhat(cfg, z, aff1, wu_pack, ybi, packs, bn_mode)
+    yd = torch.cat([yh, torch.zeros_like(yh)], dim=-1).to(dout.dtype)
+    st = None
+    if packs[0].ln2_w is not None:
+        st = torch.empty((cfg.E, yh.shape[1], 2), dtype=torch.float32)
+        for e, pk in enumerate(packs):
+            _, t = _xg_post_t(cfg, yd, bn2_wb, pk, e)
+            mean, rstd = _ln_stats(t)
+            st[e, :, 0], st[e, :, 1] = mean[:, 0], rstd[:, 0]
+    xg_post_bwd(cfg, dout, yd, st, bn2_wb, bn_mode, packs, probs, dprobs, red2, egr)
+    return yd, act.to(dout.dtype)
+
+
 def _xg_bn2_coeffs(cfg, bn2_wb, bn, bn_mode, red2, rows, e):
     C = cfg.C
     alpha, beta, gamma = torch.ones(C), torch.zeros(C), torch.zeros(C)

@@ -246,66 +246,120 @@ def test_dataparallel_matches_single_device():
 
 
 # ------------------------------------------------------------------------------------------------ stack vs stack oracle
+_LISTS = ("a1", "audio_moe_adapter_blocks_p1"), ("v1", "vis_moe_adapter_blocks_p1"), ("a2", "audio_moe_adapter_blocks_p2"), ("v2", "vis_moe_adapter_blocks_p2")
+_ORACLE_CACHE = {}
+
+
 def _load_oracle_weights(model, ostack):
-    lists = {"a1": model.audio_moe_adapter_blocks_p1, "v1": model.vis_moe_adapter_blocks_p1,
-             "a2": model.audio_moe_adapter_blocks_p2, "v2": model.vis_moe_adapter_blocks_p2}
-    for i, entry in enumerate(ostack.adapters):
-        for name, (spec, sd) in entry.items():
-            lists[name][i].load_state_dict({k: v.detach() for k, v in sd.items()}, strict=True)
+    for key, attr in _LISTS:
+        for i, entry in enumerate(ostack.adapters):
+            spec, sd = entry[key]
+            getattr(model, attr)[i].load_state_dict({k: v.detach() for k, v in sd.items()}, strict=True)
+
+
+def _oracle_stack_reference(variant, BT, rounded):
+    """CPU fp32 oracle stack: loss, parameter gradients (dict name -> tensor), input gradients; cached per (variant, BT, rounded)"""
+    key = (variant, BT, rounded)
+    if key not in _ORACLE_CACHE:
+        ostack = SO.OracleStack(variant, seed=0)
+        toks = SO.make_stage_tokens(variant, BT, seed=77)
+        if rounded:
+            toks = {s: (a.detach().bfloat16().float().requires_grad_(), v.detach().bfloat16().float().requires_grad_()) for s, (a, v) in toks.items()}
+        init = [{k: {kk: v.detach().clone() for kk, v in sd.items()} for k, (spec, sd) in entry.items()} for entry in ostack.adapters]
+        loss = ostack.step(toks)
+        pg = {f"{k}[{i}].{kk}": v.grad.detach() for i, entry in enumerate(ostack.adapters) for k, (spec, sd) in entry.items()
+              for kk, v in sd.items() if v.is_floating_point() and v.grad is not None}
+        _ORACLE_CACHE[key] = (loss, pg, {s: (a.grad, v.grad) for s, (a, v) in toks.items()}, init,
+                              {s: (a.detach(), v.detach()) for s, (a, v) in toks.items()})
+    return _ORACLE_CACHE[key]
+
+
+def _errors(loss, pgrads, igrads, ref):
+    loss_ref, pg_ref, ig_ref, _, toks = ref
+    num = den = 0.0
+    worst = ("", 0.0)
+    for k, g_ref in pg_ref.items():
+        g = pgrads[k]
+        num += (g.float().cpu().double() - g_ref.double()).pow(2).sum().item()
+        den += g_ref.double().pow(2).sum().item()
+        if g_ref.numel() > 1 and g_ref.norm() > 1e-3 * (den ** 0.5 / max(len(pg_ref), 1)):
+            e = util.fro_err(g, g_ref)
+            if e > worst[1]:
+                worst = (k, e)
+    gin = max(max(util.fro_err(igrads[s][j], ig_ref[s][j]) for j in (0, 1)) for s in ig_ref)
+    ntok = sum(a.numel() + v.numel() for a, v in toks.values())
+    return {"loss": float(loss), "loss_ref": loss_ref, "loss_abs_err_per_elem": abs(float(loss) - loss_ref) / ntok,
+            "param_grad_fro": (num / max(den, 1e-300)) ** 0.5, "worst_param": worst[0], "worst_param_fro": worst[1], "input_grad_fro": gin}
 
 
 def _stack_errors(variant, BT, dtype):
     from avmoe_b200 import stack as S
-    ostack = SO.OracleStack(variant, seed=0)
-    toks = SO.make_stage_tokens(variant, BT, seed=77)
-    if dtype == torch.bfloat16:
-        toks = {s: (a.detach().bfloat16().float().requires_grad_(), v.detach().bfloat16().float().requires_grad_()) for s, (a, v) in toks.items()}
+    ref = _oracle_stack_reference(variant, BT, dtype == torch.bfloat16)
     model = S.AdapterStack(variant, seed=0)
-    _load_oracle_weights(model, ostack)            # before the oracle step: BatchNorm running buffers mutate in training mode
+    for key, attr in _LISTS:
+        for i, entry in enumerate(ref[3]):
+            getattr(model, attr)[i].load_state_dict(entry[key], strict=True)
     model = model.cuda().train()
-    loss_ref = ostack.step(toks)
-    leaves = {s: (a.detach().to("cuda", dtype).requires_grad_(), v.detach().to("cuda", dtype).requires_grad_()) for s, (a, v) in toks.items()}
+    leaves = {s: (a.to("cuda", dtype).requires_grad_(), v.to("cuda", dtype).requires_grad_()) for s, (a, v) in ref[4].items()}
     loss = model(leaves)
     loss.backward()
     torch.cuda.synchronize()
-    lists = {"a1": model.audio_moe_adapter_blocks_p1, "v1": model.vis_moe_adapter_blocks_p1,
-             "a2": model.audio_moe_adapter_blocks_p2, "v2": model.vis_moe_adapter_blocks_p2}
-    num = den = 0.0
-    worst = ("", 0.0)
-    for i, entry in enumerate(ostack.adapters):
-        for name, (spec, sd) in entry.items():
-            for k, p in lists[name][i].named_parameters():
-                g_ref = sd[k].grad
-                assert p.grad is not None and g_ref is not None, (name, i, k)
-                d = (p.grad.float().cpu().double() - g_ref.double())
-                num += d.pow(2).sum().item()
-                den += g_ref.double().pow(2).sum().item()
-                if g_ref.numel() > 1:
-                    e = util.fro_err(p.grad, g_ref)
-                    if e > worst[1]:
-                        worst = (f"{name}[{i}].{k}", e)
-    gin = max(max(util.fro_err(leaves[s][j].grad, toks[s][j].grad) for j in (0, 1)) for s in toks)
-    # the loss is sum(f_a) + sum(f_v): compare against its own scale per token (|loss| can cancel to ~0)
-    ntok = sum(a.numel() + v.numel() for a, v in toks.values())
-    return {"loss": float(loss.item()), "loss_ref": loss_ref, "loss_abs_err_per_elem": abs(float(loss.item()) - loss_ref) / ntok,
-            "param_grad_fro": (num / max(den, 1e-300)) ** 0.5, "worst_param": worst[0], "worst_param_fro": worst[1], "input_grad_fro": gin}
+    pg = {f"{key}[{i}].{k}": p.grad for key, attr in _LISTS for i, m in enumerate(getattr(model, attr)) for k, p in m.named_parameters()}
+    return _errors(loss.item(), pg, {s: (a.grad, v.grad) for s, (a, v) in leaves.items()}, ref)
+
+
+def _eager_stack_errors(variant, BT, autocast):
+    """COMPARATOR: the reference's own modules (staged copies, else the oracle port) in PyTorch eager on the GPU with torch's default
+    precision flags (cuDNN TF32 convolutions), optionally under bf16 autocast, against the same CPU fp32 oracle."""
+    from oracle import ref_loader
+    ref = _oracle_stack_reference(variant, BT, autocast)
+    use_ref = ref_loader.available()
+    st = SO.OracleStack(variant, seed=0, use_reference=use_ref, device="cuda")
+    toks = {s: (a.cuda().requires_grad_(), v.cuda().requires_grad_()) for s, (a, v) in ref[4].items()}
+    if autocast:
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            loss = st.step(toks)
+    else:
+        loss = st.step(toks)
+    if use_ref:
+        pg = {f"{k}[{i}].{kk}": p.grad for i, entry in enumerate(st.adapters) for k, (spec, mod) in entry.items() for kk, p in mod.named_parameters()}
+    else:
+        pg = {f"{k}[{i}].{kk}": v.grad for i, entry in enumerate(st.adapters) for k, (spec, sd) in entry.items() for kk, v in sd.items()
+              if v.is_floating_point() and v.grad is not None}
+    r = _errors(loss, pg, {s: (a.grad, v.grad) for s, (a, v) in toks.items()}, ref)
+    r["kind"] = "reference" if use_ref else "port"
+    return r
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16], ids=["f32", "bf16"])
+@pytest.mark.parametrize("mode", ["f32_exact", "f32", "bf16"])
 @pytest.mark.parametrize("variant", ["ave", "avqa", "avvp", "s4", "ms3"])
-def test_stack_matches_stack_oracle(variant, dtype):
-    """The bench workload end to end: 32 (ave/ms3) or 48 chained adapters with their residuals, loss + every parameter gradient
-    + input gradients against the CPU oracle stack on the same weights and tokens."""
+def test_stack_matches_stack_oracle(variant, mode, monkeypatch):
+    """The bench workload end to end: 32 (ave/ms3) or 48 chained adapters with their residuals -- loss, every parameter gradient,
+    input gradients -- against the CPU oracle stack on the same weights and tokens.
+
+      f32_exact  fp32 streams with every GEMM on exact fp32 FMAs: pins the kernels and the hand-derived backward of the whole chain
+      f32        fp32 streams, TF32 resampler GEMMs (the reference's own GPU default for its 1x1 convolution)
+      bf16       the product default
+    The un-scaled softmaxes amplify operand rounding through the chain (T = 87 latent tokens in S4/MS3 most of all), so the
+    tensor-core modes are bounded by an INDEPENDENT execution at the same precision: the reference's modules in PyTorch eager on
+    the same GPU (cuDNN TF32 / bf16 autocast), measured against the same oracle in the same test."""
+    from avmoe_b200 import ops
     BT = 4
-    r = _stack_errors(variant, BT, dtype)
-    _dump(f"stack_{variant}_{'bf16' if dtype == torch.bfloat16 else 'f32'}", r)
-    if dtype == torch.float32:
-        assert r["loss_abs_err_per_elem"] < 1e-4
-        assert r["param_grad_fro"] < 6e-2 and r["input_grad_fro"] < 6e-2
-    else:
-        assert r["loss_abs_err_per_elem"] < 2e-3
-        assert r["param_grad_fro"] < 2e-1 and r["input_grad_fro"] < 2e-1
+    if mode == "f32_exact":
+        monkeypatch.setattr(ops, "_GEMM_IMPL_OVERRIDE", 1)
+    r = _stack_errors(variant, BT, torch.bfloat16 if mode == "bf16" else torch.float32)
+    if mode == "f32_exact":
+        _dump(f"stack_{variant}_{mode}", r)
+        assert r["loss_abs_err_per_elem"] < 1e-6
+        assert r["param_grad_fro"] < 5e-3 and r["input_grad_fro"] < 2e-2
+        return
+    cmp_ = _eager_stack_errors(variant, BT, mode == "bf16")
+    _dump(f"stack_{variant}_{mode}", {"ours": r, "gpu_eager_comparator": cmp_})
+    tol_l, tol_g = (1e-4, 6e-2) if mode == "f32" else (2e-3, 2e-1)
+    assert r["loss_abs_err_per_elem"] < max(tol_l, 1.5 * cmp_["loss_abs_err_per_elem"])
+    assert r["param_grad_fro"] < max(tol_g, 1.5 * cmp_["param_grad_fro"])
+    assert r["input_grad_fro"] < max(tol_g, 1.5 * cmp_["input_grad_fro"])
 
 
 @pytest.mark.gpu

@@ -1,0 +1,188 @@
+"""Unit parity of the row-fused expert passes (csrc/rowfused.cu) against their torch statements in tests/kernel_emulation.py,
+kernel by kernel through the C ABI: the packed tensor-core operand layout, the back pass (bn1 affine .. combine + residual),
+its backward, the front pass (latent attention of a row .. down projection) and its backward."""
+import pytest
+import torch
+
+from avmoe_b200.functional import BN_OFF, BN_TRAIN, PRE_AUX_ADD, PRE_AUX_REPLACE, PRE_LATENT, PRE_NONE, ExpertGrads, ExpertPack
+from tests import kernel_emulation as KE
+from tests.test_expert_rows_gpu import _cfg, _rand
+
+pytestmark = pytest.mark.gpu
+
+
+def _fro(a, b):
+    a, b = a.detach().double().cpu(), b.detach().double().cpu()
+    return ((a - b).norm() / b.norm().clamp_min(1e-30)).item()
+
+
+def unpack_b(buf: torch.Tensor, nb: int, Nn: int, K: int, hi_lo: bool):
+    """host-side inverse of the documented packed-B layout (include/avmoe_b200.h, csrc/mma_tile.cuh) -> B [nb, K16, N16] fp32
+    (hi_lo: hi + lo summed)"""
+    NP = (Nn + 7) // 8 if hi_lo else (Nn + 15) // 16
+    KS = (K + 15) // 16
+    w = buf.cpu().view(torch.bfloat16).float().view(nb, NP, KS, 32, 4, 2)      # [.., lane, reg, elem]
+    out = torch.zeros((nb, KS * 16, NP * (8 if hi_lo else 16)))
+    for lane in range(32):
+        g, t = lane >> 2, lane & 3
+        for r in range(4):
+            half = r & 1
+            for i in range(2):
+                k = 8 * half + 2 * t + i
+                for p in range(NP):
+                    n = p * 8 + g if hi_lo else (2 * p + (r >> 1)) * 8 + g
+                    vals = w[:, p, :, lane, r, i]                               # [nb, KS]
+                    for s in range(KS):
+                        out[:, 16 * s + k, n] += vals[:, s]
+    return out
+
+
+@pytest.mark.parametrize("Nn,K,groups,local_k,hi_lo", [(96, 12, 2, True, False), (24, 192, 2, True, False), (192, 24, 4, False, False),
+                                                        (32, 96, 1, True, True), (87, 384, 1, True, True), (96, 87, 1, True, False)])
+def test_pack_b_layout(Nn, K, groups, local_k, hi_lo):
+    from avmoe_b200 import ops
+    g = torch.Generator().manual_seed(Nn + K)
+    nb = 2
+    if groups == 1:
+        src = torch.randn((nb, Nn, K), generator=g)
+        dense = src.clone()
+        sn, sk, bs = K, 1, Nn * K
+    elif local_k:                     # conv weight [Nn, K/groups] (k local to its group)
+        src = torch.randn((nb, Nn, K // groups), generator=g)
+        dense = torch.zeros((nb, Nn, K))
+        for q in range(groups):
+            dense[:, q * (Nn // groups):(q + 1) * (Nn // groups), q * (K // groups):(q + 1) * (K // groups)] = src[:, q * (Nn // groups):(q + 1) * (Nn // groups)]
+        sn, sk, bs = K // groups, 1, Nn * (K // groups)
+    else:                             # conv weight [K, Nn/groups] used transposed (n local to its group)
+        src = torch.randn((nb, K, Nn // groups), generator=g)
+        dense = torch.zeros((nb, Nn, K))
+        for q in range(groups):
+            dense[:, q * (Nn // groups):(q + 1) * (Nn // groups), q * (K // groups):(q + 1) * (K // groups)] = \
+                src[:, q * (K // groups):(q + 1) * (K // groups)].transpose(1, 2)
+        sn, sk, bs = 1, Nn // groups, K * (Nn // groups)
+    scale_n = torch.rand((nb, Nn), generator=g) + 0.5
+    scale_k = torch.rand((nb, K), generator=g) + 0.5
+    buf = ops.rf_pack_b(src.cuda(), nb=nb, bstride=bs, stride_n=sn, stride_k=sk, Nn=Nn, K=K, groups=groups, group_local_k=local_k,
+                        scale_n=scale_n.cuda(), scale_k=scale_k.cuda(), hi_lo=hi_lo)
+    torch.cuda.synchronize()
+    got = unpack_b(buf, nb, Nn, K, hi_lo)
+    want = (dense * scale_n[:, :, None] * scale_k[:, None, :]).transpose(1, 2)      # B[k][n]
+    assert (got[:, K:, :].abs().max() == 0) and (got[:, :, Nn:].abs().max() == 0), "padding must be zero"
+    tol = 2 ** -16 if hi_lo else 2 ** -8
+    assert ((got[:, :K, :Nn] - want).abs() <= tol * want.abs() + 1e-30).all()
+
+
+# (BT, N, C, r, G, E)
+BACK_GEOMS = [(3, 24, 16, 8, 2, 2), (2, 37, 96, 8, 2, 2), (2, 50, 192, 8, 2, 2), (2, 36, 192, 8, 4, 3), (3, 16, 384, 8, 2, 2),
+              (2, 19, 768, 8, 2, 2), (1, 40, 96, 2, 2, 4), (2, 64, 768, 8, 4, 3)]
+
+
+def _make_back(BT, N, C, r, G, E, ln, gate, bn, seed=0):
+    g = torch.Generator().manual_seed(seed)
+    cfg = _cfg(N, C, r, G, E)
+    Cr = C // r
+    packs = []
+    for e in range(E):
+        pk = ExpertPack(pre_kind=PRE_NONE, relu=(e == 0))
+        if ln:
+            pk.ln2_w, pk.ln2_b = _rand(g, C) * 0.2 + 1.0, _rand(g, C) * 0.1
+        pk.wu = _rand(g, C, Cr // G) * max(Cr // G, 1) ** -0.5
+        if gate:
+            pk.gate = _rand(g, 1) * 0.3 + 0.7
+        packs.append(pk)
+    z = _rand(g, BT, N, E, Cr)
+    probs = torch.softmax(_rand(g, BT, E), dim=-1)
+    aff1 = save2 = bn2_wb = None
+    if bn:
+        aff1 = torch.stack([_rand(g, E, Cr) * 0.3 + 1.0, _rand(g, E, Cr) * 0.2], dim=-1).contiguous()
+        save2 = torch.stack([_rand(g, E, C) * 0.2, torch.rand(E, C, generator=g) + 0.5], dim=-1).contiguous()
+        bn2_wb = [(_rand(g, C) * 0.2 + 1.0, _rand(g, C) * 0.1) for _ in range(E)]
+    res = _rand(g, BT, N, C)
+    dout = _rand(g, BT, N, C)
+    return cfg, packs, z, probs, aff1, save2, bn2_wb, res, dout
+
+
+def _cuda_packs(packs):
+    out = []
+    for pk in packs:
+        q = ExpertPack(pre_kind=pk.pre_kind, relu=pk.relu)
+        for name in ("gate_pre", "aux", "ln1_w", "ln1_b", "wd", "wu", "ln2_w", "ln2_b", "gate"):
+            t = getattr(pk, name)
+            setattr(q, name, None if t is None else t.cuda())
+        out.append(q)
+    return out
+
+
+@pytest.mark.parametrize("ln,gate,bn,use_res", [(True, True, True, True), (True, False, False, False), (False, True, True, False),
+                                                (False, False, False, True)])
+@pytest.mark.parametrize("geom", BACK_GEOMS, ids=[str(g) for g in BACK_GEOMS])
+def test_rf_back_fwd(geom, ln, gate, bn, use_res):
+    from avmoe_b200 import ops
+    cfg, packs, z, probs, aff1, save2, bn2_wb, res, dout = _make_back(*geom, ln, gate, bn)
+    bn_mode = BN_TRAIN if bn else BN_OFF
+    bf = torch.bfloat16
+    resq = res.to(bf)
+    BT, N, C = res.shape
+    # expected (fp32 emulation on the same operands; the kernel rounds a and the folded weights to bf16)
+    wud, ybi = KE.rf_prep_up(cfg, packs, save2, bn_mode)
+    want = torch.empty((BT, N, C))
+    KE.rf_back_fwd(cfg, z, aff1, wud, ybi, bn2_wb, bn_mode, packs, probs, want, resq.float() if use_res else None)
+    cp = _cuda_packs(packs)
+    pack, ybi_c = ops.rf_prep_up(cfg, cp, None if save2 is None else save2.cuda(), bn_mode)
+    assert torch.allclose(ybi_c.cpu(), ybi, atol=1e-6)
+    out = torch.empty((BT, N, C), device="cuda", dtype=bf)
+    ops.rf_back_fwd(cfg, z.cuda(), None if aff1 is None else aff1.cuda(), pack, ybi_c, None if bn2_wb is None else [(w.cuda(), b.cuda()) for w, b in bn2_wb],
+                    bn_mode, cp, probs.cuda(), out, resq.cuda() if use_res else None)
+    torch.cuda.synchronize()
+    assert _fro(out.float(), want) < 1.2e-2, _fro(out.float(), want)
+
+
+@pytest.mark.parametrize("ln,gate,bn", [(True, True, True), (True, False, False), (False, True, True)])
+@pytest.mark.parametrize("geom", BACK_GEOMS, ids=[str(g) for g in BACK_GEOMS])
+def test_rf_back_bwd(geom, ln, gate, bn):
+    from avmoe_b200 import ops
+    cfg, packs, z, probs, aff1, save2, bn2_wb, res, dout = _make_back(*geom, ln, gate, bn, seed=1)
+    bn_mode = BN_TRAIN if bn else BN_OFF
+    bf = torch.bfloat16
+    BT, N, C = dout.shape
+    E, Cr = cfg.E, cfg.Cr
+    doutq = dout.to(bf)
+
+    def grads(dev):
+        out = []
+        for pk in packs:
+            gr = ExpertGrads()
+            if ln:
+                gr.ln2_w, gr.ln2_b = torch.zeros(C, device=dev), torch.zeros(C, device=dev)
+            if gate:
+                gr.gate = torch.zeros(1, device=dev)
+            out.append(gr)
+        return out
+
+    wud, ybi = KE.rf_prep_up(cfg, packs, save2, bn_mode)
+    egr_ref = grads("cpu")
+    dprobs_ref = torch.zeros((BT, E))
+    red2_ref = torch.zeros((E, C, 2), dtype=torch.float64)
+    yd_ref, act_ref = KE.rf_back_bwd(cfg, doutq.float(), z, aff1, wud, ybi, bn2_wb, bn_mode, packs, probs, dprobs_ref, red2_ref, egr_ref)
+    cp = _cuda_packs(packs)
+    pack, ybi_c = ops.rf_prep_up(cfg, cp, None if save2 is None else save2.cuda(), bn_mode)
+    egr = grads("cuda")
+    dprobs = torch.zeros((BT, E), device="cuda")
+    red2 = torch.zeros((E, C, 2), device="cuda", dtype=torch.float64)
+    yd, act = ops.rf_back_bwd(cfg, doutq.cuda(), z.cuda(), None if aff1 is None else aff1.cuda(), pack, ybi_c,
+                              None if bn2_wb is None else [(w.cuda(), b.cuda()) for w, b in bn2_wb], bn_mode, cp, probs.cuda(), dprobs, red2, egr)
+    torch.cuda.synchronize()
+    tol = 1.5e-2
+    assert _fro(act[:, :, :Cr].float(), act_ref[:, :, :Cr].float()) < tol
+    assert act[:, :, Cr:].abs().max().item() == 0
+    assert _fro(yd[:, :, :C].float(), yd_ref[:, :, :C].float()) < tol
+    assert _fro(yd[:, :, C:].float(), yd_ref[:, :, C:].float()) < 2 * tol
+    assert _fro(dprobs, dprobs_ref) < tol
+    if bn:
+        assert _fro(red2[:, :, 0], red2_ref[:, :, 0]) < 2 * tol or (red2[:, :, 0].cpu() - red2_ref[:, :, 0]).abs().max() < 0.05 * red2_ref.abs().max()
+        assert _fro(red2[:, :, 1], red2_ref[:, :, 1]) < 2 * tol or (red2[:, :, 1].cpu() - red2_ref[:, :, 1]).abs().max() < 0.05 * red2_ref.abs().max()
+    for gr, gr_ref in zip(egr, egr_ref):
+        if ln:
+            assert _fro(gr.ln2_w, gr_ref.ln2_w) < tol and _fro(gr.ln2_b, gr_ref.ln2_b) < tol
+        if gate:
+            assert abs(gr.gate.item() - gr_ref.gate.item()) < tol * max(1.0, abs(gr_ref.gate.item()))
