@@ -129,6 +129,19 @@ class RfBackArgs(C.Structure):
     ]
 
 
+class RfFrontArgs(C.Structure):
+    """avmoe_rf_front_args: the row-fused front pass (latent attention of a row .. down projection) and its backward."""
+    _fields_ = [
+        ("BT", C.c_int32), ("N", C.c_int32), ("C", C.c_int32), ("Cr", C.c_int32), ("Crp", C.c_int32), ("G", C.c_int32),
+        ("E", C.c_int32), ("T", C.c_int32), ("has_ln", C.c_int32), ("_pad", C.c_int32),
+        ("ex", Expert * MAX_EXPERTS),
+        ("tok_s2", _PtrArr), ("tok_xr", _PtrArr),
+        ("wd_pack", C.c_void_p), ("wd_csum", C.c_void_p), ("c2", C.c_void_p), ("wdt_pack", C.c_void_p),
+        ("x", C.c_void_p), ("z", C.c_void_p), ("dz", C.c_void_p), ("dpool_x", C.c_void_p), ("dx", C.c_void_p), ("xl", C.c_void_p),
+        ("a2", _PtrArr), ("ds2", _PtrArr),
+    ]
+
+
 class BnArgs(C.Structure):
     _fields_ = [
         ("E", C.c_int32), ("C", C.c_int32), ("Cr", C.c_int32), ("G", C.c_int32), ("train", C.c_int32), ("_pad", C.c_int32),

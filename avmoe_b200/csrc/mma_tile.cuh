@@ -35,8 +35,7 @@ __device__ __forceinline__ float2 unpack_bf16x2(uint32_t v) {
 }
 
 __device__ __forceinline__ void mma16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
-  asm volatile(
-      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
+  asm("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
       : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
       : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
@@ -48,7 +47,8 @@ __device__ __forceinline__ void ldmatrix_a(uint32_t (&a)[4], const unsigned char
   const uint32_t addr = (uint32_t)__cvta_generic_to_shared(tile + row * pitch + col * 2);
   asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];\n"
                : "=r"(a[0]), "=r"(a[1]), "=r"(a[2]), "=r"(a[3])
-               : "r"(addr));
+               : "r"(addr)
+               : "memory");
 }
 
 __device__ __forceinline__ uint4 ldg_b(const uint4* packed, int pair, int ks, int s, int lane) {
@@ -62,6 +62,10 @@ __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src)
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
+
+// floor(i / d) for 0 <= i < 2^15 and 1 <= d <= 2^9 by a precomputed reciprocal (tile loops: i / chunks-per-row)
+__device__ __forceinline__ uint32_t magic_of(uint32_t d) { return ((1u << 24) + d - 1) / d; }
+__device__ __forceinline__ uint32_t magic_div(uint32_t i, uint32_t magic) { return (uint32_t)(((uint64_t)i * magic) >> 24); }
 
 // sum over the 4 lanes of a quad (the lanes that share accumulator rows g / g+8)
 __device__ __forceinline__ float quad_sum(float v) {

@@ -21,6 +21,7 @@ static constexpr int kMaxC = 1536;
 __global__ void rf_pack_b_kernel(const float* __restrict__ src, long long bstride, long long stride_n, long long stride_k, int nb, int Nn,
                                  int K, int groups, int group_local_k, const float* __restrict__ scale_n, int sns,
                                  const float* __restrict__ scale_k, int sks, int hi_lo, uint4* __restrict__ dst, int NP, int KS) {
+  // NP comes from the padded n extent (Nn_pad): columns n >= Nn are zero
   const long long total = (long long)nb * NP * KS * 32;
   const int ng = Nn / groups, kg = K / groups;
   for (long long o = blockIdx.x * (long long)blockDim.x + threadIdx.x; o < total; o += (long long)gridDim.x * blockDim.x) {
@@ -69,9 +70,10 @@ __global__ void rf_pack_b_kernel(const float* __restrict__ src, long long bstrid
 __device__ __forceinline__ void tile_load_async(unsigned char* tile, int pitch, const __nv_bfloat16* gsrc, long long r0, long long rows, int C,
                                                 int lane) {
   const int chunks = C >> 3;                      // 16-byte chunks per row
+  const uint32_t mg = magic_of(chunks);
   const int nrow = (int)min(16LL, rows - r0);
   for (int i = lane; i < nrow * chunks; i += 32) {
-    const int r = i / chunks, ch = i - r * chunks;
+    const int r = (int)magic_div(i, mg), ch = i - r * chunks;
     cp_async16(tile + r * pitch + ch * 16, gsrc + (r0 + r) * C + ch * 8);
   }
 }
@@ -80,9 +82,10 @@ template <bool ADD>
 __device__ __forceinline__ void tile_store(const unsigned char* tile, int pitch, __nv_bfloat16* gdst, long long ld, const __nv_bfloat16* gres,
                                            long long r0, long long rows, int C, int lane) {
   const int chunks = C >> 3;
+  const uint32_t mg = magic_of(chunks);
   const int nrow = (int)min(16LL, rows - r0);
   for (int i = lane; i < nrow * chunks; i += 32) {
-    const int r = i / chunks, ch = i - r * chunks;
+    const int r = (int)magic_div(i, mg), ch = i - r * chunks;
     uint4 v = *reinterpret_cast<const uint4*>(tile + r * pitch + ch * 16);
     if (ADD) {
       const uint4 q = __ldg(reinterpret_cast<const uint4*>(gres + (r0 + r) * C + ch * 8));
@@ -103,14 +106,48 @@ __device__ __forceinline__ uint32_t& tile_at(unsigned char* tile, int pitch, int
 
 // ------------------------------------------------------------------------------------------------ back pass (forward and backward)
 // k-steps of the up projection that can be non-zero for the n-tile pair starting at column c0 (block-diagonal weights)
-__device__ __forceinline__ void up_ksteps(int c0, int C, int Cr, int G, int& lo, int& hi) {
-  const int cg = C / G, crg = Cr / G;
-  const int g0 = c0 / cg, g1 = (c0 + 15) / cg;
-  lo = (g0 * crg) >> 4;
-  hi = min((Cr + 15) >> 4, ((g1 + 1) * crg + 15) >> 4);
+struct GroupGeom {
+  int cg, crg, kmax;
+  uint32_t mg;
+  __device__ GroupGeom(int C, int Cr, int G) : cg(C / G), crg(Cr / G), kmax((Cr + 15) >> 4), mg(magic_of(C / G)) {}
+};
+__device__ __forceinline__ void up_ksteps(int c0, const GroupGeom& gg, int& lo, int& hi) {
+  const int g0 = (int)magic_div(c0, gg.mg), g1 = (int)magic_div(c0 + 15, gg.mg);
+  lo = (g0 * gg.crg) >> 4;
+  hi = min(gg.kmax, ((g1 + 1) * gg.crg + 15) >> 4);
 }
 
-template <int E, int CRK, bool BWD>
+// Per-CTA table of the per-channel parameters of the back pass, 12 floats per channel pair (c, c+1) of expert e:
+//   [0,1] ybi   [2,3] bn2 weight (1 without BatchNorm)   [4,5] bn2 bias (0)   [6,7] ln_post weight (1)   [8,9] ln_post bias (0)
+// read as three 16-byte shared-memory loads per n-tile instead of five global loads.
+__device__ __forceinline__ void back_param_table(float* tab, const avmoe_rf_back_args& p, int E, int C) {
+  for (int i = threadIdx.x; i < E * (C >> 1); i += blockDim.x) {
+    const int e = i / (C >> 1), c = (i - e * (C >> 1)) * 2;
+    float* q = tab + (size_t)i * 12;
+    const float2 yb = __ldg(reinterpret_cast<const float2*>(p.ybi + (size_t)e * C + c));
+    q[0] = yb.x; q[1] = yb.y;
+    float2 w = make_float2(1.f, 1.f), b = make_float2(0.f, 0.f);
+    if (p.bn2_w[e]) { w = __ldg(reinterpret_cast<const float2*>(p.bn2_w[e] + c)); b = __ldg(reinterpret_cast<const float2*>(p.bn2_b[e] + c)); }
+    q[2] = w.x; q[3] = w.y; q[4] = b.x; q[5] = b.y;
+    w = make_float2(1.f, 1.f); b = make_float2(0.f, 0.f);
+    if (p.ex[e].ln2_w) { w = __ldg(reinterpret_cast<const float2*>(p.ex[e].ln2_w + c)); b = __ldg(reinterpret_cast<const float2*>(p.ex[e].ln2_b + c)); }
+    q[6] = w.x; q[7] = w.y; q[8] = b.x; q[9] = b.y;
+    q[10] = q[11] = 0.f;
+  }
+}
+struct ColParams { float2 ybi, bw, bb, lw, lb; };
+__device__ __forceinline__ ColParams load_col_params(const float* tab, int e, int C, int c) {
+  const float4* q = reinterpret_cast<const float4*>(tab + ((size_t)e * (C >> 1) + (c >> 1)) * 12);
+  const float4 a = q[0], b = q[1];
+  const float2 d = *reinterpret_cast<const float2*>(q + 2);
+  ColParams r;
+  r.ybi = make_float2(a.x, a.y); r.bw = make_float2(a.z, a.w); r.bb = make_float2(b.x, b.y); r.lw = make_float2(b.z, b.w); r.lb = d;
+  return r;
+}
+
+// NPR > 0: C == 16 * NPR and the normalised up projection of the whole tile stays in registers (one tensor-core sweep per expert);
+// NPR == 0: the tile is recomputed in every sweep (K = bottleneck channels, a handful of MMAs per n-tile pair).
+template <int E, int CRK, int NPR, bool BWD>
 __global__ void __launch_bounds__(256) rf_back_kernel(const avmoe_rf_back_args p, long long rows, int tiles_per_cta) {
   extern __shared__ __align__(16) unsigned char smem[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
@@ -119,18 +156,22 @@ __global__ void __launch_bounds__(256) rf_back_kernel(const avmoe_rf_back_args p
   const int pitch = C * 2 + 16;
   const int NP = C >> 4;
   const float invC = 1.f / C;
-  // shared memory: [BWD: per-CTA column accumulators E x 4 x C fp32 + E gate sums] [per warp: 1 (fwd) or 3 (bwd) tiles]
-  float* colacc = reinterpret_cast<float*>(smem);
-  const size_t acc_bytes = BWD ? ((size_t)E * 4 * C + 32) * sizeof(float) : 0;
-  unsigned char* wbase = smem + acc_bytes + (size_t)warp * (BWD ? 3 : 1) * 16 * pitch;
+  const GroupGeom gg(C, Cr, p.G);
+  // shared memory: [parameter table E x C/2 x 12 fp32] [BWD: per-warp column accumulators E x 4 x C fp32, E gate sums]
+  //                [per warp: 1 (fwd) or 3 (bwd) tiles]
+  float* tab = reinterpret_cast<float*>(smem);
+  const size_t tab_floats = (size_t)E * (C >> 1) * 12;
+  float* colacc_all = tab + tab_floats;
+  const size_t acc_floats = BWD ? (size_t)nwarps * E * 4 * C + 32 : 0;
+  float* gateacc = colacc_all + (BWD ? (size_t)nwarps * E * 4 * C : 0);
+  float* wacc = colacc_all + (size_t)warp * E * 4 * C;      // this warp's private accumulators: plain read-modify-write
+  unsigned char* wbase = smem + (tab_floats + acc_floats) * sizeof(float) + (size_t)warp * (BWD ? 3 : 1) * 16 * pitch;
   unsigned char* t_stage = wbase;                         // fwd: out tile; bwd: dy2 tile
   unsigned char* t_dout = wbase + (BWD ? 16 * pitch : 0);
   unsigned char* t_yh = wbase + (BWD ? 32 * pitch : 0);
-  if (BWD) {
-    for (int i = threadIdx.x; i < E * 4 * C + 32; i += blockDim.x) colacc[i] = 0.f;
-    __syncthreads();
-  }
-  float* gateacc = colacc + (size_t)E * 4 * C;
+  back_param_table(tab, p, E, C);
+  if (BWD) for (int i = threadIdx.x; i < (int)acc_floats; i += blockDim.x) colacc_all[i] = 0.f;
+  __syncthreads();
   const uint4* wup = static_cast<const uint4*>(p.wu_pack);
   const size_t wu_stride = (size_t)NP * CRK * 32;        // uint4 per expert
   const long long ntiles = (rows + 15) >> 4;
@@ -197,14 +238,14 @@ __global__ void __launch_bounds__(256) rf_back_kernel(const avmoe_rf_back_args p
       scA[e] = vA ? __ldg(p.probs + bA * E + e) * gate[e] : 0.f;
       scB[e] = vB ? __ldg(p.probs + bB * E + e) * gate[e] : 0.f;
     }
-    // yhat (normalised up projection) of an n-tile pair: acc[h][0..3], h = n-tile within the pair
+    // normalised up projection yhat of an n-tile pair: acc[h][0..3], h = n-tile within the pair
     auto up_pair = [&](int e, int pr, float (&acc)[2][4]) {
 #pragma unroll
       for (int h = 0; h < 2; ++h)
 #pragma unroll
         for (int i = 0; i < 4; ++i) acc[h][i] = 0.f;
-      int lo, hi;
-      up_ksteps(pr << 4, C, Cr, p.G, lo, hi);
+      int lo = 0, hi = CRK;
+      if (CRK > 1) up_ksteps(pr << 4, gg, lo, hi);
       const uint4* w = wup + e * wu_stride;
 #pragma unroll
       for (int s = 0; s < CRK; ++s) {
@@ -214,120 +255,140 @@ __global__ void __launch_bounds__(256) rf_back_kernel(const avmoe_rf_back_args p
           mma16816(acc[1], af[e][s], b.z, b.w);
         }
       }
-#pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        const float2 yb = __ldg(reinterpret_cast<const float2*>(p.ybi + (size_t)e * C + (pr << 4) + h * 8 + 2 * t));
-        acc[h][0] += yb.x; acc[h][1] += yb.y; acc[h][2] += yb.x; acc[h][3] += yb.y;
-      }
     };
-    // bn2 affine: the tensor ln_post sees
-    auto bn2_aff = [&](int e, int c, float (&v)[4]) {
-      if (p.bn2_w[e]) {
-        const float2 w = __ldg(reinterpret_cast<const float2*>(p.bn2_w[e] + c)), b = __ldg(reinterpret_cast<const float2*>(p.bn2_b[e] + c));
-        v[0] = v[0] * w.x + b.x; v[1] = v[1] * w.y + b.y; v[2] = v[2] * w.x + b.x; v[3] = v[3] * w.y + b.y;
-      }
-    };
-    // ---- pass 1: ln_post row statistics (one pass, fp32 sums)
-    float mean[E][2], rstd[E][2];
+    if (BWD) { cp_async_wait<0>(); __syncwarp(); }
+    constexpr bool OREG = NPR > 0 && NPR <= 6;      // forward: the combined output tile stays in registers too
+    float o[OREG ? NPR : 1][2][4];
+    if (!BWD && OREG) {
 #pragma unroll
-    for (int e = 0; e < E; ++e) {
-      mean[e][0] = mean[e][1] = 0.f;
-      rstd[e][0] = rstd[e][1] = 1.f;
-      if (p.ex[e].ln2_w) {
-        float s1A = 0.f, s2A = 0.f, s1B = 0.f, s2B = 0.f;
-        for (int pr = 0; pr < NP; ++pr) {
-          float acc[2][4];
-          up_pair(e, pr, acc);
-#pragma unroll
-          for (int h = 0; h < 2; ++h) {
-            bn2_aff(e, (pr << 4) + h * 8 + 2 * t, acc[h]);
-            s1A += acc[h][0] + acc[h][1]; s2A += acc[h][0] * acc[h][0] + acc[h][1] * acc[h][1];
-            s1B += acc[h][2] + acc[h][3]; s2B += acc[h][2] * acc[h][2] + acc[h][3] * acc[h][3];
-          }
-        }
-        s1A = quad_sum(s1A); s2A = quad_sum(s2A); s1B = quad_sum(s1B); s2B = quad_sum(s2B);
-        mean[e][0] = s1A * invC; mean[e][1] = s1B * invC;
-        rstd[e][0] = rsqrtf(fmaxf(s2A * invC - mean[e][0] * mean[e][0], 0.f) + kLnEps);
-        rstd[e][1] = rsqrtf(fmaxf(s2B * invC - mean[e][1] * mean[e][1], 0.f) + kLnEps);
-      }
-    }
-    if (!BWD) {
-      // ---- pass 2: out = (res +) sum_e probs*gate * ln_post(bn2(yhat_e))
-      for (int pr = 0; pr < NP; ++pr) {
-        float o[2][4];
+      for (int pr = 0; pr < (OREG ? NPR : 1); ++pr)
 #pragma unroll
         for (int h = 0; h < 2; ++h)
 #pragma unroll
-          for (int i = 0; i < 4; ++i) o[h][i] = 0.f;
+          for (int i = 0; i < 4; ++i) o[pr][h][i] = 0.f;
+    }
 #pragma unroll
-        for (int e = 0; e < E; ++e) {
-          float acc[2][4];
+    for (int e = 0; e < E; ++e) {
+      const bool has_ln = p.ex[e].ln2_w != nullptr;
+      const bool has_bn = p.bn2_w[e] != nullptr;
+      float yreg[NPR > 0 ? NPR : 1][2][4];
+      // ---- sweep 1: yhat (kept in registers when NPR > 0), ln_post row statistics of y2 = bn2 affine(yhat)
+      float mean0 = 0.f, mean1 = 0.f, rstd0 = 1.f, rstd1 = 1.f;
+      {
+        float s1A = 0.f, s2A = 0.f, s1B = 0.f, s2B = 0.f;
+        auto body = [&](int pr, float (&acc)[2][4]) {
           up_pair(e, pr, acc);
 #pragma unroll
           for (int h = 0; h < 2; ++h) {
-            const int c = (pr << 4) + h * 8 + 2 * t;
-            bn2_aff(e, c, acc[h]);
-            if (p.ex[e].ln2_w) {
-              const float2 w = __ldg(reinterpret_cast<const float2*>(p.ex[e].ln2_w + c)), b = __ldg(reinterpret_cast<const float2*>(p.ex[e].ln2_b + c));
-              acc[h][0] = (acc[h][0] - mean[e][0]) * rstd[e][0] * w.x + b.x;
-              acc[h][1] = (acc[h][1] - mean[e][0]) * rstd[e][0] * w.y + b.y;
-              acc[h][2] = (acc[h][2] - mean[e][1]) * rstd[e][1] * w.x + b.x;
-              acc[h][3] = (acc[h][3] - mean[e][1]) * rstd[e][1] * w.y + b.y;
-            }
-            o[h][0] += scA[e] * acc[h][0]; o[h][1] += scA[e] * acc[h][1];
-            o[h][2] += scB[e] * acc[h][2]; o[h][3] += scB[e] * acc[h][3];
+            const ColParams cp = load_col_params(tab, e, C, (pr << 4) + h * 8 + 2 * t);
+            acc[h][0] += cp.ybi.x; acc[h][1] += cp.ybi.y; acc[h][2] += cp.ybi.x; acc[h][3] += cp.ybi.y;
+            const float y0 = acc[h][0] * cp.bw.x + cp.bb.x, y1 = acc[h][1] * cp.bw.y + cp.bb.y;
+            const float y2 = acc[h][2] * cp.bw.x + cp.bb.x, y3 = acc[h][3] * cp.bw.y + cp.bb.y;
+            s1A += y0 + y1; s2A += y0 * y0 + y1 * y1; s1B += y2 + y3; s2B += y2 * y2 + y3 * y3;
           }
-        }
+        };
+        if (NPR > 0) {
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          const int c = (pr << 4) + h * 8 + 2 * t;
-          tile_at(t_stage, pitch, g, c) = pack_bf16x2(o[h][0], o[h][1]);
-          tile_at(t_stage, pitch, g + 8, c) = pack_bf16x2(o[h][2], o[h][3]);
+          for (int pr = 0; pr < (NPR > 0 ? NPR : 1); ++pr) body(pr, yreg[pr]);
+        } else if (has_ln) {
+          for (int pr = 0; pr < NP; ++pr) { float acc[2][4]; body(pr, acc); }
+        }
+        if (has_ln) {
+          s1A = quad_sum(s1A); s2A = quad_sum(s2A); s1B = quad_sum(s1B); s2B = quad_sum(s2B);
+          mean0 = s1A * invC; mean1 = s1B * invC;
+          rstd0 = rsqrtf(fmaxf(s2A * invC - mean0 * mean0, 0.f) + kLnEps);
+          rstd1 = rsqrtf(fmaxf(s2B * invC - mean1 * mean1, 0.f) + kLnEps);
         }
       }
-      __syncwarp();
-      if (p.res) tile_store<true>(t_stage, pitch, static_cast<__nv_bfloat16*>(p.out), C, static_cast<const __nv_bfloat16*>(p.res), r0, rows, C, lane);
-      else tile_store<false>(t_stage, pitch, static_cast<__nv_bfloat16*>(p.out), C, nullptr, r0, rows, C, lane);
-      __syncwarp();
-    } else {
-      cp_async_wait<0>();
-      __syncwarp();
+      // yhat of a pair for the later sweeps
+      auto yhat_pair = [&](int pr, float (&acc)[2][4]) {
+        up_pair(e, pr, acc);
 #pragma unroll
-      for (int e = 0; e < E; ++e) {
-        const bool has_ln = p.ex[e].ln2_w != nullptr;
-        const bool has_bn = p.bn2_w[e] != nullptr;
-        float* acc_e = colacc + (size_t)e * 4 * C;       // [4][C]: d ln2_w, d ln2_b, sum dy2, sum dy2*yhat
-        // ---- pass 2: <dout, o_e> per row (d probs, d gate), ln_post backward row sums, d ln_post weight/bias column sums
+        for (int h = 0; h < 2; ++h) {
+          const float2 yb = *reinterpret_cast<const float2*>(tab + ((size_t)e * (C >> 1) + (pr << 3) + h * 4 + t) * 12);
+          acc[h][0] += yb.x; acc[h][1] += yb.y; acc[h][2] += yb.x; acc[h][3] += yb.y;
+        }
+      };
+      if (!BWD) {
+        // ---- sweep 2 (forward): out += probs*gate * ln_post(bn2(yhat_e))
+        auto body = [&](int pr, const float (&yh)[2][4], float (&oo)[2][4]) {
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            const ColParams cp = load_col_params(tab, e, C, (pr << 4) + h * 8 + 2 * t);
+            const float y0 = yh[h][0] * cp.bw.x + cp.bb.x, y1 = yh[h][1] * cp.bw.y + cp.bb.y;
+            const float y2 = yh[h][2] * cp.bw.x + cp.bb.x, y3 = yh[h][3] * cp.bw.y + cp.bb.y;
+            oo[h][0] += scA[e] * ((y0 - mean0) * rstd0 * cp.lw.x + cp.lb.x);
+            oo[h][1] += scA[e] * ((y1 - mean0) * rstd0 * cp.lw.y + cp.lb.y);
+            oo[h][2] += scB[e] * ((y2 - mean1) * rstd1 * cp.lw.x + cp.lb.x);
+            oo[h][3] += scB[e] * ((y3 - mean1) * rstd1 * cp.lw.y + cp.lb.y);
+          }
+        };
+        if (OREG) {
+#pragma unroll
+          for (int pr = 0; pr < (OREG ? NPR : 1); ++pr) body(pr, yreg[pr], o[pr]);
+        } else {
+#pragma unroll
+          for (int pr = 0; pr < (NPR > 0 ? NPR : NP); ++pr) {
+            if (NPR == 0 && pr >= NP) break;
+            float acc[2][4], oo[2][4];
+            if (NPR > 0) {
+#pragma unroll
+              for (int h = 0; h < 2; ++h)
+#pragma unroll
+                for (int i = 0; i < 4; ++i) acc[h][i] = yreg[NPR > 0 ? pr : 0][h][i];
+            } else {
+              yhat_pair(pr, acc);
+            }
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+              const int c = (pr << 4) + h * 8 + 2 * t;
+              if (e == 0) { oo[h][0] = oo[h][1] = oo[h][2] = oo[h][3] = 0.f; }
+              else {
+                const float2 pA = unpack_bf16x2(tile_at(t_stage, pitch, g, c)), pB = unpack_bf16x2(tile_at(t_stage, pitch, g + 8, c));
+                oo[h][0] = pA.x; oo[h][1] = pA.y; oo[h][2] = pB.x; oo[h][3] = pB.y;
+              }
+            }
+            body(pr, acc, oo);
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+              const int c = (pr << 4) + h * 8 + 2 * t;
+              tile_at(t_stage, pitch, g, c) = pack_bf16x2(oo[h][0], oo[h][1]);
+              tile_at(t_stage, pitch, g + 8, c) = pack_bf16x2(oo[h][2], oo[h][3]);
+            }
+          }
+        }
+      } else {
+        float* acc_e = wacc + (size_t)e * 4 * C;       // [4][C]: d ln2_w, d ln2_b, sum dy2, sum dy2*yhat
+        // ---- sweep 2: <dout, o_e> per row (d probs, d gate), ln_post backward row sums, d ln_post weight/bias column sums
         float dotA = 0.f, dotB = 0.f, maA = 0.f, maB = 0.f, mbA = 0.f, mbB = 0.f;
-        for (int pr = 0; pr < NP; ++pr) {
-          float acc[2][4];
-          up_pair(e, pr, acc);
+        auto body2 = [&](int pr, const float (&yh)[2][4]) {
           float cs[8];
 #pragma unroll
           for (int h = 0; h < 2; ++h) {
             const int c = (pr << 4) + h * 8 + 2 * t;
-            bn2_aff(e, c, acc[h]);
+            const ColParams cp = load_col_params(tab, e, C, c);
             const float2 dA = unpack_bf16x2(tile_at(t_dout, pitch, g, c)), dB = unpack_bf16x2(tile_at(t_dout, pitch, g + 8, c));
-            const float d[4] = {dA.x, dA.y, dB.x, dB.y};
-            float2 w = make_float2(1.f, 1.f), b = make_float2(0.f, 0.f);
-            if (has_ln) { w = __ldg(reinterpret_cast<const float2*>(p.ex[e].ln2_w + c)); b = __ldg(reinterpret_cast<const float2*>(p.ex[e].ln2_b + c)); }
-            float xh[4];
-            xh[0] = (acc[h][0] - mean[e][0]) * rstd[e][0]; xh[1] = (acc[h][1] - mean[e][0]) * rstd[e][0];
-            xh[2] = (acc[h][2] - mean[e][1]) * rstd[e][1]; xh[3] = (acc[h][3] - mean[e][1]) * rstd[e][1];
-            dotA += d[0] * (xh[0] * w.x + b.x) + d[1] * (xh[1] * w.y + b.y);
-            dotB += d[2] * (xh[2] * w.x + b.x) + d[3] * (xh[3] * w.y + b.y);
-            const float t0 = scA[e] * d[0], t1 = scA[e] * d[1], t2 = scB[e] * d[2], t3 = scB[e] * d[3];   // d o_e
-            maA += t0 * w.x + t1 * w.y; maB += t2 * w.x + t3 * w.y;
-            mbA += t0 * w.x * xh[0] + t1 * w.y * xh[1]; mbB += t2 * w.x * xh[2] + t3 * w.y * xh[3];
-            cs[4 * h + 0] = t0 * xh[0] + t2 * xh[2]; cs[4 * h + 1] = t1 * xh[1] + t3 * xh[3];    // d ln2_w columns c, c+1
-            cs[4 * h + 2] = t0 + t2; cs[4 * h + 3] = t1 + t3;                                      // d ln2_b
+            const float xh0 = (yh[h][0] * cp.bw.x + cp.bb.x - mean0) * rstd0, xh1 = (yh[h][1] * cp.bw.y + cp.bb.y - mean0) * rstd0;
+            const float xh2 = (yh[h][2] * cp.bw.x + cp.bb.x - mean1) * rstd1, xh3 = (yh[h][3] * cp.bw.y + cp.bb.y - mean1) * rstd1;
+            dotA += dA.x * (xh0 * cp.lw.x + cp.lb.x) + dA.y * (xh1 * cp.lw.y + cp.lb.y);
+            dotB += dB.x * (xh2 * cp.lw.x + cp.lb.x) + dB.y * (xh3 * cp.lw.y + cp.lb.y);
+            const float t0 = scA[e] * dA.x, t1 = scA[e] * dA.y, t2 = scB[e] * dB.x, t3 = scB[e] * dB.y;   // d o_e
+            maA += t0 * cp.lw.x + t1 * cp.lw.y; maB += t2 * cp.lw.x + t3 * cp.lw.y;
+            mbA += t0 * cp.lw.x * xh0 + t1 * cp.lw.y * xh1; mbB += t2 * cp.lw.x * xh2 + t3 * cp.lw.y * xh3;
+            cs[4 * h + 0] = t0 * xh0 + t2 * xh2; cs[4 * h + 1] = t1 * xh1 + t3 * xh3;    // d ln2_w columns c, c+1
+            cs[4 * h + 2] = t0 + t2; cs[4 * h + 3] = t1 + t3;                            // d ln2_b
           }
-          if (has_ln) {
-            // cs index i -> (h = i>>2, quantity q = (i>>1)&1, column offset i&1)
+          if (has_ln) {     // cs index i -> (h = i>>2, quantity (i>>1)&1, column offset i&1)
             const float s = reduce_scatter8(cs, lane);
             const int i = rs_index(lane);
-            atomicAdd(acc_e + ((i >> 1) & 1) * C + (pr << 4) + (i >> 2) * 8 + 2 * t + (i & 1), s);
+            acc_e[((i >> 1) & 1) * C + (pr << 4) + (i >> 2) * 8 + 2 * t + (i & 1)] += s;
           }
+        };
+        if (NPR > 0) {
+#pragma unroll
+          for (int pr = 0; pr < (NPR > 0 ? NPR : 1); ++pr) body2(pr, yreg[pr]);
+        } else {
+          for (int pr = 0; pr < NP; ++pr) { float acc[2][4]; yhat_pair(pr, acc); body2(pr, acc); }
         }
         dotA = quad_sum(dotA); dotB = quad_sum(dotB);
         maA = quad_sum(maA) * invC; maB = quad_sum(maB) * invC; mbA = quad_sum(mbA) * invC; mbB = quad_sum(mbB) * invC;
@@ -344,50 +405,68 @@ __global__ void __launch_bounds__(256) rf_back_kernel(const avmoe_rf_back_args p
           if (vA) atomicAdd(p.dprobs + bA * E + e, gate[e] * dotA);
           if (vB) atomicAdd(p.dprobs + bB * E + e, gate[e] * dotB);
         }
-        // ---- pass 3: dy2 = gradient at the bn2 output; yhat; bn2 batch reductions
-        __nv_bfloat16* yd = static_cast<__nv_bfloat16*>(p.yd) + (size_t)e * rows * 2 * C;
-        for (int pr = 0; pr < NP; ++pr) {
-          float acc[2][4];
-          up_pair(e, pr, acc);
+        // ---- sweep 3: dy2 = gradient at the bn2 output; yhat; bn2 batch reductions
+        auto body3 = [&](int pr, const float (&yh)[2][4]) {
           float cs[8];
 #pragma unroll
           for (int h = 0; h < 2; ++h) {
             const int c = (pr << 4) + h * 8 + 2 * t;
-            const float yh[4] = {acc[h][0], acc[h][1], acc[h][2], acc[h][3]};
-            tile_at(t_yh, pitch, g, c) = pack_bf16x2(yh[0], yh[1]);
-            tile_at(t_yh, pitch, g + 8, c) = pack_bf16x2(yh[2], yh[3]);
-            bn2_aff(e, c, acc[h]);
+            const ColParams cp = load_col_params(tab, e, C, c);
+            tile_at(t_yh, pitch, g, c) = pack_bf16x2(yh[h][0], yh[h][1]);
+            tile_at(t_yh, pitch, g + 8, c) = pack_bf16x2(yh[h][2], yh[h][3]);
             const float2 dA = unpack_bf16x2(tile_at(t_dout, pitch, g, c)), dB = unpack_bf16x2(tile_at(t_dout, pitch, g + 8, c));
             float dy[4] = {scA[e] * dA.x, scA[e] * dA.y, scB[e] * dB.x, scB[e] * dB.y};
             if (has_ln) {
-              const float2 w = __ldg(reinterpret_cast<const float2*>(p.ex[e].ln2_w + c));
-              const float xh0 = (acc[h][0] - mean[e][0]) * rstd[e][0], xh1 = (acc[h][1] - mean[e][0]) * rstd[e][0];
-              const float xh2 = (acc[h][2] - mean[e][1]) * rstd[e][1], xh3 = (acc[h][3] - mean[e][1]) * rstd[e][1];
-              dy[0] = rstd[e][0] * (dy[0] * w.x - maA - mbA * xh0);
-              dy[1] = rstd[e][0] * (dy[1] * w.y - maA - mbA * xh1);
-              dy[2] = rstd[e][1] * (dy[2] * w.x - maB - mbB * xh2);
-              dy[3] = rstd[e][1] * (dy[3] * w.y - maB - mbB * xh3);
+              const float xh0 = (yh[h][0] * cp.bw.x + cp.bb.x - mean0) * rstd0, xh1 = (yh[h][1] * cp.bw.y + cp.bb.y - mean0) * rstd0;
+              const float xh2 = (yh[h][2] * cp.bw.x + cp.bb.x - mean1) * rstd1, xh3 = (yh[h][3] * cp.bw.y + cp.bb.y - mean1) * rstd1;
+              dy[0] = rstd0 * (dy[0] * cp.lw.x - maA - mbA * xh0);
+              dy[1] = rstd0 * (dy[1] * cp.lw.y - maA - mbA * xh1);
+              dy[2] = rstd1 * (dy[2] * cp.lw.x - maB - mbB * xh2);
+              dy[3] = rstd1 * (dy[3] * cp.lw.y - maB - mbB * xh3);
             }
             tile_at(t_stage, pitch, g, c) = pack_bf16x2(dy[0], dy[1]);
             tile_at(t_stage, pitch, g + 8, c) = pack_bf16x2(dy[2], dy[3]);
             cs[4 * h + 0] = dy[0] + dy[2]; cs[4 * h + 1] = dy[1] + dy[3];
-            cs[4 * h + 2] = dy[0] * yh[0] + dy[2] * yh[2]; cs[4 * h + 3] = dy[1] * yh[1] + dy[3] * yh[3];
+            cs[4 * h + 2] = dy[0] * yh[h][0] + dy[2] * yh[h][2]; cs[4 * h + 3] = dy[1] * yh[h][1] + dy[3] * yh[h][3];
           }
           if (has_bn) {
             const float s = reduce_scatter8(cs, lane);
             const int i = rs_index(lane);
-            atomicAdd(acc_e + (2 + ((i >> 1) & 1)) * C + (pr << 4) + (i >> 2) * 8 + 2 * t + (i & 1), s);
+            acc_e[(2 + ((i >> 1) & 1)) * C + (pr << 4) + (i >> 2) * 8 + 2 * t + (i & 1)] += s;
           }
+        };
+        if (NPR > 0) {
+#pragma unroll
+          for (int pr = 0; pr < (NPR > 0 ? NPR : 1); ++pr) body3(pr, yreg[pr]);
+        } else {
+          for (int pr = 0; pr < NP; ++pr) { float acc[2][4]; yhat_pair(pr, acc); body3(pr, acc); }
         }
         __syncwarp();
+        __nv_bfloat16* yd = static_cast<__nv_bfloat16*>(p.yd) + (size_t)e * rows * 2 * C;
         tile_store<false>(t_yh, pitch, yd, 2 * C, nullptr, r0, rows, C, lane);
         tile_store<false>(t_stage, pitch, yd + C, 2 * C, nullptr, r0, rows, C, lane);
         __syncwarp();
       }
     }
+    if (!BWD) {
+      if (OREG) {
+#pragma unroll
+        for (int pr = 0; pr < (OREG ? NPR : 1); ++pr)
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            const int c = (pr << 4) + h * 8 + 2 * t;
+            tile_at(t_stage, pitch, g, c) = pack_bf16x2(o[pr][h][0], o[pr][h][1]);
+            tile_at(t_stage, pitch, g + 8, c) = pack_bf16x2(o[pr][h][2], o[pr][h][3]);
+          }
+      }
+      __syncwarp();
+      if (p.res) tile_store<true>(t_stage, pitch, static_cast<__nv_bfloat16*>(p.out), C, static_cast<const __nv_bfloat16*>(p.res), r0, rows, C, lane);
+      else tile_store<false>(t_stage, pitch, static_cast<__nv_bfloat16*>(p.out), C, nullptr, r0, rows, C, lane);
+      __syncwarp();
+    }
   }
   if (BWD) {
-    // ---- flush the per-CTA column accumulators and gate sums
+    // ---- flush: gate sums, then the per-warp column accumulators summed over the CTA's warps
 #pragma unroll
     for (int e = 0; e < E; ++e) {
       float s = gate_sum[e];
@@ -395,14 +474,12 @@ __global__ void __launch_bounds__(256) rf_back_kernel(const avmoe_rf_back_args p
       if (lane == 0 && p.ex[e].gate) atomicAdd(gateacc + e, s);
     }
     __syncthreads();
-    for (int i = threadIdx.x; i < E * C; i += blockDim.x) {
-      const int e = i / C, c = i - e * C;
-      const float* a = colacc + (size_t)e * 4 * C;
-      if (p.ex[e].ln2_w) { atomicAdd(p.ex[e].g_ln2_w + c, a[c]); atomicAdd(p.ex[e].g_ln2_b + c, a[C + c]); }
-      if (p.bn2_w[e]) {
-        atomicAdd(p.red2 + ((size_t)e * C + c) * 2, (double)a[2 * C + c]);
-        atomicAdd(p.red2 + ((size_t)e * C + c) * 2 + 1, (double)a[3 * C + c]);
-      }
+    for (int i = threadIdx.x; i < E * 4 * C; i += blockDim.x) {
+      float s = 0.f;
+      for (int w = 0; w < nwarps; ++w) s += colacc_all[(size_t)w * E * 4 * C + i];
+      const int e = i / (4 * C), q = (i - e * 4 * C) / C, c = i - e * 4 * C - q * C;
+      if (q < 2) { if (p.ex[e].ln2_w) atomicAdd((q == 0 ? p.ex[e].g_ln2_w : p.ex[e].g_ln2_b) + c, s); }
+      else if (p.bn2_w[e]) atomicAdd(p.red2 + ((size_t)e * C + c) * 2 + (q - 2), (double)s);
     }
     if (threadIdx.x < E && p.ex[threadIdx.x].gate) atomicAdd(p.ex[threadIdx.x].g_gate, gateacc[threadIdx.x]);
   }
@@ -418,29 +495,32 @@ static int back_check(const avmoe_rf_back_args* a, bool bwd, const char* who) {
   return 0;
 }
 
-template <int E, int CRK>
+template <int E, int CRK, int NPR>
 static int launch_back(const avmoe_rf_back_args* a, bool bwd, cudaStream_t st) {
   const long long rows = (long long)a->BT * a->N;
   const long long ntiles = (rows + 15) / 16;
   const int pitch = a->C * 2 + 16;
-  const size_t per_warp = (size_t)(bwd ? 3 : 1) * 16 * pitch;
-  const size_t acc_bytes = bwd ? ((size_t)E * 4 * a->C + 32) * sizeof(float) : 0;
+  const size_t tab_bytes = (size_t)E * (a->C / 2) * 12 * sizeof(float);
+  const size_t per_warp = (size_t)(bwd ? 3 : 1) * 16 * pitch + (bwd ? (size_t)E * 4 * a->C * sizeof(float) : 0);
+  const size_t fixed = tab_bytes + (bwd ? 32 * sizeof(float) : 0);
   int warps = 8;
-  while (warps > 1 && acc_bytes + warps * per_warp > 100 * 1024) warps >>= 1;    // two CTAs per SM where possible
-  const size_t smem = acc_bytes + warps * per_warp;
+  while (warps > 1 && fixed + warps * per_warp > 100 * 1024) warps >>= 1;    // two CTAs per SM where possible
+  if (warps == 1 && fixed + 2 * per_warp <= 227 * 1024) warps = 2;
+  const size_t smem = fixed + warps * per_warp;
   AVMOE_CHECK_ARG(smem <= 227 * 1024, "rf_back: tile does not fit shared memory");
   // persistent-style grid: a few CTAs per SM, each owning a contiguous range of tiles (one flush of the column sums per CTA)
-  long long ctas = (long long)num_sms() * (smem > 64 * 1024 ? 2 : 4);
+  long long ctas = (long long)num_sms() * (smem > 110 * 1024 ? 1 : 2);
+  if (!bwd) ctas *= 2;
   long long tpc = (ntiles + ctas - 1) / ctas;
   tpc = (tpc + warps - 1) / warps * warps;
   if (tpc < warps) tpc = warps;
   const unsigned grid = (unsigned)((ntiles + tpc - 1) / tpc);
   if (bwd) {
-    AVMOE_CUDA(cudaFuncSetAttribute(rf_back_kernel<E, CRK, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    rf_back_kernel<E, CRK, true><<<grid, warps * 32, smem, st>>>(*a, rows, (int)tpc);
+    AVMOE_CUDA(cudaFuncSetAttribute(rf_back_kernel<E, CRK, NPR, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    rf_back_kernel<E, CRK, NPR, true><<<grid, warps * 32, smem, st>>>(*a, rows, (int)tpc);
   } else {
-    AVMOE_CUDA(cudaFuncSetAttribute(rf_back_kernel<E, CRK, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    rf_back_kernel<E, CRK, false><<<grid, warps * 32, smem, st>>>(*a, rows, (int)tpc);
+    AVMOE_CUDA(cudaFuncSetAttribute(rf_back_kernel<E, CRK, NPR, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    rf_back_kernel<E, CRK, NPR, false><<<grid, warps * 32, smem, st>>>(*a, rows, (int)tpc);
   }
   AVMOE_LAUNCH_CHECK("rf_back_kernel");
   return 0;
@@ -449,11 +529,14 @@ static int launch_back(const avmoe_rf_back_args* a, bool bwd, cudaStream_t st) {
 template <int E>
 static int dispatch_back_crk(const avmoe_rf_back_args* a, bool bwd, cudaStream_t st) {
   const int crk = (a->Cr + 15) / 16;
+  // the stage-1 shapes of the r = 8 variants (C = 96 / 192) keep the whole up-projection tile in registers
+  if (a->C == 96 && crk == 1) return launch_back<E, 1, 6>(a, bwd, st);
+  if (a->C == 192 && crk == 2) return launch_back<E, 2, 12>(a, bwd, st);
   switch (crk) {
-    case 1: return launch_back<E, 1>(a, bwd, st);
-    case 2: return launch_back<E, 2>(a, bwd, st);
-    case 3: return launch_back<E, 3>(a, bwd, st);
-    case 6: return launch_back<E, 6>(a, bwd, st);
+    case 1: return launch_back<E, 1, 0>(a, bwd, st);
+    case 2: return launch_back<E, 2, 0>(a, bwd, st);
+    case 3: return launch_back<E, 3, 0>(a, bwd, st);
+    case 6: return launch_back<E, 6, 0>(a, bwd, st);
     default: break;
   }
   set_error("rf_back: unsupported bottleneck width %d", a->Cr);
@@ -473,6 +556,561 @@ static int dispatch_back(const avmoe_rf_back_args* a, bool bwd, cudaStream_t st)
   return AVMOE_E_BADARG;
 }
 
+// ------------------------------------------------------------------------------------------------ column sums of a packed operand
+__global__ void rf_colsum_kernel(const uint4* __restrict__ packed, int nb, int NP, int KS, float* __restrict__ csum) {
+  const int total = nb * NP * 16;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int b = i / (NP * 16), n = i - b * NP * 16;
+    const int p = n >> 4, hi = (n >> 3) & 1, g = n & 7;
+    float s = 0.f;
+    for (int ks = 0; ks < KS; ++ks)
+      for (int t = 0; t < 4; ++t) {
+        const uint4 w = packed[(((size_t)b * NP + p) * KS + ks) * 32 + g * 4 + t];
+        const float2 a = unpack_bf16x2(hi ? w.z : w.x), c = unpack_bf16x2(hi ? w.w : w.y);
+        s += (a.x + a.y) + (c.x + c.y);
+      }
+    csum[i] = s;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ front pass
+// Shared by forward and backward: the expert's ln_before input u on this warp's 16-row tile.
+//   NONE        u = x                                   (t_u is not written; the x tile is used directly)
+//   AUX_ADD     u = x + gate_pre * aux                  AUX_REPLACE  u = aux            (aux tile staged in t_u / t_d first)
+//   LATENT      u = x + gate_pre * softmax_T(x tok'^T) tok'      (net_trans_v3.py:386-390)
+// Row statistics (mean, rstd over C) of the fp32 u are returned for rows g and g+8.
+template <int NT>
+struct LatentRegs {
+  float S[NT][4];             // logits -> probabilities A2 (fp32), accumulator layout over the T columns
+  uint32_t P[NT / 2][4];      // A2 rounded to bf16 as A fragments (k = latent token)
+};
+
+template <int NT>
+__device__ __forceinline__ void latent_probs(LatentRegs<NT>& L, const unsigned char* t_x, int pitch, int C, int T, const uint4* ts2, int lane) {
+  const int t = lane & 3;
+  const int KSc = C >> 4;
+#pragma unroll
+  for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+    for (int i = 0; i < 4; ++i) L.S[nt][i] = 0.f;
+  for (int s = 0; s < KSc; ++s) {
+    uint32_t a[4];
+    ldmatrix_a(a, t_x, pitch, s << 4, lane);
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt) {
+      const uint4 b = ldg_b(ts2, nt, KSc, s, lane);     // (hi, lo) halves of tok' for latent tokens 8nt..8nt+7
+      mma16816(L.S[nt], a, b.x, b.y);
+      mma16816(L.S[nt], a, b.z, b.w);
+    }
+  }
+  float mA = -3.0e38f, mB = -3.0e38f;
+#pragma unroll
+  for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const bool ok = 8 * nt + 2 * t + i < T;
+      if (!ok) { L.S[nt][i] = -3.0e38f; L.S[nt][2 + i] = -3.0e38f; }
+      mA = fmaxf(mA, L.S[nt][i]); mB = fmaxf(mB, L.S[nt][2 + i]);
+    }
+  mA = quad_max(mA); mB = quad_max(mB);
+  float sA = 0.f, sB = 0.f;
+#pragma unroll
+  for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const bool ok = 8 * nt + 2 * t + i < T;
+      L.S[nt][i] = ok ? __expf(L.S[nt][i] - mA) : 0.f;
+      L.S[nt][2 + i] = ok ? __expf(L.S[nt][2 + i] - mB) : 0.f;
+      sA += L.S[nt][i]; sB += L.S[nt][2 + i];
+    }
+  sA = 1.f / quad_sum(sA); sB = 1.f / quad_sum(sB);
+#pragma unroll
+  for (int nt = 0; nt < NT; ++nt) {
+    L.S[nt][0] *= sA; L.S[nt][1] *= sA; L.S[nt][2] *= sB; L.S[nt][3] *= sB;
+  }
+#pragma unroll
+  for (int ks = 0; ks < NT / 2; ++ks) {
+    L.P[ks][0] = pack_bf16x2(L.S[2 * ks][0], L.S[2 * ks][1]);
+    L.P[ks][1] = pack_bf16x2(L.S[2 * ks][2], L.S[2 * ks][3]);
+    L.P[ks][2] = pack_bf16x2(L.S[2 * ks + 1][0], L.S[2 * ks + 1][1]);
+    L.P[ks][3] = pack_bf16x2(L.S[2 * ks + 1][2], L.S[2 * ks + 1][3]);
+  }
+}
+
+// x_res for one n-tile pair of channels: acc[h][0..3] = (A2 tok')[rows g / g+8][16pr + 8h + 2t ..]
+template <int NT>
+__device__ __forceinline__ void latent_xr_pair(const LatentRegs<NT>& L, const uint4* txr, int pr, int lane, float (&acc)[2][4]) {
+#pragma unroll
+  for (int h = 0; h < 2; ++h)
+#pragma unroll
+    for (int i = 0; i < 4; ++i) acc[h][i] = 0.f;
+#pragma unroll
+  for (int ks = 0; ks < NT / 2; ++ks) {
+    const uint4 b = ldg_b(txr, pr, NT / 2, ks, lane);
+    mma16816(acc[0], L.P[ks], b.x, b.y);
+    mma16816(acc[1], L.P[ks], b.z, b.w);
+  }
+}
+
+struct RowStats { float muA, muB, rsA, rsB; };
+
+__device__ __forceinline__ RowStats finish_stats(float s1A, float s2A, float s1B, float s2B, float invC, bool has_ln) {
+  RowStats r;
+  if (!has_ln) { r.muA = r.muB = 0.f; r.rsA = r.rsB = 1.f; return r; }
+  s1A = quad_sum(s1A); s2A = quad_sum(s2A); s1B = quad_sum(s1B); s2B = quad_sum(s2B);
+  r.muA = s1A * invC; r.muB = s1B * invC;
+  r.rsA = rsqrtf(fmaxf(s2A * invC - r.muA * r.muA, 0.f) + kLnEps);
+  r.rsB = rsqrtf(fmaxf(s2B * invC - r.muB * r.muB, 0.f) + kLnEps);
+  return r;
+}
+
+// builds u of expert `ex` (into t_u unless kind == NONE) and returns its row statistics.  For AUX kinds the aux tile must already
+// be resident in `t_aux`.  LATENT fills L (probabilities stay live for the backward).
+template <int NT>
+__device__ __forceinline__ RowStats build_u(const avmoe_expert& ex, const unsigned char* t_x, unsigned char* t_u, const unsigned char* t_aux,
+                                           int pitch, int C, int T, bool has_ln, const uint4* ts2, const uint4* txr, LatentRegs<NT>& L, int lane) {
+  const int g = lane >> 2, t = lane & 3;
+  const int NP = C >> 4;
+  const float invC = 1.f / C;
+  const int kind = ex.pre_kind;
+  const float gate = (kind == AVMOE_PRE_LATENT || kind == AVMOE_PRE_AUX_ADD) ? __ldg(ex.gate_pre) : 0.f;
+  float s1A = 0.f, s2A = 0.f, s1B = 0.f, s2B = 0.f;
+  if (kind == AVMOE_PRE_LATENT) latent_probs<NT>(L, t_x, pitch, C, T, ts2, lane);
+  for (int pr = 0; pr < NP; ++pr) {
+    float acc[2][4];
+    if (kind == AVMOE_PRE_LATENT) latent_xr_pair<NT>(L, txr, pr, lane, acc);
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int c = (pr << 4) + h * 8 + 2 * t;
+      const float2 xA = unpack_bf16x2(tile_at(const_cast<unsigned char*>(t_x), pitch, g, c));
+      const float2 xB = unpack_bf16x2(tile_at(const_cast<unsigned char*>(t_x), pitch, g + 8, c));
+      float u[4] = {xA.x, xA.y, xB.x, xB.y};
+      if (kind == AVMOE_PRE_LATENT) {
+        u[0] += gate * acc[h][0]; u[1] += gate * acc[h][1]; u[2] += gate * acc[h][2]; u[3] += gate * acc[h][3];
+      } else if (kind != AVMOE_PRE_NONE) {
+        const float2 aA = unpack_bf16x2(tile_at(const_cast<unsigned char*>(t_aux), pitch, g, c));
+        const float2 aB = unpack_bf16x2(tile_at(const_cast<unsigned char*>(t_aux), pitch, g + 8, c));
+        if (kind == AVMOE_PRE_AUX_ADD) { u[0] += gate * aA.x; u[1] += gate * aA.y; u[2] += gate * aB.x; u[3] += gate * aB.y; }
+        else { u[0] = aA.x; u[1] = aA.y; u[2] = aB.x; u[3] = aB.y; }
+      }
+      if (kind != AVMOE_PRE_NONE) {
+        tile_at(t_u, pitch, g, c) = pack_bf16x2(u[0], u[1]);
+        tile_at(t_u, pitch, g + 8, c) = pack_bf16x2(u[2], u[3]);
+      }
+      s1A += u[0] + u[1]; s2A += u[0] * u[0] + u[1] * u[1];
+      s1B += u[2] + u[3]; s2B += u[2] * u[2] + u[3] * u[3];
+    }
+  }
+  __syncwarp();
+  return finish_stats(s1A, s2A, s1B, s2B, invC, has_ln);
+}
+
+template <int CRK, int NT>
+__global__ void __launch_bounds__(256) rf_front_fwd_kernel(const avmoe_rf_front_args p, long long rows, int tiles_per_cta) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  const int g = lane >> 2, t = lane & 3;
+  const int C = p.C, Cr = p.Cr, E = p.E;
+  const int pitch = C * 2 + 16;
+  const int KSc = C >> 4;
+  unsigned char* t_x = smem + (size_t)warp * 2 * 16 * pitch;
+  unsigned char* t_u = t_x + 16 * pitch;
+  const long long ntiles = rows >> 4;
+  const long long tile0 = (long long)blockIdx.x * tiles_per_cta;
+  const long long tile1 = min(ntiles, tile0 + tiles_per_cta);
+  const uint4* wd = static_cast<const uint4*>(p.wd_pack);
+  const size_t wd_stride = (size_t)CRK * KSc * 32;
+  const size_t s2_stride = (size_t)NT * KSc * 32, xr_stride = (size_t)KSc * (NT / 2) * 32;
+  for (long long tile = tile0 + warp; tile < tile1; tile += nwarps) {
+    const long long r0 = tile << 4;
+    const long long b = r0 / p.N;
+    const long long rowA = r0 + g, rowB = r0 + g + 8;
+    tile_load_async(t_x, pitch, static_cast<const __nv_bfloat16*>(p.x), r0, rows, C, lane);
+    cp_async_commit();
+    cp_async_wait<0>();
+    __syncwarp();
+    for (int e = 0; e < E; ++e) {
+      const avmoe_expert& ex = p.ex[e];
+      const int kind = ex.pre_kind;
+      if (kind == AVMOE_PRE_AUX_ADD || kind == AVMOE_PRE_AUX_REPLACE) {    // aux tile -> t_u (overwritten in place by u)
+        tile_load_async(t_u, pitch, static_cast<const __nv_bfloat16*>(ex.aux), r0, rows, C, lane);
+        cp_async_commit();
+        cp_async_wait<0>();
+        __syncwarp();
+      }
+      LatentRegs<NT> L;
+      const uint4* ts2 = kind == AVMOE_PRE_LATENT ? static_cast<const uint4*>(p.tok_s2[e]) + b * s2_stride : nullptr;
+      const uint4* txr = kind == AVMOE_PRE_LATENT ? static_cast<const uint4*>(p.tok_xr[e]) + b * xr_stride : nullptr;
+      const RowStats st = build_u<NT>(ex, t_x, t_u, t_u, pitch, C, p.T, p.has_ln != 0, ts2, txr, L, lane);
+      const unsigned char* t_a = kind == AVMOE_PRE_NONE ? t_x : t_u;
+      // grouped down projection of the ln_before output, LayerNorm folded into the operand:  z = rstd*(u W'^T - mean*colsum(W')) + W b
+      float zacc[2 * CRK][4];
+#pragma unroll
+      for (int j = 0; j < 2 * CRK; ++j)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) zacc[j][i] = 0.f;
+      const uint4* w = wd + e * wd_stride;
+      for (int s = 0; s < KSc; ++s) {
+        uint32_t a[4];
+        ldmatrix_a(a, t_a, pitch, s << 4, lane);
+#pragma unroll
+        for (int pr = 0; pr < CRK; ++pr) {
+          const uint4 bb = ldg_b(w, pr, KSc, s, lane);
+          mma16816(zacc[2 * pr], a, bb.x, bb.y);
+          mma16816(zacc[2 * pr + 1], a, bb.z, bb.w);
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 2 * CRK; ++j) {
+        const int ch = 8 * j + 2 * t;
+        if (ch < Cr) {
+          const float2 cs = __ldg(reinterpret_cast<const float2*>(p.wd_csum + (size_t)e * 16 * CRK + ch));
+          const float2 c2 = __ldg(reinterpret_cast<const float2*>(p.c2 + (size_t)e * Cr + ch));
+          float2 zA, zB;
+          zA.x = st.rsA * (zacc[j][0] - st.muA * cs.x) + c2.x; zA.y = st.rsA * (zacc[j][1] - st.muA * cs.y) + c2.y;
+          zB.x = st.rsB * (zacc[j][2] - st.muB * cs.x) + c2.x; zB.y = st.rsB * (zacc[j][3] - st.muB * cs.y) + c2.y;
+          *reinterpret_cast<float2*>(p.z + (rowA * E + e) * Cr + ch) = zA;
+          *reinterpret_cast<float2*>(p.z + (rowB * E + e) * Cr + ch) = zB;
+        }
+      }
+      __syncwarp();
+    }
+  }
+}
+
+// Backward of the front pass.  Per expert: recompute u and its statistics; d xl = dz Wd (tensor-core tile, K = bottleneck);
+// ln_before backward (two sweeps: row sums, then d u); xl is re-emitted for the weight-gradient GEMM; the pre-transform's
+// backward (gate_pre, aux gradient, or -- LATENT -- the softmax_T attention backward: dA2 = dXR tok'^T, dS2, dx += dS2 tok');
+// dx of all experts, the attention path and the router path accumulate in the warp's dx tile and are stored once.
+template <int CRK, int NT>
+__global__ void __launch_bounds__(256) rf_front_bwd_kernel(const avmoe_rf_front_args p, long long rows, int tiles_per_cta) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  const int g = lane >> 2, t = lane & 3;
+  const int C = p.C, Cr = p.Cr, E = p.E, T = p.T;
+  const int pitch = C * 2 + 16;
+  const int KSc = C >> 4, NP = C >> 4;
+  const float invC = 1.f / C;
+  const bool has_ln = p.has_ln != 0;
+  const GroupGeom gg(C, Cr, p.G);
+  // shared memory: per-CTA column accumulators [E][2][C] (d ln1_w, d ln1_b) + E gate_pre sums; per warp 4 tiles (x, u, d, dx)
+  float* colacc = reinterpret_cast<float*>(smem);
+  const size_t acc_bytes = ((size_t)E * 2 * C + 32) * sizeof(float);
+  float* gateacc = colacc + (size_t)E * 2 * C;
+  for (int i = threadIdx.x; i < E * 2 * C + 32; i += blockDim.x) colacc[i] = 0.f;
+  __syncthreads();
+  unsigned char* t_x = smem + acc_bytes + (size_t)warp * 4 * 16 * pitch;
+  unsigned char* t_u = t_x + 16 * pitch;
+  unsigned char* t_d = t_x + 32 * pitch;
+  unsigned char* t_dx = t_x + 48 * pitch;
+  const long long ntiles = rows >> 4;
+  const long long tile0 = (long long)blockIdx.x * tiles_per_cta;
+  const long long tile1 = min(ntiles, tile0 + tiles_per_cta);
+  const uint4* wdt = static_cast<const uint4*>(p.wdt_pack);
+  const size_t wdt_stride = (size_t)NP * CRK * 32;
+  const size_t s2_stride = (size_t)NT * KSc * 32, xr_stride = (size_t)KSc * (NT / 2) * 32;
+  const int Tp8 = (T + 7) & ~7;
+  for (long long tile = tile0 + warp; tile < tile1; tile += nwarps) {
+    const long long r0 = tile << 4;
+    const long long b = r0 / p.N;
+    const long long rowA = r0 + g, rowB = r0 + g + 8;
+    tile_load_async(t_x, pitch, static_cast<const __nv_bfloat16*>(p.x), r0, rows, C, lane);
+    cp_async_commit();
+    // dx tile starts from the router-path gradient (d mean_N(x)), identical for every row of the sample
+    for (int pr = 0; pr < NP; ++pr)
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int c = (pr << 4) + h * 8 + 2 * t;
+        uint32_t v = 0u;
+        if (p.dpool_x) {
+          const float2 d = __ldg(reinterpret_cast<const float2*>(p.dpool_x + b * C + c));
+          v = pack_bf16x2(d.x, d.y);
+        }
+        tile_at(t_dx, pitch, g, c) = v;
+        tile_at(t_dx, pitch, g + 8, c) = v;
+      }
+    cp_async_wait<0>();
+    __syncwarp();
+    for (int e = 0; e < E; ++e) {
+      const avmoe_expert& ex = p.ex[e];
+      const int kind = ex.pre_kind;
+      const bool aux_kind = kind == AVMOE_PRE_AUX_ADD || kind == AVMOE_PRE_AUX_REPLACE;
+      if (aux_kind) {    // aux tile -> t_d (kept for d gate_pre; overwritten element by element with the aux gradient)
+        tile_load_async(t_d, pitch, static_cast<const __nv_bfloat16*>(ex.aux), r0, rows, C, lane);
+        cp_async_commit();
+        cp_async_wait<0>();
+        __syncwarp();
+      }
+      LatentRegs<NT> L;
+      const uint4* ts2 = kind == AVMOE_PRE_LATENT ? static_cast<const uint4*>(p.tok_s2[e]) + b * s2_stride : nullptr;
+      const uint4* txr = kind == AVMOE_PRE_LATENT ? static_cast<const uint4*>(p.tok_xr[e]) + b * xr_stride : nullptr;
+      const RowStats st = build_u<NT>(ex, t_x, t_u, t_d, pitch, C, T, has_ln, ts2, txr, L, lane);
+      if (kind == AVMOE_PRE_NONE) {     // u = x: copy so that t_u can be turned into xl in place
+        const uint32_t mg = magic_of(C >> 3);
+        for (int i = lane; i < 16 * (C >> 3); i += 32) {
+          const int r = (int)magic_div(i, mg), ch = i - r * (C >> 3);
+          *reinterpret_cast<uint4*>(t_u + r * pitch + ch * 16) = *reinterpret_cast<const uint4*>(t_x + r * pitch + ch * 16);
+        }
+        __syncwarp();
+      }
+      // dz as A fragments (already bf16 in memory)
+      uint32_t dzf[CRK][4];
+      {
+        const __nv_bfloat16* dz = static_cast<const __nv_bfloat16*>(p.dz) + (size_t)e * rows * p.Crp;
+#pragma unroll
+        for (int s = 0; s < CRK; ++s)
+#pragma unroll
+          for (int kh = 0; kh < 2; ++kh) {
+            const int k0 = 16 * s + 8 * kh + 2 * t;
+            const bool ok = k0 < p.Crp;
+            dzf[s][2 * kh] = ok ? __ldg(reinterpret_cast<const uint32_t*>(dz + rowA * p.Crp + k0)) : 0u;
+            dzf[s][2 * kh + 1] = ok ? __ldg(reinterpret_cast<const uint32_t*>(dz + rowB * p.Crp + k0)) : 0u;
+          }
+      }
+      const uint4* w = wdt + e * wdt_stride;
+      auto dxl_pair = [&](int pr, float (&acc)[2][4]) {
+#pragma unroll
+        for (int h = 0; h < 2; ++h)
+#pragma unroll
+          for (int i = 0; i < 4; ++i) acc[h][i] = 0.f;
+        int lo = 0, hi = CRK;
+        if (CRK > 1) up_ksteps(pr << 4, gg, lo, hi);
+#pragma unroll
+        for (int s = 0; s < CRK; ++s)
+          if (s >= lo && s < hi) {
+            const uint4 bb = ldg_b(w, pr, CRK, s, lane);
+            mma16816(acc[0], dzf[s], bb.x, bb.y);
+            mma16816(acc[1], dzf[s], bb.z, bb.w);
+          }
+      };
+      float* acc_e = colacc + (size_t)e * 2 * C;
+      // ---- sweep A: ln_before backward row sums, d ln_before weight/bias column sums
+      float maA = 0.f, maB = 0.f, mbA = 0.f, mbB = 0.f;
+      if (has_ln) {
+        for (int pr = 0; pr < NP; ++pr) {
+          float acc[2][4];
+          dxl_pair(pr, acc);
+          float cs[8];
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            const int c = (pr << 4) + h * 8 + 2 * t;
+            const float2 uA = unpack_bf16x2(tile_at(t_u, pitch, g, c)), uB = unpack_bf16x2(tile_at(t_u, pitch, g + 8, c));
+            const float2 lw = __ldg(reinterpret_cast<const float2*>(ex.ln1_w + c));
+            const float xh0 = (uA.x - st.muA) * st.rsA, xh1 = (uA.y - st.muA) * st.rsA;
+            const float xh2 = (uB.x - st.muB) * st.rsB, xh3 = (uB.y - st.muB) * st.rsB;
+            const float d0 = acc[h][0] * lw.x, d1 = acc[h][1] * lw.y, d2 = acc[h][2] * lw.x, d3 = acc[h][3] * lw.y;
+            maA += d0 + d1; maB += d2 + d3;
+            mbA += d0 * xh0 + d1 * xh1; mbB += d2 * xh2 + d3 * xh3;
+            cs[4 * h + 0] = acc[h][0] * xh0 + acc[h][2] * xh2; cs[4 * h + 1] = acc[h][1] * xh1 + acc[h][3] * xh3;
+            cs[4 * h + 2] = acc[h][0] + acc[h][2]; cs[4 * h + 3] = acc[h][1] + acc[h][3];
+          }
+          const float s = reduce_scatter8(cs, lane);
+          const int i = rs_index(lane);
+          atomicAdd(acc_e + ((i >> 1) & 1) * C + (pr << 4) + (i >> 2) * 8 + 2 * t + (i & 1), s);
+        }
+        maA = quad_sum(maA) * invC; maB = quad_sum(maB) * invC; mbA = quad_sum(mbA) * invC; mbB = quad_sum(mbB) * invC;
+      }
+      // ---- sweep B: d u, xl (in place of u), pre-transform backward
+      const float gate = (kind == AVMOE_PRE_LATENT || kind == AVMOE_PRE_AUX_ADD) ? __ldg(ex.gate_pre) : 0.f;
+      float gsum = 0.f;
+      for (int pr = 0; pr < NP; ++pr) {
+        float acc[2][4], xr[2][4];
+        dxl_pair(pr, acc);
+        if (kind == AVMOE_PRE_LATENT) latent_xr_pair<NT>(L, txr, pr, lane, xr);
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const int c = (pr << 4) + h * 8 + 2 * t;
+          float du[4] = {acc[h][0], acc[h][1], acc[h][2], acc[h][3]};
+          if (has_ln) {
+            const float2 uA = unpack_bf16x2(tile_at(t_u, pitch, g, c)), uB = unpack_bf16x2(tile_at(t_u, pitch, g + 8, c));
+            const float2 lw = __ldg(reinterpret_cast<const float2*>(ex.ln1_w + c)), lb = __ldg(reinterpret_cast<const float2*>(ex.ln1_b + c));
+            const float xh0 = (uA.x - st.muA) * st.rsA, xh1 = (uA.y - st.muA) * st.rsA;
+            const float xh2 = (uB.x - st.muB) * st.rsB, xh3 = (uB.y - st.muB) * st.rsB;
+            du[0] = st.rsA * (du[0] * lw.x - maA - mbA * xh0); du[1] = st.rsA * (du[1] * lw.y - maA - mbA * xh1);
+            du[2] = st.rsB * (du[2] * lw.x - maB - mbB * xh2); du[3] = st.rsB * (du[3] * lw.y - maB - mbB * xh3);
+            tile_at(t_u, pitch, g, c) = pack_bf16x2(xh0 * lw.x + lb.x, xh1 * lw.y + lb.y);        // xl = ln_before(u)
+            tile_at(t_u, pitch, g + 8, c) = pack_bf16x2(xh2 * lw.x + lb.x, xh3 * lw.y + lb.y);
+          }
+          if (kind == AVMOE_PRE_LATENT) {
+            gsum += du[0] * xr[h][0] + du[1] * xr[h][1] + du[2] * xr[h][2] + du[3] * xr[h][3];
+            tile_at(t_d, pitch, g, c) = pack_bf16x2(gate * du[0], gate * du[1]);                   // dXR
+            tile_at(t_d, pitch, g + 8, c) = pack_bf16x2(gate * du[2], gate * du[3]);
+          } else if (aux_kind) {
+            const float2 aA = unpack_bf16x2(tile_at(t_d, pitch, g, c)), aB = unpack_bf16x2(tile_at(t_d, pitch, g + 8, c));
+            const float sc = kind == AVMOE_PRE_AUX_ADD ? gate : 1.f;
+            gsum += du[0] * aA.x + du[1] * aA.y + du[2] * aB.x + du[3] * aB.y;
+            tile_at(t_d, pitch, g, c) = pack_bf16x2(sc * du[0], sc * du[1]);                       // d aux
+            tile_at(t_d, pitch, g + 8, c) = pack_bf16x2(sc * du[2], sc * du[3]);
+          }
+          if (kind != AVMOE_PRE_AUX_REPLACE) {
+            const float2 aA = unpack_bf16x2(tile_at(t_dx, pitch, g, c)), aB = unpack_bf16x2(tile_at(t_dx, pitch, g + 8, c));
+            tile_at(t_dx, pitch, g, c) = pack_bf16x2(aA.x + du[0], aA.y + du[1]);
+            tile_at(t_dx, pitch, g + 8, c) = pack_bf16x2(aB.x + du[2], aB.y + du[3]);
+          }
+        }
+      }
+      __syncwarp();
+      if (kind != AVMOE_PRE_NONE && kind != AVMOE_PRE_AUX_REPLACE && ex.g_gate_pre) {
+        gsum = quad_sum(gsum);
+        gsum += __shfl_xor_sync(0xffffffffu, gsum, 4); gsum += __shfl_xor_sync(0xffffffffu, gsum, 8); gsum += __shfl_xor_sync(0xffffffffu, gsum, 16);
+        if (lane == 0) atomicAdd(gateacc + e, gsum);
+      }
+      tile_store<false>(t_u, pitch, static_cast<__nv_bfloat16*>(p.xl) + (size_t)e * rows * C, C, nullptr, r0, rows, C, lane);
+      if (kind != AVMOE_PRE_NONE) tile_store<false>(t_d, pitch, static_cast<__nv_bfloat16*>(ex.g_aux), C, nullptr, r0, rows, C, lane);
+      if (kind == AVMOE_PRE_LATENT) {
+        // ---- attention backward on the tile: dA2 = dXR tok'^T, dS2 = A2 (dA2 - <A2, dA2>), dx += dS2 tok'
+        float dA[NT][4];
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+          for (int i = 0; i < 4; ++i) dA[nt][i] = 0.f;
+        for (int s = 0; s < KSc; ++s) {
+          uint32_t a[4];
+          ldmatrix_a(a, t_d, pitch, s << 4, lane);
+#pragma unroll
+          for (int nt = 0; nt < NT; ++nt) {
+            const uint4 bb = ldg_b(ts2, nt, KSc, s, lane);
+            mma16816(dA[nt], a, bb.x, bb.y);
+            mma16816(dA[nt], a, bb.z, bb.w);
+          }
+        }
+        float dotA = 0.f, dotB = 0.f;
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt) {
+          dotA += L.S[nt][0] * dA[nt][0] + L.S[nt][1] * dA[nt][1];
+          dotB += L.S[nt][2] * dA[nt][2] + L.S[nt][3] * dA[nt][3];
+        }
+        dotA = quad_sum(dotA); dotB = quad_sum(dotB);
+        __nv_bfloat16* a2 = static_cast<__nv_bfloat16*>(p.a2[e]);
+        __nv_bfloat16* ds2 = static_cast<__nv_bfloat16*>(p.ds2[e]);
+        uint32_t dSf[NT / 2][4];
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt) {
+          const float s0 = L.S[nt][0] * (dA[nt][0] - dotA), s1 = L.S[nt][1] * (dA[nt][1] - dotA);
+          const float s2 = L.S[nt][2] * (dA[nt][2] - dotB), s3 = L.S[nt][3] * (dA[nt][3] - dotB);
+          const uint32_t pA = pack_bf16x2(s0, s1), pB = pack_bf16x2(s2, s3);
+          dSf[nt >> 1][(nt & 1) * 2] = pA;
+          dSf[nt >> 1][(nt & 1) * 2 + 1] = pB;
+          const int col = 8 * nt + 2 * t;
+          if (col < Tp8) {
+            *reinterpret_cast<uint32_t*>(a2 + rowA * Tp8 + col) = pack_bf16x2(L.S[nt][0], L.S[nt][1]);
+            *reinterpret_cast<uint32_t*>(a2 + rowB * Tp8 + col) = pack_bf16x2(L.S[nt][2], L.S[nt][3]);
+            *reinterpret_cast<uint32_t*>(ds2 + rowA * Tp8 + col) = pA;
+            *reinterpret_cast<uint32_t*>(ds2 + rowB * Tp8 + col) = pB;
+          }
+        }
+        for (int pr = 0; pr < NP; ++pr) {
+          float acc[2][4];
+#pragma unroll
+          for (int h = 0; h < 2; ++h)
+#pragma unroll
+            for (int i = 0; i < 4; ++i) acc[h][i] = 0.f;
+#pragma unroll
+          for (int ks = 0; ks < NT / 2; ++ks) {
+            const uint4 bb = ldg_b(txr, pr, NT / 2, ks, lane);
+            mma16816(acc[0], dSf[ks], bb.x, bb.y);
+            mma16816(acc[1], dSf[ks], bb.z, bb.w);
+          }
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            const int c = (pr << 4) + h * 8 + 2 * t;
+            const float2 aA = unpack_bf16x2(tile_at(t_dx, pitch, g, c)), aB = unpack_bf16x2(tile_at(t_dx, pitch, g + 8, c));
+            tile_at(t_dx, pitch, g, c) = pack_bf16x2(aA.x + acc[h][0], aA.y + acc[h][1]);
+            tile_at(t_dx, pitch, g + 8, c) = pack_bf16x2(aB.x + acc[h][2], aB.y + acc[h][3]);
+          }
+        }
+      }
+      __syncwarp();
+    }
+    tile_store<false>(t_dx, pitch, static_cast<__nv_bfloat16*>(p.dx), C, nullptr, r0, rows, C, lane);
+    __syncwarp();
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < E * C; i += blockDim.x) {
+    const int e = i / C, c = i - e * C;
+    if (has_ln) {
+      atomicAdd(p.ex[e].g_ln1_w + c, colacc[(size_t)e * 2 * C + c]);
+      atomicAdd(p.ex[e].g_ln1_b + c, colacc[(size_t)e * 2 * C + C + c]);
+    }
+  }
+  if (threadIdx.x < E && p.ex[threadIdx.x].g_gate_pre) atomicAdd(p.ex[threadIdx.x].g_gate_pre, gateacc[threadIdx.x]);
+}
+
+static int front_check(const avmoe_rf_front_args* a, bool bwd, const char* who) {
+  AVMOE_CHECK_ARG(a != nullptr, "%s: null args", who);
+  AVMOE_CHECK_ARG(avmoe_rf_supported(a->C, a->Cr, a->E, a->T) && a->N % 16 == 0, "%s: geometry not supported (C=%d Cr=%d E=%d T=%d N=%d)", who,
+                  a->C, a->Cr, a->E, a->T, a->N);
+  AVMOE_CHECK_ARG(a->x && a->c2, "%s: null tensor", who);
+  for (int e = 0; e < a->E; ++e) {
+    const avmoe_expert& ex = a->ex[e];
+    if (ex.pre_kind == AVMOE_PRE_LATENT) AVMOE_CHECK_ARG(a->tok_s2[e] && a->tok_xr[e] && ex.gate_pre, "%s: latent expert %d lacks operands", who, e);
+    if (ex.pre_kind == AVMOE_PRE_AUX_ADD) AVMOE_CHECK_ARG(ex.aux && ex.gate_pre, "%s: aux expert %d lacks operands", who, e);
+    if (ex.pre_kind == AVMOE_PRE_AUX_REPLACE) AVMOE_CHECK_ARG(ex.aux != nullptr, "%s: aux expert %d lacks operands", who, e);
+    if (a->has_ln) AVMOE_CHECK_ARG(ex.ln1_w && ex.ln1_b, "%s: ln_before parameters missing", who);
+    if (bwd) {
+      if (ex.pre_kind != AVMOE_PRE_NONE) AVMOE_CHECK_ARG(ex.g_aux != nullptr, "%s: expert %d needs g_aux", who, e);
+      if (ex.pre_kind == AVMOE_PRE_LATENT) AVMOE_CHECK_ARG(a->a2[e] && a->ds2[e], "%s: latent expert %d needs a2/ds2", who, e);
+      if (a->has_ln) AVMOE_CHECK_ARG(ex.g_ln1_w && ex.g_ln1_b, "%s: ln_before gradient accumulators missing", who);
+    }
+  }
+  if (bwd) AVMOE_CHECK_ARG(a->dz && a->dx && a->xl && a->wdt_pack, "%s: null backward tensor", who);
+  else AVMOE_CHECK_ARG(a->z && a->wd_pack && a->wd_csum, "%s: null forward tensor", who);
+  return 0;
+}
+
+template <int CRK, int NT>
+static int launch_front(const avmoe_rf_front_args* a, bool bwd, cudaStream_t st) {
+  const long long rows = (long long)a->BT * a->N;
+  const long long ntiles = rows / 16;
+  const int pitch = a->C * 2 + 16;
+  const size_t per_warp = (size_t)(bwd ? 4 : 2) * 16 * pitch;
+  const size_t acc_bytes = bwd ? ((size_t)a->E * 2 * a->C + 32) * sizeof(float) : 0;
+  int warps = 8;
+  while (warps > 1 && acc_bytes + warps * per_warp > 110 * 1024) warps >>= 1;
+  if (acc_bytes + warps * per_warp > 227 * 1024) { set_error("rf_front: tile does not fit shared memory (C=%d)", a->C); return AVMOE_E_BADARG; }
+  if (warps == 1 && acc_bytes + 2 * per_warp <= 227 * 1024) warps = 2;
+  const size_t smem = acc_bytes + warps * per_warp;
+  long long ctas = (long long)num_sms() * (smem > 110 * 1024 ? 1 : 2);
+  if (!bwd) ctas *= 2;      // no per-CTA accumulators to flush: finer tiles balance better
+  long long tpc = (ntiles + ctas - 1) / ctas;
+  tpc = (tpc + warps - 1) / warps * warps;
+  if (tpc < warps) tpc = warps;
+  const unsigned grid = (unsigned)((ntiles + tpc - 1) / tpc);
+  if (bwd) {
+    AVMOE_CUDA(cudaFuncSetAttribute(rf_front_bwd_kernel<CRK, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    rf_front_bwd_kernel<CRK, NT><<<grid, warps * 32, smem, st>>>(*a, rows, (int)tpc);
+  } else {
+    AVMOE_CUDA(cudaFuncSetAttribute(rf_front_fwd_kernel<CRK, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    rf_front_fwd_kernel<CRK, NT><<<grid, warps * 32, smem, st>>>(*a, rows, (int)tpc);
+  }
+  AVMOE_LAUNCH_CHECK("rf_front_kernel");
+  return 0;
+}
+
+template <int CRK>
+static int dispatch_front_nt(const avmoe_rf_front_args* a, bool bwd, cudaStream_t st) {
+  const int nt = ((a->T + 15) / 16) * 2;
+  if (nt <= 2) return launch_front<CRK, 2>(a, bwd, st);
+  if (nt <= 4) return launch_front<CRK, 4>(a, bwd, st);
+  if (nt <= 12) return launch_front<CRK, 12>(a, bwd, st);
+  set_error("rf_front: unsupported latent token count %d", a->T);
+  return AVMOE_E_BADARG;
+}
+
+static int dispatch_front(const avmoe_rf_front_args* a, bool bwd, cudaStream_t st) {
+  const int rc = front_check(a, bwd, bwd ? "rf_front_bwd" : "rf_front_fwd");
+  if (rc) return rc;
+  switch ((a->Cr + 15) / 16) {
+    case 1: return dispatch_front_nt<1>(a, bwd, st);
+    case 2: return dispatch_front_nt<2>(a, bwd, st);
+    case 3: return dispatch_front_nt<3>(a, bwd, st);
+    case 6: return dispatch_front_nt<6>(a, bwd, st);
+    default: break;
+  }
+  set_error("rf_front: unsupported bottleneck width %d", a->Cr);
+  return AVMOE_E_BADARG;
+}
+
 }  // namespace rf
 }  // namespace avmoe
 
@@ -489,11 +1127,12 @@ extern "C" int64_t avmoe_rf_pack_b_bytes(int nb, int Nn, int K, int hi_lo) {
 
 extern "C" int avmoe_rf_pack_b(const float* src, int64_t bstride, int64_t stride_n, int64_t stride_k, int nb, int Nn, int K, int groups,
                                int group_local_k, const float* scale_n, int scale_n_stride, const float* scale_k, int scale_k_stride,
-                               int hi_lo, void* dst, avmoe_stream_t stream) {
+                               int hi_lo, int Nn_pad, void* dst, avmoe_stream_t stream) {
   using namespace avmoe;
   AVMOE_CHECK_ARG(src && dst && nb > 0 && Nn > 0 && K > 0 && groups >= 1, "rf_pack_b: bad arguments");
   AVMOE_CHECK_ARG(Nn % groups == 0 && K % groups == 0, "rf_pack_b: groups must divide both extents");
-  const int NP = hi_lo ? (Nn + 7) / 8 : (Nn + 15) / 16, KS = (K + 15) / 16;
+  const int Nl = Nn_pad > Nn ? Nn_pad : Nn;
+  const int NP = hi_lo ? (Nl + 7) / 8 : (Nl + 15) / 16, KS = (K + 15) / 16;
   const long long total = (long long)nb * NP * KS * 32;
   const int threads = 256;
   const unsigned grid = (unsigned)std::min<long long>((total + threads - 1) / threads, 4096);
@@ -509,4 +1148,20 @@ extern "C" int avmoe_rf_back_fwd(const avmoe_rf_back_args* a, avmoe_stream_t str
 }
 extern "C" int avmoe_rf_back_bwd(const avmoe_rf_back_args* a, avmoe_stream_t stream) {
   return avmoe::rf::dispatch_back(a, true, reinterpret_cast<cudaStream_t>(stream));
+}
+
+extern "C" int avmoe_rf_colsum(const void* packed, int nb, int Nn, int K, float* csum, avmoe_stream_t stream) {
+  using namespace avmoe;
+  AVMOE_CHECK_ARG(packed && csum && nb > 0 && Nn > 0 && K > 0, "rf_colsum: bad arguments");
+  const int NP = (Nn + 15) / 16, KS = (K + 15) / 16;
+  const int total = nb * NP * 16;
+  rf::rf_colsum_kernel<<<(total + 127) / 128, 128, 0, reinterpret_cast<cudaStream_t>(stream)>>>(static_cast<const uint4*>(packed), nb, NP, KS, csum);
+  AVMOE_LAUNCH_CHECK("rf_colsum_kernel");
+  return 0;
+}
+extern "C" int avmoe_rf_front_fwd(const avmoe_rf_front_args* a, avmoe_stream_t stream) {
+  return avmoe::rf::dispatch_front(a, false, reinterpret_cast<cudaStream_t>(stream));
+}
+extern "C" int avmoe_rf_front_bwd(const avmoe_rf_front_args* a, avmoe_stream_t stream) {
+  return avmoe::rf::dispatch_front(a, true, reinterpret_cast<cudaStream_t>(stream));
 }

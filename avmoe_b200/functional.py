@@ -310,17 +310,28 @@ def fused_experts_fwd(K, cfg, x, tokp, packs, probs, P, bufs, prefixes, bn_mode)
     return out, z, bn
 
 
-def gemm_experts_fwd(K, cfg, x, packs, probs, P, bufs, prefixes, bn_mode, res=None):
+def gemm_experts_fwd(K, cfg, x, packs, probs, P, bufs, prefixes, bn_mode, res=None, front_toks=None):
     """Experts with every channel contraction on the tcgen05 GEMM (block-diagonal dense weights) and streaming row kernels
-    in between (csrc/expert_rows.cu).  Returns (out, z, bn, saved-for-backward)."""
+    in between (csrc/expert_rows.cu).  Returns (out, z, bn, saved-for-backward).
+
+    front_toks (dict expert -> packed tok' operands, possibly empty) selects the row-fused front pass (csrc/rowfused.cu): the
+    latent attention of each row, gate_pre residual, ln_before and the down projection run on one 16-row tile per warp and only
+    z is written (experts of pre_kind PRE_LATENT are evaluated in place; nothing is saved, the backward recomputes)."""
     BT, N, C = x.shape
     E, Cr = cfg.E, cfg.Cr
     rows = BT * N
     dev, f32, dt = x.device, torch.float32, x.dtype
-    wdd, wdt = K.xg_prep_weights(cfg, packs, dt)                                  # [E,Cr,C], [E,C,Crp]
-    xl, ln1s = K.xg_ln_pre_fwd(cfg, x, packs)                                     # [E,rows,C]
     z = torch.empty((BT, N, E, Cr), device=dev, dtype=f32)
-    K.bgemm(xl, wdd, out=z.view(rows, E, Cr).permute(1, 0, 2))                    # down projection, all experts in one launch
+    front = None
+    if front_toks is not None:
+        prep = K.rf_prep_front(cfg, packs)
+        K.rf_front_fwd(cfg, x, packs, front_toks, prep, z)
+        xl = ln1s = wdt = None
+        front = (front_toks, prep)
+    else:
+        wdd, wdt = K.xg_prep_weights(cfg, packs, dt)                              # [E,Cr,C], [E,C,Crp]
+        xl, ln1s = K.xg_ln_pre_fwd(cfg, x, packs)                                 # [E,rows,C]
+        K.bgemm(xl, wdd, out=z.view(rows, E, Cr).permute(1, 0, 2))                # down projection, all experts in one launch
     bn = bn2_wb = suma = None
     if bn_mode != BN_OFF:
         bn_w, bn_b = _bn_params(P, bufs, prefixes)
@@ -345,24 +356,25 @@ def gemm_experts_fwd(K, cfg, x, packs, probs, P, bufs, prefixes, bn_mode, res=No
         wu_pack, ybi = K.rf_prep_up(cfg, packs, bn[3] if bn else None, bn_mode)
         out = torch.empty_like(x)
         K.rf_back_fwd(cfg, z, bn[0] if bn else None, wu_pack, ybi, bn2_wb, bn_mode, packs, probs, out, res)
-        return out, z, bn, (xl, ln1s, None, None, None, wdt, suma, (wu_pack, ybi))
+        return out, z, bn, (xl, ln1s, None, None, None, wdt, suma, (wu_pack, ybi), front)
     act = K.xg_bn_act(cfg, z, bn[0] if bn else None, packs, dt, bn_mode)          # [E,rows,Crp]
     wud, ybi = K.xg_prep_up(cfg, packs, bn[3] if bn else None, bn_mode, dt)       # bn2 normalisation folded into the operand
     yd = torch.empty((E, rows, 2 * C), device=dev, dtype=dt)
     K.bgemm(act, wud, out=yd[:, :, :C], col_bias=ybi)                             # up projection -> normalised y (per-expert bias)
     out = torch.empty_like(x)
     ln2s = K.xg_post_fwd(cfg, yd, bn2_wb, packs, probs, out, res)                    # residual add folded in (row a9)
-    return out, z, bn, (xl, ln1s, act, yd, ln2s, wdt, suma, None)
+    return out, z, bn, (xl, ln1s, act, yd, ln2s, wdt, suma, None, front)
 
 
 def gemm_experts_bwd(K, cfg, x, dout, z, bn, bn_mode, packs, egr, probs, P, prefixes, saved):
-    """Backward of gemm_experts_fwd up to the ln_before input: returns (dprobs, red1, red2, dxl, ln1s)."""
+    """Backward of gemm_experts_fwd up to the ln_before input: returns (dprobs, red1, red2, dxl, ln1s, pending).
+    With the row-fused front pass, `pending` carries what rf_front_finish needs once the router gradient is known."""
     BT, N, C = x.shape
     E, Cr = cfg.E, cfg.Cr
     Crp = K.pad_bottleneck(Cr)
     rows = BT * N
     dev, f32, dt = x.device, torch.float32, x.dtype
-    xl, ln1s, act, yd, ln2s, wdt, suma, rf = saved
+    xl, ln1s, act, yd, ln2s, wdt, suma, rf, front = saved
     bn2_wb = [(P[p + "bn2.weight"], P[p + "bn2.bias"]) for p in prefixes] if bn_mode != BN_OFF else None
     red2 = torch.zeros((E, C, 2), device=dev, dtype=torch.float64) if bn_mode != BN_OFF else None
     red1 = torch.zeros((E, Cr, 2), device=dev, dtype=torch.float64) if bn_mode != BN_OFF else None
@@ -378,13 +390,30 @@ def gemm_experts_bwd(K, cfg, x, dout, z, bn, bn_mode, packs, egr, probs, P, pref
     for e in range(E):
         K.gemm(yd[e], act[e], a_kmajor=False, b_kmajor=False, out=pwu[e], split_k=K.split_k_hint(rows, 2 * C, Crp))
     dz = K.xg_bn1_bwd(cfg, da, z, bn, bn_mode, packs, red1, dt)                            # relu mask + bn1 backward
+    if front is not None:
+        return dprobs, red1, red2, None, None, (dz, pwu, bn2_wb, suma, front)
     dxl = torch.empty((E, rows, C), device=dev, dtype=dt)
     pwd = torch.empty((E, Crp, C), device=dev, dtype=f32)
     K.bgemm(dz, wdt, out=dxl)                                                              # d xl = dz · Wd  (all experts)
     for e in range(E):
         K.gemm(dz[e], xl[e], a_kmajor=False, b_kmajor=False, out=pwd[e], split_k=K.split_k_hint(rows, Crp, C))
     K.xg_finish_wgrads(cfg, packs, egr, bn2_wb, bn, bn_mode, red2, BT, pwd, pwu, suma)
-    return dprobs, red1, red2, dxl, ln1s
+    return dprobs, red1, red2, dxl, ln1s, None
+
+
+def rf_front_finish(K, cfg, x, packs, egr, bn, bn_mode, red2, pending, dpool_x, dx):
+    """Second half of the expert backward on the row-fused path: the front pass backward (dx, xl, d aux / dXR, A2 | dS2), then the
+    down-projection weight-gradient GEMMs on the re-emitted xl and the grouped weight-gradient finish.  Returns {expert: (A2, dS2)}."""
+    dz, pwu, bn2_wb, suma, (toks, prep) = pending
+    BT, N, C = x.shape
+    rows = BT * N
+    Crp = K.pad_bottleneck(cfg.Cr)
+    xl, lat = K.rf_front_bwd(cfg, x, packs, egr, toks, prep, dz, dpool_x, dx)
+    pwd = torch.empty((cfg.E, Crp, C), device=x.device, dtype=torch.float32)
+    for e in range(cfg.E):
+        K.gemm(dz[e], xl[e], a_kmajor=False, b_kmajor=False, out=pwd[e], split_k=K.split_k_hint(rows, Crp, C))
+    K.xg_finish_wgrads(cfg, packs, egr, bn2_wb, bn, bn_mode, red2, BT, pwd, pwu, suma)
+    return lat
 
 
 # -------------------------------------------------------------------------------------------------
@@ -446,6 +475,12 @@ class MoEAdapterFunction(torch.autograd.Function):
         # "always" forces the GEMM path for either dtype (tests).
         _flag = getattr(K, "USE_GEMM_ATTENTION", False)
         use_gemm_attn = _flag == "always" or (bool(_flag) and x.dtype == torch.bfloat16)
+        _xflag = getattr(K, "USE_GEMM_EXPERTS", False)
+        xg_wanted = _xflag == "always" or (bool(_xflag) and x.dtype == torch.bfloat16)
+        # row-fused front pass (csrc/rowfused.cu): the row <- latent-token attention runs inside the expert front kernel
+        rf_front = (use_gemm_attn and xg_wanted and bool(getattr(K, "USE_ROWFUSED", False)) and K.rf_supported(cfg, x.dtype)
+                    and cfg.N % 16 == 0)
+        front_toks = {} if rf_front else None
         for e, (pfx, (pre, relu)) in enumerate(zip(prefixes, kinds)):
             pk = ExpertPack(pre_kind=pre, relu=relu)
             multimodal = e < cfg.Mm
@@ -456,10 +491,15 @@ class MoEAdapterFunction(torch.autograd.Function):
                 if use_gemm_attn:   # latent attention on the tensor-core GEMM; the expert kernels see x + gate*x_res as an aux-add
                     kv = v if multimodal else x
                     tokp_e, tokp_op, A12 = gemm_latent_fwd(K, kv, P[pfx + "my_tokens"])
-                    pk.aux, A2 = gemm_attn2_fwd(K, x, tokp_op, T)
-                    pk.pre_kind = PRE_AUX_ADD
-                    aux_saved[e] = (not multimodal, tokp_e, tokp_op, A12, A2)
-                    aux_kind[e] = "latent_gemm"
+                    if rf_front:
+                        front_toks[e] = K.rf_pack_tokens(tokp_e)
+                        aux_saved[e] = (not multimodal, tokp_e, None, A12, None)
+                        aux_kind[e] = "latent_rf"
+                    else:
+                        pk.aux, A2 = gemm_attn2_fwd(K, x, tokp_op, T)
+                        pk.pre_kind = PRE_AUX_ADD
+                        aux_saved[e] = (not multimodal, tokp_e, tokp_op, A12, A2)
+                        aux_kind[e] = "latent_gemm"
                 else:
                     pk.latent_slot = len(latent_tokens)
                     latent_tokens.append(P[pfx + "my_tokens"])
@@ -497,11 +537,10 @@ class MoEAdapterFunction(torch.autograd.Function):
                     K.latent_fwd(x if kv_is_x else v, [latent_tokens[i] for i in slots], slots, tokp, lse)
         # bf16 streams run the expert projections on the tensor-core GEMM with streaming row kernels in between
         # ("gemm experts"); fp32 streams keep the fused kernels (exact fp32 contractions).  "always" forces it (tests).
-        _xflag = getattr(K, "USE_GEMM_EXPERTS", False)
-        use_xg = (_xflag == "always" or (bool(_xflag) and x.dtype == torch.bfloat16)) and all(pk.pre_kind != PRE_LATENT for pk in packs)
+        use_xg = xg_wanted and (rf_front or all(pk.pre_kind != PRE_LATENT for pk in packs))
         xg_saved = None
         if use_xg:
-            out, z, bn, xg_saved = gemm_experts_fwd(K, cfg, x, packs, probs, P, bufs, prefixes, bn_mode, res)
+            out, z, bn, xg_saved = gemm_experts_fwd(K, cfg, x, packs, probs, P, bufs, prefixes, bn_mode, res, front_toks)
         else:
             out, z, bn = fused_experts_fwd(K, cfg, x, tokp, packs, probs, P, bufs, prefixes, bn_mode)
             if res is not None:
@@ -574,7 +613,7 @@ class MoEAdapterFunction(torch.autograd.Function):
                 pk.gate_pre = P[pfx + ctx.gate_keys[e]]
             if pk.gate_pre is not None:
                 want(g, "gate_pre", (1,))
-            if pre in (PRE_AUX_ADD, PRE_AUX_REPLACE):
+            if pre in (PRE_AUX_ADD, PRE_AUX_REPLACE) or ctx.aux_kind.get(e) == "latent_rf":     # latent_rf: receives dXR
                 g.aux = torch.empty((BT, N, C), device=dev, dtype=x.dtype)
             if cfg.ln_before:
                 pk.ln1_w, pk.ln1_b = P[pfx + "ln_before.weight"], P[pfx + "ln_before.bias"]
@@ -597,7 +636,8 @@ class MoEAdapterFunction(torch.autograd.Function):
         # 1. expert back (BN2 batch reductions first when training with BN)
         use_xg = ctx.xg_saved is not None
         if use_xg:
-            dprobs, red1, red2, dxl, ln1s = gemm_experts_bwd(K, cfg, x, dout, z, ctx.bn, bn_mode, packs, egr, probs, P, prefixes, ctx.xg_saved)
+            dprobs, red1, red2, dxl, ln1s, pending = gemm_experts_bwd(K, cfg, x, dout, z, ctx.bn, bn_mode, packs, egr, probs, P, prefixes,
+                                                                      ctx.xg_saved)
             red2b = red2
         else:
             red2 = None
@@ -622,7 +662,10 @@ class MoEAdapterFunction(torch.autograd.Function):
         nl = 0 if tokp is None else tokp.shape[1]
         dtokp = torch.zeros((BT, nl, T, C), device=dev, dtype=f32) if nl else None
         dx = torch.empty_like(x)
-        if use_xg:
+        lat_rf = {}
+        if use_xg and pending is not None:
+            lat_rf = rf_front_finish(K, cfg, x, packs, egr, ctx.bn, bn_mode, red2, pending, dpool_x, dx)
+        elif use_xg:
             K.xg_ln_pre_bwd(cfg, x, dxl, ln1s, packs, dpool_x, dx, egr)
         else:
             K.expert_front_bwd(cfg, x, tokp, dzt, z, ctx.bn, bn_mode, red1, packs, dpool_x, dx, dtokp, egr)
@@ -637,9 +680,14 @@ class MoEAdapterFunction(torch.autograd.Function):
                 dmp = K.mha_bwd(x, mp, ctx.aux_saved[e], egr[e].aux, dx)         # accumulates into dx
                 for n, g in zip(("in_proj_weight", "in_proj_bias", "out_proj.weight", "out_proj.bias"), dmp):
                     grads[pfx + "self_attention." + n] = g
-            elif kind == "latent_gemm":
+            elif kind in ("latent_gemm", "latent_rf"):
                 kv_is_x, tokp_e, tokp_op, A12, A2 = ctx.aux_saved[e]
-                dtokp_e = gemm_attn2_bwd(K, x, tokp_op, A2, egr[e].aux, T, dx)   # adds into dx
+                if kind == "latent_rf":     # the front backward already produced dS2 and added dS2·tok' into dx
+                    a2, ds2 = lat_rf[e]
+                    dtokp_e = K.bgemm(a2[:, :, :T], egr[e].aux, a_kmajor=False, b_kmajor=False, out_dtype=f32)      # A2ᵀ·dXR
+                    K.add_into(dtokp_e, K.bgemm(ds2[:, :, :T], x, a_kmajor=False, b_kmajor=False, out_dtype=f32))   # + dS2ᵀ·x
+                else:
+                    dtokp_e = gemm_attn2_bwd(K, x, tokp_op, A2, egr[e].aux, T, dx)   # adds into dx
                 fold_pool = not kv_is_x and dv is None                           # router path d mean_N(v): once, in the epilogue
                 dkv, dtok = gemm_latent_bwd(K, x if kv_is_x else v, P[pfx + "my_tokens"], tokp_e, A12, dtokp_e, T,
                                             dkv_bias=dpool_v if fold_pool else None)

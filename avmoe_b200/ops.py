@@ -592,7 +592,9 @@ def _xg_args(cfg, packs, egr=None, *, BT, dtype, bn_mode=0, bn2_wb=None):
     keep = []
     for e, pk in enumerate(packs):
         ex = a.ex[e]
-        ex.pre_kind, ex.relu = pk.pre_kind, int(pk.relu)
+        # latent experts reach these row kernels only on the row-fused path, whose front passes own the pre-transform:
+        # the remaining xg kernels (statistics, bn1 backward, weight-gradient finish) never look at x
+        ex.pre_kind, ex.relu = (0 if pk.pre_kind == 1 else pk.pre_kind), int(pk.relu)
         for name in ("gate_pre", "aux", "ln1_w", "ln1_b", "wd", "wu", "ln2_w", "ln2_b", "gate"):
             t = getattr(pk, name)
             if t is not None:
@@ -742,12 +744,12 @@ def rf_pack_bytes(nb: int, Nn: int, K: int, hi_lo: bool = False) -> int:
 
 def rf_pack_b(src: torch.Tensor, *, nb: int, bstride: int, stride_n: int, stride_k: int, Nn: int, K: int, groups: int = 1,
               group_local_k: bool = True, scale_n: Optional[torch.Tensor] = None, scale_k: Optional[torch.Tensor] = None, hi_lo: bool = False,
-              out: Optional[torch.Tensor] = None) -> torch.Tensor:
+              Nn_pad: int = 0, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """fp32 matrix -> packed tensor-core B operand B[k][n] (mma fragment order, bf16; include/avmoe_b200.h avmoe_rf_pack_b).
     Returns a uint8 tensor; ``out`` may be a slice of a larger arena."""
     _require_cuda(src)
     assert src.dtype == torch.float32
-    nbytes = rf_pack_bytes(nb, Nn, K, hi_lo)
+    nbytes = rf_pack_bytes(nb, max(Nn, Nn_pad), K, hi_lo)
     if out is None:
         out = torch.empty(nbytes, device=src.device, dtype=torch.uint8)
     assert out.numel() == nbytes and out.is_contiguous() and out.data_ptr() % 16 == 0
@@ -755,8 +757,96 @@ def rf_pack_b(src: torch.Tensor, *, nb: int, bstride: int, stride_n: int, stride
         assert sc is None or sc.dtype == torch.float32
     _lib_call("rf_pack_b", _ptr(src), C.c_int64(bstride), C.c_int64(stride_n), C.c_int64(stride_k), nb, Nn, K, groups, int(group_local_k),
               _ptr(scale_n), 0 if scale_n is None else scale_n.stride(-1), _ptr(scale_k), 0 if scale_k is None else scale_k.stride(-1),
-              int(hi_lo), _ptr(out), _stream())
+              int(hi_lo), Nn_pad, _ptr(out), _stream())
     return out
+
+
+def rf_prep_front(cfg, packs):
+    """Weight operands of the row-fused front pass: packed down projection with ln_before's weight folded in, the column sums
+    of that (rounded) operand for the mean fold, c2 = Wd · ln_before.bias, and the transposed operand of the backward."""
+    dev = packs[0].wd.device
+    C_, Cr, G = cfg.C, cfg.Cr, cfg.G
+    cg, crg = C_ // G, Cr // G
+    has_ln = packs[0].ln1_w is not None
+    one_f, one_b = rf_pack_bytes(1, Cr, C_), rf_pack_bytes(1, C_, Cr)
+    wd_pack = torch.empty(cfg.E * one_f, device=dev, dtype=torch.uint8)
+    wdt_pack = torch.empty(cfg.E * one_b, device=dev, dtype=torch.uint8)
+    crp16 = (Cr + 15) // 16 * 16
+    csum = torch.empty((cfg.E, crp16), device=dev, dtype=torch.float32)
+    c2 = torch.zeros((cfg.E, Cr), device=dev, dtype=torch.float32)
+    for e, pk in enumerate(packs):
+        wd = pk.wd.contiguous()                                                   # [Cr, C/G]
+        rf_pack_b(wd, nb=1, bstride=0, stride_n=cg, stride_k=1, Nn=Cr, K=C_, groups=G, group_local_k=True,
+                  scale_k=pk.ln1_w.contiguous() if has_ln else None, out=wd_pack[e * one_f:(e + 1) * one_f])
+        rf_pack_b(wd, nb=1, bstride=0, stride_n=1, stride_k=cg, Nn=C_, K=Cr, groups=G, group_local_k=False, out=wdt_pack[e * one_b:(e + 1) * one_b])
+        if has_ln:
+            c2[e] = (wd.view(G, crg, cg) * pk.ln1_b.view(G, 1, cg)).sum(-1).reshape(Cr)
+    _lib_call("rf_colsum", _ptr(wd_pack), cfg.E, Cr, C_, _ptr(csum), _stream())
+    return {"wd_pack": wd_pack, "wdt_pack": wdt_pack, "wd_csum": csum, "c2": c2, "has_ln": has_ln}
+
+
+def rf_pack_tokens(tokp: torch.Tensor):
+    """updated latent tokens tok' [BT,T,C] fp32 -> (packed hi/lo logits operand B[k=c][n=t], packed B[k=t][n=c]) per sample"""
+    BT, T, Cc = tokp.shape
+    tokp = tokp.contiguous()
+    tp16 = (T + 15) // 16 * 16
+    s2 = rf_pack_b(tokp, nb=BT, bstride=T * Cc, stride_n=Cc, stride_k=1, Nn=T, K=Cc, hi_lo=True, Nn_pad=tp16)
+    xr = rf_pack_b(tokp, nb=BT, bstride=T * Cc, stride_n=1, stride_k=Cc, Nn=Cc, K=T)
+    return s2, xr
+
+
+def _rf_front_args(cfg, packs, egr, toks, prep, *, BT):
+    a = _lib.RfFrontArgs()
+    a.BT, a.N, a.C, a.Cr, a.Crp, a.G, a.E, a.T = BT, cfg.N, cfg.C, cfg.Cr, pad_bottleneck(cfg.Cr), cfg.G, cfg.E, cfg.T
+    a.has_ln = int(prep["has_ln"])
+    keep = []
+    for e, pk in enumerate(packs):
+        ex = a.ex[e]
+        ex.pre_kind, ex.relu = pk.pre_kind, int(pk.relu)
+        for name in ("gate_pre", "aux", "ln1_w", "ln1_b"):
+            t = getattr(pk, name)
+            if t is not None:
+                t = t.contiguous()
+                keep.append(t)
+                setattr(ex, name, t.data_ptr())
+        if egr is not None:
+            for name in ("gate_pre", "aux", "ln1_w", "ln1_b"):
+                t = getattr(egr[e], name)
+                if t is not None:
+                    assert t.is_contiguous()
+                    setattr(ex, "g_" + name, t.data_ptr())
+        if e in toks:
+            a.tok_s2[e], a.tok_xr[e] = toks[e][0].data_ptr(), toks[e][1].data_ptr()
+    _set(a, wd_pack=prep["wd_pack"], wd_csum=prep["wd_csum"], c2=prep["c2"], wdt_pack=prep["wdt_pack"])
+    return a, keep
+
+
+def rf_front_fwd(cfg, x, packs, toks, prep, z):
+    """x (+aux, tok') -> z [BT,N,E,Cr] fp32: latent attention of each row, gate_pre residual, ln_before, grouped down projection
+    (replaces S2 GEMM + softmax_rows + A2·tok' GEMM + xg_ln_pre_fwd + down GEMM; nothing but z is written)."""
+    _require_cuda(x, z)
+    a, keep = _rf_front_args(cfg, packs, None, toks, prep, BT=x.shape[0])
+    _set(a, x=x, z=z)
+    _lib_call("rf_front_fwd", C.byref(a), _stream(), _bytes=_nbytes(x, z) + sum(_nbytes(pk.aux) for pk in packs))
+
+
+def rf_front_bwd(cfg, x, packs, egr, toks, prep, dz, dpool_x, dx):
+    """dz, x (+aux, tok') -> dx, xl [E,rows,C], per latent expert (A2, dS2) [BT,N,Tp8]; egr[e].aux receives d aux (for latent experts
+    dXR), egr[e].gate_pre / ln1_w / ln1_b accumulate."""
+    BT, N, Cc = x.shape
+    rows = BT * N
+    xl = torch.empty((cfg.E, rows, Cc), device=x.device, dtype=x.dtype)
+    tp8 = round8(cfg.T)
+    lat = {}
+    a, keep = _rf_front_args(cfg, packs, egr, toks, prep, BT=BT)
+    for e in toks:
+        a2 = torch.empty((BT, N, tp8), device=x.device, dtype=x.dtype)
+        ds2 = torch.empty((BT, N, tp8), device=x.device, dtype=x.dtype)
+        lat[e] = (a2, ds2)
+        a.a2[e], a.ds2[e] = a2.data_ptr(), ds2.data_ptr()
+    _set(a, x=x, dz=dz, dpool_x=dpool_x, dx=dx, xl=xl)
+    _lib_call("rf_front_bwd", C.byref(a), _stream(), _bytes=_nbytes(x, dz, dx, xl) + sum(2 * _nbytes(pk.aux) for pk in packs))
+    return xl, lat
 
 
 def rf_prep_up(cfg, packs, save2, bn_mode):

@@ -109,12 +109,15 @@ class AdapterStack(nn.Module):
     def stages(self):
         return [s for s, _ in VARIANT_SITES[self.variant]]
 
+    router_noise = True    # AVS variants: draw the reference's training-time router noise (PVT_AVSModel_v2.py:294-296); parity tests turn it off
     fuse_residual = True   # fold the call-site add f = f + adapter(f, other) into the adapter's combine epilogue
 
     def _call(self, mod, x_tok, o_tok):
         """reference call-site convention: permuted [BT,C,N,1] views in, residual in the same layout out."""
         xv = x_tok.permute(0, 2, 1).unsqueeze(-1)
         kw = {"residual": xv} if self.fuse_residual else {}
+        if self.variant in ("s4", "ms3"):
+            kw["is_training"] = bool(self.router_noise and self.training)
         res = mod(xv, o_tok.permute(0, 2, 1).unsqueeze(-1), **kw)
         out = res[0].squeeze(-1).permute(0, 2, 1)
         aux = res[-1] if self.variant in ("avvp", "s4", "ms3") and torch.is_tensor(res[-1]) else None

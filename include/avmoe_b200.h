@@ -330,8 +330,11 @@ int avmoe_batch_sum_add(const float* in, float* out /* += */, int BT, int64_t L,
  * n-tile each (NP = ceil(Nn/8)). */
 int avmoe_rf_pack_b(const float* src, int64_t bstride, int64_t stride_n, int64_t stride_k, int nb, int Nn, int K, int groups,
                     int group_local_k, const float* scale_n, int scale_n_stride, const float* scale_k, int scale_k_stride, int hi_lo,
-                    void* dst, avmoe_stream_t stream);
+                    int Nn_pad /* layout extent of n (>= Nn, extra columns zero); 0 = Nn */, void* dst, avmoe_stream_t stream);
 int64_t avmoe_rf_pack_b_bytes(int nb, int Nn, int K, int hi_lo);
+/* csum[b][n] = sum_k of the bf16 elements of a packed (not hi/lo) operand, n < 16*ceil(Nn/16): the LayerNorm mean fold of the
+ * front pass uses the column sums of exactly the rounded weights the tensor cores see */
+int avmoe_rf_colsum(const void* packed, int nb, int Nn, int K, float* csum, avmoe_stream_t stream);
 
 typedef struct {
   int32_t BT, N, C, Cr, Crp, G, E, bn_mode;
@@ -352,7 +355,30 @@ typedef struct {
 } avmoe_rf_back_args;
 int avmoe_rf_back_fwd(const avmoe_rf_back_args* a, avmoe_stream_t stream);
 int avmoe_rf_back_bwd(const avmoe_rf_back_args* a, avmoe_stream_t stream);
-/* 1 when the row-fused passes support this geometry (C % 16 == 0, C/r <= 96, E <= 4, T <= 96), else 0 (callers use the GEMM path) */
+
+typedef struct {
+  int32_t BT, N, C, Cr, Crp, G, E, T, has_ln, _pad;
+  avmoe_expert ex[AVMOE_MAX_EXPERTS];      /* pre_kind, gate_pre, aux, ln1_w, ln1_b (+ g_gate_pre, g_aux, g_ln1_w, g_ln1_b in the backward;
+                                              for AVMOE_PRE_LATENT experts g_aux receives dXR = gate_pre * d(x_pre), [rows,C]) */
+  const void* tok_s2[AVMOE_MAX_EXPERTS];   /* PRE_LATENT: per-sample packed hi/lo operand B[k=c][n=t] = tok'[b][t][c] (K=C, Nn=T padded to 16) */
+  const void* tok_xr[AVMOE_MAX_EXPERTS];   /* PRE_LATENT: per-sample packed operand B[k=t][n=c] = tok'[b][t][c] (K=T, Nn=C) */
+  const void* wd_pack;       /* E operands B[k=c][n=j] = ln1_w[c] * dense down_sampler[j][c] (K=C, Nn=Cr) */
+  const float* wd_csum;      /* [E,16*ceil(Cr/16)] avmoe_rf_colsum of wd_pack */
+  const float* c2;           /* [E,Cr] dense down_sampler · ln1_b (zeros without ln_before) */
+  const void* wdt_pack;      /* backward: E operands B[k=j][n=c] = dense down_sampler[j][c] (K=Cr, Nn=C) */
+  const void* x;             /* [rows,C] */
+  float* z;                  /* [rows,E,Cr] fp32 (forward output) */
+  const void* dz;            /* [E,rows,Crp] gradient at the down-projection output (backward) */
+  const float* dpool_x;      /* [BT,C] router-path gradient per token (already /N) or NULL */
+  void* dx;                  /* [rows,C] */
+  void* xl;                  /* [E,rows,C] ln_before output, operand of the weight-gradient GEMM */
+  void* a2[AVMOE_MAX_EXPERTS];   /* PRE_LATENT: [rows,Tp8] softmax_T probabilities (operand of the d tok' GEMM) */
+  void* ds2[AVMOE_MAX_EXPERTS];  /* PRE_LATENT: [rows,Tp8] gradient at the logits */
+} avmoe_rf_front_args;
+int avmoe_rf_front_fwd(const avmoe_rf_front_args* a, avmoe_stream_t stream);
+int avmoe_rf_front_bwd(const avmoe_rf_front_args* a, avmoe_stream_t stream);
+/* 1 when the row-fused passes support this geometry (C % 16 == 0, C/r <= 96, 2 <= E <= 4, T <= 96), else 0 (callers use the GEMM path);
+ * the front passes additionally need N % 16 == 0 (a 16-row tile never straddles two samples' latent tokens) */
 int avmoe_rf_supported(int C, int Cr, int E, int T);
 
 #ifdef __cplusplus

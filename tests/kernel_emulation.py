@@ -809,6 +809,65 @@ def rf_back_bwd(cfg, dout, z, aff1, wu_pack, ybi, bn2_wb, bn_mode, packs, probs,
     return yd, act.to(dout.dtype)
 
 
+def rf_prep_front(cfg, packs):
+    return {"has_ln": packs[0].ln1_w is not None}
+
+
+def rf_pack_tokens(tokp):
+    return tokp, tokp        # emulated "packed" operands: the fp32 tokens themselves
+
+
+def _rf_aux_packs(cfg, x, packs, toks):
+    """latent experts restated as aux-add experts (aux = softmax_T(x tok'^T) tok'), plus the probabilities"""
+    out, probs = [], {}
+    for e, pk in enumerate(packs):
+        if pk.pre_kind == PRE_LATENT:
+            tp = toks[e][0].float()
+            a2 = torch.softmax(x.float() @ tp.transpose(1, 2), dim=-1)
+            q = ExpertPack(pre_kind=PRE_AUX_ADD, relu=pk.relu, gate_pre=pk.gate_pre, aux=a2 @ tp, ln1_w=pk.ln1_w, ln1_b=pk.ln1_b,
+                           wd=pk.wd, wu=pk.wu, ln2_w=pk.ln2_w, ln2_b=pk.ln2_b, gate=pk.gate)
+            probs[e] = a2
+            out.append(q)
+        else:
+            out.append(pk)
+    return out, probs
+
+
+def rf_front_fwd(cfg, x, packs, toks, prep, z):
+    BT, N, C = x.shape
+    ap, _ = _rf_aux_packs(cfg, x, packs, toks)
+    xl, _ = xg_ln_pre_fwd(cfg, x.float(), ap)
+    for e, pk in enumerate(packs):
+        z[:, :, e, :] = (xl[e].float() @ _dense_wd(pk.wd, cfg).t()).reshape(BT, N, cfg.Cr)
+
+
+def rf_front_bwd(cfg, x, packs, egr, toks, prep, dz, dpool_x, dx):
+    BT, N, C = x.shape
+    ap, a2s = _rf_aux_packs(cfg, x, packs, toks)
+    xl, st = xg_ln_pre_fwd(cfg, x.float(), ap)
+    dxl = torch.stack([dz[e, :, :cfg.Cr].float() @ _dense_wd(pk.wd, cfg) for e, pk in enumerate(packs)])
+    for e, pk in enumerate(packs):      # latent experts: the aux gradient buffer is the dXR the caller allocated
+        if egr[e].aux is None and pk.pre_kind == PRE_LATENT:
+            egr[e].aux = torch.empty((BT, N, C), dtype=x.dtype)
+    dxf = torch.empty((BT, N, C), dtype=torch.float32)
+    xg_ln_pre_bwd(cfg, x.float(), dxl, st, ap, dpool_x, dxf, egr)
+    lat = {}
+    tp8 = round8(cfg.T)
+    for e, pk in enumerate(packs):
+        if pk.pre_kind == PRE_LATENT:
+            tp = toks[e][0].float()
+            a2 = a2s[e]
+            da2 = egr[e].aux.float() @ tp.transpose(1, 2)
+            ds2 = a2 * (da2 - (a2 * da2).sum(-1, keepdim=True))
+            dxf = dxf + ds2 @ tp
+            A2 = torch.zeros((BT, N, tp8), dtype=x.dtype)
+            D2 = torch.zeros((BT, N, tp8), dtype=x.dtype)
+            A2[:, :, :cfg.T], D2[:, :, :cfg.T] = a2.to(x.dtype), ds2.to(x.dtype)
+            lat[e] = (A2, D2)
+    dx.copy_(dxf.to(dx.dtype))
+    return xl.to(x.dtype), lat
+
+
 def _xg_bn2_coeffs(cfg, bn2_wb, bn, bn_mode, red2, rows, e):
     C = cfg.C
     alpha, beta, gamma = torch.ones(C), torch.zeros(C), torch.zeros(C)

@@ -136,3 +136,28 @@ def test_tiny_batches_cuda(variant, BT, dtype):
     got = _run_module(build_module(spec, sd, kernels=None), spec, x, o, gout, True, "cuda", dtype)
     tol, gtol = (1e-3, 6e-2) if dtype == torch.float32 else (2e-2, 3e-1)
     _compare(spec, ref, got, tol, gtol)
+
+
+@pytest.mark.parametrize("training", [True, False])
+@pytest.mark.parametrize("variant,overrides", [("ave", {}), ("avqa", {}), ("avvp", dict(lb_loss=True)), ("s4", {}), ("ms3", {}),
+                                               ("ave", dict(ln_before=False, ln_post=False, use_bn=False)), ("ave", dict(Mm=2, Ms=1, T=20))])
+def test_rowfused_orchestration_emulated(variant, overrides, training, monkeypatch):
+    """token counts that are multiples of 16 take the row-fused front pass (latent attention inside the expert front kernel, nothing
+    saved, backward recomputes): the orchestration around it -- operand packing, the two-phase backward, the d tok' contractions fed
+    by the A2 | dS2 the front backward emits -- against the oracle on the kernel emulation."""
+    import dataclasses
+    monkeypatch.setattr(KE, "USE_GEMM_ATTENTION", "always")
+    monkeypatch.setattr(KE, "USE_GEMM_EXPERTS", "always")
+    calls = {"fwd": 0, "bwd": 0}
+    fwd, bwd = KE.rf_front_fwd, KE.rf_front_bwd
+    monkeypatch.setattr(KE, "rf_front_fwd", lambda *a, **k: (calls.__setitem__("fwd", calls["fwd"] + 1), fwd(*a, **k))[1])
+    monkeypatch.setattr(KE, "rf_front_bwd", lambda *a, **k: (calls.__setitem__("bwd", calls["bwd"] + 1), bwd(*a, **k))[1])
+    spec = dataclasses.replace(O.spec_for(variant, 3, "audio", **overrides), C=64, N=32, Cx=96, Nx=16)
+    sd = O.make_state_dict(spec, seed=3)
+    BT = 3
+    x, o = O.make_tokens(BT, spec.N, spec.C, 11), O.make_tokens(BT, spec.Nx, spec.Cx, 12)
+    gout = torch.randn((BT, spec.N, spec.C), generator=torch.Generator().manual_seed(13))
+    ref = _run_oracle(spec, sd, x, o, gout, training)
+    got = _run_module(build_module(spec, sd, kernels=KE), spec, x, o, gout, training, "cpu", torch.float32)
+    assert calls == {"fwd": 1, "bwd": 1}, calls
+    _compare(spec, ref, got, 5e-5, 5e-4)

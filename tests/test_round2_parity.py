@@ -300,6 +300,7 @@ def _stack_errors(variant, BT, dtype):
         for i, entry in enumerate(ref[3]):
             getattr(model, attr)[i].load_state_dict(entry[key], strict=True)
     model = model.cuda().train()
+    model.router_noise = False          # the oracle stack runs without router noise (injected-noise parity is tested per adapter)
     leaves = {s: (a.to("cuda", dtype).requires_grad_(), v.to("cuda", dtype).requires_grad_()) for s, (a, v) in ref[4].items()}
     loss = model(leaves)
     loss.backward()
