@@ -134,17 +134,17 @@ class _MoEAdapterBase(nn.Module):
         assert t.dim() == 4 and t.shape[-1] == 1, "expected [BT, C, N, 1]"
         return t.squeeze(-1).permute(0, 2, 1).contiguous()
 
-    def _run(self, x, vis_token, noise: Optional[torch.Tensor] = None, residual: Optional[torch.Tensor] = None):
+    def _run(self, x, vis_token, noise: Optional[torch.Tensor] = None, residual: Optional[torch.Tensor] = None, mha_keep=None):
         K = self._kernel_namespace()
         if K.__name__.endswith(".ops") and not x.is_cuda:
             raise RuntimeError("avmoe_b200 has no CPU path: move the module and its inputs to a CUDA device")
         xt, ot = self._token_major(x), self._token_major(vis_token)
-        if self.cfg.self_attn == "mha" and self.training:
-            for m in self.singlemodal_experts:
-                if m.self_attention.dropout != 0.0:
-                    raise RuntimeError("attention dropout inside the AVS-v1 MultiheadAttention is RNG-dependent; set "
-                                       "self_attention.dropout = 0 or call .eval() (SURVEY.md §8c caveat 3)")
         state = {"cfg": self.cfg, "K": K, "training": self.training, "buffers": self._bn_buffers(), "noise": noise}
+        if self.cfg.self_attn == "mha":     # AVS-v1: nn.MultiheadAttention(dropout=0.2) drops attention probabilities in training
+            drops = {float(m.self_attention.dropout) for m in self.singlemodal_experts}
+            assert len(drops) <= 1, "single-modal experts must share one attention dropout rate"
+            state["mha_dropout"] = drops.pop() if (drops and self.training) else 0.0
+            state["mha_keep"] = mha_keep
         rt = None if residual is None else self._token_major(residual).to(xt.dtype)
         out, probs, lb, idx = Fn.MoEAdapterFunction.apply(state, xt, ot, rt, *self._flat_params())
         return out.permute(0, 2, 1).unsqueeze(-1), idx.unsqueeze(-1), probs.unsqueeze(1), lb
@@ -214,14 +214,16 @@ class MoEAdapterAVS(_MoEAdapterBase):
                     conv_dim_in, conv_dim_out, linear_in, linear_out, sa, _opt_get(opt, "use_load_balacing_loss", 0) == 1)
         self.noise_std = 0.01   # PVT_AVSModel_v2.py:295
 
-    def forward(self, x, vis_token=None, is_training=True, noise: Optional[torch.Tensor] = None, residual=None):
+    def forward(self, x, vis_token=None, is_training=True, noise: Optional[torch.Tensor] = None, residual=None, mha_keep=None):
         """``noise`` ([BT,E], optional) lets a caller inject the router noise tensor for reproducible parity runs;
-        by default it is drawn with torch.randn exactly where the reference draws it."""
+        by default it is drawn with torch.randn exactly where the reference draws it.  ``mha_keep`` (AVS-v1, optional): one uint8
+        keep mask [N,4,BT,BT] per single-modal expert for the attention dropout; by default drawn from torch's generator in
+        training mode."""
         if is_training and noise is None:
             noise = torch.randn((x.shape[0], self.cfg.E), device=x.device, dtype=torch.float32) * self.noise_std
         if not is_training:
             noise = None
-        out, idx, probs, lb = self._run(x, vis_token, noise, residual=residual)
+        out, idx, probs, lb = self._run(x, vis_token, noise, residual=residual, mha_keep=mha_keep)
         return out, idx, probs, (lb if self.cfg.lb_loss else 0.)
 
 

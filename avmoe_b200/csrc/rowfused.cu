@@ -367,7 +367,9 @@ __global__ void __launch_bounds__(256) rf_back_kernel(const avmoe_rf_back_args p
           for (int h = 0; h < 2; ++h) {
             const int c = (pr << 4) + h * 8 + 2 * t;
             const ColParams cp = load_col_params(tab, e, C, c);
-            const float2 dA = unpack_bf16x2(tile_at(t_dout, pitch, g, c)), dB = unpack_bf16x2(tile_at(t_dout, pitch, g + 8, c));
+            float2 dA = unpack_bf16x2(tile_at(t_dout, pitch, g, c)), dB = unpack_bf16x2(tile_at(t_dout, pitch, g + 8, c));
+            if (!vA) dA = make_float2(0.f, 0.f);     // rows beyond the tensor were not staged: their tile rows hold stale data
+            if (!vB) dB = make_float2(0.f, 0.f);
             const float xh0 = (yh[h][0] * cp.bw.x + cp.bb.x - mean0) * rstd0, xh1 = (yh[h][1] * cp.bw.y + cp.bb.y - mean0) * rstd0;
             const float xh2 = (yh[h][2] * cp.bw.x + cp.bb.x - mean1) * rstd1, xh3 = (yh[h][3] * cp.bw.y + cp.bb.y - mean1) * rstd1;
             dotA += dA.x * (xh0 * cp.lw.x + cp.lb.x) + dA.y * (xh1 * cp.lw.y + cp.lb.y);
@@ -414,7 +416,9 @@ __global__ void __launch_bounds__(256) rf_back_kernel(const avmoe_rf_back_args p
             const ColParams cp = load_col_params(tab, e, C, c);
             tile_at(t_yh, pitch, g, c) = pack_bf16x2(yh[h][0], yh[h][1]);
             tile_at(t_yh, pitch, g + 8, c) = pack_bf16x2(yh[h][2], yh[h][3]);
-            const float2 dA = unpack_bf16x2(tile_at(t_dout, pitch, g, c)), dB = unpack_bf16x2(tile_at(t_dout, pitch, g + 8, c));
+            float2 dA = unpack_bf16x2(tile_at(t_dout, pitch, g, c)), dB = unpack_bf16x2(tile_at(t_dout, pitch, g + 8, c));
+            if (!vA) dA = make_float2(0.f, 0.f);     // rows beyond the tensor were not staged: their tile rows hold stale data
+            if (!vB) dB = make_float2(0.f, 0.f);
             float dy[4] = {scA[e] * dA.x, scA[e] * dA.y, scB[e] * dB.x, scB[e] * dB.y};
             if (has_ln) {
               const float xh0 = (yh[h][0] * cp.bw.x + cp.bb.x - mean0) * rstd0, xh1 = (yh[h][1] * cp.bw.y + cp.bb.y - mean0) * rstd0;

@@ -72,7 +72,7 @@ __global__ void add_into_kernel(T* __restrict__ dst, const T* __restrict__ a, co
 // contractions read them in place from global memory (row pitch NB*3C).  S lives in shared memory as [L][L+4].
 template <typename T>
 __global__ void __launch_bounds__(256) mha_attn_fwd_kernel(const float* __restrict__ qkv, T* __restrict__ ctx, int L, int NB, int C, int hd,
-                                                           float scale, int staged) {
+                                                           float scale, int staged, const unsigned char* __restrict__ keep, float keep_scale) {
   extern __shared__ float sm[];
   constexpr bool kExact = std::is_same<T, float>::value;
   const int ldh = hd + 4, lds = L + 4;
@@ -106,7 +106,12 @@ __global__ void __launch_bounds__(256) mha_attn_fwd_kernel(const float* __restri
     for (int j = lane; j < L; j += 32) { const float e = expf(S[i * lds + j] - mx); S[i * lds + j] = e; sum += e; }
     sum = warp_sum(sum);
     const float inv = 1.f / sum;
-    for (int j = lane; j < L; j += 32) S[i * lds + j] *= inv;
+    if (keep) {    // attention-probability dropout (nn.MultiheadAttention dropout): kept entries scaled by 1/(1-p)
+      const unsigned char* kr = keep + (((long long)nb * gridDim.y + h) * L + i) * L;
+      for (int j = lane; j < L; j += 32) S[i * lds + j] = kr[j] ? S[i * lds + j] * inv * keep_scale : 0.f;
+    } else {
+      for (int j = lane; j < L; j += 32) S[i * lds + j] *= inv;
+    }
   }
   __syncthreads();
   contract<kExact>(L, hd, L, S, lds, 1, v, rs, 1, [&](int i, int d, float val) {
@@ -117,7 +122,8 @@ __global__ void __launch_bounds__(256) mha_attn_fwd_kernel(const float* __restri
 // backward: recompute att; dv = attᵀ dctx; datt = dctx vᵀ; ds = att*(datt - rowsum(att*datt)); dq = scale * ds k; dk = scale * dsᵀ q
 template <typename T>
 __global__ void __launch_bounds__(256) mha_attn_bwd_kernel(const float* __restrict__ qkv, const float* __restrict__ dctx, T* __restrict__ dqkv,
-                                                           int L, int NB, int C, int hd, float scale, int staged) {
+                                                           int L, int NB, int C, int hd, float scale, int staged,
+                                                           const unsigned char* __restrict__ keep, float keep_scale) {
   extern __shared__ float sm[];
   constexpr bool kExact = std::is_same<T, float>::value;
   const int ldh = hd + 4, lds = L + 4;
@@ -157,9 +163,21 @@ __global__ void __launch_bounds__(256) mha_attn_bwd_kernel(const float* __restri
     sum = warp_sum(sum);
     const float inv = 1.f / sum;
     float r = 0.f;
-    for (int j = lane; j < L; j += 32) { const float a = A[i * lds + j] * inv; A[i * lds + j] = a; r = fmaf(a, D[i * lds + j], r); }
+    const unsigned char* kr = keep ? keep + (((long long)nb * gridDim.y + h) * L + i) * L : nullptr;
+    // with dropout the context used att*m (m = keep/(1-p)): the gradient at the un-dropped probabilities is datt*m
+    for (int j = lane; j < L; j += 32) {
+      const float a = A[i * lds + j] * inv;
+      const float m = kr ? (kr[j] ? keep_scale : 0.f) : 1.f;
+      const float d = D[i * lds + j] * m;
+      A[i * lds + j] = a; D[i * lds + j] = d;
+      r = fmaf(a, d, r);
+    }
     r = warp_sum(r);
-    for (int j = lane; j < L; j += 32) D[i * lds + j] = A[i * lds + j] * (D[i * lds + j] - r);
+    for (int j = lane; j < L; j += 32) {
+      const float a = A[i * lds + j];
+      D[i * lds + j] = a * (D[i * lds + j] - r);
+      if (kr) A[i * lds + j] = kr[j] ? a * keep_scale : 0.f;      // dv contracts the dropped probabilities
+    }
   }
   __syncthreads();
   T* out = dqkv + (long long)nb * 3 * C + h * hd;
@@ -204,7 +222,8 @@ extern "C" int avmoe_add_into(void* dst, const void* a, const void* b, const voi
   return 0;
 }
 
-extern "C" int avmoe_mha_attn_fwd(const float* qkv, void* ctx, int L, int NB, int C, int heads, int dtype, avmoe_stream_t stream) {
+extern "C" int avmoe_mha_attn_fwd(const float* qkv, void* ctx, int L, int NB, int C, int heads, int dtype, const unsigned char* keep,
+                                  float keep_scale, avmoe_stream_t stream) {
   AVMOE_CHECK_ARG(qkv && ctx && L > 0 && NB > 0 && C > 0 && heads > 0 && C % heads == 0, "mha_attn_fwd: bad arguments");
   AVMOE_CHECK_ARG(heads <= 65535, "mha_attn_fwd: grid too large");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
@@ -218,16 +237,17 @@ extern "C" int avmoe_mha_attn_fwd(const float* qkv, void* ctx, int L, int NB, in
   dim3 grid(NB, heads);
   if (dtype == AVMOE_F32) {
     AVMOE_CUDA(cudaFuncSetAttribute(mha_attn_fwd_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    mha_attn_fwd_kernel<float><<<grid, 256, smem, st>>>(qkv, (float*)ctx, L, NB, C, hd, scale, staged);
+    mha_attn_fwd_kernel<float><<<grid, 256, smem, st>>>(qkv, (float*)ctx, L, NB, C, hd, scale, staged, keep, keep_scale);
   } else {
     AVMOE_CUDA(cudaFuncSetAttribute(mha_attn_fwd_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    mha_attn_fwd_kernel<__nv_bfloat16><<<grid, 256, smem, st>>>(qkv, (__nv_bfloat16*)ctx, L, NB, C, hd, scale, staged);
+    mha_attn_fwd_kernel<__nv_bfloat16><<<grid, 256, smem, st>>>(qkv, (__nv_bfloat16*)ctx, L, NB, C, hd, scale, staged, keep, keep_scale);
   }
   AVMOE_LAUNCH_CHECK("mha_attn_fwd_kernel");
   return 0;
 }
 
-extern "C" int avmoe_mha_attn_bwd(const float* qkv, const float* dctx, void* dqkv, int L, int NB, int C, int heads, int dtype, avmoe_stream_t stream) {
+extern "C" int avmoe_mha_attn_bwd(const float* qkv, const float* dctx, void* dqkv, int L, int NB, int C, int heads, int dtype,
+                                  const unsigned char* keep, float keep_scale, avmoe_stream_t stream) {
   AVMOE_CHECK_ARG(qkv && dctx && dqkv && L > 0 && NB > 0 && C > 0 && heads > 0 && C % heads == 0, "mha_attn_bwd: bad arguments");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const int hd = C / heads;
@@ -240,10 +260,10 @@ extern "C" int avmoe_mha_attn_bwd(const float* qkv, const float* dctx, void* dqk
   dim3 grid(NB, heads);
   if (dtype == AVMOE_F32) {
     AVMOE_CUDA(cudaFuncSetAttribute(mha_attn_bwd_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    mha_attn_bwd_kernel<float><<<grid, 256, smem, st>>>(qkv, dctx, (float*)dqkv, L, NB, C, hd, scale, staged);
+    mha_attn_bwd_kernel<float><<<grid, 256, smem, st>>>(qkv, dctx, (float*)dqkv, L, NB, C, hd, scale, staged, keep, keep_scale);
   } else {
     AVMOE_CUDA(cudaFuncSetAttribute(mha_attn_bwd_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    mha_attn_bwd_kernel<__nv_bfloat16><<<grid, 256, smem, st>>>(qkv, dctx, (__nv_bfloat16*)dqkv, L, NB, C, hd, scale, staged);
+    mha_attn_bwd_kernel<__nv_bfloat16><<<grid, 256, smem, st>>>(qkv, dctx, (__nv_bfloat16*)dqkv, L, NB, C, hd, scale, staged, keep, keep_scale);
   }
   AVMOE_LAUNCH_CHECK("mha_attn_bwd_kernel");
   return 0;

@@ -77,3 +77,32 @@ def shard_batch(total: int, rank: int, world: int):
     base, rem = divmod(total, world)
     start = rank * base + min(rank, rem)
     return start, start + base + (1 if rank < rem else 0)
+
+
+class FlatGradientReducer:
+    """All-reduce (sum) of a FlatParameters gradient buffer in place, in a few large buckets issued back to back on NCCL's stream;
+    the division by the world size is NOT applied here -- FusedAdam.step(grad_scale=1/world) folds it into the update, so the
+    gradient bytes cross HBM once for the collective and once for the optimizer and are never packed twice or unpacked."""
+
+    def __init__(self, flat, bucket_bytes: int = 128 << 20, group=None):
+        self.flat = flat
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        n = flat.numel
+        per = max(1, bucket_bytes // 4)
+        self.ranges = [(s, min(n, s + per)) for s in range(0, n, per)]
+
+    @property
+    def grad_scale(self) -> float:
+        return 1.0 / self.world
+
+    def reduce(self, gather: bool = True):
+        """gather per-tensor gradients into the flat buffer (unless the caller already did) and all-reduce it in place"""
+        if gather:
+            self.flat.gather_grads()
+        if self.world == 1:
+            return []
+        works = [dist.all_reduce(self.flat.grad[s:e], op=dist.ReduceOp.SUM, group=self.group, async_op=True) for s, e in self.ranges]
+        for w in works:
+            w.wait()
+        return works

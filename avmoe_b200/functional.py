@@ -512,7 +512,15 @@ class MoEAdapterFunction(torch.autograd.Function):
                 pk.gate_pre = P[pfx + gate_key]
             elif pre == PRE_AUX_REPLACE:  # AVS v1 MHA over the BT axis (PVT_AVSModel_v2.py:212-215)
                 mp = [P[pfx + "self_attention." + n] for n in ("in_proj_weight", "in_proj_bias", "out_proj.weight", "out_proj.bias")]
-                pk.aux, mha_saved = K.mha_fwd(x, mp)
+                # attention-probability dropout of nn.MultiheadAttention(dropout=0.2) in training (PVT_AVSModel_v2.py:139-142): a keep
+                # mask drawn from torch's generator where the reference's dropout draws, or injected by the caller (parity runs)
+                keep, p_drop = None, float(state.get("mha_dropout", 0.0))
+                inj = state.get("mha_keep")
+                if inj is not None:
+                    keep = inj[e - cfg.Mm].to(device=dev, dtype=torch.uint8).contiguous()
+                elif training and p_drop > 0.0:
+                    keep = (torch.rand((N, 4, BT, BT), device=dev) >= p_drop).to(torch.uint8)
+                pk.aux, mha_saved = K.mha_fwd(x, mp, keep, 1.0 / (1.0 - p_drop) if keep is not None else 1.0)
                 aux_saved[e] = mha_saved
                 aux_kind[e] = "mha"
             gate_keys.append(gate_key)

@@ -959,22 +959,25 @@ def selfattn_nxn_bwd(x, lse, daux, dx):
         _lib_call("add_into", _ptr(dxc), _ptr(t1), _ptr(t2), _ptr(t3), C.c_int64(dxc.numel()), _dt(dxc), _stream())
 
 
-def mha_fwd(x, mp):
-    """AVS-v1 single-modal pre-transform: nn.MultiheadAttention(C, 4) over the BT axis of x [BT,N,C]."""
+def mha_fwd(x, mp, keep=None, keep_scale: float = 1.0):
+    """AVS-v1 single-modal pre-transform: nn.MultiheadAttention(C, 4) over the BT axis of x [BT,N,C].
+    keep [N,heads,BT,BT] uint8 (optional): attention dropout mask; kept probabilities are scaled by keep_scale = 1/(1-p)."""
     _require_cuda(x)
     w_in, b_in, w_out, b_out = mp
     L, NB, Cc = x.shape
     x2 = x.reshape(L * NB, Cc)
     qkv = gemm(x2, prep_weight(w_in, x.dtype, False), out_dtype=torch.float32, col_bias=b_in.contiguous())      # [L*NB,3C] fp32
     ctx = torch.empty((L, NB, Cc), device=x.device, dtype=x.dtype)
-    _lib_call("mha_attn_fwd", _ptr(qkv), _ptr(ctx), L, NB, Cc, MHA_HEADS, _dt(x), _stream())
+    if keep is not None:
+        assert keep.dtype == torch.uint8 and keep.shape == (NB, MHA_HEADS, L, L) and keep.is_contiguous()
+    _lib_call("mha_attn_fwd", _ptr(qkv), _ptr(ctx), L, NB, Cc, MHA_HEADS, _dt(x), _ptr(keep), C.c_float(keep_scale), _stream())
     out = gemm(ctx.reshape(L * NB, Cc), prep_weight(w_out, x.dtype, False), col_bias=b_out.contiguous()).reshape(L, NB, Cc)
-    return out, (qkv, ctx)
+    return out, (qkv, ctx, keep, keep_scale)
 
 
 def mha_bwd(x, mp, saved, daux, dx):
     w_in, b_in, w_out, b_out = mp
-    qkv, ctx = saved
+    qkv, ctx, keep, keep_scale = saved
     L, NB, Cc = x.shape
     rows = L * NB
     g2 = daux.reshape(rows, Cc)
@@ -983,7 +986,7 @@ def mha_bwd(x, mp, saved, daux, dx):
     _, db_out, _ = reduce_bias(daux)
     dctx = gemm(g2, prep_weight(w_out, x.dtype, True), out_dtype=f32)                                                            # g·W_out   fp32
     dqkv = torch.empty((L, NB, 3 * Cc), device=x.device, dtype=x.dtype)
-    _lib_call("mha_attn_bwd", _ptr(qkv), _ptr(dctx), _ptr(dqkv), L, NB, Cc, MHA_HEADS, _dt(x), _stream())
+    _lib_call("mha_attn_bwd", _ptr(qkv), _ptr(dctx), _ptr(dqkv), L, NB, Cc, MHA_HEADS, _dt(x), _ptr(keep), C.c_float(keep_scale), _stream())
     dq2 = dqkv.reshape(rows, 3 * Cc)
     dw_in = gemm(dq2, x.reshape(rows, Cc), a_kmajor=False, b_kmajor=False, out_dtype=f32, split_k=split_k_hint(rows, 3 * Cc, Cc))  # dqkvᵀ·x
     _, db_in, _ = reduce_bias(dqkv)

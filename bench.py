@@ -164,7 +164,8 @@ def run_ours(args):
     import torch
     import torch.distributed as dist
     from avmoe_b200 import ops, stack as S
-    from avmoe_b200.dist import GradientAllReducer
+    from avmoe_b200.dist import FlatGradientReducer
+    from avmoe_b200.optim import FlatParameters, FusedAdam
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -180,7 +181,11 @@ def run_ours(args):
     model = S.AdapterStack(args.variant, seed=0).to(dev)
     model.train()
     params = [p for p in model.parameters() if p.requires_grad]
-    reducer = GradientAllReducer(params) if world > 1 else None
+    # all adapter + router parameters live in one flat fp32 buffer: the gradient all-reduce runs on its flat gradient twin in
+    # place (one multi-tensor gather, no unpack) and the fused Adam consumes it directly with the 1/world folded in
+    flat = FlatParameters(params)
+    adam = FusedAdam(flat, lr=5e-4)                      # AVMOE/AVE/train.sh: lr 5e-4
+    reducer = FlatGradientReducer(flat) if world > 1 else None
     tokens_dev = S.make_stage_tokens(args.variant, BT, dtype, dev, seed=1000 + rank)
     tokens_host = S.make_stage_tokens(args.variant, BT, dtype, None, seed=1000 + rank, pin=True)
     tokens_per_step = S.tokens_per_segment(args.variant) * BT
@@ -196,7 +201,8 @@ def run_ours(args):
         loss = model(leaves)
         loss.backward()
         if reducer is not None and reduce:
-            reducer.reduce()
+            flat.gather_grads(clear=False)
+            reducer.reduce(gather=False)
         return loss
 
     def barrier():
@@ -256,7 +262,8 @@ def run_ours(args):
                 tokens_dev[s][1].copy_(v, non_blocking=True)
         graph.replay()
         if reducer is not None:
-            reducer.reduce()
+            flat.gather_grads(clear=False)
+            reducer.reduce(gather=False)
         return graph_loss
 
     for _ in range(2):
@@ -313,6 +320,18 @@ def run_ours(args):
         ms_e2e = timed(lambda: e2e_loop(args.steps), 1) / args.steps
     e2e = {"value": tokens_per_step * world / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d_bytes * world,
            "d2h_bytes_per_step": 4 * world, "ms_per_step": ms_e2e}
+
+    # ---- optimizer step on the flat buffers (reported next to the step; the metric itself is fwd+bwd as BASELINE.json defines it)
+    flat.gather_grads(clear=False)
+    lr_keep = adam.param_groups[0]["lr"]
+    adam.param_groups[0]["lr"] = 0.0                     # timing only: the weights (and hence the timed workload) stay as they are
+    for _ in range(2):
+        adam.step(grad_scale=1.0 / world)
+    adam_ms = timed(lambda: adam.step(grad_scale=1.0 / world), 5) / 5
+    gather_ms = timed(lambda: flat.gather_grads(clear=False), 5) / 5
+    adam.param_groups[0]["lr"] = lr_keep
+    optimizer = {"fused_adam_ms": adam_ms, "gather_grads_ms": gather_ms, "params": flat.numel,
+                 "adam_GBps": 28.0 * flat.numel / (adam_ms * 1e-3) / 1e9}
 
     # ---- roofline: per-kernel CUDA-event timing of one extra (untimed) step, on the launching stream ---------------------
     roofline = None
@@ -420,7 +439,7 @@ def run_ours(args):
                 "config": {"workload": workload_name(args), "variant": args.variant, "BT_per_gpu": BT, "tokens_per_step_per_gpu": tokens_per_step,
                            "adapter_calls_per_step": 4 * len(model.sites), "launch": launch_mode, "parallelism": f"dp{world} (batch-sharded, grad all-reduce)" if world > 1 else "single GPU",
                            "l2": f"inputs+weights per step ({(h2d_bytes + sum(p.numel() * 4 for p in params)) / 1e6:.0f} MB) exceed the 126 MB L2; no explicit flush"},
-                "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "kernels": kernel_table}
+                "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "optimizer": optimizer, "kernels": kernel_table}
         if cpu is not None:
             line["cpu_baseline"] = cpu
         if gpu_eager is not None:

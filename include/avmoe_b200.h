@@ -228,8 +228,13 @@ int avmoe_nxn_softmax_rows(const float* S, void* P, float* lse, int64_t rows, in
 int avmoe_nxn_bwd_rows(const float* S, const float* dAtt, const float* lse, void* att, void* dS, int64_t rows, int n, int p_dtype,
                        avmoe_stream_t stream);
 int avmoe_add_into(void* dst, const void* a, const void* b, const void* c, int64_t n, int dtype, avmoe_stream_t stream);
-int avmoe_mha_attn_fwd(const float* qkv, void* ctx, int L, int NB, int C, int heads, int dtype, avmoe_stream_t stream);
-int avmoe_mha_attn_bwd(const float* qkv, const float* dctx, void* dqkv, int L, int NB, int C, int heads, int dtype, avmoe_stream_t stream);
+/* keep [NB,heads,L,L] uint8 or NULL: attention-probability dropout mask of nn.MultiheadAttention(dropout=0.2)
+ * (avs_s4/model/PVT_AVSModel_v2.py:139-142); kept probabilities are scaled by keep_scale = 1/(1-p).  The host layer draws the mask
+ * from torch's generator (or takes an injected one for parity runs) and hands the same mask to the backward. */
+int avmoe_mha_attn_fwd(const float* qkv, void* ctx, int L, int NB, int C, int heads, int dtype, const unsigned char* keep, float keep_scale,
+                       avmoe_stream_t stream);
+int avmoe_mha_attn_bwd(const float* qkv, const float* dctx, void* dqkv, int L, int NB, int C, int heads, int dtype, const unsigned char* keep,
+                       float keep_scale, avmoe_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
  * GEMM-based expert path (bf16 streams).  The grouped 1x1 down/up projections of an expert (net_trans_v3.py:393-401, "down_sampler" /
@@ -380,6 +385,15 @@ int avmoe_rf_front_bwd(const avmoe_rf_front_args* a, avmoe_stream_t stream);
 /* 1 when the row-fused passes support this geometry (C % 16 == 0, C/r <= 96, 2 <= E <= 4, T <= 96), else 0 (callers use the GEMM path);
  * the front passes additionally need N % 16 == 0 (a 16-row tile never straddles two samples' latent tokens) */
 int avmoe_rf_supported(int C, int Cr, int E, int T);
+
+/* ------------------------------------------------------------------------------------------
+ * Fused Adam on the flat parameter buffer (torch.optim.Adam semantics, AVMOE/AVE/main_trans_v3.py:311-323: default betas/eps,
+ * L2 weight decay added to the gradient, bias correction by `step` >= 1).  p, g, m, v: n fp32 each (16-byte aligned).
+ * grad_scale multiplies the gradient first (1/world of the data-parallel average, 1/accum of gradient accumulation);
+ * zero_grad != 0 clears g in the same pass.
+ * ------------------------------------------------------------------------------------------ */
+int avmoe_adam_flat(float* p, float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2, float eps, float weight_decay,
+                    float grad_scale, int64_t step, int zero_grad, avmoe_stream_t stream);
 
 #ifdef __cplusplus
 }

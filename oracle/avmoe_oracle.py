@@ -151,7 +151,7 @@ def route(x, v, sd, noise=None):
     return probs, torch.argmax(probs, dim=-1), logits
 
 
-def expert(x, v, sd, prefix, spec: AdapterSpec, multimodal: bool, training: bool, new_buffers=None):
+def expert(x, v, sd, prefix, spec: AdapterSpec, multimodal: bool, training: bool, new_buffers=None, mha_dropout_mask=None):
     """One ExpertAdapter on token-major tensors -> [BT,N,C]."""
     p = prefix
     if multimodal:
@@ -160,7 +160,7 @@ def expert(x, v, sd, prefix, spec: AdapterSpec, multimodal: bool, training: bool
         att = torch.softmax(x @ x.transpose(1, 2), dim=-1)                    # [BT,N,N] rows i, cols j
         x = x + sd[p + "gate_av"] * (att.transpose(1, 2) @ x)                 # out_j = sum_i att[i,j] x_i
     elif spec.self_attn == "mha":     # replaces x (no residual)
-        x = _mha_over_batch_axis(x, sd, p + "self_attention")
+        x = _mha_over_batch_axis(x, sd, p + "self_attention", mha_dropout_mask)
     elif spec.self_attn == "latent":
         x = x + sd[p + "gate_self"] * _latent_attention(x, x, sd[p + "my_tokens"])
     if spec.ln_before:
@@ -189,8 +189,11 @@ def load_balancing_loss(probs):
 
 
 def moe_adapter_forward(x, o, sd: Dict[str, torch.Tensor], spec: AdapterSpec, training: bool = True,
-                        noise: Optional[torch.Tensor] = None, new_buffers: Optional[dict] = None):
+                        noise: Optional[torch.Tensor] = None, new_buffers: Optional[dict] = None, mha_dropout_masks=None):
     """Full MoEAdapter forward on token-major inputs.
+
+    mha_dropout_masks (AVS-v1 only): one tensor per single-modal expert, [N*heads, BT, BT], already scaled by 1/(1-p) -- the
+    attention-probability dropout of nn.MultiheadAttention(dropout=0.2) (PVT_AVSModel_v2.py:139-142) with an injected mask.
 
     x [BT,N,C], o [BT,Nx,Cx] -> dict(out [BT,N,C], probs [BT,E], idx [BT] int64, lb_loss, v)."""
     v = resample(o, sd)
@@ -201,7 +204,8 @@ def moe_adapter_forward(x, o, sd: Dict[str, torch.Tensor], spec: AdapterSpec, tr
         out = out + probs[:, e, None, None] * expert(x, v, sd, f"multimodal_experts.{m}.", spec, True, training, new_buffers)
         e += 1
     for s in range(spec.Ms):
-        out = out + probs[:, e, None, None] * expert(x, v, sd, f"singlemodal_experts.{s}.", spec, False, training, new_buffers)
+        out = out + probs[:, e, None, None] * expert(x, v, sd, f"singlemodal_experts.{s}.", spec, False, training, new_buffers,
+                                                     None if mha_dropout_masks is None else mha_dropout_masks[s])
         e += 1
     lb = load_balancing_loss(probs.unsqueeze(1)) if spec.lb_loss else None
     return {"out": out, "probs": probs, "idx": idx, "logits": logits, "lb_loss": lb, "v": v}

@@ -274,7 +274,7 @@ def selfattn_nxn_bwd(x, lse_rows, daux, dx):
 
 
 # ------------------------------------------------------------------------------------------------ AVS v1 MHA over the BT axis
-def mha_fwd(x, mp):
+def mha_fwd(x, mp, keep=None, keep_scale=1.0):
     w_in, b_in, w_out, b_out = mp
     L, B, C = x.shape
     hd = C // MHA_HEADS
@@ -286,14 +286,15 @@ def mha_fwd(x, mp):
         return t.reshape(L, B * MHA_HEADS, hd).transpose(0, 1)
     qh, kh, vh = heads(q), heads(k), heads(v)
     att = torch.softmax((qh / math.sqrt(hd)) @ kh.transpose(1, 2), dim=-1)
-    ctxv = (att @ vh).transpose(0, 1).reshape(L, B, C)
+    mask = None if keep is None else keep.reshape(B * MHA_HEADS, L, L).float() * keep_scale
+    ctxv = ((att if mask is None else att * mask) @ vh).transpose(0, 1).reshape(L, B, C)
     out = ctxv @ w_out.t() + b_out
-    return out.to(x.dtype), (qkv, att, ctxv)
+    return out.to(x.dtype), (qkv, att, ctxv, mask)
 
 
 def mha_bwd(x, mp, saved, daux, dx):
     w_in, b_in, w_out, b_out = mp
-    qkv, att, ctxv = saved
+    qkv, att, ctxv, mask = saved
     L, B, C = x.shape
     hd = C // MHA_HEADS
     g = daux.float()
@@ -306,7 +307,9 @@ def mha_bwd(x, mp, saved, daux, dx):
     q, k, v = qkv.split(C, dim=-1)
     qh, kh, vh, dch = heads(q), heads(k), heads(v), heads(dctx)
     datt = dch @ vh.transpose(1, 2)
-    dvh = att.transpose(1, 2) @ dch
+    dvh = (att if mask is None else att * mask).transpose(1, 2) @ dch
+    if mask is not None:
+        datt = datt * mask
     ds = att * (datt - (att * datt).sum(-1, keepdim=True))
     dqh = (ds @ kh) / math.sqrt(hd)
     dkh = ds.transpose(1, 2) @ (qh / math.sqrt(hd))

@@ -122,6 +122,13 @@ def test_cuda_matches_oracle_at_backbone_shapes(variant, stage, modality, dtype)
     out, idx, dx, do, dparams, _ = _cuda_run(spec, sd, x, o, gout, dtype)
     tol = TOL_F32 if dtype == torch.float32 else TOL_BF16
     gtol = GTOL_F32 if dtype == torch.float32 else GTOL_BF16
+    if dtype == torch.bfloat16:
+        # the gradient bound of the bf16 streams is tied to an INDEPENDENT bf16 execution of the same math: the oracle's plain
+        # torch ops on this GPU under torch.autocast(bfloat16) (what AMP gives the reference), measured against the same fp32
+        # oracle.  Where that comparator itself exceeds the fixed bound (deep / wide shapes), 1.5x its error is the bound.
+        from tools.parity_report import _eager_autocast
+        _, edx, edo, _ = _eager_autocast(spec, sd, x, o, gout)
+        gtol = max(gtol, 1.5 * max(util.fro_err(edx, dx_ref), util.fro_err(edo, do_ref)))
     _check(spec, res, dx_ref, do_ref, dp_ref, out, idx, dx, do, dparams, tol, gtol)
 
 

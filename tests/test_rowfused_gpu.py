@@ -174,7 +174,7 @@ def test_rf_back_bwd(geom, ln, gate, bn):
     torch.cuda.synchronize()
     tol = 1.5e-2
     assert _fro(act[:, :, :Cr].float(), act_ref[:, :, :Cr].float()) < tol
-    assert act[:, :, Cr:].abs().max().item() == 0
+    assert act[:, :, Cr:].abs().sum().item() == 0
     assert _fro(yd[:, :, :C].float(), yd_ref[:, :, :C].float()) < tol
     assert _fro(yd[:, :, C:].float(), yd_ref[:, :, C:].float()) < 2 * tol
     assert _fro(dprobs, dprobs_ref) < tol
@@ -184,8 +184,8 @@ def test_rf_back_bwd(geom, ln, gate, bn):
     for gr, gr_ref in zip(egr, egr_ref):
         if ln:
             assert _fro(gr.ln2_w, gr_ref.ln2_w) < tol and _fro(gr.ln2_b, gr_ref.ln2_b) < tol
-        if gate:
-            assert abs(gr.gate.item() - gr_ref.gate.item()) < tol * max(1.0, abs(gr_ref.gate.item()))
+        if gate:     # a sum of rows*C signed terms: the rounding noise of the bf16 operands scales with sqrt(rows*C), not with the sum
+            assert abs(gr.gate.item() - gr_ref.gate.item()) < tol * max(1.0, abs(gr_ref.gate.item())) + 4e-3 * (BT * N * C) ** 0.5
 
 
 # ------------------------------------------------------------------------------------------------ front pass
@@ -296,10 +296,10 @@ def test_rf_front_bwd(geom, ln):
         if pk.pre_kind != PRE_NONE:
             assert _fro(egr[e].aux.float(), egr_ref[e].aux.float()) < tol, e
         if pk.gate_pre is not None:
-            assert abs(egr[e].gate_pre.item() - egr_ref[e].gate_pre.item()) < tol * max(1.0, abs(egr_ref[e].gate_pre.item())), e
+            assert abs(egr[e].gate_pre.item() - egr_ref[e].gate_pre.item()) < tol * max(1.0, abs(egr_ref[e].gate_pre.item())) + 4e-3 * (BT * N * C) ** 0.5, e
         if ln:
             assert _fro(egr[e].ln1_w, egr_ref[e].ln1_w) < tol and _fro(egr[e].ln1_b, egr_ref[e].ln1_b) < tol, e
         if pk.pre_kind == PRE_LATENT:
             assert _fro(lat[e][0][:, :, :T].float(), lat_ref[e][0][:, :, :T].float()) < tol, e
             assert _fro(lat[e][1][:, :, :T].float(), lat_ref[e][1][:, :, :T].float()) < 2 * tol, e
-            assert lat[e][0][:, :, T:].abs().max().item() == 0 if lat[e][0].shape[2] > T else True
+            assert lat[e][0][:, :, T:].abs().sum().item() == 0

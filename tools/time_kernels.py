@@ -18,9 +18,9 @@ def main():
     # wrap every C-ABI call with events
     times = collections.defaultdict(list)
     orig_call, orig_check = ops._lib_call, None
-    def timed_call(name, *args):
+    def timed_call(name, *args, **kw):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record(); orig_call(name, *args); e1.record()
+        e0.record(); orig_call(name, *args, **kw); e1.record()
         times[name].append((e0, e1))
     ops._lib_call = timed_call
     ops.GEMM_PROFILE = []
