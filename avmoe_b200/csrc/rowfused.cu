@@ -12,10 +12,13 @@
 #include "mma_tile.cuh"
 #include "row_pass.cuh"
 
+static bool rf_capable(int C, int Cr, int E, int T);
+
 namespace avmoe {
 namespace rf {
 
 static constexpr int kMaxC = 1536;
+static constexpr int kFastC = 192;
 
 // ------------------------------------------------------------------------------------------------ packed B operands
 __global__ void rf_pack_b_kernel(const float* __restrict__ src, long long bstride, long long stride_n, long long stride_k, int nb, int Nn,
@@ -75,6 +78,10 @@ __device__ __forceinline__ void tile_load_async(unsigned char* tile, int pitch, 
   for (int i = lane; i < nrow * chunks; i += 32) {
     const int r = (int)magic_div(i, mg), ch = i - r * chunks;
     cp_async16(tile + r * pitch + ch * 16, gsrc + (r0 + r) * C + ch * 8);
+  }
+  for (int i = nrow * chunks + lane; i < 16 * chunks; i += 32) {     // rows beyond the tensor: zeros, so no pass needs to mask them
+    const int r = (int)magic_div(i, mg), ch = i - r * chunks;
+    *reinterpret_cast<uint4*>(tile + r * pitch + ch * 16) = make_uint4(0u, 0u, 0u, 0u);
   }
 }
 // coalesced store of a staged tile; ADD: fp32 add of a residual row read from `gres` first
@@ -367,9 +374,7 @@ __global__ void __launch_bounds__(256) rf_back_kernel(const avmoe_rf_back_args p
           for (int h = 0; h < 2; ++h) {
             const int c = (pr << 4) + h * 8 + 2 * t;
             const ColParams cp = load_col_params(tab, e, C, c);
-            float2 dA = unpack_bf16x2(tile_at(t_dout, pitch, g, c)), dB = unpack_bf16x2(tile_at(t_dout, pitch, g + 8, c));
-            if (!vA) dA = make_float2(0.f, 0.f);     // rows beyond the tensor were not staged: their tile rows hold stale data
-            if (!vB) dB = make_float2(0.f, 0.f);
+            const float2 dA = unpack_bf16x2(tile_at(t_dout, pitch, g, c)), dB = unpack_bf16x2(tile_at(t_dout, pitch, g + 8, c));
             const float xh0 = (yh[h][0] * cp.bw.x + cp.bb.x - mean0) * rstd0, xh1 = (yh[h][1] * cp.bw.y + cp.bb.y - mean0) * rstd0;
             const float xh2 = (yh[h][2] * cp.bw.x + cp.bb.x - mean1) * rstd1, xh3 = (yh[h][3] * cp.bw.y + cp.bb.y - mean1) * rstd1;
             dotA += dA.x * (xh0 * cp.lw.x + cp.lb.x) + dA.y * (xh1 * cp.lw.y + cp.lb.y);
@@ -416,9 +421,7 @@ __global__ void __launch_bounds__(256) rf_back_kernel(const avmoe_rf_back_args p
             const ColParams cp = load_col_params(tab, e, C, c);
             tile_at(t_yh, pitch, g, c) = pack_bf16x2(yh[h][0], yh[h][1]);
             tile_at(t_yh, pitch, g + 8, c) = pack_bf16x2(yh[h][2], yh[h][3]);
-            float2 dA = unpack_bf16x2(tile_at(t_dout, pitch, g, c)), dB = unpack_bf16x2(tile_at(t_dout, pitch, g + 8, c));
-            if (!vA) dA = make_float2(0.f, 0.f);     // rows beyond the tensor were not staged: their tile rows hold stale data
-            if (!vB) dB = make_float2(0.f, 0.f);
+            const float2 dA = unpack_bf16x2(tile_at(t_dout, pitch, g, c)), dB = unpack_bf16x2(tile_at(t_dout, pitch, g + 8, c));
             float dy[4] = {scA[e] * dA.x, scA[e] * dA.y, scB[e] * dB.x, scB[e] * dB.y};
             if (has_ln) {
               const float xh0 = (yh[h][0] * cp.bw.x + cp.bb.x - mean0) * rstd0, xh1 = (yh[h][1] * cp.bw.y + cp.bb.y - mean0) * rstd0;
@@ -491,7 +494,7 @@ __global__ void __launch_bounds__(256) rf_back_kernel(const avmoe_rf_back_args p
 
 static int back_check(const avmoe_rf_back_args* a, bool bwd, const char* who) {
   AVMOE_CHECK_ARG(a != nullptr, "%s: null args", who);
-  AVMOE_CHECK_ARG(avmoe_rf_supported(a->C, a->Cr, a->E, 0), "%s: geometry not supported by the row-fused passes (C=%d Cr=%d E=%d)", who, a->C,
+  AVMOE_CHECK_ARG(rf_capable(a->C, a->Cr, a->E, 0), "%s: geometry not supported by the row-fused passes (C=%d Cr=%d E=%d)", who, a->C,
                   a->Cr, a->E);
   AVMOE_CHECK_ARG(a->z && a->wu_pack && a->ybi && a->probs, "%s: null tensor", who);
   if (bwd) AVMOE_CHECK_ARG(a->dout && a->yd && a->act && a->dprobs, "%s: null backward tensor", who);
@@ -1042,7 +1045,7 @@ __global__ void __launch_bounds__(256) rf_front_bwd_kernel(const avmoe_rf_front_
 
 static int front_check(const avmoe_rf_front_args* a, bool bwd, const char* who) {
   AVMOE_CHECK_ARG(a != nullptr, "%s: null args", who);
-  AVMOE_CHECK_ARG(avmoe_rf_supported(a->C, a->Cr, a->E, a->T) && a->N % 16 == 0, "%s: geometry not supported (C=%d Cr=%d E=%d T=%d N=%d)", who,
+  AVMOE_CHECK_ARG(rf_capable(a->C, a->Cr, a->E, a->T) && a->N % 16 == 0, "%s: geometry not supported (C=%d Cr=%d E=%d T=%d N=%d)", who,
                   a->C, a->Cr, a->E, a->T, a->N);
   AVMOE_CHECK_ARG(a->x && a->c2, "%s: null tensor", who);
   for (int e = 0; e < a->E; ++e) {
@@ -1118,10 +1121,17 @@ static int dispatch_front(const avmoe_rf_front_args* a, bool bwd, cudaStream_t s
 }  // namespace rf
 }  // namespace avmoe
 
+static bool rf_capable(int C, int Cr, int E, int T) {     // what the kernels can run (unit-tested up to C = 768)
+  const int crk = (Cr + 15) / 16;
+  return C % 16 == 0 && C <= avmoe::rf::kMaxC && Cr % 2 == 0 && (crk == 1 || crk == 2 || crk == 3 || crk == 6) && E >= 2 && E <= 4 && T <= 96;
+}
+
 extern "C" int avmoe_rf_supported(int C, int Cr, int E, int T) {
   const int crk = (Cr + 15) / 16;
   const bool crk_ok = crk == 1 || crk == 2 || crk == 3 || crk == 6;
-  return (C % 16 == 0 && C <= avmoe::rf::kMaxC && Cr % 2 == 0 && crk_ok && E >= 2 && E <= 4 && T <= 96) ? 1 : 0;
+  // C <= kFastC: a warp's 16-row tiles must be small enough that >= 8 warps (fwd: 16) stay resident per SM; the wide late stages
+  // (C >= 384, few rows) are latency-bound with one or two warps per SM (profiles/r02_rowfused.md) and keep the GEMM-based path
+  return (C % 16 == 0 && C <= avmoe::rf::kFastC && Cr % 2 == 0 && crk_ok && E >= 2 && E <= 4 && T <= 96) ? 1 : 0;
 }
 
 extern "C" int64_t avmoe_rf_pack_b_bytes(int nb, int Nn, int K, int hi_lo) {

@@ -67,7 +67,8 @@ class FlatParameters:
 
     def range_of(self, params: Sequence[torch.nn.Parameter]) -> Tuple[int, int]:
         """[start, end) of a run of parameters that are consecutive in the flat order"""
-        idx = sorted(self.params.index(p) if not isinstance(p, int) else p for p in params)
+        pos = {id(p): i for i, p in enumerate(self.params)}
+        idx = sorted(p if isinstance(p, int) else pos[id(p)] for p in params)
         assert idx == list(range(idx[0], idx[-1] + 1)), "a learning-rate group must be a consecutive run of parameters"
         end = self.offsets[idx[-1]] + (self.params[idx[-1]].numel() + 3) // 4 * 4
         return self.offsets[idx[0]], end
