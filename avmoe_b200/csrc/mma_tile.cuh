@@ -52,7 +52,7 @@ __device__ __forceinline__ void ldmatrix_a(uint32_t (&a)[4], const unsigned char
 }
 
 __device__ __forceinline__ uint4 ldg_b(const uint4* packed, int pair, int ks, int s, int lane) {
-  return __ldg(packed + ((size_t)pair * ks + s) * 32 + lane);
+  return __ldg(packed + (((pair * ks + s) << 5) + lane));      // 32-bit index: a packed operand is far below 2^31 words
 }
 
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {

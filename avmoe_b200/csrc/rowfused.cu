@@ -110,6 +110,14 @@ __device__ __forceinline__ void tile_store(const unsigned char* tile, int pitch,
 __device__ __forceinline__ uint32_t& tile_at(unsigned char* tile, int pitch, int row, int col) {
   return *reinterpret_cast<uint32_t*>(tile + row * pitch + col * 2);
 }
+// the two tile rows a lane touches in accumulator layout (g and g+8) as 32-bit words: element pair (row, columns c, c+1) = A[c >> 1]
+struct TileRows {
+  uint32_t* A;
+  uint32_t* B;
+  __device__ __forceinline__ TileRows(const unsigned char* tile, int pitch, int g)
+      : A(reinterpret_cast<uint32_t*>(const_cast<unsigned char*>(tile) + g * pitch)),
+        B(reinterpret_cast<uint32_t*>(const_cast<unsigned char*>(tile) + (g + 8) * pitch)) {}
+};
 
 // ------------------------------------------------------------------------------------------------ back pass (forward and backward)
 // k-steps of the up projection that can be non-zero for the n-tile pair starting at column c0 (block-diagonal weights)
@@ -165,17 +173,16 @@ __global__ void __launch_bounds__(256) rf_back_kernel(const avmoe_rf_back_args p
   const float invC = 1.f / C;
   const GroupGeom gg(C, Cr, p.G);
   // shared memory: [parameter table E x C/2 x 12 fp32] [BWD: per-warp column accumulators E x 4 x C fp32, E gate sums]
-  //                [per warp: 1 (fwd) or 3 (bwd) tiles]
+  //                [per warp: one tile -- the out staging tile (fwd) or the dout tile (bwd)]
   float* tab = reinterpret_cast<float*>(smem);
   const size_t tab_floats = (size_t)E * (C >> 1) * 12;
   float* colacc_all = tab + tab_floats;
   const size_t acc_floats = BWD ? (size_t)nwarps * E * 4 * C + 32 : 0;
   float* gateacc = colacc_all + (BWD ? (size_t)nwarps * E * 4 * C : 0);
   float* wacc = colacc_all + (size_t)warp * E * 4 * C;      // this warp's private accumulators: plain read-modify-write
-  unsigned char* wbase = smem + (tab_floats + acc_floats) * sizeof(float) + (size_t)warp * (BWD ? 3 : 1) * 16 * pitch;
-  unsigned char* t_stage = wbase;                         // fwd: out tile; bwd: dy2 tile
-  unsigned char* t_dout = wbase + (BWD ? 16 * pitch : 0);
-  unsigned char* t_yh = wbase + (BWD ? 32 * pitch : 0);
+  unsigned char* wbase = smem + (tab_floats + acc_floats) * sizeof(float) + (size_t)warp * 16 * pitch;
+  unsigned char* t_stage = wbase;                         // fwd: out tile
+  unsigned char* t_dout = wbase;                          // bwd: dout tile
   back_param_table(tab, p, E, C);
   if (BWD) for (int i = threadIdx.x; i < (int)acc_floats; i += blockDim.x) colacc_all[i] = 0.f;
   __syncthreads();
@@ -279,25 +286,40 @@ __global__ void __launch_bounds__(256) rf_back_kernel(const avmoe_rf_back_args p
       const bool has_ln = p.ex[e].ln2_w != nullptr;
       const bool has_bn = p.bn2_w[e] != nullptr;
       float yreg[NPR > 0 ? NPR : 1][2][4];
-      // ---- sweep 1: yhat (kept in registers when NPR > 0), ln_post row statistics of y2 = bn2 affine(yhat)
+      // ---- sweep 1: yhat (kept in registers when NPR > 0), ln_post row statistics of y2 = bn2 affine(yhat); in the backward also
+      //      the row sums of dout against y2 from which <dout, o_e> and the ln_post backward row means follow without another sweep:
+      //      S1 = sum d*lw*y2, S2 = sum d*lw, S3 = sum d*lb   ->   <d, o> = rstd*(S1 - mean*S2) + S3,
+      //      mean_c(d o_hat) = sc*S2/C,  mean_c(d o_hat * xhat) = sc*rstd*(S1 - mean*S2)/C
       float mean0 = 0.f, mean1 = 0.f, rstd0 = 1.f, rstd1 = 1.f;
+      float S1A = 0.f, S2A = 0.f, S3A = 0.f, S1B = 0.f, S2B = 0.f, S3B = 0.f;
+      const uint32_t* dpA = reinterpret_cast<const uint32_t*>(t_dout + g * pitch) + t;          // dout at accumulator positions
+      const uint32_t* dpB = reinterpret_cast<const uint32_t*>(t_dout + (g + 8) * pitch) + t;
+      const float* tabe = tab + ((size_t)e * (C >> 1) + t) * 12;                               // + (8*pr + 4*h) * 12
       {
         float s1A = 0.f, s2A = 0.f, s1B = 0.f, s2B = 0.f;
         auto body = [&](int pr, float (&acc)[2][4]) {
           up_pair(e, pr, acc);
 #pragma unroll
           for (int h = 0; h < 2; ++h) {
-            const ColParams cp = load_col_params(tab, e, C, (pr << 4) + h * 8 + 2 * t);
-            acc[h][0] += cp.ybi.x; acc[h][1] += cp.ybi.y; acc[h][2] += cp.ybi.x; acc[h][3] += cp.ybi.y;
-            const float y0 = acc[h][0] * cp.bw.x + cp.bb.x, y1 = acc[h][1] * cp.bw.y + cp.bb.y;
-            const float y2 = acc[h][2] * cp.bw.x + cp.bb.x, y3 = acc[h][3] * cp.bw.y + cp.bb.y;
-            s1A += y0 + y1; s2A += y0 * y0 + y1 * y1; s1B += y2 + y3; s2B += y2 * y2 + y3 * y3;
+            const float4* q = reinterpret_cast<const float4*>(tabe + ((pr << 3) + (h << 2)) * 12);
+            const float4 qa = q[0], qb = q[1];       // ybi.xy bw.xy | bb.xy lw.xy
+            acc[h][0] += qa.x; acc[h][1] += qa.y; acc[h][2] += qa.x; acc[h][3] += qa.y;
+            const float y0 = fmaf(acc[h][0], qa.z, qb.x), y1 = fmaf(acc[h][1], qa.w, qb.y);
+            const float y2 = fmaf(acc[h][2], qa.z, qb.x), y3 = fmaf(acc[h][3], qa.w, qb.y);
+            s1A += y0 + y1; s2A = fmaf(y0, y0, fmaf(y1, y1, s2A)); s1B += y2 + y3; s2B = fmaf(y2, y2, fmaf(y3, y3, s2B));
+            if (BWD) {
+              const float2 lb = *reinterpret_cast<const float2*>(q + 2);
+              const float2 dA = unpack_bf16x2(dpA[(pr << 3) + (h << 2)]), dB = unpack_bf16x2(dpB[(pr << 3) + (h << 2)]);
+              const float w0 = dA.x * qb.z, w1 = dA.y * qb.w, w2 = dB.x * qb.z, w3 = dB.y * qb.w;
+              S1A = fmaf(w0, y0, fmaf(w1, y1, S1A)); S2A += w0 + w1; S3A = fmaf(dA.x, lb.x, fmaf(dA.y, lb.y, S3A));
+              S1B = fmaf(w2, y2, fmaf(w3, y3, S1B)); S2B += w2 + w3; S3B = fmaf(dB.x, lb.x, fmaf(dB.y, lb.y, S3B));
+            }
           }
         };
         if (NPR > 0) {
 #pragma unroll
           for (int pr = 0; pr < (NPR > 0 ? NPR : 1); ++pr) body(pr, yreg[pr]);
-        } else if (has_ln) {
+        } else if (has_ln || BWD) {
           for (int pr = 0; pr < NP; ++pr) { float acc[2][4]; body(pr, acc); }
         }
         if (has_ln) {
@@ -366,30 +388,62 @@ __global__ void __launch_bounds__(256) rf_back_kernel(const avmoe_rf_back_args p
         }
       } else {
         float* acc_e = wacc + (size_t)e * 4 * C;       // [4][C]: d ln2_w, d ln2_b, sum dy2, sum dy2*yhat
-        // ---- sweep 2: <dout, o_e> per row (d probs, d gate), ln_post backward row sums, d ln_post weight/bias column sums
-        float dotA = 0.f, dotB = 0.f, maA = 0.f, maB = 0.f, mbA = 0.f, mbB = 0.f;
+        S1A = quad_sum(S1A); S2A = quad_sum(S2A); S3A = quad_sum(S3A); S1B = quad_sum(S1B); S2B = quad_sum(S2B); S3B = quad_sum(S3B);
+        const float aA = S1A - mean0 * S2A, aB = S1B - mean1 * S2B;
+        float dotA = rstd0 * aA + S3A, dotB = rstd1 * aB + S3B;                                 // <dout, o_e> per row
+        const float maA = has_ln ? scA[e] * S2A * invC : 0.f, maB = has_ln ? scB[e] * S2B * invC : 0.f;
+        const float mbA = has_ln ? scA[e] * rstd0 * aA * invC : 0.f, mbB = has_ln ? scB[e] * rstd1 * aB * invC : 0.f;
+        const float nmr0 = -mean0 * rstd0, nmr1 = -mean1 * rstd1;
+        // d probs[b,e] += gate * <dout, o_e>; d gate += probs * <dout, o_e>
+        if (!vA) dotA = 0.f;
+        if (!vB) dotB = 0.f;
+        if (t == 0 && p.ex[e].gate) gate_sum[e] += __ldg(p.probs + bA * E + e) * dotA + __ldg(p.probs + bB * E + e) * dotB;
+        const long long b_first = r0 / N, b_last = min(r0 + 15, rows - 1) / N;
+        if (b_first == b_last) {          // the usual case: the tile lies inside one sample -> one atomic per tile
+          float sdot = t == 0 ? dotA + dotB : 0.f;
+          sdot += __shfl_xor_sync(0xffffffffu, sdot, 4); sdot += __shfl_xor_sync(0xffffffffu, sdot, 8); sdot += __shfl_xor_sync(0xffffffffu, sdot, 16);
+          if (lane == 0) atomicAdd(p.dprobs + b_first * E + e, gate[e] * sdot);
+        } else if (t == 0) {
+          if (vA) atomicAdd(p.dprobs + bA * E + e, gate[e] * dotA);
+          if (vB) atomicAdd(p.dprobs + bB * E + e, gate[e] * dotB);
+        }
+        // ---- sweep 2: dy2 = gradient at the bn2 output, yhat out, column sums (d ln_post weight / bias, bn2 batch reductions)
+        const int ri = rs_index(lane);
+        float* accp = acc_e + ((ri >> 1) & 1) * C + (ri >> 2) * 8 + 2 * t + (ri & 1);            // + 16*pr (+ 2*C for the bn2 sums)
+        // yhat | dy2 go straight from registers to yd [rows, 2C] (rows g / g+8; a quad writes 16 contiguous bytes per row)
+        __nv_bfloat16* yde = static_cast<__nv_bfloat16*>(p.yd) + (size_t)e * rows * 2 * C;
+        uint32_t* yhA = reinterpret_cast<uint32_t*>(yde + rowA * 2 * C) + t;
+        uint32_t* yhB = reinterpret_cast<uint32_t*>(yde + rowB * 2 * C) + t;
+        uint32_t* dyA = yhA + (C >> 1);
+        uint32_t* dyB = yhB + (C >> 1);
         auto body2 = [&](int pr, const float (&yh)[2][4]) {
-          float cs[8];
+          float cl[8], cb[8];
 #pragma unroll
           for (int h = 0; h < 2; ++h) {
-            const int c = (pr << 4) + h * 8 + 2 * t;
-            const ColParams cp = load_col_params(tab, e, C, c);
-            const float2 dA = unpack_bf16x2(tile_at(t_dout, pitch, g, c)), dB = unpack_bf16x2(tile_at(t_dout, pitch, g + 8, c));
-            const float xh0 = (yh[h][0] * cp.bw.x + cp.bb.x - mean0) * rstd0, xh1 = (yh[h][1] * cp.bw.y + cp.bb.y - mean0) * rstd0;
-            const float xh2 = (yh[h][2] * cp.bw.x + cp.bb.x - mean1) * rstd1, xh3 = (yh[h][3] * cp.bw.y + cp.bb.y - mean1) * rstd1;
-            dotA += dA.x * (xh0 * cp.lw.x + cp.lb.x) + dA.y * (xh1 * cp.lw.y + cp.lb.y);
-            dotB += dB.x * (xh2 * cp.lw.x + cp.lb.x) + dB.y * (xh3 * cp.lw.y + cp.lb.y);
-            const float t0 = scA[e] * dA.x, t1 = scA[e] * dA.y, t2 = scB[e] * dB.x, t3 = scB[e] * dB.y;   // d o_e
-            maA += t0 * cp.lw.x + t1 * cp.lw.y; maB += t2 * cp.lw.x + t3 * cp.lw.y;
-            mbA += t0 * cp.lw.x * xh0 + t1 * cp.lw.y * xh1; mbB += t2 * cp.lw.x * xh2 + t3 * cp.lw.y * xh3;
-            cs[4 * h + 0] = t0 * xh0 + t2 * xh2; cs[4 * h + 1] = t1 * xh1 + t3 * xh3;    // d ln2_w columns c, c+1
-            cs[4 * h + 2] = t0 + t2; cs[4 * h + 3] = t1 + t3;                            // d ln2_b
+            const int o4 = (pr << 3) + (h << 2);
+            const float4* q = reinterpret_cast<const float4*>(tabe + o4 * 12);
+            const float4 qa = q[0], qb = q[1];
+            const float2 dA = unpack_bf16x2(dpA[o4]), dB = unpack_bf16x2(dpB[o4]);
+            if (vA) yhA[o4] = pack_bf16x2(yh[h][0], yh[h][1]);
+            if (vB) yhB[o4] = pack_bf16x2(yh[h][2], yh[h][3]);
+            const float t0 = scA[e] * dA.x, t1 = scA[e] * dA.y, t2 = scB[e] * dB.x, t3 = scB[e] * dB.y;      // d o_e
+            float dy0 = t0, dy1 = t1, dy2 = t2, dy3 = t3;
+            float x0 = 0.f, x1 = 0.f, x2 = 0.f, x3 = 0.f;
+            if (has_ln) {
+              x0 = fmaf(fmaf(yh[h][0], qa.z, qb.x), rstd0, nmr0); x1 = fmaf(fmaf(yh[h][1], qa.w, qb.y), rstd0, nmr0);
+              x2 = fmaf(fmaf(yh[h][2], qa.z, qb.x), rstd1, nmr1); x3 = fmaf(fmaf(yh[h][3], qa.w, qb.y), rstd1, nmr1);
+              dy0 = rstd0 * fmaf(-mbA, x0, fmaf(t0, qb.z, -maA)); dy1 = rstd0 * fmaf(-mbA, x1, fmaf(t1, qb.w, -maA));
+              dy2 = rstd1 * fmaf(-mbB, x2, fmaf(t2, qb.z, -maB)); dy3 = rstd1 * fmaf(-mbB, x3, fmaf(t3, qb.w, -maB));
+            }
+            if (vA) dyA[o4] = pack_bf16x2(dy0, dy1);
+            if (vB) dyB[o4] = pack_bf16x2(dy2, dy3);
+            cl[4 * h + 0] = fmaf(t0, x0, t2 * x2); cl[4 * h + 1] = fmaf(t1, x1, t3 * x3);             // d ln2_w columns c, c+1
+            cl[4 * h + 2] = t0 + t2; cl[4 * h + 3] = t1 + t3;                                        // d ln2_b
+            cb[4 * h + 0] = dy0 + dy2; cb[4 * h + 1] = dy1 + dy3;                                    // sum dy2
+            cb[4 * h + 2] = fmaf(dy0, yh[h][0], dy2 * yh[h][2]); cb[4 * h + 3] = fmaf(dy1, yh[h][1], dy3 * yh[h][3]);   // sum dy2*yhat
           }
-          if (has_ln) {     // cs index i -> (h = i>>2, quantity (i>>1)&1, column offset i&1)
-            const float s = reduce_scatter8(cs, lane);
-            const int i = rs_index(lane);
-            acc_e[((i >> 1) & 1) * C + (pr << 4) + (i >> 2) * 8 + 2 * t + (i & 1)] += s;
-          }
+          if (has_ln) accp[pr << 4] += reduce_scatter8(cl, lane);      // index i -> (h = i>>2, quantity (i>>1)&1, column offset i&1)
+          if (has_bn) accp[2 * C + (pr << 4)] += reduce_scatter8(cb, lane);
         };
         if (NPR > 0) {
 #pragma unroll
@@ -397,62 +451,6 @@ __global__ void __launch_bounds__(256) rf_back_kernel(const avmoe_rf_back_args p
         } else {
           for (int pr = 0; pr < NP; ++pr) { float acc[2][4]; yhat_pair(pr, acc); body2(pr, acc); }
         }
-        dotA = quad_sum(dotA); dotB = quad_sum(dotB);
-        maA = quad_sum(maA) * invC; maB = quad_sum(maB) * invC; mbA = quad_sum(mbA) * invC; mbB = quad_sum(mbB) * invC;
-        // d probs[b,e] += gate * <dout, o_e>; d gate += probs * <dout, o_e>
-        if (!vA) dotA = 0.f;
-        if (!vB) dotB = 0.f;
-        if (t == 0 && p.ex[e].gate) gate_sum[e] += __ldg(p.probs + bA * E + e) * dotA + __ldg(p.probs + bB * E + e) * dotB;
-        const long long b_first = r0 / N, b_last = min(r0 + 15, rows - 1) / N;
-        if (b_first == b_last) {          // the usual case: the tile lies inside one sample -> one atomic per tile
-          float s = t == 0 ? dotA + dotB : 0.f;
-          s += __shfl_xor_sync(0xffffffffu, s, 4); s += __shfl_xor_sync(0xffffffffu, s, 8); s += __shfl_xor_sync(0xffffffffu, s, 16);
-          if (lane == 0) atomicAdd(p.dprobs + b_first * E + e, gate[e] * s);
-        } else if (t == 0) {
-          if (vA) atomicAdd(p.dprobs + bA * E + e, gate[e] * dotA);
-          if (vB) atomicAdd(p.dprobs + bB * E + e, gate[e] * dotB);
-        }
-        // ---- sweep 3: dy2 = gradient at the bn2 output; yhat; bn2 batch reductions
-        auto body3 = [&](int pr, const float (&yh)[2][4]) {
-          float cs[8];
-#pragma unroll
-          for (int h = 0; h < 2; ++h) {
-            const int c = (pr << 4) + h * 8 + 2 * t;
-            const ColParams cp = load_col_params(tab, e, C, c);
-            tile_at(t_yh, pitch, g, c) = pack_bf16x2(yh[h][0], yh[h][1]);
-            tile_at(t_yh, pitch, g + 8, c) = pack_bf16x2(yh[h][2], yh[h][3]);
-            const float2 dA = unpack_bf16x2(tile_at(t_dout, pitch, g, c)), dB = unpack_bf16x2(tile_at(t_dout, pitch, g + 8, c));
-            float dy[4] = {scA[e] * dA.x, scA[e] * dA.y, scB[e] * dB.x, scB[e] * dB.y};
-            if (has_ln) {
-              const float xh0 = (yh[h][0] * cp.bw.x + cp.bb.x - mean0) * rstd0, xh1 = (yh[h][1] * cp.bw.y + cp.bb.y - mean0) * rstd0;
-              const float xh2 = (yh[h][2] * cp.bw.x + cp.bb.x - mean1) * rstd1, xh3 = (yh[h][3] * cp.bw.y + cp.bb.y - mean1) * rstd1;
-              dy[0] = rstd0 * (dy[0] * cp.lw.x - maA - mbA * xh0);
-              dy[1] = rstd0 * (dy[1] * cp.lw.y - maA - mbA * xh1);
-              dy[2] = rstd1 * (dy[2] * cp.lw.x - maB - mbB * xh2);
-              dy[3] = rstd1 * (dy[3] * cp.lw.y - maB - mbB * xh3);
-            }
-            tile_at(t_stage, pitch, g, c) = pack_bf16x2(dy[0], dy[1]);
-            tile_at(t_stage, pitch, g + 8, c) = pack_bf16x2(dy[2], dy[3]);
-            cs[4 * h + 0] = dy[0] + dy[2]; cs[4 * h + 1] = dy[1] + dy[3];
-            cs[4 * h + 2] = dy[0] * yh[h][0] + dy[2] * yh[h][2]; cs[4 * h + 3] = dy[1] * yh[h][1] + dy[3] * yh[h][3];
-          }
-          if (has_bn) {
-            const float s = reduce_scatter8(cs, lane);
-            const int i = rs_index(lane);
-            acc_e[(2 + ((i >> 1) & 1)) * C + (pr << 4) + (i >> 2) * 8 + 2 * t + (i & 1)] += s;
-          }
-        };
-        if (NPR > 0) {
-#pragma unroll
-          for (int pr = 0; pr < (NPR > 0 ? NPR : 1); ++pr) body3(pr, yreg[pr]);
-        } else {
-          for (int pr = 0; pr < NP; ++pr) { float acc[2][4]; yhat_pair(pr, acc); body3(pr, acc); }
-        }
-        __syncwarp();
-        __nv_bfloat16* yd = static_cast<__nv_bfloat16*>(p.yd) + (size_t)e * rows * 2 * C;
-        tile_store<false>(t_yh, pitch, yd, 2 * C, nullptr, r0, rows, C, lane);
-        tile_store<false>(t_stage, pitch, yd + C, 2 * C, nullptr, r0, rows, C, lane);
-        __syncwarp();
       }
     }
     if (!BWD) {
@@ -508,7 +506,7 @@ static int launch_back(const avmoe_rf_back_args* a, bool bwd, cudaStream_t st) {
   const long long ntiles = (rows + 15) / 16;
   const int pitch = a->C * 2 + 16;
   const size_t tab_bytes = (size_t)E * (a->C / 2) * 12 * sizeof(float);
-  const size_t per_warp = (size_t)(bwd ? 3 : 1) * 16 * pitch + (bwd ? (size_t)E * 4 * a->C * sizeof(float) : 0);
+  const size_t per_warp = (size_t)16 * pitch + (bwd ? (size_t)E * 4 * a->C * sizeof(float) : 0);
   const size_t fixed = tab_bytes + (bwd ? 32 * sizeof(float) : 0);
   int warps = 8;
   while (warps > 1 && fixed + warps * per_warp > 100 * 1024) warps >>= 1;    // two CTAs per SM where possible
@@ -516,8 +514,7 @@ static int launch_back(const avmoe_rf_back_args* a, bool bwd, cudaStream_t st) {
   const size_t smem = fixed + warps * per_warp;
   AVMOE_CHECK_ARG(smem <= 227 * 1024, "rf_back: tile does not fit shared memory");
   // persistent-style grid: a few CTAs per SM, each owning a contiguous range of tiles (one flush of the column sums per CTA)
-  long long ctas = (long long)num_sms() * (smem > 110 * 1024 ? 1 : 2);
-  if (!bwd) ctas *= 2;
+  long long ctas = (long long)num_sms() * (bwd ? 3 : 6);
   long long tpc = (ntiles + ctas - 1) / ctas;
   tpc = (tpc + warps - 1) / warps * warps;
   if (tpc < warps) tpc = warps;
@@ -536,9 +533,7 @@ static int launch_back(const avmoe_rf_back_args* a, bool bwd, cudaStream_t st) {
 template <int E>
 static int dispatch_back_crk(const avmoe_rf_back_args* a, bool bwd, cudaStream_t st) {
   const int crk = (a->Cr + 15) / 16;
-  // the stage-1 shapes of the r = 8 variants (C = 96 / 192) keep the whole up-projection tile in registers
-  if (a->C == 96 && crk == 1) return launch_back<E, 1, 6>(a, bwd, st);
-  if (a->C == 192 && crk == 2) return launch_back<E, 2, 12>(a, bwd, st);
+  // (NPR > 0, the register-resident variant, measured slower than recomputing: 170-190 registers halve the resident warps)
   switch (crk) {
     case 1: return launch_back<E, 1, 0>(a, bwd, st);
     case 2: return launch_back<E, 2, 0>(a, bwd, st);
@@ -671,62 +666,43 @@ __device__ __forceinline__ RowStats finish_stats(float s1A, float s2A, float s1B
   return r;
 }
 
-// builds u of expert `ex` (into t_u unless kind == NONE) and returns its row statistics.  For AUX kinds the aux tile must already
-// be resident in `t_aux`.  LATENT fills L (probabilities stay live for the backward).
-template <int NT>
-__device__ __forceinline__ RowStats build_u(const avmoe_expert& ex, const unsigned char* t_x, unsigned char* t_u, const unsigned char* t_aux,
-                                           int pitch, int C, int T, bool has_ln, const uint4* ts2, const uint4* txr, LatentRegs<NT>& L, int lane) {
-  const int g = lane >> 2, t = lane & 3;
-  const int NP = C >> 4;
-  const float invC = 1.f / C;
-  const int kind = ex.pre_kind;
-  const float gate = (kind == AVMOE_PRE_LATENT || kind == AVMOE_PRE_AUX_ADD) ? __ldg(ex.gate_pre) : 0.f;
-  float s1A = 0.f, s2A = 0.f, s1B = 0.f, s2B = 0.f;
-  if (kind == AVMOE_PRE_LATENT) latent_probs<NT>(L, t_x, pitch, C, T, ts2, lane);
-  for (int pr = 0; pr < NP; ++pr) {
-    float acc[2][4];
-    if (kind == AVMOE_PRE_LATENT) latent_xr_pair<NT>(L, txr, pr, lane, acc);
-#pragma unroll
-    for (int h = 0; h < 2; ++h) {
-      const int c = (pr << 4) + h * 8 + 2 * t;
-      const float2 xA = unpack_bf16x2(tile_at(const_cast<unsigned char*>(t_x), pitch, g, c));
-      const float2 xB = unpack_bf16x2(tile_at(const_cast<unsigned char*>(t_x), pitch, g + 8, c));
-      float u[4] = {xA.x, xA.y, xB.x, xB.y};
-      if (kind == AVMOE_PRE_LATENT) {
-        u[0] += gate * acc[h][0]; u[1] += gate * acc[h][1]; u[2] += gate * acc[h][2]; u[3] += gate * acc[h][3];
-      } else if (kind != AVMOE_PRE_NONE) {
-        const float2 aA = unpack_bf16x2(tile_at(const_cast<unsigned char*>(t_aux), pitch, g, c));
-        const float2 aB = unpack_bf16x2(tile_at(const_cast<unsigned char*>(t_aux), pitch, g + 8, c));
-        if (kind == AVMOE_PRE_AUX_ADD) { u[0] += gate * aA.x; u[1] += gate * aA.y; u[2] += gate * aB.x; u[3] += gate * aB.y; }
-        else { u[0] = aA.x; u[1] = aA.y; u[2] = aB.x; u[3] = aB.y; }
-      }
-      if (kind != AVMOE_PRE_NONE) {
-        tile_at(t_u, pitch, g, c) = pack_bf16x2(u[0], u[1]);
-        tile_at(t_u, pitch, g + 8, c) = pack_bf16x2(u[2], u[3]);
-      }
-      s1A += u[0] + u[1]; s2A += u[0] * u[0] + u[1] * u[1];
-      s1B += u[2] + u[3]; s2B += u[2] * u[2] + u[3] * u[3];
-    }
+// u (the ln_before input of one expert) for the four elements a lane owns in one n-tile: rows g / g+8, columns c, c+1.
+//   NONE u = x    AUX_ADD u = x + gate*aux    AUX_REPLACE u = aux    LATENT u = x + gate*x_res  (xr = the lane's x_res values)
+__device__ __forceinline__ void make_u(int kind, float gate, const TileRows& Rx, const TileRows& Raux, int c, const float (&xr)[4], float (&u)[4]) {
+  const float2 xA = unpack_bf16x2(Rx.A[c >> 1]), xB = unpack_bf16x2(Rx.B[c >> 1]);
+  u[0] = xA.x; u[1] = xA.y; u[2] = xB.x; u[3] = xB.y;
+  if (kind == AVMOE_PRE_LATENT) {
+    u[0] = fmaf(gate, xr[0], u[0]); u[1] = fmaf(gate, xr[1], u[1]); u[2] = fmaf(gate, xr[2], u[2]); u[3] = fmaf(gate, xr[3], u[3]);
+  } else if (kind != AVMOE_PRE_NONE) {
+    const float2 aA = unpack_bf16x2(Raux.A[c >> 1]), aB = unpack_bf16x2(Raux.B[c >> 1]);
+    if (kind == AVMOE_PRE_AUX_ADD) { u[0] = fmaf(gate, aA.x, u[0]); u[1] = fmaf(gate, aA.y, u[1]); u[2] = fmaf(gate, aB.x, u[2]); u[3] = fmaf(gate, aB.y, u[3]); }
+    else { u[0] = aA.x; u[1] = aA.y; u[2] = aB.x; u[3] = aB.y; }
   }
-  __syncwarp();
-  return finish_stats(s1A, s2A, s1B, s2B, invC, has_ln);
 }
 
+// Forward front pass.  Per expert ONE sweep over the n-tile pairs of the channel axis: x_res of the pair (latent experts: A2 tok' on
+// the tensor cores), u, its LayerNorm sums, and -- u of a pair being exactly the A fragment of one k-step (accumulator layout ->
+// operand layout, the usual attention trick) -- the down projection accumulates in the same sweep.  LayerNorm is folded into the
+// operand (z = rstd*(u W'^T - mean*colsum(W')) + W b), so the statistics are only needed in the epilogue; u never touches
+// shared memory.  The per-row (mean, rstd) are saved for the backward.
 template <int CRK, int NT>
-__global__ void __launch_bounds__(256) rf_front_fwd_kernel(const avmoe_rf_front_args p, long long rows, int tiles_per_cta) {
+__global__ void __launch_bounds__(256) rf_front_fwd_kernel(const avmoe_rf_front_args p, long long rows, int tiles_per_cta, int ntile_bufs) {
   extern __shared__ __align__(16) unsigned char smem[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
   const int g = lane >> 2, t = lane & 3;
   const int C = p.C, Cr = p.Cr, E = p.E;
   const int pitch = C * 2 + 16;
-  const int KSc = C >> 4;
-  unsigned char* t_x = smem + (size_t)warp * 2 * 16 * pitch;
-  unsigned char* t_u = t_x + 16 * pitch;
+  const int KSc = C >> 4, NP = C >> 4;
+  const float invC = 1.f / C;
+  const bool has_ln = p.has_ln != 0;
+  unsigned char* t_x = smem + (size_t)warp * ntile_bufs * 16 * pitch;
+  unsigned char* t_aux = t_x + (ntile_bufs > 1 ? 16 * pitch : 0);
+  const TileRows Rx(t_x, pitch, g), Raux(t_aux, pitch, g);
   const long long ntiles = rows >> 4;
   const long long tile0 = (long long)blockIdx.x * tiles_per_cta;
   const long long tile1 = min(ntiles, tile0 + tiles_per_cta);
   const uint4* wd = static_cast<const uint4*>(p.wd_pack);
-  const size_t wd_stride = (size_t)CRK * KSc * 32;
+  const int wd_stride = CRK * KSc * 32;
   const size_t s2_stride = (size_t)NT * KSc * 32, xr_stride = (size_t)KSc * (NT / 2) * 32;
   for (long long tile = tile0 + warp; tile < tile1; tile += nwarps) {
     const long long r0 = tile << 4;
@@ -739,33 +715,53 @@ __global__ void __launch_bounds__(256) rf_front_fwd_kernel(const avmoe_rf_front_
     for (int e = 0; e < E; ++e) {
       const avmoe_expert& ex = p.ex[e];
       const int kind = ex.pre_kind;
-      if (kind == AVMOE_PRE_AUX_ADD || kind == AVMOE_PRE_AUX_REPLACE) {    // aux tile -> t_u (overwritten in place by u)
-        tile_load_async(t_u, pitch, static_cast<const __nv_bfloat16*>(ex.aux), r0, rows, C, lane);
+      if (kind == AVMOE_PRE_AUX_ADD || kind == AVMOE_PRE_AUX_REPLACE) {
+        __syncwarp();
+        tile_load_async(t_aux, pitch, static_cast<const __nv_bfloat16*>(ex.aux), r0, rows, C, lane);
         cp_async_commit();
         cp_async_wait<0>();
         __syncwarp();
       }
+      const float gate = (kind == AVMOE_PRE_LATENT || kind == AVMOE_PRE_AUX_ADD) ? __ldg(ex.gate_pre) : 0.f;
       LatentRegs<NT> L;
-      const uint4* ts2 = kind == AVMOE_PRE_LATENT ? static_cast<const uint4*>(p.tok_s2[e]) + b * s2_stride : nullptr;
-      const uint4* txr = kind == AVMOE_PRE_LATENT ? static_cast<const uint4*>(p.tok_xr[e]) + b * xr_stride : nullptr;
-      const RowStats st = build_u<NT>(ex, t_x, t_u, t_u, pitch, C, p.T, p.has_ln != 0, ts2, txr, L, lane);
-      const unsigned char* t_a = kind == AVMOE_PRE_NONE ? t_x : t_u;
-      // grouped down projection of the ln_before output, LayerNorm folded into the operand:  z = rstd*(u W'^T - mean*colsum(W')) + W b
+      const uint4* ts2 = nullptr;
+      const uint4* txr = nullptr;
+      if (kind == AVMOE_PRE_LATENT) {
+        ts2 = static_cast<const uint4*>(p.tok_s2[e]) + b * s2_stride;
+        txr = static_cast<const uint4*>(p.tok_xr[e]) + b * xr_stride;
+        latent_probs<NT>(L, t_x, pitch, C, p.T, ts2, lane);
+      }
       float zacc[2 * CRK][4];
 #pragma unroll
       for (int j = 0; j < 2 * CRK; ++j)
 #pragma unroll
         for (int i = 0; i < 4; ++i) zacc[j][i] = 0.f;
       const uint4* w = wd + e * wd_stride;
-      for (int s = 0; s < KSc; ++s) {
+      float s1A = 0.f, s2A = 0.f, s1B = 0.f, s2B = 0.f;
+      for (int pr = 0; pr < NP; ++pr) {
+        float xr[2][4];
+        if (kind == AVMOE_PRE_LATENT) latent_xr_pair<NT>(L, txr, pr, lane, xr);
         uint32_t a[4];
-        ldmatrix_a(a, t_a, pitch, s << 4, lane);
 #pragma unroll
-        for (int pr = 0; pr < CRK; ++pr) {
-          const uint4 bb = ldg_b(w, pr, KSc, s, lane);
-          mma16816(zacc[2 * pr], a, bb.x, bb.y);
-          mma16816(zacc[2 * pr + 1], a, bb.z, bb.w);
+        for (int h = 0; h < 2; ++h) {
+          float u[4];
+          make_u(kind, gate, Rx, Raux, (pr << 4) + h * 8 + 2 * t, xr[h], u);
+          s1A += u[0] + u[1]; s2A = fmaf(u[0], u[0], fmaf(u[1], u[1], s2A));
+          s1B += u[2] + u[3]; s2B = fmaf(u[2], u[2], fmaf(u[3], u[3], s2B));
+          a[2 * h] = pack_bf16x2(u[0], u[1]);          // (row g,   k = 8h + 2t ..)
+          a[2 * h + 1] = pack_bf16x2(u[2], u[3]);      // (row g+8, k = 8h + 2t ..)
         }
+#pragma unroll
+        for (int prz = 0; prz < CRK; ++prz) {
+          const uint4 bb = ldg_b(w, prz, KSc, pr, lane);
+          mma16816(zacc[2 * prz], a, bb.x, bb.y);
+          mma16816(zacc[2 * prz + 1], a, bb.z, bb.w);
+        }
+      }
+      const RowStats st = finish_stats(s1A, s2A, s1B, s2B, invC, has_ln);
+      if (has_ln && p.ln1_stats && t == 0) {
+        *reinterpret_cast<float2*>(p.ln1_stats + ((size_t)e * rows + rowA) * 2) = make_float2(st.muA, st.rsA);
+        *reinterpret_cast<float2*>(p.ln1_stats + ((size_t)e * rows + rowB) * 2) = make_float2(st.muB, st.rsB);
       }
 #pragma unroll
       for (int j = 0; j < 2 * CRK; ++j) {
@@ -780,17 +776,21 @@ __global__ void __launch_bounds__(256) rf_front_fwd_kernel(const avmoe_rf_front_
           *reinterpret_cast<float2*>(p.z + (rowB * E + e) * Cr + ch) = zB;
         }
       }
-      __syncwarp();
     }
+    __syncwarp();
   }
 }
 
-// Backward of the front pass.  Per expert: recompute u and its statistics; d xl = dz Wd (tensor-core tile, K = bottleneck);
-// ln_before backward (two sweeps: row sums, then d u); xl is re-emitted for the weight-gradient GEMM; the pre-transform's
-// backward (gate_pre, aux gradient, or -- LATENT -- the softmax_T attention backward: dA2 = dXR tok'^T, dS2, dx += dS2 tok');
+// Backward of the front pass.  Per expert two sweeps over the n-tile pairs, u recomputed in registers each time (x tile + x_res
+// on the tensor cores), d xl = dz Wd as K = bottleneck MMAs:
+//   sweep A  ln_before backward row sums; d ln_before weight / bias column sums (8-lane reduce-scatter -> per-warp accumulators)
+//   sweep B  d u; xl re-emitted for the weight-gradient GEMM (straight from registers); pre-transform backward: d gate_pre,
+//            d aux / dXR (registers -> global), and for latent experts dXR of a pair IS the A fragment of one k-step of
+//            dA2 = dXR tok'^T, which accumulates in the same sweep
+//   tail     latent experts: dS2 = A2 (dA2 - <A2, dA2>), A2 | dS2 out, dx += dS2 tok'
 // dx of all experts, the attention path and the router path accumulate in the warp's dx tile and are stored once.
 template <int CRK, int NT>
-__global__ void __launch_bounds__(256) rf_front_bwd_kernel(const avmoe_rf_front_args p, long long rows, int tiles_per_cta) {
+__global__ void __launch_bounds__(256) rf_front_bwd_kernel(const avmoe_rf_front_args p, long long rows, int tiles_per_cta, int ntile_bufs) {
   extern __shared__ __align__(16) unsigned char smem[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
   const int g = lane >> 2, t = lane & 3;
@@ -800,23 +800,25 @@ __global__ void __launch_bounds__(256) rf_front_bwd_kernel(const avmoe_rf_front_
   const float invC = 1.f / C;
   const bool has_ln = p.has_ln != 0;
   const GroupGeom gg(C, Cr, p.G);
-  // shared memory: per-CTA column accumulators [E][2][C] (d ln1_w, d ln1_b) + E gate_pre sums; per warp 4 tiles (x, u, d, dx)
-  float* colacc = reinterpret_cast<float*>(smem);
-  const size_t acc_bytes = ((size_t)E * 2 * C + 32) * sizeof(float);
-  float* gateacc = colacc + (size_t)E * 2 * C;
-  for (int i = threadIdx.x; i < E * 2 * C + 32; i += blockDim.x) colacc[i] = 0.f;
+  // shared memory: per-warp column accumulators [E][2][C] (d ln1_w, d ln1_b), E gate_pre sums; per warp 2 or 3 tiles (x, dx, aux)
+  float* colacc_all = reinterpret_cast<float*>(smem);
+  const size_t acc_floats = (size_t)nwarps * E * 2 * C + 32;
+  float* gateacc = colacc_all + (size_t)nwarps * E * 2 * C;
+  float* wacc = colacc_all + (size_t)warp * E * 2 * C;
+  for (int i = threadIdx.x; i < (int)acc_floats; i += blockDim.x) colacc_all[i] = 0.f;
   __syncthreads();
-  unsigned char* t_x = smem + acc_bytes + (size_t)warp * 4 * 16 * pitch;
-  unsigned char* t_u = t_x + 16 * pitch;
-  unsigned char* t_d = t_x + 32 * pitch;
-  unsigned char* t_dx = t_x + 48 * pitch;
+  unsigned char* t_x = smem + acc_floats * sizeof(float) + (size_t)warp * ntile_bufs * 16 * pitch;
+  unsigned char* t_dx = t_x + 16 * pitch;
+  unsigned char* t_aux = t_x + (ntile_bufs > 2 ? 32 * pitch : 0);
+  const TileRows Rx(t_x, pitch, g), Rdx(t_dx, pitch, g), Raux(t_aux, pitch, g);
   const long long ntiles = rows >> 4;
   const long long tile0 = (long long)blockIdx.x * tiles_per_cta;
   const long long tile1 = min(ntiles, tile0 + tiles_per_cta);
   const uint4* wdt = static_cast<const uint4*>(p.wdt_pack);
-  const size_t wdt_stride = (size_t)NP * CRK * 32;
+  const int wdt_stride = NP * CRK * 32;
   const size_t s2_stride = (size_t)NT * KSc * 32, xr_stride = (size_t)KSc * (NT / 2) * 32;
   const int Tp8 = (T + 7) & ~7;
+  const int ri = rs_index(lane);
   for (long long tile = tile0 + warp; tile < tile1; tile += nwarps) {
     const long long r0 = tile << 4;
     const long long b = r0 / p.N;
@@ -833,8 +835,8 @@ __global__ void __launch_bounds__(256) rf_front_bwd_kernel(const avmoe_rf_front_
           const float2 d = __ldg(reinterpret_cast<const float2*>(p.dpool_x + b * C + c));
           v = pack_bf16x2(d.x, d.y);
         }
-        tile_at(t_dx, pitch, g, c) = v;
-        tile_at(t_dx, pitch, g + 8, c) = v;
+        Rdx.A[c >> 1] = v;
+        Rdx.B[c >> 1] = v;
       }
     cp_async_wait<0>();
     __syncwarp();
@@ -842,24 +844,30 @@ __global__ void __launch_bounds__(256) rf_front_bwd_kernel(const avmoe_rf_front_
       const avmoe_expert& ex = p.ex[e];
       const int kind = ex.pre_kind;
       const bool aux_kind = kind == AVMOE_PRE_AUX_ADD || kind == AVMOE_PRE_AUX_REPLACE;
-      if (aux_kind) {    // aux tile -> t_d (kept for d gate_pre; overwritten element by element with the aux gradient)
-        tile_load_async(t_d, pitch, static_cast<const __nv_bfloat16*>(ex.aux), r0, rows, C, lane);
+      if (aux_kind) {
+        __syncwarp();
+        tile_load_async(t_aux, pitch, static_cast<const __nv_bfloat16*>(ex.aux), r0, rows, C, lane);
         cp_async_commit();
         cp_async_wait<0>();
         __syncwarp();
       }
+      const float gate = (kind == AVMOE_PRE_LATENT || kind == AVMOE_PRE_AUX_ADD) ? __ldg(ex.gate_pre) : 0.f;
       LatentRegs<NT> L;
-      const uint4* ts2 = kind == AVMOE_PRE_LATENT ? static_cast<const uint4*>(p.tok_s2[e]) + b * s2_stride : nullptr;
-      const uint4* txr = kind == AVMOE_PRE_LATENT ? static_cast<const uint4*>(p.tok_xr[e]) + b * xr_stride : nullptr;
-      const RowStats st = build_u<NT>(ex, t_x, t_u, t_d, pitch, C, T, has_ln, ts2, txr, L, lane);
-      if (kind == AVMOE_PRE_NONE) {     // u = x: copy so that t_u can be turned into xl in place
-        const uint32_t mg = magic_of(C >> 3);
-        for (int i = lane; i < 16 * (C >> 3); i += 32) {
-          const int r = (int)magic_div(i, mg), ch = i - r * (C >> 3);
-          *reinterpret_cast<uint4*>(t_u + r * pitch + ch * 16) = *reinterpret_cast<const uint4*>(t_x + r * pitch + ch * 16);
-        }
-        __syncwarp();
+      const uint4* ts2 = nullptr;
+      const uint4* txr = nullptr;
+      if (kind == AVMOE_PRE_LATENT) {
+        ts2 = static_cast<const uint4*>(p.tok_s2[e]) + b * s2_stride;
+        txr = static_cast<const uint4*>(p.tok_xr[e]) + b * xr_stride;
+        latent_probs<NT>(L, t_x, pitch, C, T, ts2, lane);
       }
+      RowStats st;
+      st.muA = st.muB = 0.f; st.rsA = st.rsB = 1.f;
+      if (has_ln) {     // saved by the forward
+        const float2 sA = __ldg(reinterpret_cast<const float2*>(p.ln1_stats + ((size_t)e * rows + rowA) * 2));
+        const float2 sB = __ldg(reinterpret_cast<const float2*>(p.ln1_stats + ((size_t)e * rows + rowB) * 2));
+        st.muA = sA.x; st.rsA = sA.y; st.muB = sB.x; st.rsB = sB.y;
+      }
+      const float nmA = -st.muA * st.rsA, nmB = -st.muB * st.rsB;
       // dz as A fragments (already bf16 in memory)
       uint32_t dzf[CRK][4];
       {
@@ -890,102 +898,104 @@ __global__ void __launch_bounds__(256) rf_front_bwd_kernel(const avmoe_rf_front_
             mma16816(acc[1], dzf[s], bb.z, bb.w);
           }
       };
-      float* acc_e = colacc + (size_t)e * 2 * C;
+      float* accp = wacc + (size_t)e * 2 * C + ((ri >> 1) & 1) * C + (ri >> 2) * 8 + 2 * t + (ri & 1);     // + 16*pr
       // ---- sweep A: ln_before backward row sums, d ln_before weight/bias column sums
       float maA = 0.f, maB = 0.f, mbA = 0.f, mbB = 0.f;
       if (has_ln) {
         for (int pr = 0; pr < NP; ++pr) {
-          float acc[2][4];
+          float acc[2][4], xr[2][4];
           dxl_pair(pr, acc);
+          if (kind == AVMOE_PRE_LATENT) latent_xr_pair<NT>(L, txr, pr, lane, xr);
           float cs[8];
 #pragma unroll
           for (int h = 0; h < 2; ++h) {
             const int c = (pr << 4) + h * 8 + 2 * t;
-            const float2 uA = unpack_bf16x2(tile_at(t_u, pitch, g, c)), uB = unpack_bf16x2(tile_at(t_u, pitch, g + 8, c));
+            float u[4];
+            make_u(kind, gate, Rx, Raux, c, xr[h], u);
             const float2 lw = __ldg(reinterpret_cast<const float2*>(ex.ln1_w + c));
-            const float xh0 = (uA.x - st.muA) * st.rsA, xh1 = (uA.y - st.muA) * st.rsA;
-            const float xh2 = (uB.x - st.muB) * st.rsB, xh3 = (uB.y - st.muB) * st.rsB;
+            const float xh0 = fmaf(u[0], st.rsA, nmA), xh1 = fmaf(u[1], st.rsA, nmA), xh2 = fmaf(u[2], st.rsB, nmB), xh3 = fmaf(u[3], st.rsB, nmB);
             const float d0 = acc[h][0] * lw.x, d1 = acc[h][1] * lw.y, d2 = acc[h][2] * lw.x, d3 = acc[h][3] * lw.y;
             maA += d0 + d1; maB += d2 + d3;
-            mbA += d0 * xh0 + d1 * xh1; mbB += d2 * xh2 + d3 * xh3;
-            cs[4 * h + 0] = acc[h][0] * xh0 + acc[h][2] * xh2; cs[4 * h + 1] = acc[h][1] * xh1 + acc[h][3] * xh3;
+            mbA = fmaf(d0, xh0, fmaf(d1, xh1, mbA)); mbB = fmaf(d2, xh2, fmaf(d3, xh3, mbB));
+            cs[4 * h + 0] = fmaf(acc[h][0], xh0, acc[h][2] * xh2); cs[4 * h + 1] = fmaf(acc[h][1], xh1, acc[h][3] * xh3);
             cs[4 * h + 2] = acc[h][0] + acc[h][2]; cs[4 * h + 3] = acc[h][1] + acc[h][3];
           }
-          const float s = reduce_scatter8(cs, lane);
-          const int i = rs_index(lane);
-          atomicAdd(acc_e + ((i >> 1) & 1) * C + (pr << 4) + (i >> 2) * 8 + 2 * t + (i & 1), s);
+          accp[pr << 4] += reduce_scatter8(cs, lane);
         }
         maA = quad_sum(maA) * invC; maB = quad_sum(maB) * invC; mbA = quad_sum(mbA) * invC; mbB = quad_sum(mbB) * invC;
       }
-      // ---- sweep B: d u, xl (in place of u), pre-transform backward
-      const float gate = (kind == AVMOE_PRE_LATENT || kind == AVMOE_PRE_AUX_ADD) ? __ldg(ex.gate_pre) : 0.f;
+      // ---- sweep B: d u, xl out, pre-transform backward (latent: dA2 accumulates on the tensor cores)
       float gsum = 0.f;
+      float dA[NT][4];
+#pragma unroll
+      for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) dA[nt][i] = 0.f;
+      __nv_bfloat16* xl = static_cast<__nv_bfloat16*>(p.xl) + (size_t)e * rows * C;
+      __nv_bfloat16* gaux = static_cast<__nv_bfloat16*>(ex.g_aux);
       for (int pr = 0; pr < NP; ++pr) {
         float acc[2][4], xr[2][4];
         dxl_pair(pr, acc);
         if (kind == AVMOE_PRE_LATENT) latent_xr_pair<NT>(L, txr, pr, lane, xr);
+        uint32_t ga[4];
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
           const int c = (pr << 4) + h * 8 + 2 * t;
+          float u[4];
+          make_u(kind, gate, Rx, Raux, c, xr[h], u);
           float du[4] = {acc[h][0], acc[h][1], acc[h][2], acc[h][3]};
+          float x0 = u[0], x1 = u[1], x2 = u[2], x3 = u[3];          // xl without ln_before
           if (has_ln) {
-            const float2 uA = unpack_bf16x2(tile_at(t_u, pitch, g, c)), uB = unpack_bf16x2(tile_at(t_u, pitch, g + 8, c));
             const float2 lw = __ldg(reinterpret_cast<const float2*>(ex.ln1_w + c)), lb = __ldg(reinterpret_cast<const float2*>(ex.ln1_b + c));
-            const float xh0 = (uA.x - st.muA) * st.rsA, xh1 = (uA.y - st.muA) * st.rsA;
-            const float xh2 = (uB.x - st.muB) * st.rsB, xh3 = (uB.y - st.muB) * st.rsB;
-            du[0] = st.rsA * (du[0] * lw.x - maA - mbA * xh0); du[1] = st.rsA * (du[1] * lw.y - maA - mbA * xh1);
-            du[2] = st.rsB * (du[2] * lw.x - maB - mbB * xh2); du[3] = st.rsB * (du[3] * lw.y - maB - mbB * xh3);
-            tile_at(t_u, pitch, g, c) = pack_bf16x2(xh0 * lw.x + lb.x, xh1 * lw.y + lb.y);        // xl = ln_before(u)
-            tile_at(t_u, pitch, g + 8, c) = pack_bf16x2(xh2 * lw.x + lb.x, xh3 * lw.y + lb.y);
+            const float xh0 = fmaf(u[0], st.rsA, nmA), xh1 = fmaf(u[1], st.rsA, nmA), xh2 = fmaf(u[2], st.rsB, nmB), xh3 = fmaf(u[3], st.rsB, nmB);
+            du[0] = st.rsA * fmaf(-mbA, xh0, fmaf(du[0], lw.x, -maA)); du[1] = st.rsA * fmaf(-mbA, xh1, fmaf(du[1], lw.y, -maA));
+            du[2] = st.rsB * fmaf(-mbB, xh2, fmaf(du[2], lw.x, -maB)); du[3] = st.rsB * fmaf(-mbB, xh3, fmaf(du[3], lw.y, -maB));
+            x0 = fmaf(xh0, lw.x, lb.x); x1 = fmaf(xh1, lw.y, lb.y); x2 = fmaf(xh2, lw.x, lb.x); x3 = fmaf(xh3, lw.y, lb.y);
           }
+          *reinterpret_cast<uint32_t*>(xl + rowA * C + c) = pack_bf16x2(x0, x1);       // xl = ln_before(u), operand of dWd
+          *reinterpret_cast<uint32_t*>(xl + rowB * C + c) = pack_bf16x2(x2, x3);
           if (kind == AVMOE_PRE_LATENT) {
-            gsum += du[0] * xr[h][0] + du[1] * xr[h][1] + du[2] * xr[h][2] + du[3] * xr[h][3];
-            tile_at(t_d, pitch, g, c) = pack_bf16x2(gate * du[0], gate * du[1]);                   // dXR
-            tile_at(t_d, pitch, g + 8, c) = pack_bf16x2(gate * du[2], gate * du[3]);
+            gsum = fmaf(du[0], xr[h][0], fmaf(du[1], xr[h][1], fmaf(du[2], xr[h][2], fmaf(du[3], xr[h][3], gsum))));
+            ga[2 * h] = pack_bf16x2(gate * du[0], gate * du[1]);                       // dXR, also the A fragment of dA2's k-step
+            ga[2 * h + 1] = pack_bf16x2(gate * du[2], gate * du[3]);
           } else if (aux_kind) {
-            const float2 aA = unpack_bf16x2(tile_at(t_d, pitch, g, c)), aB = unpack_bf16x2(tile_at(t_d, pitch, g + 8, c));
+            const float2 aA = unpack_bf16x2(Raux.A[c >> 1]), aB = unpack_bf16x2(Raux.B[c >> 1]);
             const float sc = kind == AVMOE_PRE_AUX_ADD ? gate : 1.f;
-            gsum += du[0] * aA.x + du[1] * aA.y + du[2] * aB.x + du[3] * aB.y;
-            tile_at(t_d, pitch, g, c) = pack_bf16x2(sc * du[0], sc * du[1]);                       // d aux
-            tile_at(t_d, pitch, g + 8, c) = pack_bf16x2(sc * du[2], sc * du[3]);
+            gsum = fmaf(du[0], aA.x, fmaf(du[1], aA.y, fmaf(du[2], aB.x, fmaf(du[3], aB.y, gsum))));
+            ga[2 * h] = pack_bf16x2(sc * du[0], sc * du[1]);                           // d aux
+            ga[2 * h + 1] = pack_bf16x2(sc * du[2], sc * du[3]);
+          }
+          if (kind != AVMOE_PRE_NONE) {
+            *reinterpret_cast<uint32_t*>(gaux + rowA * C + c) = ga[2 * h];
+            *reinterpret_cast<uint32_t*>(gaux + rowB * C + c) = ga[2 * h + 1];
           }
           if (kind != AVMOE_PRE_AUX_REPLACE) {
-            const float2 aA = unpack_bf16x2(tile_at(t_dx, pitch, g, c)), aB = unpack_bf16x2(tile_at(t_dx, pitch, g + 8, c));
-            tile_at(t_dx, pitch, g, c) = pack_bf16x2(aA.x + du[0], aA.y + du[1]);
-            tile_at(t_dx, pitch, g + 8, c) = pack_bf16x2(aB.x + du[2], aB.y + du[3]);
+            const float2 pA = unpack_bf16x2(Rdx.A[c >> 1]), pB = unpack_bf16x2(Rdx.B[c >> 1]);
+            Rdx.A[c >> 1] = pack_bf16x2(pA.x + du[0], pA.y + du[1]);
+            Rdx.B[c >> 1] = pack_bf16x2(pB.x + du[2], pB.y + du[3]);
+          }
+        }
+        if (kind == AVMOE_PRE_LATENT) {
+#pragma unroll
+          for (int nt = 0; nt < NT; ++nt) {
+            const uint4 bb = ldg_b(ts2, nt, KSc, pr, lane);
+            mma16816(dA[nt], ga, bb.x, bb.y);
+            mma16816(dA[nt], ga, bb.z, bb.w);
           }
         }
       }
-      __syncwarp();
       if (kind != AVMOE_PRE_NONE && kind != AVMOE_PRE_AUX_REPLACE && ex.g_gate_pre) {
         gsum = quad_sum(gsum);
         gsum += __shfl_xor_sync(0xffffffffu, gsum, 4); gsum += __shfl_xor_sync(0xffffffffu, gsum, 8); gsum += __shfl_xor_sync(0xffffffffu, gsum, 16);
         if (lane == 0) atomicAdd(gateacc + e, gsum);
       }
-      tile_store<false>(t_u, pitch, static_cast<__nv_bfloat16*>(p.xl) + (size_t)e * rows * C, C, nullptr, r0, rows, C, lane);
-      if (kind != AVMOE_PRE_NONE) tile_store<false>(t_d, pitch, static_cast<__nv_bfloat16*>(ex.g_aux), C, nullptr, r0, rows, C, lane);
       if (kind == AVMOE_PRE_LATENT) {
-        // ---- attention backward on the tile: dA2 = dXR tok'^T, dS2 = A2 (dA2 - <A2, dA2>), dx += dS2 tok'
-        float dA[NT][4];
-#pragma unroll
-        for (int nt = 0; nt < NT; ++nt)
-#pragma unroll
-          for (int i = 0; i < 4; ++i) dA[nt][i] = 0.f;
-        for (int s = 0; s < KSc; ++s) {
-          uint32_t a[4];
-          ldmatrix_a(a, t_d, pitch, s << 4, lane);
-#pragma unroll
-          for (int nt = 0; nt < NT; ++nt) {
-            const uint4 bb = ldg_b(ts2, nt, KSc, s, lane);
-            mma16816(dA[nt], a, bb.x, bb.y);
-            mma16816(dA[nt], a, bb.z, bb.w);
-          }
-        }
+        // ---- attention backward on the tile: dS2 = A2 (dA2 - <A2, dA2>), dx += dS2 tok'
         float dotA = 0.f, dotB = 0.f;
 #pragma unroll
         for (int nt = 0; nt < NT; ++nt) {
-          dotA += L.S[nt][0] * dA[nt][0] + L.S[nt][1] * dA[nt][1];
-          dotB += L.S[nt][2] * dA[nt][2] + L.S[nt][3] * dA[nt][3];
+          dotA = fmaf(L.S[nt][0], dA[nt][0], fmaf(L.S[nt][1], dA[nt][1], dotA));
+          dotB = fmaf(L.S[nt][2], dA[nt][2], fmaf(L.S[nt][3], dA[nt][3], dotB));
         }
         dotA = quad_sum(dotA); dotB = quad_sum(dotB);
         __nv_bfloat16* a2 = static_cast<__nv_bfloat16*>(p.a2[e]);
@@ -1021,23 +1031,24 @@ __global__ void __launch_bounds__(256) rf_front_bwd_kernel(const avmoe_rf_front_
 #pragma unroll
           for (int h = 0; h < 2; ++h) {
             const int c = (pr << 4) + h * 8 + 2 * t;
-            const float2 aA = unpack_bf16x2(tile_at(t_dx, pitch, g, c)), aB = unpack_bf16x2(tile_at(t_dx, pitch, g + 8, c));
-            tile_at(t_dx, pitch, g, c) = pack_bf16x2(aA.x + acc[h][0], aA.y + acc[h][1]);
-            tile_at(t_dx, pitch, g + 8, c) = pack_bf16x2(aB.x + acc[h][2], aB.y + acc[h][3]);
+            const float2 pA = unpack_bf16x2(Rdx.A[c >> 1]), pB = unpack_bf16x2(Rdx.B[c >> 1]);
+            Rdx.A[c >> 1] = pack_bf16x2(pA.x + acc[h][0], pA.y + acc[h][1]);
+            Rdx.B[c >> 1] = pack_bf16x2(pB.x + acc[h][2], pB.y + acc[h][3]);
           }
         }
       }
-      __syncwarp();
     }
+    __syncwarp();
     tile_store<false>(t_dx, pitch, static_cast<__nv_bfloat16*>(p.dx), C, nullptr, r0, rows, C, lane);
     __syncwarp();
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < E * C; i += blockDim.x) {
-    const int e = i / C, c = i - e * C;
-    if (has_ln) {
-      atomicAdd(p.ex[e].g_ln1_w + c, colacc[(size_t)e * 2 * C + c]);
-      atomicAdd(p.ex[e].g_ln1_b + c, colacc[(size_t)e * 2 * C + C + c]);
+  if (has_ln) {
+    for (int i = threadIdx.x; i < E * 2 * C; i += blockDim.x) {
+      float sum = 0.f;
+      for (int wq = 0; wq < nwarps; ++wq) sum += colacc_all[(size_t)wq * E * 2 * C + i];
+      const int e = i / (2 * C), q = (i - e * 2 * C) / C, c = i - e * 2 * C - q * C;
+      atomicAdd((q == 0 ? p.ex[e].g_ln1_w : p.ex[e].g_ln1_b) + c, sum);
     }
   }
   if (threadIdx.x < E && p.ex[threadIdx.x].g_gate_pre) atomicAdd(p.ex[threadIdx.x].g_gate_pre, gateacc[threadIdx.x]);
@@ -1062,6 +1073,7 @@ static int front_check(const avmoe_rf_front_args* a, bool bwd, const char* who) 
   }
   if (bwd) AVMOE_CHECK_ARG(a->dz && a->dx && a->xl && a->wdt_pack, "%s: null backward tensor", who);
   else AVMOE_CHECK_ARG(a->z && a->wd_pack && a->wd_csum, "%s: null forward tensor", who);
+  if (a->has_ln && bwd) AVMOE_CHECK_ARG(a->ln1_stats != nullptr, "%s: ln1_stats (saved by the forward) missing", who);
   return 0;
 }
 
@@ -1070,25 +1082,27 @@ static int launch_front(const avmoe_rf_front_args* a, bool bwd, cudaStream_t st)
   const long long rows = (long long)a->BT * a->N;
   const long long ntiles = rows / 16;
   const int pitch = a->C * 2 + 16;
-  const size_t per_warp = (size_t)(bwd ? 4 : 2) * 16 * pitch;
-  const size_t acc_bytes = bwd ? ((size_t)a->E * 2 * a->C + 32) * sizeof(float) : 0;
+  bool has_aux = false;
+  for (int e = 0; e < a->E; ++e) has_aux |= a->ex[e].pre_kind == AVMOE_PRE_AUX_ADD || a->ex[e].pre_kind == AVMOE_PRE_AUX_REPLACE;
+  const int bufs = (bwd ? 2 : 1) + (has_aux ? 1 : 0);           // x (+ dx in the backward) (+ aux)
+  const size_t per_warp = (size_t)bufs * 16 * pitch + (bwd ? (size_t)a->E * 2 * a->C * sizeof(float) : 0);
+  const size_t fixed = bwd ? 32 * sizeof(float) : 0;
   int warps = 8;
-  while (warps > 1 && acc_bytes + warps * per_warp > 110 * 1024) warps >>= 1;
-  if (acc_bytes + warps * per_warp > 227 * 1024) { set_error("rf_front: tile does not fit shared memory (C=%d)", a->C); return AVMOE_E_BADARG; }
-  if (warps == 1 && acc_bytes + 2 * per_warp <= 227 * 1024) warps = 2;
-  const size_t smem = acc_bytes + warps * per_warp;
-  long long ctas = (long long)num_sms() * (smem > 110 * 1024 ? 1 : 2);
-  if (!bwd) ctas *= 2;      // no per-CTA accumulators to flush: finer tiles balance better
+  while (warps > 1 && fixed + warps * per_warp > 100 * 1024) warps >>= 1;
+  if (fixed + warps * per_warp > 227 * 1024) { set_error("rf_front: tile does not fit shared memory (C=%d)", a->C); return AVMOE_E_BADARG; }
+  const size_t smem = fixed + warps * per_warp;
+  // a few CTAs per SM, each owning a contiguous range of tiles; the backward flushes its column sums once per CTA
+  long long ctas = (long long)num_sms() * (bwd ? 3 : 6);
   long long tpc = (ntiles + ctas - 1) / ctas;
   tpc = (tpc + warps - 1) / warps * warps;
   if (tpc < warps) tpc = warps;
   const unsigned grid = (unsigned)((ntiles + tpc - 1) / tpc);
   if (bwd) {
     AVMOE_CUDA(cudaFuncSetAttribute(rf_front_bwd_kernel<CRK, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    rf_front_bwd_kernel<CRK, NT><<<grid, warps * 32, smem, st>>>(*a, rows, (int)tpc);
+    rf_front_bwd_kernel<CRK, NT><<<grid, warps * 32, smem, st>>>(*a, rows, (int)tpc, bufs);
   } else {
     AVMOE_CUDA(cudaFuncSetAttribute(rf_front_fwd_kernel<CRK, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    rf_front_fwd_kernel<CRK, NT><<<grid, warps * 32, smem, st>>>(*a, rows, (int)tpc);
+    rf_front_fwd_kernel<CRK, NT><<<grid, warps * 32, smem, st>>>(*a, rows, (int)tpc, bufs);
   }
   AVMOE_LAUNCH_CHECK("rf_front_kernel");
   return 0;

@@ -325,9 +325,9 @@ def gemm_experts_fwd(K, cfg, x, packs, probs, P, bufs, prefixes, bn_mode, res=No
     front = None
     if front_toks is not None:
         prep = K.rf_prep_front(cfg, packs)
-        K.rf_front_fwd(cfg, x, packs, front_toks, prep, z)
+        ln1_saved = K.rf_front_fwd(cfg, x, packs, front_toks, prep, z)
         xl = ln1s = wdt = None
-        front = (front_toks, prep)
+        front = (front_toks, prep, ln1_saved)
     else:
         wdd, wdt = K.xg_prep_weights(cfg, packs, dt)                              # [E,Cr,C], [E,C,Crp]
         xl, ln1s = K.xg_ln_pre_fwd(cfg, x, packs)                                 # [E,rows,C]
@@ -404,11 +404,11 @@ def gemm_experts_bwd(K, cfg, x, dout, z, bn, bn_mode, packs, egr, probs, P, pref
 def rf_front_finish(K, cfg, x, packs, egr, bn, bn_mode, red2, pending, dpool_x, dx):
     """Second half of the expert backward on the row-fused path: the front pass backward (dx, xl, d aux / dXR, A2 | dS2), then the
     down-projection weight-gradient GEMMs on the re-emitted xl and the grouped weight-gradient finish.  Returns {expert: (A2, dS2)}."""
-    dz, pwu, bn2_wb, suma, (toks, prep) = pending
+    dz, pwu, bn2_wb, suma, (toks, prep, ln1_saved) = pending
     BT, N, C = x.shape
     rows = BT * N
     Crp = K.pad_bottleneck(cfg.Cr)
-    xl, lat = K.rf_front_bwd(cfg, x, packs, egr, toks, prep, dz, dpool_x, dx)
+    xl, lat = K.rf_front_bwd(cfg, x, packs, egr, toks, prep, ln1_saved, dz, dpool_x, dx)
     pwd = torch.empty((cfg.E, Crp, C), device=x.device, dtype=torch.float32)
     for e in range(cfg.E):
         K.gemm(dz[e], xl[e], a_kmajor=False, b_kmajor=False, out=pwd[e], split_k=K.split_k_hint(rows, Crp, C))

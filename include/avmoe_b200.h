@@ -379,6 +379,7 @@ typedef struct {
   void* xl;                  /* [E,rows,C] ln_before output, operand of the weight-gradient GEMM */
   void* a2[AVMOE_MAX_EXPERTS];   /* PRE_LATENT: [rows,Tp8] softmax_T probabilities (operand of the d tok' GEMM) */
   void* ds2[AVMOE_MAX_EXPERTS];  /* PRE_LATENT: [rows,Tp8] gradient at the logits */
+  float* ln1_stats;          /* [E,rows,2] ln_before (mean, rstd) per row: written by the forward, read by the backward */
 } avmoe_rf_front_args;
 int avmoe_rf_front_fwd(const avmoe_rf_front_args* a, avmoe_stream_t stream);
 int avmoe_rf_front_bwd(const avmoe_rf_front_args* a, avmoe_stream_t stream);

@@ -842,9 +842,10 @@ def rf_front_fwd(cfg, x, packs, toks, prep, z):
     xl, _ = xg_ln_pre_fwd(cfg, x.float(), ap)
     for e, pk in enumerate(packs):
         z[:, :, e, :] = (xl[e].float() @ _dense_wd(pk.wd, cfg).t()).reshape(BT, N, cfg.Cr)
+    return None      # the CUDA kernel returns the saved ln_before statistics; the emulation recomputes them
 
 
-def rf_front_bwd(cfg, x, packs, egr, toks, prep, dz, dpool_x, dx):
+def rf_front_bwd(cfg, x, packs, egr, toks, prep, ln1_stats, dz, dpool_x, dx):
     BT, N, C = x.shape
     ap, a2s = _rf_aux_packs(cfg, x, packs, toks)
     xl, st = xg_ln_pre_fwd(cfg, x.float(), ap)

@@ -280,14 +280,16 @@ def test_rf_front_bwd(geom, ln):
 
     egr_ref = grads("cpu")
     dx_ref = torch.empty((BT, N, C))
-    xl_ref, lat_ref = KE.rf_front_bwd(cfg, x.float(), [_f32_aux(pk) for pk in packs], egr_ref, {e: (t, t) for e, t in toks.items()}, None,
+    xl_ref, lat_ref = KE.rf_front_bwd(cfg, x.float(), [_f32_aux(pk) for pk in packs], egr_ref, {e: (t, t) for e, t in toks.items()}, None, None,
                                       dz.float(), dpool, dx_ref)
     cp = _cuda_packs(packs)
     prep = ops.rf_prep_front(cfg, cp)
     ctoks = {e: ops.rf_pack_tokens(t.cuda()) for e, t in toks.items()}
     egr = grads("cuda")
     dx = torch.empty((BT, N, C), device="cuda", dtype=torch.bfloat16)
-    xl, lat = ops.rf_front_bwd(cfg, x.cuda(), cp, egr, ctoks, prep, dz.cuda(), dpool.cuda(), dx)
+    zscratch = torch.empty((BT, N, E, Cr), device="cuda")
+    ln1s = ops.rf_front_fwd(cfg, x.cuda(), cp, ctoks, prep, zscratch)      # the forward saves the ln_before statistics
+    xl, lat = ops.rf_front_bwd(cfg, x.cuda(), cp, egr, ctoks, prep, ln1s, dz.cuda(), dpool.cuda(), dx)
     torch.cuda.synchronize()
     tol = 2e-2
     assert _fro(xl.float(), xl_ref.float()) < tol
