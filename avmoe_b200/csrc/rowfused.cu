@@ -119,6 +119,34 @@ struct TileRows {
         B(reinterpret_cast<uint32_t*>(const_cast<unsigned char*>(tile) + (g + 8) * pitch)) {}
 };
 
+// Per-warp staging block for one n-tile pair (16 rows x 16 bf16 columns): values leave the tensor-core accumulator layout as 4-byte
+// words, a __syncwarp later every lane moves one 16-byte chunk, so each row's 32 bytes reach global memory as ONE full sector
+// (4-byte stores straight from the accumulator layout half-fill two sectors per row and were measured ~40 % slower end to end).
+struct PairStager {
+  static constexpr int kPitch = 80;            // 32 data bytes + padding: conflict-free 4-byte writes, 16-byte aligned rows
+  static constexpr int kBytes = 16 * kPitch;
+  uint32_t* wA;
+  uint32_t* wB;
+  const uint4* rd;
+  int row, ch;
+  __device__ __forceinline__ PairStager(unsigned char* buf, int lane) {
+    const int g = lane >> 2, t = lane & 3;
+    wA = reinterpret_cast<uint32_t*>(buf + g * kPitch) + t;
+    wB = reinterpret_cast<uint32_t*>(buf + (g + 8) * kPitch) + t;
+    row = lane >> 1;
+    ch = lane & 1;
+    rd = reinterpret_cast<const uint4*>(buf + row * kPitch + ch * 16);
+  }
+  __device__ __forceinline__ void put(int h, uint32_t a, uint32_t b) { wA[4 * h] = a; wB[4 * h] = b; }
+  // gdst: element (tile row 0, first column of the pair); ld in elements
+  __device__ __forceinline__ void flush(__nv_bfloat16* gdst, long long ld, bool row_valid) {
+    __syncwarp();
+    const uint4 v = *rd;
+    if (row_valid) *reinterpret_cast<uint4*>(gdst + row * ld + ch * 8) = v;
+    __syncwarp();
+  }
+};
+
 // ------------------------------------------------------------------------------------------------ back pass (forward and backward)
 // k-steps of the up projection that can be non-zero for the n-tile pair starting at column c0 (block-diagonal weights)
 struct GroupGeom {
@@ -180,9 +208,11 @@ __global__ void __launch_bounds__(256) rf_back_kernel(const avmoe_rf_back_args p
   const size_t acc_floats = BWD ? (size_t)nwarps * E * 4 * C + 32 : 0;
   float* gateacc = colacc_all + (BWD ? (size_t)nwarps * E * 4 * C : 0);
   float* wacc = colacc_all + (size_t)warp * E * 4 * C;      // this warp's private accumulators: plain read-modify-write
-  unsigned char* wbase = smem + (tab_floats + acc_floats) * sizeof(float) + (size_t)warp * 16 * pitch;
+  const size_t warp_bytes = (size_t)16 * pitch + (BWD ? 2 * PairStager::kBytes : 0);
+  unsigned char* wbase = smem + (tab_floats + acc_floats) * sizeof(float) + (size_t)warp * warp_bytes;
   unsigned char* t_stage = wbase;                         // fwd: out tile
   unsigned char* t_dout = wbase;                          // bwd: dout tile
+  PairStager st_yh(wbase + 16 * pitch, lane), st_dy(wbase + 16 * pitch + PairStager::kBytes, lane);
   back_param_table(tab, p, E, C);
   if (BWD) for (int i = threadIdx.x; i < (int)acc_floats; i += blockDim.x) colacc_all[i] = 0.f;
   __syncthreads();
@@ -410,12 +440,9 @@ __global__ void __launch_bounds__(256) rf_back_kernel(const avmoe_rf_back_args p
         // ---- sweep 2: dy2 = gradient at the bn2 output, yhat out, column sums (d ln_post weight / bias, bn2 batch reductions)
         const int ri = rs_index(lane);
         float* accp = acc_e + ((ri >> 1) & 1) * C + (ri >> 2) * 8 + 2 * t + (ri & 1);            // + 16*pr (+ 2*C for the bn2 sums)
-        // yhat | dy2 go straight from registers to yd [rows, 2C] (rows g / g+8; a quad writes 16 contiguous bytes per row)
-        __nv_bfloat16* yde = static_cast<__nv_bfloat16*>(p.yd) + (size_t)e * rows * 2 * C;
-        uint32_t* yhA = reinterpret_cast<uint32_t*>(yde + rowA * 2 * C) + t;
-        uint32_t* yhB = reinterpret_cast<uint32_t*>(yde + rowB * 2 * C) + t;
-        uint32_t* dyA = yhA + (C >> 1);
-        uint32_t* dyB = yhB + (C >> 1);
+        // yhat | dy2 -> yd [rows, 2C] through the per-warp pair stagers (full 32-byte sectors per row)
+        __nv_bfloat16* yde = static_cast<__nv_bfloat16*>(p.yd) + (size_t)e * rows * 2 * C + r0 * 2 * C;
+        const bool st_valid = r0 + st_yh.row < rows;
         auto body2 = [&](int pr, const float (&yh)[2][4]) {
           float cl[8], cb[8];
 #pragma unroll
@@ -424,8 +451,7 @@ __global__ void __launch_bounds__(256) rf_back_kernel(const avmoe_rf_back_args p
             const float4* q = reinterpret_cast<const float4*>(tabe + o4 * 12);
             const float4 qa = q[0], qb = q[1];
             const float2 dA = unpack_bf16x2(dpA[o4]), dB = unpack_bf16x2(dpB[o4]);
-            if (vA) yhA[o4] = pack_bf16x2(yh[h][0], yh[h][1]);
-            if (vB) yhB[o4] = pack_bf16x2(yh[h][2], yh[h][3]);
+            st_yh.put(h, pack_bf16x2(yh[h][0], yh[h][1]), pack_bf16x2(yh[h][2], yh[h][3]));
             const float t0 = scA[e] * dA.x, t1 = scA[e] * dA.y, t2 = scB[e] * dB.x, t3 = scB[e] * dB.y;      // d o_e
             float dy0 = t0, dy1 = t1, dy2 = t2, dy3 = t3;
             float x0 = 0.f, x1 = 0.f, x2 = 0.f, x3 = 0.f;
@@ -435,13 +461,14 @@ __global__ void __launch_bounds__(256) rf_back_kernel(const avmoe_rf_back_args p
               dy0 = rstd0 * fmaf(-mbA, x0, fmaf(t0, qb.z, -maA)); dy1 = rstd0 * fmaf(-mbA, x1, fmaf(t1, qb.w, -maA));
               dy2 = rstd1 * fmaf(-mbB, x2, fmaf(t2, qb.z, -maB)); dy3 = rstd1 * fmaf(-mbB, x3, fmaf(t3, qb.w, -maB));
             }
-            if (vA) dyA[o4] = pack_bf16x2(dy0, dy1);
-            if (vB) dyB[o4] = pack_bf16x2(dy2, dy3);
+            st_dy.put(h, pack_bf16x2(dy0, dy1), pack_bf16x2(dy2, dy3));
             cl[4 * h + 0] = fmaf(t0, x0, t2 * x2); cl[4 * h + 1] = fmaf(t1, x1, t3 * x3);             // d ln2_w columns c, c+1
             cl[4 * h + 2] = t0 + t2; cl[4 * h + 3] = t1 + t3;                                        // d ln2_b
             cb[4 * h + 0] = dy0 + dy2; cb[4 * h + 1] = dy1 + dy3;                                    // sum dy2
             cb[4 * h + 2] = fmaf(dy0, yh[h][0], dy2 * yh[h][2]); cb[4 * h + 3] = fmaf(dy1, yh[h][1], dy3 * yh[h][3]);   // sum dy2*yhat
           }
+          st_yh.flush(yde + (pr << 4), 2 * C, st_valid);
+          st_dy.flush(yde + C + (pr << 4), 2 * C, st_valid);
           if (has_ln) accp[pr << 4] += reduce_scatter8(cl, lane);      // index i -> (h = i>>2, quantity (i>>1)&1, column offset i&1)
           if (has_bn) accp[2 * C + (pr << 4)] += reduce_scatter8(cb, lane);
         };
@@ -506,7 +533,7 @@ static int launch_back(const avmoe_rf_back_args* a, bool bwd, cudaStream_t st) {
   const long long ntiles = (rows + 15) / 16;
   const int pitch = a->C * 2 + 16;
   const size_t tab_bytes = (size_t)E * (a->C / 2) * 12 * sizeof(float);
-  const size_t per_warp = (size_t)16 * pitch + (bwd ? (size_t)E * 4 * a->C * sizeof(float) : 0);
+  const size_t per_warp = (size_t)16 * pitch + (bwd ? (size_t)E * 4 * a->C * sizeof(float) + 2 * PairStager::kBytes : 0);
   const size_t fixed = tab_bytes + (bwd ? 32 * sizeof(float) : 0);
   int warps = 8;
   while (warps > 1 && fixed + warps * per_warp > 100 * 1024) warps >>= 1;    // two CTAs per SM where possible
@@ -807,10 +834,12 @@ __global__ void __launch_bounds__(256) rf_front_bwd_kernel(const avmoe_rf_front_
   float* wacc = colacc_all + (size_t)warp * E * 2 * C;
   for (int i = threadIdx.x; i < (int)acc_floats; i += blockDim.x) colacc_all[i] = 0.f;
   __syncthreads();
-  unsigned char* t_x = smem + acc_floats * sizeof(float) + (size_t)warp * ntile_bufs * 16 * pitch;
+  const size_t warp_bytes = (size_t)ntile_bufs * 16 * pitch + 2 * PairStager::kBytes;
+  unsigned char* t_x = smem + acc_floats * sizeof(float) + (size_t)warp * warp_bytes;
   unsigned char* t_dx = t_x + 16 * pitch;
   unsigned char* t_aux = t_x + (ntile_bufs > 2 ? 32 * pitch : 0);
   const TileRows Rx(t_x, pitch, g), Rdx(t_dx, pitch, g), Raux(t_aux, pitch, g);
+  PairStager st_xl(t_x + (size_t)ntile_bufs * 16 * pitch, lane), st_ga(t_x + (size_t)ntile_bufs * 16 * pitch + PairStager::kBytes, lane);
   const long long ntiles = rows >> 4;
   const long long tile0 = (long long)blockIdx.x * tiles_per_cta;
   const long long tile1 = min(ntiles, tile0 + tiles_per_cta);
@@ -952,8 +981,7 @@ __global__ void __launch_bounds__(256) rf_front_bwd_kernel(const avmoe_rf_front_
             du[2] = st.rsB * fmaf(-mbB, xh2, fmaf(du[2], lw.x, -maB)); du[3] = st.rsB * fmaf(-mbB, xh3, fmaf(du[3], lw.y, -maB));
             x0 = fmaf(xh0, lw.x, lb.x); x1 = fmaf(xh1, lw.y, lb.y); x2 = fmaf(xh2, lw.x, lb.x); x3 = fmaf(xh3, lw.y, lb.y);
           }
-          *reinterpret_cast<uint32_t*>(xl + rowA * C + c) = pack_bf16x2(x0, x1);       // xl = ln_before(u), operand of dWd
-          *reinterpret_cast<uint32_t*>(xl + rowB * C + c) = pack_bf16x2(x2, x3);
+          st_xl.put(h, pack_bf16x2(x0, x1), pack_bf16x2(x2, x3));                        // xl = ln_before(u), operand of dWd
           if (kind == AVMOE_PRE_LATENT) {
             gsum = fmaf(du[0], xr[h][0], fmaf(du[1], xr[h][1], fmaf(du[2], xr[h][2], fmaf(du[3], xr[h][3], gsum))));
             ga[2 * h] = pack_bf16x2(gate * du[0], gate * du[1]);                       // dXR, also the A fragment of dA2's k-step
@@ -965,16 +993,15 @@ __global__ void __launch_bounds__(256) rf_front_bwd_kernel(const avmoe_rf_front_
             ga[2 * h] = pack_bf16x2(sc * du[0], sc * du[1]);                           // d aux
             ga[2 * h + 1] = pack_bf16x2(sc * du[2], sc * du[3]);
           }
-          if (kind != AVMOE_PRE_NONE) {
-            *reinterpret_cast<uint32_t*>(gaux + rowA * C + c) = ga[2 * h];
-            *reinterpret_cast<uint32_t*>(gaux + rowB * C + c) = ga[2 * h + 1];
-          }
+          if (kind != AVMOE_PRE_NONE) st_ga.put(h, ga[2 * h], ga[2 * h + 1]);
           if (kind != AVMOE_PRE_AUX_REPLACE) {
             const float2 pA = unpack_bf16x2(Rdx.A[c >> 1]), pB = unpack_bf16x2(Rdx.B[c >> 1]);
             Rdx.A[c >> 1] = pack_bf16x2(pA.x + du[0], pA.y + du[1]);
             Rdx.B[c >> 1] = pack_bf16x2(pB.x + du[2], pB.y + du[3]);
           }
         }
+        st_xl.flush(xl + r0 * C + (pr << 4), C, true);
+        if (kind != AVMOE_PRE_NONE) st_ga.flush(gaux + r0 * C + (pr << 4), C, true);
         if (kind == AVMOE_PRE_LATENT) {
 #pragma unroll
           for (int nt = 0; nt < NT; ++nt) {
@@ -1085,7 +1112,7 @@ static int launch_front(const avmoe_rf_front_args* a, bool bwd, cudaStream_t st)
   bool has_aux = false;
   for (int e = 0; e < a->E; ++e) has_aux |= a->ex[e].pre_kind == AVMOE_PRE_AUX_ADD || a->ex[e].pre_kind == AVMOE_PRE_AUX_REPLACE;
   const int bufs = (bwd ? 2 : 1) + (has_aux ? 1 : 0);           // x (+ dx in the backward) (+ aux)
-  const size_t per_warp = (size_t)bufs * 16 * pitch + (bwd ? (size_t)a->E * 2 * a->C * sizeof(float) : 0);
+  const size_t per_warp = (size_t)bufs * 16 * pitch + (bwd ? (size_t)a->E * 2 * a->C * sizeof(float) + 2 * PairStager::kBytes : 0);
   const size_t fixed = bwd ? 32 * sizeof(float) : 0;
   int warps = 8;
   while (warps > 1 && fixed + warps * per_warp > 100 * 1024) warps >>= 1;
