@@ -560,7 +560,8 @@ static int launch_back(const avmoe_rf_back_args* a, bool bwd, cudaStream_t st) {
 template <int E>
 static int dispatch_back_crk(const avmoe_rf_back_args* a, bool bwd, cudaStream_t st) {
   const int crk = (a->Cr + 15) / 16;
-  // (NPR > 0, the register-resident variant, measured slower than recomputing: 170-190 registers halve the resident warps)
+  // C = 96 (stage-1 audio): the whole up-projection tile stays in registers (backward 372 vs 538 us, profiles/r02_rowfused.md)
+  if (a->C == 96 && crk == 1) return launch_back<E, 1, 6>(a, bwd, st);
   switch (crk) {
     case 1: return launch_back<E, 1, 0>(a, bwd, st);
     case 2: return launch_back<E, 2, 0>(a, bwd, st);
