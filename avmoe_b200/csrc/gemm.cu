@@ -697,7 +697,22 @@ static uint64_t make_desc_base(int code, bool kmajor, int BK) {
   return layout_bits(code) | (1ull << 46) | (sbo << 32) | (lbo << 16);
 }
 
+// cuTensorMapEncodeTiled is a DRIVER call and needs a current context on the calling thread.  A thread that has only ever been
+// handed a device by torch (nn.DataParallel's per-replica worker threads, AVMOE/AVVP/main.py:420-421) may not have one bound yet
+// (CUDA_ERROR_INVALID_CONTEXT); a runtime call that touches the device binds the primary context.  Once per thread and device.
+static int ensure_context() {
+  static thread_local int bound_dev = -1;
+  int dev = 0;
+  AVMOE_CUDA(cudaGetDevice(&dev));
+  if (dev != bound_dev) {
+    AVMOE_CUDA(cudaFree(nullptr));
+    bound_dev = dev;
+  }
+  return 0;
+}
+
 int gemm_dispatch(const avmoe_gemm_args* a, cudaStream_t st) {
+  if (int rc = ensure_context()) return rc;
   AVMOE_CHECK_ARG(a && a->A && a->B && a->D, "gemm: null pointer");
   AVMOE_CHECK_ARG(a->M > 0 && a->N > 0 && a->K > 0, "gemm: empty problem M=%lld N=%lld K=%lld", (long long)a->M, (long long)a->N, (long long)a->K);
   AVMOE_CHECK_ARG(a->dtype == AVMOE_F32 || a->dtype == AVMOE_BF16, "gemm: bad dtype");

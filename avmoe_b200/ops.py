@@ -731,9 +731,16 @@ def xg_finish_wgrads(cfg, packs, egr, bn2_wb, bn, bn_mode, red2, BT, pwd, pwu, s
 USE_ROWFUSED = True   # bf16 streams: fused per-row expert passes on warp-level tensor-core tiles (csrc/rowfused.cu) where supported
 
 
+_RF_MAX_C = int(_os.environ.get("AVMOE_RF_MAX_C", "0"))   # diagnostics: widen the row-fused path beyond its default C <= 192
+
+
 def rf_supported(cfg, dtype) -> bool:
-    """geometry check of the row-fused passes (C % 16 == 0, C/r <= 96, 2 <= E <= 4, T <= 96); bf16 streams only"""
-    return dtype == torch.bfloat16 and bool(_lib.load().avmoe_rf_supported(cfg.C, cfg.Cr, cfg.E, cfg.T))
+    """geometry check of the row-fused passes (C % 16 == 0, C <= 192, C/r <= 96, 2 <= E <= 4, T <= 96); bf16 streams only"""
+    if dtype != torch.bfloat16:
+        return False
+    if _RF_MAX_C and cfg.C <= _RF_MAX_C:
+        return bool(_lib.load().avmoe_rf_supported(min(cfg.C, 192), cfg.Cr, cfg.E, cfg.T)) and cfg.C % 16 == 0
+    return bool(_lib.load().avmoe_rf_supported(cfg.C, cfg.Cr, cfg.E, cfg.T))
 
 
 def rf_pack_bytes(nb: int, Nn: int, K: int, hi_lo: bool = False) -> int:
