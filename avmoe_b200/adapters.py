@@ -122,6 +122,10 @@ class _MoEAdapterBase(nn.Module):
             obj = self
             for part in n.split("."):
                 obj = getattr(obj, part)
+            # DataParallel's broadcast_coalesced hands replicas views at arbitrary 4-byte offsets of one flat buffer; the kernels
+            # read parameters with 8/16-byte vector loads, so a misaligned replica tensor is re-homed (differentiable clone)
+            if obj.data_ptr() % 16 != 0:
+                obj = obj.clone()
             out.append(obj)
         return out
 

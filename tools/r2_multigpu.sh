@@ -2,7 +2,7 @@
 # usage: r2_multigpu.sh N "variant variant ..."   -- one torchrun bench line per variant at N GPUs (kept under gpurun_out/, copied to profiles/)
 N=$1; shift
 mkdir -p gpurun_out
-if [ "$N" = "2" ]; then
+if [ "$N" = "2" ] || [ "$N" = "4" ]; then
   timeout 600 python -m pytest tests/test_round2_parity.py -m gpu -q -k "dataparallel or non_current" --tb=short -W ignore 2>&1 | tail -15 > gpurun_out/r2_dp_tests.log
   tail -5 gpurun_out/r2_dp_tests.log
 fi
