@@ -138,7 +138,7 @@ class RfFrontArgs(C.Structure):
         ("tok_s2", _PtrArr), ("tok_xr", _PtrArr),
         ("wd_pack", C.c_void_p), ("wd_csum", C.c_void_p), ("c2", C.c_void_p), ("wdt_pack", C.c_void_p),
         ("x", C.c_void_p), ("z", C.c_void_p), ("dz", C.c_void_p), ("dpool_x", C.c_void_p), ("dx", C.c_void_p), ("xl", C.c_void_p),
-        ("a2", _PtrArr), ("ds2", _PtrArr), ("ln1_stats", C.c_void_p),
+        ("a2", _PtrArr), ("ds2", _PtrArr), ("ln1_stats", C.c_void_p), ("dres", C.c_void_p),
     ]
 
 

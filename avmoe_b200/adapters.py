@@ -150,6 +150,9 @@ class _MoEAdapterBase(nn.Module):
             state["mha_dropout"] = drops.pop() if (drops and self.training) else 0.0
             state["mha_keep"] = mha_keep
         rt = None if residual is None else self._token_major(residual).to(xt.dtype)
+        # the reference call sites add the adapter output to the very stream it reads (f = f + adapter(f, other)): then the residual's
+        # gradient is folded into dx inside the backward instead of a separate accumulation pass
+        state["res_is_x"] = rt is not None and rt.data_ptr() == xt.data_ptr() and rt.shape == xt.shape
         out, probs, lb, idx = Fn.MoEAdapterFunction.apply(state, xt, ot, rt, *self._flat_params())
         return out.permute(0, 2, 1).unsqueeze(-1), idx.unsqueeze(-1), probs.unsqueeze(1), lb
 

@@ -854,21 +854,28 @@ __global__ void __launch_bounds__(256) rf_front_bwd_kernel(const avmoe_rf_front_
     const long long b = r0 / p.N;
     const long long rowA = r0 + g, rowB = r0 + g + 8;
     tile_load_async(t_x, pitch, static_cast<const __nv_bfloat16*>(p.x), r0, rows, C, lane);
+    if (p.dres) tile_load_async(t_dx, pitch, static_cast<const __nv_bfloat16*>(p.dres), r0, rows, C, lane);
     cp_async_commit();
-    // dx tile starts from the router-path gradient (d mean_N(x)), identical for every row of the sample
+    cp_async_wait<0>();
+    __syncwarp();
+    // dx tile starts from the router-path gradient (d mean_N(x)), identical for every row of the sample, plus -- when the folded
+    // residual stream is x itself -- the gradient that passes straight through the residual add
     for (int pr = 0; pr < NP; ++pr)
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
         const int c = (pr << 4) + h * 8 + 2 * t;
-        uint32_t v = 0u;
-        if (p.dpool_x) {
-          const float2 d = __ldg(reinterpret_cast<const float2*>(p.dpool_x + b * C + c));
-          v = pack_bf16x2(d.x, d.y);
+        float2 d = make_float2(0.f, 0.f);
+        if (p.dpool_x) d = __ldg(reinterpret_cast<const float2*>(p.dpool_x + b * C + c));
+        if (p.dres) {
+          const float2 rA = unpack_bf16x2(Rdx.A[c >> 1]), rB = unpack_bf16x2(Rdx.B[c >> 1]);
+          Rdx.A[c >> 1] = pack_bf16x2(rA.x + d.x, rA.y + d.y);
+          Rdx.B[c >> 1] = pack_bf16x2(rB.x + d.x, rB.y + d.y);
+        } else {
+          const uint32_t v = pack_bf16x2(d.x, d.y);
+          Rdx.A[c >> 1] = v;
+          Rdx.B[c >> 1] = v;
         }
-        Rdx.A[c >> 1] = v;
-        Rdx.B[c >> 1] = v;
       }
-    cp_async_wait<0>();
     __syncwarp();
     for (int e = 0; e < E; ++e) {
       const avmoe_expert& ex = p.ex[e];

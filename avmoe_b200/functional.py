@@ -344,10 +344,8 @@ def gemm_experts_fwd(K, cfg, x, packs, probs, P, bufs, prefixes, bn_mode, res=No
         else:
             aff1, save1 = K.bn1_finalize(cfg, None, rows, bn_w, bn_b, False)
         aff2, save2 = K.bn2_finalize(cfg, moments, rows, packs, bn_w, bn_b, bn_mode == BN_TRAIN)
-        if bn_mode == BN_TRAIN:
-            for p in prefixes:
-                bufs[p + "bn1.num_batches_tracked"] += 1
-                bufs[p + "bn2.num_batches_tracked"] += 1
+        if bn_mode == BN_TRAIN:    # one multi-tensor launch instead of 2E tiny ones
+            torch._foreach_add_([bufs[p + f"bn{i}.num_batches_tracked"] for p in prefixes for i in (1, 2)], 1)
         bn = (aff1, save1, aff2, save2)
         bn2_wb = [(P[p + "bn2.weight"], P[p + "bn2.bias"]) for p in prefixes]
     if bool(getattr(K, "USE_ROWFUSED", False)) and K.rf_supported(cfg, dt):
@@ -401,14 +399,14 @@ def gemm_experts_bwd(K, cfg, x, dout, z, bn, bn_mode, packs, egr, probs, P, pref
     return dprobs, red1, red2, dxl, ln1s, None
 
 
-def rf_front_finish(K, cfg, x, packs, egr, bn, bn_mode, red2, pending, dpool_x, dx):
+def rf_front_finish(K, cfg, x, packs, egr, bn, bn_mode, red2, pending, dpool_x, dx, dres=None):
     """Second half of the expert backward on the row-fused path: the front pass backward (dx, xl, d aux / dXR, A2 | dS2), then the
     down-projection weight-gradient GEMMs on the re-emitted xl and the grouped weight-gradient finish.  Returns {expert: (A2, dS2)}."""
     dz, pwu, bn2_wb, suma, (toks, prep, ln1_saved) = pending
     BT, N, C = x.shape
     rows = BT * N
     Crp = K.pad_bottleneck(cfg.Cr)
-    xl, lat = K.rf_front_bwd(cfg, x, packs, egr, toks, prep, ln1_saved, dz, dpool_x, dx)
+    xl, lat = K.rf_front_bwd(cfg, x, packs, egr, toks, prep, ln1_saved, dz, dpool_x, dx, dres)
     pwd = torch.empty((cfg.E, Crp, C), device=x.device, dtype=torch.float32)
     for e in range(cfg.E):
         K.gemm(dz[e], xl[e], a_kmajor=False, b_kmajor=False, out=pwd[e], split_k=K.split_k_hint(rows, Crp, C))
@@ -671,8 +669,13 @@ class MoEAdapterFunction(torch.autograd.Function):
         dtokp = torch.zeros((BT, nl, T, C), device=dev, dtype=f32) if nl else None
         dx = torch.empty_like(x)
         lat_rf = {}
+        # residual stream == x (the reference call sites: f = f + adapter(f, other)): its gradient is dout itself; folded into dx here
+        # so autograd does not run a separate accumulation pass over the token stream
+        fold_res = bool(state.get("res_is_x")) and ctx.needs_input_grad[3]
+        res_folded = False
         if use_xg and pending is not None:
-            lat_rf = rf_front_finish(K, cfg, x, packs, egr, ctx.bn, bn_mode, red2, pending, dpool_x, dx)
+            lat_rf = rf_front_finish(K, cfg, x, packs, egr, ctx.bn, bn_mode, red2, pending, dpool_x, dx, dout if fold_res else None)
+            res_folded = fold_res
         elif use_xg:
             K.xg_ln_pre_bwd(cfg, x, dxl, ln1s, packs, dpool_x, dx, egr)
         else:
@@ -752,5 +755,8 @@ class MoEAdapterFunction(torch.autograd.Function):
             if bn_mode != BN_OFF:
                 grads[pfx + "bn1.weight"], grads[pfx + "bn1.bias"] = r1[e, :, 1], r1[e, :, 0]
                 grads[pfx + "bn2.weight"], grads[pfx + "bn2.bias"] = r2[e, :, 1], r2[e, :, 0]
-        dres = dout if ctx.needs_input_grad[3] else None                      # residual passes the gradient through
+        if fold_res and not res_folded:
+            K.add_into(dx, dout)
+            res_folded = True
+        dres = dout if (ctx.needs_input_grad[3] and not res_folded) else None   # residual passes the gradient through
         return (None, dx, do, dres) + tuple(grads[n] for n in names)

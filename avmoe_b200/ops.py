@@ -839,7 +839,7 @@ def rf_front_fwd(cfg, x, packs, toks, prep, z):
     return st
 
 
-def rf_front_bwd(cfg, x, packs, egr, toks, prep, ln1_stats, dz, dpool_x, dx):
+def rf_front_bwd(cfg, x, packs, egr, toks, prep, ln1_stats, dz, dpool_x, dx, dres=None):
     """dz, x (+aux, tok') -> dx, xl [E,rows,C], per latent expert (A2, dS2) [BT,N,Tp8]; egr[e].aux receives d aux (for latent experts
     dXR), egr[e].gate_pre / ln1_w / ln1_b accumulate."""
     BT, N, Cc = x.shape
@@ -853,7 +853,7 @@ def rf_front_bwd(cfg, x, packs, egr, toks, prep, ln1_stats, dz, dpool_x, dx):
         ds2 = torch.empty((BT, N, tp8), device=x.device, dtype=x.dtype)
         lat[e] = (a2, ds2)
         a.a2[e], a.ds2[e] = a2.data_ptr(), ds2.data_ptr()
-    _set(a, x=x, dz=dz, dpool_x=dpool_x, dx=dx, xl=xl, ln1_stats=ln1_stats)
+    _set(a, x=x, dz=dz, dpool_x=dpool_x, dx=dx, xl=xl, ln1_stats=ln1_stats, dres=dres)
     _lib_call("rf_front_bwd", C.byref(a), _stream(), _bytes=_nbytes(x, dz, dx, xl) + sum(2 * _nbytes(pk.aux) for pk in packs))
     return xl, lat
 

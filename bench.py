@@ -383,13 +383,21 @@ def run_ours(args):
             ach = d["bytes"] / (d["ms"] * 1e-3) / 1e9
             name = "gemm_tcgen05_kernel (skinny expert-projection / latent-attention GEMMs)" if dom == HB else f"{dom}_kernel"
             traffic = traffic_src = None
-            if dom == HB:   # ncu --set full DRAM bytes vs algorithmic bytes of the same launches (profiles/r01_traffic_gemm.json)
+            if dom == HB:   # DRAM bytes per GEMM launch from the ncu pass over one step of the same command (profiles/r02_dram_step.json:
+                            # all tcgen05 GEMM launches of the step, tensor-bound ones included), else round 1's measured dram/algorithmic ratio
                 try:
-                    tr = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic_gemm.json")))
-                    traffic = tr["dram_to_algorithmic_ratio"] * d["bytes"] / max(d["n"], 1)
-                    traffic_src = "profiles/r01_traffic_gemm.json: measured dram/algorithmic ratio x algorithmic bytes per launch"
+                    dr = json.load(open(os.path.join(ROOT, "profiles", "r02_dram_step.json")))
+                    gk = [v for k, v in dr["by_kernel"].items() if "gemm_tcgen05" in k][0]
+                    traffic = gk["GB"] * 1e9 / gk["n"]
+                    traffic_src = ("profiles/r02_dram_step.json: ncu dram__bytes_read+write of the %d tcgen05 GEMM launches of one step / launches "
+                                   "(all GEMM launches; round-1 capture of the skinny group alone: 0.94 x algorithmic)" % gk["n"])
                 except Exception:
-                    pass
+                    try:
+                        tr = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic_gemm.json")))
+                        traffic = tr["dram_to_algorithmic_ratio"] * d["bytes"] / max(d["n"], 1)
+                        traffic_src = "profiles/r01_traffic_gemm.json: measured dram/algorithmic ratio x algorithmic bytes per launch"
+                    except Exception:
+                        pass
             roofline = {"bound": "hbm", "kernel": name, "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak,
                         "traffic": traffic, "traffic_source": traffic_src, "algorithmic_bytes_per_launch": d["bytes"] / max(d["n"], 1)}
         gt = agg.get(TB)

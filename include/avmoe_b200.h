@@ -380,6 +380,8 @@ typedef struct {
   void* a2[AVMOE_MAX_EXPERTS];   /* PRE_LATENT: [rows,Tp8] softmax_T probabilities (operand of the d tok' GEMM) */
   void* ds2[AVMOE_MAX_EXPERTS];  /* PRE_LATENT: [rows,Tp8] gradient at the logits */
   float* ln1_stats;          /* [E,rows,2] ln_before (mean, rstd) per row: written by the forward, read by the backward */
+  const void* dres;          /* [rows,C] or NULL (backward): gradient of the folded residual when the residual stream IS x -- added into dx
+                              * here instead of by a separate autograd accumulation pass */
 } avmoe_rf_front_args;
 int avmoe_rf_front_fwd(const avmoe_rf_front_args* a, avmoe_stream_t stream);
 int avmoe_rf_front_bwd(const avmoe_rf_front_args* a, avmoe_stream_t stream);

@@ -845,7 +845,7 @@ def rf_front_fwd(cfg, x, packs, toks, prep, z):
     return None      # the CUDA kernel returns the saved ln_before statistics; the emulation recomputes them
 
 
-def rf_front_bwd(cfg, x, packs, egr, toks, prep, ln1_stats, dz, dpool_x, dx):
+def rf_front_bwd(cfg, x, packs, egr, toks, prep, ln1_stats, dz, dpool_x, dx, dres=None):
     BT, N, C = x.shape
     ap, a2s = _rf_aux_packs(cfg, x, packs, toks)
     xl, st = xg_ln_pre_fwd(cfg, x.float(), ap)
@@ -868,6 +868,8 @@ def rf_front_bwd(cfg, x, packs, egr, toks, prep, ln1_stats, dz, dpool_x, dx):
             D2 = torch.zeros((BT, N, tp8), dtype=x.dtype)
             A2[:, :, :cfg.T], D2[:, :, :cfg.T] = a2.to(x.dtype), ds2.to(x.dtype)
             lat[e] = (A2, D2)
+    if dres is not None:
+        dxf = dxf + dres.float()
     dx.copy_(dxf.to(dx.dtype))
     return xl.to(x.dtype), lat
 

@@ -141,12 +141,13 @@ def _residual_run(mod, x, o, gout, device, dtype, fused):
     return f.detach().float().cpu(), xc.grad.float().cpu(), oc.grad.float().cpu()
 
 
+@pytest.mark.parametrize("N", [24, 32])          # 32: the row-fused path (residual gradient folded inside rf_front_bwd)
 @pytest.mark.parametrize("gemm_paths", [True, False])
-def test_residual_fold_emulated(gemm_paths, monkeypatch):
+def test_residual_fold_emulated(gemm_paths, N, monkeypatch):
     monkeypatch.setattr(KE, "USE_GEMM_ATTENTION", "always" if gemm_paths else False)
     monkeypatch.setattr(KE, "USE_GEMM_EXPERTS", "always" if gemm_paths else False)
     import dataclasses
-    spec = dataclasses.replace(O.spec_for("ave", 3, "audio"), C=64, N=24, Cx=96, Nx=20)
+    spec = dataclasses.replace(O.spec_for("ave", 3, "audio"), C=64, N=N, Cx=96, Nx=20)
     sd = O.make_state_dict(spec, seed=3)
     x, o = O.make_tokens(3, spec.N, spec.C, 11), O.make_tokens(3, spec.Nx, spec.Cx, 12)
     gout = torch.randn((3, spec.N, spec.C), generator=torch.Generator().manual_seed(13))
