@@ -14,6 +14,7 @@
 // Replaces: nn.Conv2d(Nx->N,1x1) over the token axis + nn.Linear(Cx->C)
 //           (AVMOE/AVE/nets/net_trans_v3.py:445-446,469-471) and their autograd.
 #include <atomic>
+#include <stdlib.h>
 #include <mutex>
 
 #include "common.cuh"
@@ -705,7 +706,11 @@ static int ensure_context() {
   int dev = 0;
   AVMOE_CUDA(cudaGetDevice(&dev));
   if (dev != bound_dev) {
-    AVMOE_CUDA(cudaFree(nullptr));
+    // never during a stream capture (cudaFree is a prohibited call there, and a capturing thread necessarily has a context)
+    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+    const bool capturing = cudaStreamIsCapturing(cudaStreamPerThread, &cs) != cudaSuccess || cs != cudaStreamCaptureStatusNone;
+    (void)cudaGetLastError();
+    if (!capturing && getenv("AVMOE_NO_CTX_BIND") == nullptr) AVMOE_CUDA(cudaFree(nullptr));
     bound_dev = dev;
   }
   return 0;

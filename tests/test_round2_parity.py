@@ -461,3 +461,4 @@ def test_mha_dropout_default_draw_cuda():
         d = mod(xv, ov, is_training=False)[0]
     assert (a - b).abs().max().item() > 0 and torch.equal(c, d)
     assert util.fro_err(a, c) < 1.0       # dropped attention: a different, but not an unrelated, output
+
