@@ -23,18 +23,34 @@ __global__ void __launch_bounds__(1024) softmax_cols_kernel(const float* __restr
   __shared__ float flse[128];
   const int b = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const float* s = S + (long long)b * Nk * lds;
+  // Each warp walks its rows in groups of kU with all kU row loads issued before any is used: one 128-byte request per warp
+  // in flight (the plain loop) leaves a 1024-thread CTA at a few GB/s; kU independent requests per warp hide the latency.
+  constexpr int kU = 8, kU2 = 4;   // pass 2 also holds store addresses: 4 rows keep it inside the 64-register budget
   float mx[4], sm[4];
 #pragma unroll
   for (int k = 0; k < 4; ++k) { mx[k] = -INFINITY; sm[k] = 0.f; }
-  for (int r = warp; r < Nk; r += 32) {
+  const int nk4 = (T + 31) >> 5;      // column blocks of 32 this sample uses (warp-uniform)
+  for (int r0 = warp; r0 < Nk; r0 += 32 * kU) {
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-      const int t = lane + 32 * k;
-      if (t < T) {
-        const float v = logit(s + (long long)r * lds, t, off_lo);
-        const float m2 = fmaxf(mx[k], v);
-        sm[k] = sm[k] * expf(mx[k] - m2) + expf(v - m2);
-        mx[k] = m2;
+      if (k < nk4) {
+        const int t = lane + 32 * k;
+        float v[kU];
+#pragma unroll
+        for (int u = 0; u < kU; ++u) {
+          const int r = r0 + 32 * u;
+          v[u] = (t < T && r < Nk) ? logit(s + (long long)r * lds, t, off_lo) : -INFINITY;
+        }
+        float m2 = mx[k];
+#pragma unroll
+        for (int u = 0; u < kU; ++u) m2 = fmaxf(m2, v[u]);
+        if (m2 > -INFINITY) {
+          float acc = sm[k] * expf(mx[k] - m2);
+#pragma unroll
+          for (int u = 0; u < kU; ++u) acc += expf(v[u] - m2);     // exp(-inf) = 0 for the padded rows / columns
+          sm[k] = acc;
+          mx[k] = m2;
+        }
       }
     }
   }
@@ -46,22 +62,35 @@ __global__ void __launch_bounds__(1024) softmax_cols_kernel(const float* __restr
     float M = -INFINITY;
     for (int w = 0; w < 32; ++w) M = fmaxf(M, smax[w][t]);
     float L = 0.f;
-    for (int w = 0; w < 32; ++w) L += ssum[w][t] * expf(smax[w][t] - M);
+    for (int w = 0; w < 32; ++w) L += ssum[w][t] > 0.f ? ssum[w][t] * expf(smax[w][t] - M) : 0.f;
     const float l = M + logf(L);
     flse[t] = l;
     lse[(long long)b * T + t] = l;
   }
   __syncthreads();
   TP* p = P + (long long)b * Nk * ldp;
-  for (int r = warp; r < Nk; r += 32) {
+  for (int r0 = warp; r0 < Nk; r0 += 32 * kU2) {
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
       const int t = lane + 32 * k;
       if (t < T) {
-        const float pv = expf(logit(s + (long long)r * lds, t, off_lo) - flse[t]);
-        const TP hi = from_f32<TP>(pv);
-        p[(long long)r * ldp + t] = hi;
-        if (p_lo) p[(long long)r * ldp + p_lo + t] = from_f32<TP>(pv - to_f32(hi));   // residual: R = (hi + lo)·kv keeps ~16 bits of A1
+        const float l = flse[t];
+        float v[kU2];
+#pragma unroll
+        for (int u = 0; u < kU2; ++u) {
+          const int r = r0 + 32 * u;
+          v[u] = r < Nk ? logit(s + (long long)r * lds, t, off_lo) : 0.f;
+        }
+#pragma unroll
+        for (int u = 0; u < kU2; ++u) {
+          const int r = r0 + 32 * u;
+          if (r < Nk) {
+            const float pv = expf(v[u] - l);
+            const TP hi = from_f32<TP>(pv);
+            p[(long long)r * ldp + t] = hi;
+            if (p_lo) p[(long long)r * ldp + p_lo + t] = from_f32<TP>(pv - to_f32(hi));   // residual: R = (hi + lo)·kv keeps ~16 bits of A1
+          }
+        }
       }
     }
   }
@@ -164,11 +193,22 @@ __global__ void cast_split_kernel(const float* __restrict__ in, __nv_bfloat16* _
 }
 
 // ---- out[i] += sum_b in[b][i]
+// block (32, 8): x -> element, y -> slice of the batch; the 8 partial sums are combined in a fixed order (deterministic)
 __global__ void batch_sum_add_kernel(const float* __restrict__ in, float* __restrict__ out, int BT, long long L) {
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < L; i += (long long)gridDim.x * blockDim.x) {
-    float s = 0.f;
-    for (int b = 0; b < BT; ++b) s += in[(long long)b * L + i];
-    out[i] += s;
+  __shared__ float red[8][33];
+  const long long i = blockIdx.x * 32LL + threadIdx.x;
+  float s = 0.f;
+  if (i < L) {
+#pragma unroll 4
+    for (int b = threadIdx.y; b < BT; b += 8) s += in[(long long)b * L + i];
+  }
+  red[threadIdx.y][threadIdx.x] = s;
+  __syncthreads();
+  if (threadIdx.y == 0 && i < L) {
+    float t = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) t += red[k][threadIdx.x];
+    out[i] += t;
   }
 }
 
@@ -251,8 +291,8 @@ extern "C" int avmoe_add_rowvec(void* d, const float* vec, int BT, int N, int C,
 
 extern "C" int avmoe_batch_sum_add(const float* in, float* out, int BT, int64_t L, avmoe_stream_t stream) {
   AVMOE_CHECK_ARG(in && out && BT > 0 && L > 0, "batch_sum_add: bad arguments");
-  const int grid = (int)min((long long)(4 * num_sms()), (long long)((L + 255) / 256));
-  batch_sum_add_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(in, out, BT, L);
+  AVMOE_CHECK_ARG((L + 31) / 32 < (1ll << 31), "batch_sum_add: too many elements");
+  batch_sum_add_kernel<<<(unsigned)((L + 31) / 32), dim3(32, 8), 0, reinterpret_cast<cudaStream_t>(stream)>>>(in, out, BT, L);
   AVMOE_LAUNCH_CHECK("batch_sum_add_kernel");
   return 0;
 }

@@ -346,6 +346,141 @@ __global__ void __launch_bounds__(kThreads) bn_moments_blk_kernel(const avmoe_ex
   }
 }
 
+// Square-blocked form (the default): a work item is a BJ x BJ block of one group's symmetric moment matrix (upper triangle
+// only; the mirror is written on output) or BJ first moments.  Per row an item costs two BJ-wide shared loads for BJ*BJ FMAs
+// (bn_moments_blk: kB+1 scalar loads for kB FMAs -- shared-load bound), and the tile is a flat copy of z's rows.
+template <int BJ>
+struct MomVec;
+template <>
+struct MomVec<4> { using type = float4; };
+template <>
+struct MomVec<2> { using type = float2; };
+
+template <int BJ, int kItems>
+__global__ void __launch_bounds__(kThreads, kItems <= 3 ? 2 : 1) bn_moments_sq_kernel(const avmoe_expert_args p, double* m1, double* m2, int TN, long long rows_total) {
+  extern __shared__ __align__(16) float sm[];
+  using Vec = typename MomVec<BJ>::type;
+  const int Cr = p.Cr, G = p.G, Crg = Cr / G, E = p.E;
+  const int ECr = E * Cr;                 // multiple of BJ (launcher)
+  float* as = sm;                         // [TN][ECr]
+  float* colp = sm + (size_t)TN * ECr;    // [3][ECr]: bn1 scale, shift, relu flag per bottleneck column
+  for (int q = threadIdx.x; q < ECr; q += blockDim.x) {
+    colp[q] = p.aff1[q * 2];
+    colp[ECr + q] = p.aff1[q * 2 + 1];
+    colp[2 * ECr + q] = p.ex[q / Cr].relu ? 1.f : 0.f;
+  }
+  const int nb = Crg / BJ;
+  const int per_group = nb * (nb + 1) / 2;
+  const int n_sq = E * G * per_group, n_items = n_sq + ECr / BJ;
+  float acc[kItems][BJ][BJ];
+  int cj[kItems], ck[kItems];             // tile columns of the item's two operands; cj = -1: first moments of ck.., -2: no item
+  const int items_pad = kItems == 1 ? min(kThreads, (n_items + 31) & ~31) : kThreads;      // whole warps per row group
+  const int rgroups = kItems == 1 ? kThreads / items_pad : 1;
+  const int rg = kItems == 1 ? (int)threadIdx.x / items_pad : 0;
+#pragma unroll
+  for (int t = 0; t < kItems; ++t) {
+#pragma unroll
+    for (int a = 0; a < BJ; ++a)
+#pragma unroll
+      for (int b = 0; b < BJ; ++b) acc[t][a][b] = 0.f;
+    // few items (narrow bottleneck): the threads left over form extra row groups, each taking every rgroups-th row of the tile
+    const int gi = kItems == 1 ? (int)threadIdx.x % items_pad : (int)threadIdx.x + t * kThreads;
+    cj[t] = -2; ck[t] = 0;
+    if (kItems == 1 && (int)threadIdx.x / items_pad >= rgroups) {
+      // idle tail of the block
+    } else if (gi < n_sq) {
+      const int eg = gi / per_group;
+      int r = gi - eg * per_group, jb = 0;
+      while (r >= nb - jb) { r -= nb - jb; ++jb; }
+      cj[t] = eg * Crg + jb * BJ;          // e*Cr + g*Crg == (e*G + g)*Crg
+      ck[t] = eg * Crg + (jb + r) * BJ;
+    } else if (gi < n_items) {
+      cj[t] = -1; ck[t] = (gi - n_sq) * BJ;
+    }
+  }
+  __syncthreads();
+  const long long tiles = (rows_total + TN - 1) / TN;
+  for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+    const long long r0 = tile * TN;
+    const int valid = (int)min((long long)TN, rows_total - r0);
+    {   // flat, coalesced BJ-wide copy of the tile with the bn1 affine (+ReLU) applied; kDepth requests in flight per thread
+      const float* zt = p.z + r0 * ECr;
+      const int total = valid * ECr;
+      constexpr int kDepth = 8;
+      const int stride = BJ * kThreads;
+      const int sq = stride % ECr;
+      int q = (BJ * threadIdx.x) % ECr;
+      for (int i = BJ * threadIdx.x; i < total; i += kDepth * stride) {
+        Vec zv[kDepth];
+        int qq[kDepth];
+#pragma unroll
+        for (int u = 0; u < kDepth; ++u) {
+          const int ii = i + u * stride;
+          qq[u] = q;
+          if (ii < total) zv[u] = *reinterpret_cast<const Vec*>(zt + ii);
+          q += sq;
+          if (q >= ECr) q -= ECr;
+        }
+#pragma unroll
+        for (int u = 0; u < kDepth; ++u) {
+          const int ii = i + u * stride;
+          if (ii < total) {
+            float* v = reinterpret_cast<float*>(&zv[u]);
+#pragma unroll
+            for (int b = 0; b < BJ; ++b) {
+              float a = fmaf(v[b], colp[qq[u] + b], colp[ECr + qq[u] + b]);
+              if (colp[2 * ECr + qq[u] + b] != 0.f) a = fmaxf(a, 0.f);
+              v[b] = a;
+            }
+            *reinterpret_cast<Vec*>(as + ii) = zv[u];
+          }
+        }
+      }
+    }
+    __syncthreads();
+    for (int n = rg; n < valid; n += rgroups) {
+      const float* row = as + n * ECr;
+#pragma unroll
+      for (int t = 0; t < kItems; ++t) {
+        if (cj[t] == -2) continue;
+        const Vec kv = *reinterpret_cast<const Vec*>(row + ck[t]);
+        const float* ak = reinterpret_cast<const float*>(&kv);
+        if (cj[t] < 0) {
+#pragma unroll
+          for (int b = 0; b < BJ; ++b) acc[t][0][b] += ak[b];
+        } else {
+          const Vec jv = *reinterpret_cast<const Vec*>(row + cj[t]);
+          const float* aj = reinterpret_cast<const float*>(&jv);
+#pragma unroll
+          for (int a = 0; a < BJ; ++a)
+#pragma unroll
+            for (int b = 0; b < BJ; ++b) acc[t][a][b] = fmaf(aj[a], ak[b], acc[t][a][b]);
+        }
+      }
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int t = 0; t < kItems; ++t) {
+    if (cj[t] == -2) continue;
+    if (cj[t] < 0) {
+#pragma unroll
+      for (int b = 0; b < BJ; ++b) atomicAdd(&m1[ck[t] + b], (double)acc[t][0][b]);
+    } else {
+      const int eg = cj[t] / Crg;
+      const int j0 = cj[t] - eg * Crg, k0 = ck[t] - eg * Crg;
+      double* mm = m2 + (long long)eg * Crg * Crg;
+#pragma unroll
+      for (int a = 0; a < BJ; ++a)
+#pragma unroll
+        for (int b = 0; b < BJ; ++b) {
+          atomicAdd(&mm[(j0 + a) * Crg + k0 + b], (double)acc[t][a][b]);
+          if (j0 != k0) atomicAdd(&mm[(k0 + b) * Crg + j0 + a], (double)acc[t][a][b]);
+        }
+    }
+  }
+}
+
 // generic (slow) variant when the moment matrix has more entries than kMomPerThread*256: one output per thread, grid-stride
 __global__ void bn_moments_big_kernel(const avmoe_expert_args p, double* m1, double* m2, long long rows_total, long long rows_per_cta) {
   const int Cr = p.Cr, G = p.G, Crg = Cr / G, E = p.E, ECr = E * Cr;
@@ -899,7 +1034,39 @@ extern "C" int avmoe_bn_moments(const avmoe_expert_args* a, double* m1, double* 
   const long long rows = (long long)a->BT * a->N;
   AVMOE_CUDA(cudaMemsetAsync(m1, 0, sizeof(double) * ECr, st));
   AVMOE_CUDA(cudaMemsetAsync(m2, 0, sizeof(double) * (size_t)a->E * a->G * Crg * Crg, st));
-  if (n_out <= (long long)kMomPerThread * kThreads) {
+  // square-blocked kernel: Crg and E*Cr multiples of the block edge, at most 4 items per thread
+  const int BJ = (Crg % 4 == 0 && ECr % 4 == 0) ? 4 : ((Crg % 2 == 0 && ECr % 2 == 0) ? 2 : 0);
+  long long n_items = 0;
+  if (BJ) n_items = (long long)a->E * a->G * ((Crg / BJ) * (Crg / BJ + 1) / 2) + ECr / BJ;
+  static const bool sq_on = []() { const char* e = getenv("AVMOE_BN_MOMENTS_SQ"); return !(e && e[0] == '0'); }();
+  if (sq_on && BJ && n_items <= 4LL * kThreads && ECr <= 2048) {
+    int TN = 8192 / ECr;
+    if (TN > 256) TN = 256;
+    if (TN < 1) TN = 1;
+    const size_t smem = sizeof(float) * ((size_t)TN * ECr + 3 * (size_t)ECr);
+    const long long tiles = (rows + TN - 1) / TN;
+    const int kI = (int)((n_items + kThreads - 1) / kThreads);
+    int occ = 1;
+#define AVMOE_MOM_SQ(BJ_, KI_)                                                                                               \
+    {                                                                                                                        \
+      if (int rc = set_smem(bn_moments_sq_kernel<BJ_, KI_>, smem, "bn_moments")) return rc;                                    \
+      AVMOE_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, bn_moments_sq_kernel<BJ_, KI_>, kThreads, smem));       \
+      if (occ < 1) occ = 1;                                                                                                  \
+      if (occ > 6) occ = 6;                                                                                                  \
+      long long cap = (4LL << 20) / n_out;                 /* bound the fp64 atomics of the final flush */                   \
+      if (cap < num_sms()) cap = num_sms();                                                                                  \
+      long long g = (long long)occ * num_sms();                                                                              \
+      if (g > cap) g = cap;                                                                                                  \
+      if (g > tiles) g = tiles;                                                                                              \
+      bn_moments_sq_kernel<BJ_, KI_><<<(int)g, kThreads, smem, st>>>(*a, m1, m2, TN, rows);                                   \
+    }
+    if (BJ == 4) {
+      if (kI == 1) AVMOE_MOM_SQ(4, 1) else if (kI == 2) AVMOE_MOM_SQ(4, 2) else if (kI == 3) AVMOE_MOM_SQ(4, 3) else AVMOE_MOM_SQ(4, 4)
+    } else {
+      if (kI == 1) AVMOE_MOM_SQ(2, 1) else if (kI == 2) AVMOE_MOM_SQ(2, 2) else if (kI == 3) AVMOE_MOM_SQ(2, 3) else AVMOE_MOM_SQ(2, 4)
+    }
+#undef AVMOE_MOM_SQ
+  } else if (n_out <= (long long)kMomPerThread * kThreads) {
     int TN = 8192 / (ECr + 1);
     if (TN > 128) TN = 128;
     if (TN < 1) TN = 1;

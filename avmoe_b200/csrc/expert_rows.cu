@@ -171,7 +171,7 @@ __global__ void __launch_bounds__(256) xg_ln_pre_fwd_kernel(const avmoe_xg_args 
 
 // ------------------------------------------------------------------------------------------------ forward: bn2 affine + ln_post + combine
 template <typename T, int kMaxV, int kTeam>
-__global__ void __launch_bounds__(256) xg_post_fwd_kernel(const avmoe_xg_args p, long long rows, int rpb) {
+__global__ void __launch_bounds__(256, 3) xg_post_fwd_kernel(const avmoe_xg_args p, long long rows, int rpb) {
   constexpr int kTeams = kWarps / kTeam;
   const Team<kTeam> tm;
   __shared__ float4 red[2][kWarps];

@@ -770,7 +770,17 @@ int gemm_dispatch(const avmoe_gemm_args* a, cudaStream_t st) {
   if (a->b_kmajor) pb.code = BK * es;
   // ---- tile N ---------------------------------------------------------------------------------
   int BN = 256;
-  if (a->N < 256) BN = (int)((a->N + 31) / 32) * 32;
+  if (a->N < 256) {
+    BN = (int)((a->N + 31) / 32) * 32;
+  } else {
+    // equal-width column tiles: N = 384 runs as 2 x 192 instead of 256 + a half-empty 128 (same tile count, a third less MMA and
+    // epilogue work on the critical CTA)
+    static const bool balance = []() { const char* e = getenv("AVMOE_GEMM_BN_BALANCE"); return !(e && e[0] == '0'); }();
+    if (balance) {
+      const long long nt = (a->N + 255) / 256;
+      BN = (int)((((a->N + nt - 1) / nt) + 31) / 32) * 32;
+    }
+  }
   if (!a->b_kmajor) {
     BN = (BN / pb.chunk) * pb.chunk;
     if (BN == 0) BN = pb.chunk;

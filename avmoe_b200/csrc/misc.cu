@@ -160,18 +160,30 @@ __global__ void reduce_bias_vec_kernel(const T* __restrict__ d, const float* __r
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
   float4 acc[kMaxV], accw[kMaxV];
   ROW_VECS(k, c) acc[k] = accw[k] = f4(0.f);
-  for (int n = n0 + warp; n < n1; n += nwarps) {
-    const float rw = roww ? __ldg(roww + n) : 0.f;
-    float racc = 0.f;
-    ROW_VECS(k, c) {
-      const float4 v = ldg_act4<T>(db + (long long)n * C + c);
-      acc[k] = acc[k] + v;
-      accw[k] = accw[k] + rw * v;
-      if (rows_w) racc += hsum(colw ? v * ldg4(colw + c) : v);
+  // kU rows per warp step, all requested before the first is consumed (narrow rows: one row per warp in flight is latency-bound)
+  constexpr int kU = kMaxV <= 2 ? 4 : 1;
+  for (int nb = n0 + warp; nb < n1; nb += nwarps * kU) {
+    float4 v[kU][kMaxV];
+#pragma unroll
+    for (int u = 0; u < kU; ++u) {
+      const int n = nb + u * nwarps;
+      ROW_VECS(k, c) v[u][k] = n < n1 ? ldg_act4<T>(db + (long long)n * C + c) : f4(0.f);
     }
-    if (rows_w) {
-      racc = warp_sum(racc);
-      if (lane == 0) atomicAdd(&rows_w[n], racc);
+#pragma unroll
+    for (int u = 0; u < kU; ++u) {
+      const int n = nb + u * nwarps;
+      if (n >= n1) break;                                   // warp-uniform
+      const float rw = roww ? __ldg(roww + n) : 0.f;
+      float racc = 0.f;
+      ROW_VECS(k, c) {
+        acc[k] = acc[k] + v[u][k];
+        accw[k] = accw[k] + rw * v[u][k];
+        if (rows_w) racc += hsum(colw ? v[u][k] * ldg4(colw + c) : v[u][k]);
+      }
+      if (rows_w) {
+        racc = warp_sum(racc);
+        if (lane == 0) atomicAdd(&rows_w[n], racc);
+      }
     }
   }
   ROW_VECS(k, c) {

@@ -1,45 +1,81 @@
 // Router of the AVMoE adapter: mean-pooled modalities -> Linear(2C,128) -> ReLU -> Linear(128,32) -> ReLU
 // -> Linear(32,E) (+ optional noise) -> softmax -> argmax, all in fp32 with a fixed reduction order so the
 // expert selection is reproducible bit-for-bit (AVMOE/AVE/nets/net_trans_v3.py:460-466,472-479; noise:
-// AVMOE/AVS/avs_scripts/avs_s4/model/PVT_AVSModel_v2.py:294-296).  One CTA per sample.
+// AVMOE/AVS/avs_scripts/avs_s4/model/PVT_AVSModel_v2.py:294-296).  The wide first layer is tiled over samples.
 // Also: the load-balancing loss quirk  -sum_e log(mean_b p[b,e])  (AVMOE/AVVP/nets/mgn.py:220-224).
+#include <atomic>
 #include "common.cuh"
 
 namespace avmoe {
 
 static constexpr int kH1 = 128, kH2 = 32;
 
-// grid BT, block 128.  smem: rin[2C] + h1[128] + h2[32] + logits[E]
-__global__ void router_fwd_kernel(const float* __restrict__ px, const float* __restrict__ pv, int chunks_x, int chunks_v, int C, int E,
-                                  float inv_n, const float* __restrict__ w0, const float* __restrict__ b0,
-                                  const float* __restrict__ w2, const float* __restrict__ b2, const float* __restrict__ w4,
-                                  const float* __restrict__ b4, const float* __restrict__ noise, float* __restrict__ probs,
-                                  long long* __restrict__ idx, float* __restrict__ h1o, float* __restrict__ h2o, float* __restrict__ rin_o) {
-  extern __shared__ float sm[];
-  float* rin = sm;
-  float* h1 = rin + 2 * C;
-  float* h2 = h1 + kH1;
-  float* lg = h2 + kH2;
-  const int b = blockIdx.x;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
-  for (int c = threadIdx.x; c < C; c += blockDim.x) {
-    float s = 0.f;
-    for (int k = 0; k < chunks_x; ++k) s += px[((long long)b * chunks_x + k) * C + c];
-    float t = 0.f;
-    for (int k = 0; k < chunks_v; ++k) t += pv[((long long)b * chunks_v + k) * C + c];
-    rin[c] = s * inv_n;
-    rin[C + c] = t * inv_n;
-    rin_o[(long long)b * 2 * C + c] = rin[c];
-    rin_o[(long long)b * 2 * C + C + c] = rin[C + c];
+// ---- forward, layer 1: h1 = relu(rin · W0ᵀ + b0) for a tile of kSB samples x kHB hidden units per CTA.
+// One CTA per sample (the first version) made every CTA stream all of W0 (0.4-1.6 MB fp32) from L2 behind dependent
+// load->FMA chains; here a CTA reads only its kHB rows of W0 and reuses each weight for kSB samples held in shared memory.
+// Each (sample, unit) sum keeps the same order as before -- lane-strided over the inputs, then the warp tree -- so the logits,
+// and with them the selected expert, do not depend on the tiling.
+// grid (ceil(BT/kSB), kH1/kHB), block 256 (8 warps x 4 units).  smem: rin[kSB][2C]
+static constexpr int kSB = 8, kHB = 32;
+__global__ void __launch_bounds__(256) router_l1_kernel(const float* __restrict__ px, const float* __restrict__ pv, int chunks_x, int chunks_v, int BT, int C,
+                                                        float inv_n, const float* __restrict__ w0, const float* __restrict__ b0,
+                                                        float* __restrict__ h1o, float* __restrict__ rin_o) {
+  extern __shared__ float rin[];          // [kSB][2C]
+  const int b0i = blockIdx.x * kSB;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int C2 = 2 * C;
+  for (int i = threadIdx.x; i < kSB * C2; i += blockDim.x) {
+    const int s = i / C2, c2 = i - s * C2;
+    const int b = b0i + s;
+    float v = 0.f;
+    if (b < BT) {
+      float t = 0.f;
+      if (c2 < C) { for (int k = 0; k < chunks_x; ++k) t += px[((long long)b * chunks_x + k) * C + c2]; }
+      else        { for (int k = 0; k < chunks_v; ++k) t += pv[((long long)b * chunks_v + k) * C + (c2 - C)]; }
+      v = t * inv_n;
+      if (blockIdx.y == 0) rin_o[(long long)b * C2 + c2] = v;
+    }
+    rin[i] = v;
   }
   __syncthreads();
-  for (int j = warp; j < kH1; j += nwarps) {
-    const float* wr = w0 + (long long)j * 2 * C;
-    float s = 0.f;
-    for (int i = lane; i < 2 * C; i += 32) s = fmaf(wr[i], rin[i], s);
-    s = warp_sum(s);
-    if (lane == 0) { s = fmaxf(s + b0[j], 0.f); h1[j] = s; h1o[(long long)b * kH1 + j] = s; }
+  constexpr int kU = 4;                    // hidden units per warp
+  const int j0 = blockIdx.y * kHB + warp * kU;
+  float acc[kU][kSB];
+#pragma unroll
+  for (int u = 0; u < kU; ++u)
+#pragma unroll
+    for (int q = 0; q < kSB; ++q) acc[u][q] = 0.f;
+  const float* wr = w0 + (long long)j0 * C2;
+  for (int i = lane; i < C2; i += 32) {
+    float w[kU], r[kSB];
+#pragma unroll
+    for (int u = 0; u < kU; ++u) w[u] = __ldg(wr + (long long)u * C2 + i);
+#pragma unroll
+    for (int q = 0; q < kSB; ++q) r[q] = rin[q * C2 + i];
+#pragma unroll
+    for (int u = 0; u < kU; ++u)
+#pragma unroll
+      for (int q = 0; q < kSB; ++q) acc[u][q] = fmaf(w[u], r[q], acc[u][q]);
   }
+#pragma unroll
+  for (int u = 0; u < kU; ++u)
+#pragma unroll
+    for (int q = 0; q < kSB; ++q) {
+      const float t = warp_sum(acc[u][q]);
+      if (lane == 0 && b0i + q < BT) h1o[(long long)(b0i + q) * kH1 + j0 + u] = fmaxf(t + b0[j0 + u], 0.f);
+    }
+}
+
+// ---- forward, layers 2-3 + softmax + argmax: grid BT, block 128.
+__global__ void __launch_bounds__(128) router_l23_kernel(int E, const float* __restrict__ h1g, const float* __restrict__ w2, const float* __restrict__ b2,
+                                                         const float* __restrict__ w4, const float* __restrict__ b4, const float* __restrict__ noise,
+                                                         float* __restrict__ probs, long long* __restrict__ idx, float* __restrict__ h2o) {
+  __shared__ float h1[kH1];
+  __shared__ float h2[kH2];
+  __shared__ float lg[AVMOE_MAX_EXPERTS];
+  const int b = blockIdx.x;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  for (int i = threadIdx.x; i < kH1; i += blockDim.x) h1[i] = h1g[(long long)b * kH1 + i];
   __syncthreads();
   for (int j = warp; j < kH2; j += nwarps) {
     const float* wr = w2 + (long long)j * kH1;
@@ -71,15 +107,13 @@ __global__ void router_fwd_kernel(const float* __restrict__ px, const float* __r
   }
 }
 
-// grid BT, block 128: per-sample backward down to d(rin); stores dh1/dh2/dlogits for the weight-gradient kernel
-__global__ void router_bwd_sample_kernel(const float* __restrict__ dprobs, const float* __restrict__ probs, const float* __restrict__ h1,
-                                         const float* __restrict__ h2, int C, int E, float inv_n, const float* __restrict__ w0,
-                                         const float* __restrict__ w2, const float* __restrict__ w4, float* __restrict__ dlg_o,
-                                         float* __restrict__ dh2_o, float* __restrict__ dh1_o, float* __restrict__ dpool_x,
-                                         float* __restrict__ dpool_v) {
+// ---- backward, per sample down to d(h1): grid BT, block 128; stores dh1/dh2/dlogits for the weight-gradient kernel
+__global__ void __launch_bounds__(128) router_bwd_sample_kernel(const float* __restrict__ dprobs, const float* __restrict__ probs, const float* __restrict__ h1,
+                                                                const float* __restrict__ h2, int E, const float* __restrict__ w2,
+                                                                const float* __restrict__ w4, float* __restrict__ dlg_o, float* __restrict__ dh2_o,
+                                                                float* __restrict__ dh1_o) {
   __shared__ float dlg[AVMOE_MAX_EXPERTS];
   __shared__ float dh2[kH2];
-  __shared__ float dh1[kH1];
   const int b = blockIdx.x;
   if (threadIdx.x == 0) {
     float dot = 0.f;
@@ -105,16 +139,46 @@ __global__ void router_bwd_sample_kernel(const float* __restrict__ dprobs, const
     float s = 0.f;
     for (int k = 0; k < kH2; ++k) s = fmaf(dh2[k], w2[(long long)k * kH1 + j], s);
     s = h1[(long long)b * kH1 + j] > 0.f ? s : 0.f;
-    dh1[j] = s;
     dh1_o[(long long)b * kH1 + j] = s;
   }
+}
+
+// ---- backward, d(pooled input) = dh1 · W0 / n for a tile of kSB samples x 256 input columns per CTA (W0 read once per sample
+// tile, coalesced along the inputs; each column's sum runs over the 128 hidden units in order, as before)
+// grid (ceil(BT/kSB), ceil(2C/256)), block 256
+__global__ void __launch_bounds__(256) router_bwd_dpool_kernel(const float* __restrict__ dh1g, int BT, int C, float inv_n, const float* __restrict__ w0,
+                                                               float* __restrict__ dpool_x, float* __restrict__ dpool_v) {
+  __shared__ float dh1[kSB][kH1];
+  const int b0i = blockIdx.x * kSB;
+  const int C2 = 2 * C;
+  for (int i = threadIdx.x; i < kSB * kH1; i += blockDim.x) {
+    const int q = i / kH1, j = i - q * kH1;
+    dh1[q][j] = b0i + q < BT ? dh1g[(long long)(b0i + q) * kH1 + j] : 0.f;
+  }
   __syncthreads();
-  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) {
-    float s = 0.f;
-    for (int j = 0; j < kH1; ++j) s = fmaf(dh1[j], w0[(long long)j * 2 * C + i], s);
-    s *= inv_n;
-    if (i < C) dpool_x[(long long)b * C + i] = s;
-    else dpool_v[(long long)b * C + (i - C)] = s;
+  const int i = blockIdx.y * blockDim.x + threadIdx.x;
+  if (i >= C2) return;
+  float acc[kSB];
+#pragma unroll
+  for (int q = 0; q < kSB; ++q) acc[q] = 0.f;
+  constexpr int kJ = 8;                    // weight loads in flight per thread
+  for (int j0 = 0; j0 < kH1; j0 += kJ) {
+    float w[kJ];
+#pragma unroll
+    for (int u = 0; u < kJ; ++u) w[u] = __ldg(w0 + (long long)(j0 + u) * C2 + i);
+#pragma unroll
+    for (int u = 0; u < kJ; ++u)
+#pragma unroll
+      for (int q = 0; q < kSB; ++q) acc[q] = fmaf(dh1[q][j0 + u], w[u], acc[q]);
+  }
+#pragma unroll
+  for (int q = 0; q < kSB; ++q) {
+    const int b = b0i + q;
+    if (b < BT) {
+      const float v = acc[q] * inv_n;
+      if (i < C) dpool_x[(long long)b * C + i] = v;
+      else dpool_v[(long long)b * C + (i - C)] = v;
+    }
   }
 }
 
@@ -187,10 +251,22 @@ extern "C" int avmoe_router_fwd(const float* pool_x, const float* pool_v, int ch
                                 const float* noise, float* probs, int64_t* idx, float* h1, float* h2, float* rin, avmoe_stream_t stream) {
   AVMOE_CHECK_ARG(pool_x && pool_v && probs && idx && h1 && h2 && rin && w0 && w2 && w4, "router_fwd: null pointer");
   AVMOE_CHECK_ARG(E >= 1 && E <= AVMOE_MAX_EXPERTS && BT > 0 && C > 0, "router_fwd: bad sizes (E=%d)", E);
-  const size_t smem = (2 * (size_t)C + kH1 + kH2 + AVMOE_MAX_EXPERTS) * sizeof(float);
-  router_fwd_kernel<<<BT, 512, smem, reinterpret_cast<cudaStream_t>(stream)>>>(pool_x, pool_v, chunks_x, chunks_v, C, E, inv_n, w0, b0, w2, b2,
-                                                                                w4, b4, noise, probs, (long long*)idx, h1, h2, rin);
-  AVMOE_LAUNCH_CHECK("router_fwd_kernel");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const size_t smem = (size_t)kSB * 2 * C * sizeof(float);
+  AVMOE_CHECK_ARG(smem <= 200 * 1024, "router_fwd: C too large (%d)", C);
+  if (smem > 48 * 1024) {
+    static std::atomic<int> max_set[64];
+    int dev = 0;
+    AVMOE_CUDA(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64 || max_set[dev].load(std::memory_order_acquire) < (int)smem) {
+      AVMOE_CUDA(cudaFuncSetAttribute(router_l1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      if (dev >= 0 && dev < 64) max_set[dev].store(200 * 1024, std::memory_order_release);
+    }
+  }
+  router_l1_kernel<<<dim3((BT + kSB - 1) / kSB, kH1 / kHB), 256, smem, st>>>(pool_x, pool_v, chunks_x, chunks_v, BT, C, inv_n, w0, b0, h1, rin);
+  AVMOE_LAUNCH_CHECK("router_l1_kernel");
+  router_l23_kernel<<<BT, 128, 0, st>>>(E, h1, w2, b2, w4, b4, noise, probs, (long long*)idx, h2);
+  AVMOE_LAUNCH_CHECK("router_l23_kernel");
   return 0;
 }
 
@@ -204,8 +280,10 @@ extern "C" int avmoe_router_bwd(const float* dprobs, const float* probs, const f
   float* dlg = ws;
   float* dh2 = dlg + (size_t)BT * E;
   float* dh1 = dh2 + (size_t)BT * kH2;
-  router_bwd_sample_kernel<<<BT, 256, 0, st>>>(dprobs, probs, h1, h2, C, E, inv_n, w0, w2, w4, dlg, dh2, dh1, dpool_x, dpool_v);
+  router_bwd_sample_kernel<<<BT, 128, 0, st>>>(dprobs, probs, h1, h2, E, w2, w4, dlg, dh2, dh1);
   AVMOE_LAUNCH_CHECK("router_bwd_sample_kernel");
+  router_bwd_dpool_kernel<<<dim3((BT + kSB - 1) / kSB, (2 * C + 255) / 256), 256, 0, st>>>(dh1, BT, C, inv_n, w0, dpool_x, dpool_v);
+  AVMOE_LAUNCH_CHECK("router_bwd_dpool_kernel");
   const dim3 wblock(32, 8);
   router_wgrad_kernel<<<dim3((2 * C + 31) / 32, kH1), wblock, 0, st>>>(dh1, rin, dw0, db0, BT, kH1, 2 * C);
   router_wgrad_kernel<<<dim3((kH1 + 31) / 32, kH2), wblock, 0, st>>>(dh2, h1, dw2, db2, BT, kH2, kH1);

@@ -143,6 +143,16 @@ class ExpertGrads:
 # -------------------------------------------------------------------------------------------------
 # resampler: vis' = fc(conv_adapter(other))          (net_trans_v3.py:469-471)
 # -------------------------------------------------------------------------------------------------
+def _pad_k(t: torch.Tensor) -> torch.Tensor:
+    """Zero-pad the contraction (innermost) extent of a token-GEMM operand to a 16-byte row pitch: the stage-4 visual stream has
+    36 tokens (72-byte bf16 rows), which a TMA tensor map cannot address; zero columns leave the product unchanged and keep the
+    GEMM on the tensor cores instead of the generic fallback kernel."""
+    mult = 16 // t.element_size()
+    k = t.shape[-1]
+    kp = -(-k // mult) * mult
+    return t if kp == k else torch.nn.functional.pad(t, (0, kp - k))
+
+
 def resample_fwd(K, cfg: AdapterConfig, o: torch.Tensor, w_tok, b_tok, w_fc, b_fc):
     """o [BT,Nx,Cx] -> v [BT,N,C].  Returns (v, saved) where saved holds the GEMM intermediate.
 
@@ -163,12 +173,12 @@ def resample_fwd(K, cfg: AdapterConfig, o: torch.Tensor, w_tok, b_tok, w_fc, b_f
     fc_first = Cx > C
     if fc_first:
         P = K.gemm(o.reshape(BT * Nx, Cx), wf_l).reshape(BT, Nx, C)
-        Pt = K.transpose(P)                                                     # [BT,C,Nx]
+        Pt = _pad_k(K.transpose(P))                                             # [BT,C,Nx(+pad)]
         s = K.rowsum(w_fc)                                                      # [C] fp32
-        v = K.gemm(wt_l, Pt.reshape(BT * C, Nx), d_nbatch=C, row_bias=b_tok, col_scale=s, col_bias=b_fc)
+        v = K.gemm(_pad_k(wt_l), Pt.reshape(BT * C, -1), d_nbatch=C, row_bias=b_tok, col_scale=s, col_bias=b_fc)
         return v, (fc_first, P, s)
-    Ot = K.transpose(o)                                                         # [BT,Cx,Nx]
-    U = K.gemm(wt_l, Ot.reshape(BT * Cx, Nx), d_nbatch=Cx, row_bias=b_tok)      # [BT,N,Cx]
+    Ot = _pad_k(K.transpose(o))                                                 # [BT,Cx,Nx(+pad)]
+    U = K.gemm(_pad_k(wt_l), Ot.reshape(BT * Cx, -1), d_nbatch=Cx, row_bias=b_tok)      # [BT,N,Cx]
     v = K.gemm(U.reshape(BT * N, Cx), wf_l, col_bias=b_fc).reshape(BT, N, C)
     return v, (fc_first, U, None)
 
@@ -187,8 +197,8 @@ def resample_bwd(K, cfg: AdapterConfig, o: torch.Tensor, dv: torch.Tensor, saved
         # bias grads: db_fc[c] = sum dv ; db_tok[n] = sum_c dv*s[c] ; ds[c] = sum_n dv*b_tok[n]  (d rowsum(W_fc))
         db_tok, db_fc, ds = K.reduce_bias(dv, col_weight=s, row_weight=b_tok)
         dw_tok = K.gemm(dv, P, out_dtype=f32, split_k=K.split_k_hint(BT * C, N, Nx))   # sum_b dv[b]·P[b]ᵀ   [N,Nx]
-        dVt = K.transpose(dv)                                                   # [BT,C,N]
-        dP = K.gemm(wt_T, dVt.reshape(BT * C, N), d_nbatch=C)                   # W_tokᵀ·dv[b]             [BT,Nx,C]
+        dVt = _pad_k(K.transpose(dv))                                           # [BT,C,N(+pad)]
+        dP = K.gemm(_pad_k(wt_T), dVt.reshape(BT * C, -1), d_nbatch=C)          # W_tokᵀ·dv[b]             [BT,Nx,C]
         dP2 = dP.reshape(BT * Nx, C)
         dw_fc = K.gemm(dP2, o.reshape(BT * Nx, Cx), a_kmajor=False, b_kmajor=False, out_dtype=f32,
                        split_k=K.split_k_hint(BT * Nx, C, Cx), row_bias=ds)      # dPᵀ·o + ds⊗1             [C,Cx]
@@ -204,8 +214,8 @@ def resample_bwd(K, cfg: AdapterConfig, o: torch.Tensor, dv: torch.Tensor, saved
     dw_tok = K.gemm(dU, o, out_dtype=f32, split_k=K.split_k_hint(BT * Cx, N, Nx))     # sum_b dU[b]·o[b]ᵀ        [N,Nx]
     do = None
     if need_do:
-        dUt = K.transpose(dU)                                                    # [BT,Cx,N]
-        do = K.gemm(wt_T, dUt.reshape(BT * Cx, N), d_nbatch=Cx)                  # W_tokᵀ·dU[b]             [BT,Nx,Cx]
+        dUt = _pad_k(K.transpose(dU))                                            # [BT,Cx,N(+pad)]
+        do = K.gemm(_pad_k(wt_T), dUt.reshape(BT * Cx, -1), d_nbatch=Cx)         # W_tokᵀ·dU[b]             [BT,Nx,Cx]
     return do, dw_tok.reshape(N, Nx, 1, 1), db_tok, dw_fc, db_fc
 
 

@@ -37,6 +37,10 @@ def parse_args():
     ap.add_argument("--clips", type=int, default=16, help="clips per GPU (x10 segments = BT)")
     ap.add_argument("--segments", type=int, default=10)
     ap.add_argument("--dtype", default="bf16", choices=["bf16", "f32"])
+    ap.add_argument("--f32-gemm", default="tf32", choices=["tf32", "exact"],
+                    help="--dtype f32 only: 'tf32' runs the fp32 stream through the same tcgen05 GEMM orchestration as bf16 with TF32 operands "
+                         "(fp32 accumulate; the 1e-3 configuration of BASELINE.json config 2), 'exact' keeps the fused kernels whose "
+                         "contractions are plain fp32 FMAs (the drop-in's default for fp32 inputs: bit-faithful to torch's fp32 matmul, slow)")
     ap.add_argument("--cpu-sample-clips", type=int, default=2, help="clips in the bounded CPU-baseline sample (2 x 10 = the reference's own batch, AVMOE/AVE/train.sh:32-33)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-gpu-eager", action="store_true", help="skip the reported GPU comparator (reference modules in PyTorch eager on the same GPU)")
@@ -177,6 +181,8 @@ def run_ours(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     dtype = torch.bfloat16 if args.dtype == "bf16" else torch.float32
+    if dtype == torch.float32 and args.f32_gemm == "tf32":
+        ops.USE_GEMM_ATTENTION = ops.USE_GEMM_EXPERTS = "always"
     BT = args.clips * args.segments
     model = S.AdapterStack(args.variant, seed=0).to(dev)
     model.train()
@@ -444,7 +450,8 @@ def run_ours(args):
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
                 "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "bf16" if dtype == torch.bfloat16 else "f32", "data": "synthetic",
-                "config": {"workload": workload_name(args), "variant": args.variant, "BT_per_gpu": BT, "tokens_per_step_per_gpu": tokens_per_step,
+                "config": {"workload": workload_name(args), "variant": args.variant,
+                           **({"f32_gemm": args.f32_gemm} if dtype == torch.float32 else {}), "BT_per_gpu": BT, "tokens_per_step_per_gpu": tokens_per_step,
                            "adapter_calls_per_step": 4 * len(model.sites), "launch": launch_mode, "parallelism": f"dp{world} (batch-sharded, grad all-reduce)" if world > 1 else "single GPU",
                            "l2": f"inputs+weights per step ({(h2d_bytes + sum(p.numel() * 4 for p in params)) / 1e6:.0f} MB) exceed the 126 MB L2; no explicit flush"},
                 "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "optimizer": optimizer, "kernels": kernel_table}

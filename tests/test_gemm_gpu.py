@@ -190,3 +190,39 @@ def test_bgemm_accumulates_into_existing_output(dtype, impl):
     ops.bgemm(A, B, b_kmajor=False, out=D, accumulate=True, impl=impl)
     want = D0.float() + A.float() @ B.float()
     assert util.rel_err(D.float(), want) < (1e-2 if dtype == torch.bfloat16 else _tol(dtype))
+
+
+STAGE_SITES = [(stage, modality) for stage in (1, 2, 3, 4) for modality in ("audio", "visual")]
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32])
+@pytest.mark.parametrize("stage,modality", STAGE_SITES)
+def test_resampler_stays_on_tensor_cores_all_stages(stage, modality, dtype, monkeypatch):
+    """The token resampler (conv_adapter + fc, AVMOE/AVE/nets/net_trans_v3.py:445-446,469-471) forward and backward at all eight
+    backbone shapes with the no-fallback GEMM mode (impl=2 refuses the generic kernel): stage 4's 36-token stream is
+    zero-padded to a 16-byte row pitch so that it stays expressible as a TMA tensor map."""
+    from avmoe_b200 import ops, functional as F, stack as S
+    monkeypatch.setattr(ops, "_GEMM_IMPL_OVERRIDE", 2)
+    Cv, Nv, Ca, Na = S.STAGE_SHAPES[stage]
+    (C, N, Cx, Nx) = (Ca, Na, Cv, Nv) if modality == "audio" else (Cv, Nv, Ca, Na)
+    cfg = F.AdapterConfig(C=C, N=N, Cx=Cx, Nx=Nx, r=8, G=2, T=32, Mm=1, Ms=1, use_bn=True, use_gate=True, ln_before=True, ln_post=True)
+    BT = 2
+    o = _mk((BT, Nx, Cx), dtype, 1)
+    w_tok = (_mk((N, Nx, 1, 1), torch.float32, 2) / Nx ** 0.5).contiguous()
+    b_tok, b_fc = _mk((N,), torch.float32, 3), _mk((C,), torch.float32, 5)
+    w_fc = (_mk((C, Cx), torch.float32, 4) / Cx ** 0.5).contiguous()
+    v, saved = F.resample_fwd(ops, cfg, o, w_tok, b_tok, w_fc, b_fc)
+    wt = w_tok.reshape(N, Nx)
+    ref = torch.einsum("nm,bmc->bnc", wt, o.float()) + b_tok[None, :, None]
+    ref = ref @ w_fc.t() + b_fc
+    tol = 2e-2 if dtype == torch.bfloat16 else 2e-3
+    assert util.rel_err(v.float(), ref) < tol
+    dv = _mk((BT, N, C), dtype, 6)
+    do, dw_tok, db_tok, dw_fc, db_fc = F.resample_bwd(ops, cfg, o, dv, saved, w_tok, b_tok, w_fc)
+    o_ = o.float().requires_grad_()
+    wt_, wf_ = wt.clone().requires_grad_(), w_fc.clone().requires_grad_()
+    out = (torch.einsum("nm,bmc->bnc", wt_, o_) + b_tok[None, :, None]) @ wf_.t() + b_fc
+    out.backward(dv.float())
+    assert util.rel_err(do.float(), o_.grad) < tol
+    assert util.rel_err(dw_tok.reshape(N, Nx), wt_.grad) < tol
+    assert util.rel_err(dw_fc, wf_.grad) < tol
