@@ -29,6 +29,18 @@ class GemmArgs(C.Structure):
     ]
 
 
+class ResampleArgs(C.Structure):
+    """avmoe_resample_args (include/avmoe_b200.h): the op-level token-resampler entry."""
+    _fields_ = [
+        ("dtype", C.c_int32), ("BT", C.c_int32), ("N", C.c_int32), ("Nx", C.c_int32), ("C", C.c_int32), ("Cx", C.c_int32),
+        ("gemm_impl", C.c_int32),
+        ("o", C.c_void_p), ("w_tok", C.c_void_p), ("b_tok", C.c_void_p), ("w_fc", C.c_void_p), ("b_fc", C.c_void_p),
+        ("v", C.c_void_p), ("mid", C.c_void_p), ("s", C.c_void_p),
+        ("dv", C.c_void_p), ("d_o", C.c_void_p), ("dw_tok", C.c_void_p), ("db_tok", C.c_void_p), ("dw_fc", C.c_void_p), ("db_fc", C.c_void_p),
+        ("workspace", C.c_void_p), ("workspace_bytes", C.c_int64), ("launches", C.c_int32),
+    ]
+
+
 def lib_path() -> str:
     return _build.LIB_PATH
 

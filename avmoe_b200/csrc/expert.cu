@@ -460,6 +460,25 @@ __global__ void __launch_bounds__(kThreads, kItems <= 3 ? 2 : 1) bn_moments_sq_k
     }
     __syncthreads();
   }
+  if (kItems == 1 && rgroups > 1 && TN * ECr >= kThreads * BJ * BJ) {
+    // the row groups of an item are combined inside the CTA first (fixed order), so each output receives ONE fp64 atomic per CTA:
+    // same-address atomics serialise in L2, and 4-8 x as many of them had become the tail of the narrow-bottleneck launches
+    float* scr = as;                       // tile storage is free after the last barrier of the tile loop
+#pragma unroll
+    for (int a = 0; a < BJ; ++a)
+#pragma unroll
+      for (int b = 0; b < BJ; ++b) scr[(threadIdx.x * BJ + a) * BJ + b] = acc[0][a][b];
+    __syncthreads();
+    if (rg == 0) {
+      for (int g = 1; g < rgroups; ++g)
+#pragma unroll
+        for (int a = 0; a < BJ; ++a)
+#pragma unroll
+          for (int b = 0; b < BJ; ++b) acc[0][a][b] += scr[((g * items_pad + (int)threadIdx.x) * BJ + a) * BJ + b];
+    } else {
+      cj[0] = -2;
+    }
+  }
 #pragma unroll
   for (int t = 0; t < kItems; ++t) {
     if (cj[t] == -2) continue;
@@ -1052,7 +1071,7 @@ extern "C" int avmoe_bn_moments(const avmoe_expert_args* a, double* m1, double* 
       if (int rc = set_smem(bn_moments_sq_kernel<BJ_, KI_>, smem, "bn_moments")) return rc;                                    \
       AVMOE_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, bn_moments_sq_kernel<BJ_, KI_>, kThreads, smem));       \
       if (occ < 1) occ = 1;                                                                                                  \
-      if (occ > 6) occ = 6;                                                                                                  \
+      if (occ > 3) occ = 3;                                                                                                  \
       long long cap = (4LL << 20) / n_out;                 /* bound the fp64 atomics of the final flush */                   \
       if (cap < num_sms()) cap = num_sms();                                                                                  \
       long long g = (long long)occ * num_sms();                                                                              \

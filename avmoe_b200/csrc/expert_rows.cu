@@ -535,6 +535,48 @@ __global__ void xg_bn1_bwd_apply_kernel(const avmoe_xg_args p, long long rows) {
   }
 }
 
+// 4 bottleneck channels per thread (Cr % 4 == 0, Crp % 4 == 0): 16-byte loads of da and z, one 8/16-byte store of dz
+template <typename T>
+__global__ void xg_bn1_bwd_apply_vec_kernel(const avmoe_xg_args p, long long rows) {
+  const int e = blockIdx.y;
+  const unsigned q4 = (unsigned)p.Crp >> 2;
+  const unsigned total4 = (unsigned)(rows * q4);
+  const bool relu = p.ex[e].relu != 0;
+  const float inv_n = 1.f / (float)rows;
+  const float* da = p.da + (long long)e * rows * p.Crp;
+  T* dz = static_cast<T*>(p.dz) + (long long)e * rows * p.Crp;
+  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total4; i += gridDim.x * blockDim.x) {
+    const unsigned row = i / q4, cp = (i - row * q4) << 2;
+    float v[4] = {0.f, 0.f, 0.f, 0.f};
+    if ((int)cp < p.Cr) {
+      const float4 zz4 = *reinterpret_cast<const float4*>(p.z + ((long long)row * p.E + e) * p.Cr + cp);
+      const float4 d4 = *reinterpret_cast<const float4*>(da + (long long)row * p.Crp + cp);
+      const float zz[4] = {zz4.x, zz4.y, zz4.z, zz4.w};
+      const float dd[4] = {d4.x, d4.y, d4.z, d4.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int ch = e * p.Cr + cp + j;
+        float t = dd[j];
+        if (p.bn_mode == AVMOE_BN_OFF) {
+          if (relu && zz[j] <= 0.f) t = 0.f;
+        } else {
+          const float2 sb = reinterpret_cast<const float2*>(p.aff1)[ch];
+          if (relu && fmaf(zz[j], sb.x, sb.y) <= 0.f) t = 0.f;
+          if (p.bn_mode == AVMOE_BN_TRAIN) {
+            const float2 mi = reinterpret_cast<const float2*>(p.save1)[ch];
+            const float m1 = (float)(p.red1[2 * ch] * (double)inv_n), m2 = (float)(p.red1[2 * ch + 1] * (double)inv_n);
+            t = sb.x * (t - m1 - (zz[j] - mi.x) * mi.y * m2);
+          } else {
+            t *= sb.x;
+          }
+        }
+        v[j] = t;
+      }
+    }
+    st_act4<T>(dz + (long long)row * p.Crp + cp, make_float4(v[0], v[1], v[2], v[3]));
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ weight operands / weight gradients
 __device__ __forceinline__ float wd_dense(const float* wd, int r, int c, int Cr, int C, int G) {   // wd [Cr][C/G]
   const int Cg = C / G, Crg = Cr / G, g = r / Crg;
@@ -751,7 +793,10 @@ extern "C" int avmoe_xg_bn1_bwd(const avmoe_xg_args* a, avmoe_stream_t stream) {
     AVMOE_LAUNCH_CHECK("xg_bn1_bwd_reduce_kernel");
   }
   dim3 grid((unsigned)min((long long)(8 * num_sms()), (rows * a->Crp + 255) / 256), a->E);
-  if (a->dtype == AVMOE_F32) xg_bn1_bwd_apply_kernel<float><<<grid, 256, 0, st>>>(*a, rows);
+  if (a->Cr % 4 == 0 && a->Crp % 4 == 0) {
+    if (a->dtype == AVMOE_F32) xg_bn1_bwd_apply_vec_kernel<float><<<grid, 256, 0, st>>>(*a, rows);
+    else xg_bn1_bwd_apply_vec_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(*a, rows);
+  } else if (a->dtype == AVMOE_F32) xg_bn1_bwd_apply_kernel<float><<<grid, 256, 0, st>>>(*a, rows);
   else xg_bn1_bwd_apply_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(*a, rows);
   AVMOE_LAUNCH_CHECK("xg_bn1_bwd_apply_kernel");
   return 0;

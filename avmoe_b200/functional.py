@@ -165,6 +165,8 @@ def resample_fwd(K, cfg: AdapterConfig, o: torch.Tensor, w_tok, b_tok, w_fc, b_f
     The token-resampling GEMM always runs in K-major x K-major form on the tensor cores: its activation operand is
     re-laid out channel-major ([BT,c,Nx], one bandwidth-bound transpose) because tcgen05 reads MN-major operands at
     well under half the K-major rate (profiles/r01_gemm_microbench.md)."""
+    if getattr(K, "use_resample_op", lambda: False)():        # product path: the same sequence, issued from C++ in one C-ABI call
+        return K.resample_fwd_op(cfg, o, w_tok, b_tok, w_fc, b_fc)
     BT = o.shape[0]
     dt = o.dtype
     N, Nx, C, Cx = cfg.N, cfg.Nx, cfg.C, cfg.Cx
@@ -185,6 +187,8 @@ def resample_fwd(K, cfg: AdapterConfig, o: torch.Tensor, w_tok, b_tok, w_fc, b_f
 
 def resample_bwd(K, cfg: AdapterConfig, o: torch.Tensor, dv: torch.Tensor, saved, w_tok, b_tok, w_fc, need_do: bool = True):
     """Gradients of resample_fwd.  dv [BT,N,C] (activation dtype).  Returns (do, dw_tok, db_tok, dw_fc, db_fc)."""
+    if getattr(K, "use_resample_op", lambda: False)():
+        return K.resample_bwd_op(cfg, o, dv, saved, w_tok, b_tok, w_fc, need_do)
     fc_first, mid, s = saved
     BT = o.shape[0]
     dt = o.dtype
@@ -478,13 +482,16 @@ class MoEAdapterFunction(torch.autograd.Function):
         aux_saved = {}
         aux_kind: Dict[int, str] = {}
         gate_keys: List[Optional[str]] = []
-        # bf16 streams run the latent attention on the tensor-core GEMM.  fp32 streams keep the fused kernels whose
+        # bf16 streams run the latent attention on the tensor-core GEMM.  fp32 streams by default keep the fused kernels whose
         # contractions are exact fp32 FMAs, like the reference's torch.bmm (matmul TF32 is off by default in torch);
         # "always" forces the GEMM path for either dtype (tests).
+        # fp32 streams follow torch's own switch: with torch.backends.cuda.matmul.allow_tf32 they take the same GEMM orchestration
+        # with TF32 operands (what the reference's bmm/linear would do under that flag; ~10x faster than the exact kernels).
         _flag = getattr(K, "USE_GEMM_ATTENTION", False)
-        use_gemm_attn = _flag == "always" or (bool(_flag) and x.dtype == torch.bfloat16)
+        on_tc = x.dtype == torch.bfloat16 or (x.dtype == torch.float32 and bool(getattr(K, "fp32_on_tensor_cores", lambda: False)()))
+        use_gemm_attn = _flag == "always" or (bool(_flag) and on_tc)
         _xflag = getattr(K, "USE_GEMM_EXPERTS", False)
-        xg_wanted = _xflag == "always" or (bool(_xflag) and x.dtype == torch.bfloat16)
+        xg_wanted = _xflag == "always" or (bool(_xflag) and on_tc)
         # row-fused front pass (csrc/rowfused.cu): the row <- latent-token attention runs inside the expert front kernel
         rf_front = (use_gemm_attn and xg_wanted and bool(getattr(K, "USE_ROWFUSED", False)) and K.rf_supported(cfg, x.dtype)
                     and cfg.N % 16 == 0)

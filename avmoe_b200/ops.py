@@ -256,6 +256,72 @@ def split_k_hint(k_rows: int, m: int, n: int) -> int:
     return int(min(want, max(1, k_rows // 256)))
 
 
+# ------------------------------------------------------------------------------------------------ op-level token resampler
+USE_RESAMPLE_OP = True    # one C-ABI call per direction (csrc/op_resample.cu) instead of the op-by-op sequence in functional.py
+
+
+def use_resample_op() -> bool:
+    """The op-level entry is the product path; the per-GEMM / per-kernel profiling modes of bench.py need the individual calls."""
+    return bool(USE_RESAMPLE_OP) and GEMM_PROFILE is None and KERNEL_PROFILE is None
+
+
+def _resample_args(cfg, o, w_tok, b_tok, w_fc):
+    _require_cuda(o, w_tok, b_tok, w_fc)
+    assert o.dim() == 3 and tuple(o.shape[1:]) == (cfg.Nx, cfg.Cx)
+    o = o.contiguous()
+    a = _lib.ResampleArgs()
+    a.dtype, a.BT, a.N, a.Nx, a.C, a.Cx = _dt(o), o.shape[0], cfg.N, cfg.Nx, cfg.C, cfg.Cx
+    a.gemm_impl = _GEMM_IMPL_OVERRIDE
+    w_tok, w_fc, b_tok = w_tok.reshape(cfg.N, cfg.Nx).contiguous(), w_fc.contiguous(), b_tok.contiguous()
+    assert w_tok.dtype == w_fc.dtype == b_tok.dtype == torch.float32
+    a.o, a.w_tok, a.b_tok, a.w_fc = o.data_ptr(), w_tok.data_ptr(), b_tok.data_ptr(), w_fc.data_ptr()
+    return a, (o, w_tok, w_fc, b_tok)
+
+
+def _resample_run(name, a, backward, dev):
+    global LAUNCHES
+    lib = _lib.load()
+    lib.avmoe_resample_workspace_bytes.restype = C.c_int64
+    need = int(lib.avmoe_resample_workspace_bytes(C.byref(a), int(backward)))
+    ws = torch.empty(need + 256, device=dev, dtype=torch.uint8)
+    base = (ws.data_ptr() + 255) // 256 * 256
+    a.workspace, a.workspace_bytes = base, need
+    _lib.check(getattr(lib, name)(C.byref(a), _stream()), name)
+    LAUNCHES += int(a.launches)
+    return ws
+
+
+def resample_fwd_op(cfg, o, w_tok, b_tok, w_fc, b_fc):
+    """o [BT,Nx,Cx] -> (v [BT,N,C], saved) through avmoe_resample_fwd (same contract as functional.resample_fwd)."""
+    a, keep = _resample_args(cfg, o, w_tok, b_tok, w_fc)
+    BT, fc_first = o.shape[0], cfg.Cx > cfg.C
+    b_fc = b_fc.contiguous()
+    v = torch.empty((BT, cfg.N, cfg.C), device=o.device, dtype=o.dtype)
+    mid = torch.empty((BT, cfg.Nx, cfg.C) if fc_first else (BT, cfg.N, cfg.Cx), device=o.device, dtype=o.dtype)
+    s = torch.empty(cfg.C, device=o.device, dtype=torch.float32) if fc_first else None
+    a.b_fc, a.v, a.mid, a.s = b_fc.data_ptr(), v.data_ptr(), mid.data_ptr(), None if s is None else s.data_ptr()
+    _resample_run("avmoe_resample_fwd", a, False, o.device)
+    return v, (fc_first, mid, s)
+
+
+def resample_bwd_op(cfg, o, dv, saved, w_tok, b_tok, w_fc, need_do=True):
+    """Gradients through avmoe_resample_bwd: (do, dw_tok [N,Nx,1,1], db_tok, dw_fc, db_fc) (same contract as functional.resample_bwd)."""
+    fc_first, mid, s = saved
+    a, keep = _resample_args(cfg, o, w_tok, b_tok, w_fc)
+    _require_cuda(dv, mid)
+    assert dv.dtype == o.dtype and mid.is_contiguous()
+    dv = dv.contiguous()
+    f32 = dict(device=o.device, dtype=torch.float32)
+    do = torch.empty(o.shape, device=o.device, dtype=o.dtype) if need_do else None
+    dw_tok, db_tok = torch.empty((cfg.N, cfg.Nx), **f32), torch.empty(cfg.N, **f32)
+    dw_fc, db_fc = torch.empty((cfg.C, cfg.Cx), **f32), torch.empty(cfg.C, **f32)
+    a.mid, a.s, a.dv = mid.data_ptr(), None if s is None else s.data_ptr(), dv.data_ptr()
+    a.d_o = None if do is None else do.data_ptr()
+    a.dw_tok, a.db_tok, a.dw_fc, a.db_fc = dw_tok.data_ptr(), db_tok.data_ptr(), dw_fc.data_ptr(), db_fc.data_ptr()
+    _resample_run("avmoe_resample_bwd", a, True, o.device)
+    return do, dw_tok.reshape(cfg.N, cfg.Nx, 1, 1), db_tok, dw_fc, db_fc
+
+
 def pool(x: torch.Tensor) -> torch.Tensor:
     _require_cuda(x)
     assert x.dim() == 3 and x.is_contiguous()
@@ -469,6 +535,11 @@ def expert_front_bwd(cfg, x, tokp, dzt, z, bn, bn_mode, red1, packs, dpool_x, dx
 
 
 # ------------------------------------------------------------------------------------------------ GEMM-based latent attention helpers
+def fp32_on_tensor_cores() -> bool:
+    """fp32 activations: TF32 tensor-core orchestration iff torch itself is allowed TF32 matmuls (off by default, like torch)."""
+    return bool(torch.backends.cuda.matmul.allow_tf32)
+
+
 USE_GEMM_ATTENTION = True   # latent attention through tcgen05 GEMMs + streaming softmax kernels (functional.py "gemm attention")
 
 

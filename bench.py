@@ -181,8 +181,8 @@ def run_ours(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     dtype = torch.bfloat16 if args.dtype == "bf16" else torch.float32
-    if dtype == torch.float32 and args.f32_gemm == "tf32":
-        ops.USE_GEMM_ATTENTION = ops.USE_GEMM_EXPERTS = "always"
+    if dtype == torch.float32:      # the drop-in follows torch's switch for fp32 inputs (ops.fp32_on_tensor_cores)
+        torch.backends.cuda.matmul.allow_tf32 = args.f32_gemm == "tf32"
     BT = args.clips * args.segments
     model = S.AdapterStack(args.variant, seed=0).to(dev)
     model.train()

@@ -103,6 +103,44 @@ typedef struct {
 int avmoe_gemm(const avmoe_gemm_args* args, avmoe_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
+ * Op-level entry: the token resampler  vis' = fc(conv_adapter(other))  and its backward
+ * (MoEAdapter.conv_adapter + fc, AVMOE/AVE/nets/net_trans_v3.py:445-446,469-471; SURVEY.md §8a row a1, §8b "avmoe_resample_fwd/bwd").
+ * One call issues the whole launch sequence from C++ (weight casts, layout transposes, tcgen05 GEMMs, bias reductions) against a
+ * caller-provided workspace of avmoe_resample_workspace_bytes() bytes (256-byte aligned).  Association by FLOPs:
+ *   Cx > C :  mid = P = o·W_fcᵀ [BT][Nx][C],  v = W_tok·P + b_tok⊗s + 1⊗b_fc  with  s = rowsum(W_fc) [C]
+ *   else   :  mid = U = W_tok·o + b_tok⊗1 [BT][N][Cx],  v = U·W_fcᵀ + 1⊗b_fc.
+ * `mid` (and `s`) are written by the forward and must be handed back unchanged to the backward.  Activations o, v, mid, dv, d_o
+ * have element type `dtype`; weights, biases and their gradients are fp32.  d_o may be NULL (no gradient wanted for `other`).
+ * `launches` returns how many kernels / memsets the call enqueued.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct {
+  int32_t dtype;
+  int32_t BT, N, Nx, C, Cx;
+  int32_t gemm_impl;          /* forwarded to avmoe_gemm_args.impl (0 default, 1 exact SIMT, 2 tensor cores or fail) */
+  const void* o;              /* [BT][Nx][Cx] tokens of the other modality */
+  const float* w_tok;         /* conv_adapter.weight [N][Nx] */
+  const float* b_tok;         /* conv_adapter.bias   [N] */
+  const float* w_fc;          /* fc.weight [C][Cx] */
+  const float* b_fc;          /* fc.bias   [C]  (forward only) */
+  void* v;                    /* forward out [BT][N][C] */
+  void* mid;                  /* forward out / backward in (see above) */
+  float* s;                   /* forward out / backward in: rowsum(W_fc) [C]; required when Cx > C */
+  const void* dv;             /* backward in  [BT][N][C] */
+  void* d_o;                  /* backward out [BT][Nx][Cx] or NULL */
+  float* dw_tok;              /* backward out [N][Nx] */
+  float* db_tok;              /* backward out [N] */
+  float* dw_fc;               /* backward out [C][Cx] */
+  float* db_fc;               /* backward out [C] */
+  void* workspace;
+  int64_t workspace_bytes;
+  int32_t launches;           /* out */
+} avmoe_resample_args;
+
+int64_t avmoe_resample_workspace_bytes(const avmoe_resample_args* args, int backward);
+int avmoe_resample_fwd(avmoe_resample_args* args, avmoe_stream_t stream);
+int avmoe_resample_bwd(avmoe_resample_args* args, avmoe_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
  * Layout helpers feeding the GEMMs, router pooling, bias-gradient reductions.
  * ------------------------------------------------------------------------------------------ */
 /* out[b][c][r] = in[b][r][c]  (dtype pairs: f32->f32, f32->bf16, bf16->bf16) */

@@ -204,3 +204,31 @@ def test_drop_in_returns_token_major_view_and_int64_indices():
     f_a2 = f_a + out.squeeze(-1).permute(0, 2, 1)                                              # net_trans_v3.py:706
     assert f_a2.is_contiguous()
     assert isinstance(idx.squeeze().tolist(), list)                                            # net_trans_v3.py:700
+
+
+def test_fp32_follows_torch_tf32_switch(monkeypatch):
+    """fp32 inputs take the exact fused kernels by default and the TF32 tensor-core orchestration when torch itself is allowed TF32
+    matmuls (torch.backends.cuda.matmul.allow_tf32) -- the same code path the forced-"always" tests pin against the reference."""
+    from avmoe_b200 import ops
+    name = util.golden_names()[0]
+    fx = util.load_golden(name)
+
+    def run():
+        mod = build_module(fx["spec"], fx["state_dict"], kernels=None)
+        return run_module_on_fixture(mod, fx, device="cuda")
+
+    prev = torch.backends.cuda.matmul.allow_tf32
+    try:
+        torch.backends.cuda.matmul.allow_tf32 = False
+        exact = run()
+        torch.backends.cuda.matmul.allow_tf32 = True
+        switched = run()
+        torch.backends.cuda.matmul.allow_tf32 = False
+        monkeypatch.setattr(ops, "USE_GEMM_ATTENTION", "always")
+        monkeypatch.setattr(ops, "USE_GEMM_EXPERTS", "always")
+        forced = run()
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = prev
+    assert torch.equal(switched["out"], forced["out"])
+    assert not torch.equal(switched["out"], exact["out"])
+    compare_to_fixture(switched, fx, 3 * TOL_F32, gtol=GTOL_F32, tensor_core=True)

@@ -226,3 +226,55 @@ def test_resampler_stays_on_tensor_cores_all_stages(stage, modality, dtype, monk
     assert util.rel_err(do.float(), o_.grad) < tol
     assert util.rel_err(dw_tok.reshape(N, Nx), wt_.grad) < tol
     assert util.rel_err(dw_fc, wf_.grad) < tol
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32])
+@pytest.mark.parametrize("stage,modality", [(1, "audio"), (3, "visual"), (4, "audio"), (4, "visual")])
+def test_resample_op_level_entry_matches_op_by_op_sequence(stage, modality, dtype, monkeypatch):
+    """avmoe_resample_fwd / avmoe_resample_bwd (csrc/op_resample.cu: the whole launch sequence issued from C++ against a
+    caller-provided workspace) against the op-by-op sequence of functional.resample_fwd/bwd on the same inputs: same kernels in the
+    same order, so everything that is not a split-K atomic sum must agree bit for bit."""
+    from avmoe_b200 import ops, functional as F, stack as S
+    Cv, Nv, Ca, Na = S.STAGE_SHAPES[stage]
+    (C, N, Cx, Nx) = (Ca, Na, Cv, Nv) if modality == "audio" else (Cv, Nv, Ca, Na)
+    cfg = F.AdapterConfig(C=C, N=N, Cx=Cx, Nx=Nx, r=8, G=2, T=32, Mm=1, Ms=1, use_bn=True, use_gate=True, ln_before=True, ln_post=True)
+    BT = 3
+    o, dv = _mk((BT, Nx, Cx), dtype, 1), _mk((BT, N, C), dtype, 6)
+    w_tok = (_mk((N, Nx, 1, 1), torch.float32, 2) / Nx ** 0.5).contiguous()
+    w_fc = (_mk((C, Cx), torch.float32, 4) / Cx ** 0.5).contiguous()
+    b_tok, b_fc = _mk((N,), torch.float32, 3), _mk((C,), torch.float32, 5)
+    monkeypatch.setattr(ops, "USE_RESAMPLE_OP", False)
+    v0, saved0 = F.resample_fwd(ops, cfg, o, w_tok, b_tok, w_fc, b_fc)
+    g0 = F.resample_bwd(ops, cfg, o, dv, saved0, w_tok, b_tok, w_fc)
+    monkeypatch.setattr(ops, "USE_RESAMPLE_OP", True)
+    before = ops.LAUNCHES
+    v1, saved1 = F.resample_fwd(ops, cfg, o, w_tok, b_tok, w_fc, b_fc)
+    g1 = F.resample_bwd(ops, cfg, o, dv, saved1, w_tok, b_tok, w_fc)
+    assert ops.LAUNCHES - before >= 8, "the op-level entry reports the kernels it enqueued"
+    assert torch.equal(v0, v1) and torch.equal(saved0[1], saved1[1])
+    assert torch.equal(g0[0], g1[0]), "d(other)"
+    tol = 1e-5
+    for a, b, what in zip(g0[1:], g1[1:], ("dw_tok", "db_tok", "dw_fc", "db_fc")):
+        assert a.shape == b.shape, what
+        assert util.rel_err(b, a) < tol, what
+    # no gradient wanted for `other`: d_o = NULL
+    g2 = ops.resample_bwd_op(cfg, o, dv, saved1, w_tok, b_tok, w_fc, need_do=False)
+    assert g2[0] is None and util.rel_err(g2[1], g0[1]) < tol
+
+
+def test_resample_op_rejects_small_workspace():
+    """the C ABI checks the caller-provided workspace instead of writing past it"""
+    import ctypes as C
+    from avmoe_b200 import _lib
+    lib = _lib.load()
+    lib.avmoe_resample_workspace_bytes.restype = C.c_int64
+    a = _lib.ResampleArgs()
+    a.dtype, a.BT, a.N, a.Nx, a.C, a.Cx = 1, 2, 64, 36, 768, 1536
+    need = lib.avmoe_resample_workspace_bytes(C.byref(a), 0)
+    assert need > 0 and lib.avmoe_resample_workspace_bytes(C.byref(a), 1) > 0
+    t = torch.zeros(1 << 20, device="cuda", dtype=torch.uint8)
+    for f in ("o", "w_tok", "b_tok", "w_fc", "b_fc", "v", "mid", "s"):
+        setattr(a, f, t.data_ptr())
+    a.workspace, a.workspace_bytes = t.data_ptr(), 16
+    assert lib.avmoe_resample_fwd(C.byref(a), None) == -1
+    assert b"workspace" in lib.avmoe_last_error()
