@@ -238,6 +238,42 @@ MoEAdapter = MoEAdapterAVE   # default export mirrors the AVE copy
 VARIANTS = {"ave": MoEAdapterAVE, "avqa": MoEAdapterAVQA, "avvp": MoEAdapterAVVP, "s4": MoEAdapterAVS, "ms3": MoEAdapterAVS}
 
 
+def _leaf_like(t: torch.Tensor) -> torch.Tensor:
+    """A fresh LEAF with the sample's shape, strides and values (so the token-major memory under a `[BT,C,N,1]` view is kept)."""
+    out = torch.empty_strided(t.shape, t.stride(), dtype=t.dtype, device=t.device)
+    out.copy_(t.detach())
+    return out.requires_grad_(t.requires_grad or t.is_floating_point())
+
+
+def graph_adapters(modules, sample_inputs, num_warmup_iters: int = 3):
+    """Per-module CUDA graphs for a host model that calls the drop-in modules one by one (the reference's own forward,
+    `net_trans_v3.py:695-720`): an eager call costs ~50-100 Python -> C-ABI launches, a graphed call two graph replays.
+
+    `modules`: one MoEAdapter or a tuple of them IN THE ORDER the host model calls them; `sample_inputs`: the matching
+    `(x, vis_token)` tuple(s) in the call-site layout (`[BT,C,N,1]` views of token-major tensors are fine).  Wraps
+    `torch.cuda.make_graphed_callables`: the modules' `forward` is replaced in place by a graphed forward + backward for this
+    (shape, dtype, training mode); calls in another mode fall back to the eager path.  Returns the module(s).
+
+    The samples are re-created as leaf tensors with the same strides first: a sample that is a *view* of a tensor made on the
+    default stream carries autograd history (an AccumulateGrad node bound to that stream) which the side-stream capture of the
+    backward would have to synchronise with -- that invalidates the capture (`cudaErrorStreamCaptureInvalidated`).
+    Limits are torch's: positional tensor arguments only, every output a tensor (AVE / AVQA adapters; the AVVP / AVS forwards return a
+    python `0.` for a disabled load-balancing loss), no `residual=` / `noise=` keywords, outputs are static buffers overwritten by
+    the next call."""
+    single = isinstance(modules, torch.nn.Module)
+    mods = (modules,) if single else tuple(modules)
+    samples = (tuple(sample_inputs),) if single else tuple(tuple(a) for a in sample_inputs)
+    if len(mods) != len(samples):
+        raise ValueError("graph_adapters: one sample input tuple per module")
+    for args in samples:
+        for a in args:
+            if not (torch.is_tensor(a) and a.is_cuda):
+                raise RuntimeError("graph_adapters: sample inputs must be CUDA tensors (there is no CPU path)")
+    leaves = tuple(tuple(_leaf_like(a) for a in args) for args in samples)
+    graphed = torch.cuda.make_graphed_callables(mods, leaves, num_warmup_iters=num_warmup_iters)
+    return graphed[0] if single else graphed
+
+
 def patch_reference_module(module, variant: str) -> None:
     """Swap the adapter classes inside an imported reference model module (e.g. ``nets.net_trans_v3``) so that the
     unmodified model builders construct the CUDA drop-ins:  ``patch_reference_module(nets.net_trans_v3, 'ave')``."""

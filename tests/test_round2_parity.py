@@ -462,3 +462,51 @@ def test_mha_dropout_default_draw_cuda():
     assert (a - b).abs().max().item() > 0 and torch.equal(c, d)
     assert util.fro_err(a, c) < 1.0       # dropped attention: a different, but not an unrelated, output
 
+
+
+# ------------------------------------------------------------------------------------------------ per-module CUDA graphs
+@pytest.mark.gpu
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32])
+def test_graphed_adapter_matches_eager(dtype):
+    """adapters.graph_adapters: a drop-in whose forward + backward replay per-module CUDA graphs gives the same bits as the eager
+    launch path (outputs, expert selection, input and parameter gradients), call after call with fresh inputs."""
+    from avmoe_b200 import stack as S
+    from avmoe_b200.adapters import graph_adapters
+    stage, modality, BT = 3, "audio", 2
+    Cv, Nv, Ca, Na = S.STAGE_SHAPES[stage]
+    C, N, Cx, Nx = Ca, Na, Cv, Nv
+
+    def build():
+        torch.manual_seed(0)
+        m = S.build_adapter("ave", stage, modality).cuda().train()
+        with torch.no_grad():
+            for n, p in m.named_parameters():
+                if n.endswith("gate") or n.endswith("gate_av"):
+                    p.fill_(0.5)
+        return m
+
+    def tokens(seed):
+        g = torch.Generator().manual_seed(seed)
+        x = (torch.randn(BT, N, C, generator=g) + torch.randn(BT, 1, C, generator=g)).cuda().to(dtype)
+        o = (torch.randn(BT, Nx, Cx, generator=g) + torch.randn(BT, 1, Cx, generator=g)).cuda().to(dtype)
+        return x, o
+
+    eager, graphed = build(), build()
+    x0, o0 = tokens(1)
+    graph_adapters(graphed, (x0.permute(0, 2, 1).unsqueeze(-1), o0.permute(0, 2, 1).unsqueeze(-1)))
+    for seed in (2, 3):
+        res = []
+        for m in (eager, graphed):
+            m.zero_grad(set_to_none=True)
+            x, o = tokens(seed)
+            x.requires_grad_(); o.requires_grad_()
+            out, idx = m(x.permute(0, 2, 1).unsqueeze(-1), o.permute(0, 2, 1).unsqueeze(-1))
+            (out.float() * 0.5).sum().backward()
+            res.append((out.detach().clone(), idx.clone(), x.grad.clone(), o.grad.clone(), {k: p.grad.clone() for k, p in m.named_parameters() if p.grad is not None}))
+        (oe, ie, dxe, doe, pe), (og, ig, dxg, dog, pg) = res
+        assert torch.equal(ie, ig) and torch.equal(oe, og)
+        # gradients: same kernels, but the fp32 kernels and the reductions accumulate with atomics -> equal up to summation order
+        assert util.rel_err(dxg, dxe, floor=1e-12) < 1e-4 and util.rel_err(dog, doe, floor=1e-12) < 1e-4
+        assert pe.keys() == pg.keys()
+        for k in pe:   # split-K / statistic reductions use atomics: equal up to summation order
+            assert util.rel_err(pg[k], pe[k], floor=1e-6) < 1e-4, k

@@ -33,6 +33,40 @@ def main():
         t2 = time.perf_counter()
         out[f"BT{BT}"] = {"enqueue_ms_per_step": (t1 - t0) / n * 1e3, "wall_ms_per_step": (t2 - t0) / n * 1e3, "launches_per_step": ops.LAUNCHES / n}
         del model, tok
+    # a host model that calls the drop-in modules one by one (the reference's forward): eager launch path vs per-module CUDA graphs
+    try:
+        from avmoe_b200.adapters import graph_adapters
+        for stage, modality in ((3, "audio"), (1, "visual")):
+            for BT in (20,):
+                Cv, Nv, Ca, Na = S.STAGE_SHAPES[stage]
+                (C, N, Cx, Nx) = (Ca, Na, Cv, Nv) if modality == "audio" else (Cv, Nv, Ca, Na)
+                x = torch.randn(BT, N, C, device=dev).bfloat16()
+                o = torch.randn(BT, Nx, Cx, device=dev).bfloat16()
+                rec = {}
+                for kind in ("eager", "graphed"):
+                    mod = S.build_adapter("ave", stage, modality).to(dev).train()
+                    if kind == "graphed":
+                        graph_adapters(mod, (x.permute(0, 2, 1).unsqueeze(-1), o.permute(0, 2, 1).unsqueeze(-1)))
+
+                    def call():
+                        xx, oo = x.detach().requires_grad_(), o.detach().requires_grad_()
+                        res = mod(xx.permute(0, 2, 1).unsqueeze(-1), oo.permute(0, 2, 1).unsqueeze(-1))
+                        res[0].float().sum().backward()
+
+                    for _ in range(3):
+                        call()
+                    torch.cuda.synchronize()
+                    t0 = time.perf_counter()
+                    n = 20
+                    for _ in range(n):
+                        call()
+                    t1 = time.perf_counter()
+                    torch.cuda.synchronize()
+                    t2 = time.perf_counter()
+                    rec[kind] = {"enqueue_ms_per_call": (t1 - t0) / n * 1e3, "wall_ms_per_call": (t2 - t0) / n * 1e3}
+                out[f"module_ave_{stage}_{modality}_BT{BT}"] = rec
+    except Exception as ex:
+        out["module_graph_error"] = str(ex)[:300]
     print(json.dumps(out))
     os.makedirs("gpurun_out", exist_ok=True)
     json.dump(out, open("gpurun_out/host_overhead.json", "w"), indent=1)
