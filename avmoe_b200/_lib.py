@@ -41,6 +41,14 @@ class ResampleArgs(C.Structure):
     ]
 
 
+class RfTokArgs(C.Structure):
+    """avmoe_rf_tok_args (include/avmoe_b200.h): row-fused passes of the latent-token update."""
+    _fields_ = [
+        ("BT", C.c_int32), ("Nk", C.c_int32), ("C", C.c_int32), ("T", C.c_int32), ("Tp", C.c_int32), ("per_sample", C.c_int32),
+        ("kv", C.c_void_p), ("pack", C.c_void_p), ("part", C.c_void_p), ("A12", C.c_void_p), ("Dt", C.c_void_p), ("lse", C.c_void_p),
+    ]
+
+
 def lib_path() -> str:
     return _build.LIB_PATH
 

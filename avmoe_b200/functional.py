@@ -227,6 +227,11 @@ def resample_bwd(K, cfg: AdapterConfig, o: torch.Tensor, dv: torch.Tensor, saved
 # GEMM-based latent attention (net_trans_v3.py:379-390): every contraction on the tcgen05 GEMM, streaming softmax kernels
 # between them on token-major logits.  [.,T] matrices are stored with a row pitch of Tp = round8(T) (16-byte pitches for TMA).
 # -------------------------------------------------------------------------------------------------
+def A12_lo_offset(T: int) -> int:
+    """column of the bf16 rounding-residual block inside A12 [.., 2*Tp]: Tp = T rounded up to 8"""
+    return (T + 7) // 8 * 8
+
+
 def gemm_latent_fwd(K, kv: torch.Tensor, tok: torch.Tensor):
     """tok' = tok + softmax_Nk(tok·kvᵀ)·kv.   kv [BT,Nk,C], tok [T,C] fp32 -> (tok' fp32 [BT,T,C], K.split_operand(tok'),
     A12) where A12 [BT,Nk,2Tp] holds A1ᵀ (probabilities, token-major) in columns [0,T) and is reused by the backward.
@@ -234,9 +239,12 @@ def gemm_latent_fwd(K, kv: torch.Tensor, tok: torch.Tensor):
     BT, Nk, C = kv.shape
     T = tok.shape[0]
     dt = kv.dtype
-    tok_s, off, _ = K.split_operand(tok, dt)                                             # [W,C]
-    S1 = K.gemm(kv.reshape(BT * Nk, C), tok_s, out_dtype=torch.float32)                  # token-major logits kv_n · tok_t  [BT*Nk,W]
-    A12, _, p_lo = K.softmax_cols(S1.reshape(BT, Nk, -1), T, off, dt)
+    if getattr(K, "rf_tok_supported", lambda *a: False)(kv, T):      # logits recomputed per tile, never stored (csrc/rf_tokens.cu)
+        A12, p_lo = K.rf_tok_probs(kv, tok), A12_lo_offset(T)
+    else:
+        tok_s, off, _ = K.split_operand(tok, dt)                                         # [W,C]
+        S1 = K.gemm(kv.reshape(BT * Nk, C), tok_s, out_dtype=torch.float32)              # token-major logits kv_n · tok_t  [BT*Nk,W]
+        A12, _, p_lo = K.softmax_cols(S1.reshape(BT, Nk, -1), T, off, dt)
     A1 = A12 if p_lo else A12[:, :, :T]                                                  # bf16: hi and residual column blocks
     R = K.bgemm(A1, kv, a_kmajor=False, b_kmajor=False, out_dtype=torch.float32)         # A1·kv   [BT,T (or 2Tp),C]
     tokp = K.tile_add(R, tok, p_lo)
@@ -273,8 +281,11 @@ def gemm_latent_bwd(K, kv, tok, tokp, A12, dtokp, T: int, dkv_bias=None):
     f32 = torch.float32
     Dt = K.latent_dots(dtokp, tokp, tok)                                                 # sum_c dR·R  [BT,T]
     dR_s, off, dR_lp = K.split_operand(dtokp, dt)                                              # [BT,W,C]
-    dA1 = K.bgemm(kv, dR_s, out_dtype=f32)                                               # kv[b]·dR[b]ᵀ  (token-major)  [BT,Nk,W]
-    K.softmax_cols_bwd(A12, dA1, Dt, T, off)                                             # A12[:, :, Tp:Tp+T] = dS1ᵀ
+    if getattr(K, "rf_tok_supported", lambda *a: False)(kv, T):
+        K.rf_tok_ds(kv, dtokp, A12, Dt, T)                                               # dA1 recomputed per tile; A12[:, :, Tp:Tp+T] = dS1ᵀ
+    else:
+        dA1 = K.bgemm(kv, dR_s, out_dtype=f32)                                           # kv[b]·dR[b]ᵀ  (token-major)  [BT,Nk,W]
+        K.softmax_cols_bwd(A12, dA1, Dt, T, off)                                         # A12[:, :, Tp:Tp+T] = dS1ᵀ
     B12 = torch.zeros((BT, 2 * Tp, C), device=kv.device, dtype=dt)                       # [dR ; tok] stacked along K
     B12[:, :T] = dR_lp
     B12[:, Tp:Tp + T] = K.cast_to(tok, dt)

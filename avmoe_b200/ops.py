@@ -22,11 +22,11 @@ _GEMM_IMPL_OVERRIDE = int(_os.environ.get("AVMOE_GEMM_IMPL", "0"))
 LAUNCHES = 0
 GEMM_PROFILE = None   # set to a list to collect (start_event, end_event, flops, bytes, tag) per tensor-core GEMM launch
 
-_KERNELS_PER_CALL = {"transpose": 1, "cast": 1, "pool": 1, "reduce_bias": 1, "rowsum": 1, "broadcast_rows": 1, "router_fwd": 1,
-                     "router_bwd": 4, "lb_loss_fwd": 1, "lb_loss_bwd": 1, "latent_fwd": 2, "latent_bwd": 1, "expert_front_fwd": 1,
+_KERNELS_PER_CALL = {"transpose": 1, "cast": 1, "pool": 1, "reduce_bias": 1, "rowsum": 1, "broadcast_rows": 1, "router_fwd": 2,
+                     "router_bwd": 5, "lb_loss_fwd": 1, "lb_loss_bwd": 1, "latent_fwd": 2, "latent_bwd": 1, "expert_front_fwd": 1,
                      "bn1_finalize": 1, "bn2_finalize": 1, "bn_moments": 1, "expert_back_fwd": 1, "expert_back_bwd_stats": 1,
                      "expert_back_bwd": 1, "expert_front_bwd": 1, "selfattn_nxn_fwd": 2, "selfattn_nxn_bwd": 2, "mha_attn_fwd": 1,
-                     "mha_attn_bwd": 1, "xg_bn1_bwd": 2}
+                     "mha_attn_bwd": 1, "xg_bn1_bwd": 2, "rf_tok_probs": 2}
 
 
 def _dt(t: torch.Tensor) -> int:
@@ -871,6 +871,58 @@ def rf_pack_tokens(tokp: torch.Tensor):
     s2 = rf_pack_b(tokp, nb=BT, bstride=T * Cc, stride_n=Cc, stride_k=1, Nn=T, K=Cc, hi_lo=True, Nn_pad=tp16)
     xr = rf_pack_b(tokp, nb=BT, bstride=T * Cc, stride_n=1, stride_k=Cc, Nn=Cc, K=T)
     return s2, xr
+
+
+USE_ROWFUSED_TOKENS = _os.environ.get("AVMOE_RF_TOKENS", "1") != "0"   # latent-token update: logits recomputed per tile instead of the S1 / dA1 GEMMs + column-softmax passes
+# Below ~64 row tiles per sample the passes are prologue-bound (two tiles per warp) and the GEMM + column-softmax form wins:
+# stage-3 call (Nk = 256): 80 + 70 us fused vs 33 + 28 us; stage-1 call (Nk = 4096): 124 + 93 us fused vs 313 + 203 us.
+_RF_TOK_MIN_NK = int(_os.environ.get("AVMOE_RF_TOK_MIN_NK", "1024"))
+
+
+def rf_tok_supported(kv: torch.Tensor, T: int) -> bool:
+    """row-fused token-update passes (csrc/rf_tokens.cu): bf16 kv [BT,Nk,C], Nk % 16 == 0, C % 16 == 0, covered latent-token counts"""
+    if not USE_ROWFUSED_TOKENS or kv.dtype != torch.bfloat16 or kv.dim() != 3 or kv.shape[0] > 65535 or kv.shape[1] < _RF_TOK_MIN_NK:
+        return False
+    return bool(_lib.load().avmoe_rf_tok_supported(int(kv.shape[1]), int(kv.shape[2]), int(T)))
+
+
+def _rf_tok_args(kv, T, pack, A12, per_sample):
+    _require_cuda(kv, pack, A12)
+    assert kv.is_contiguous() and A12.is_contiguous() and A12.dtype == torch.bfloat16
+    BT, Nk, Cc = kv.shape
+    a = _lib.RfTokArgs()
+    a.BT, a.Nk, a.C, a.T, a.Tp, a.per_sample = BT, Nk, Cc, T, round8(T), int(per_sample)
+    assert A12.shape == (BT, Nk, 2 * a.Tp)
+    a.kv, a.pack, a.A12 = kv.data_ptr(), pack.data_ptr(), A12.data_ptr()
+    return a
+
+
+def rf_tok_probs(kv: torch.Tensor, tok: torch.Tensor):
+    """A1ᵀ = softmax over the Nk rows of kv·tokᵀ, written as bf16 hi | lo column blocks: A12 [BT,Nk,2Tp] (same layout as softmax_cols)."""
+    BT, Nk, Cc = kv.shape
+    T = tok.shape[0]
+    Tp = round8(T)
+    tok = tok.contiguous()
+    pack = rf_pack_b(tok, nb=1, bstride=T * Cc, stride_n=Cc, stride_k=1, Nn=T, K=Cc, hi_lo=True, Nn_pad=Tp)
+    A12 = torch.empty((BT, Nk, 2 * Tp), device=kv.device, dtype=torch.bfloat16)
+    nparts = int(_lib.load().avmoe_rf_tok_parts(BT, Nk))
+    part = torch.empty((BT, nparts, 2, Tp), device=kv.device, dtype=torch.float32)
+    a = _rf_tok_args(kv, T, pack, A12, False)
+    a.part = part.data_ptr()
+    _lib_call("rf_tok_probs", C.byref(a), _stream(), _bytes=2 * _nbytes(kv) + _nbytes(A12))
+    return A12
+
+
+def rf_tok_ds(kv: torch.Tensor, dR: torch.Tensor, A12: torch.Tensor, Dt: torch.Tensor, T: int):
+    """A12[:, :, Tp:Tp+T] = A1ᵀ ∘ (kv·dRᵀ − Dt)   (dR [BT,T,C] fp32, Dt [BT,T] fp32); in place, like softmax_cols_bwd"""
+    BT, Nk, Cc = kv.shape
+    Tp = round8(T)
+    dR = dR.contiguous()
+    pack = rf_pack_b(dR, nb=BT, bstride=T * Cc, stride_n=Cc, stride_k=1, Nn=T, K=Cc, hi_lo=True, Nn_pad=Tp)
+    a = _rf_tok_args(kv, T, pack, A12, True)
+    Dt = Dt.contiguous()
+    a.Dt = Dt.data_ptr()
+    _lib_call("rf_tok_ds", C.byref(a), _stream(), _bytes=_nbytes(kv) + _nbytes(A12))
 
 
 def _rf_front_args(cfg, packs, egr, toks, prep, *, BT):

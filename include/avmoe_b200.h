@@ -428,6 +428,30 @@ int avmoe_rf_front_bwd(const avmoe_rf_front_args* a, avmoe_stream_t stream);
 int avmoe_rf_supported(int C, int Cr, int E, int T);
 
 /* ------------------------------------------------------------------------------------------
+ * Row-fused passes of the latent-token update  tok' = tok + softmax_Nk(tok · kvᵀ) · kv  (net_trans_v3.py:379-384): the logits are
+ * recomputed per 16-row tile on the tensor cores and never stored (csrc/rf_tokens.cu).
+ *   avmoe_rf_tok_probs: A12[b][n][0..T) = bf16(A1ᵀ), A12[b][n][Tp..Tp+T) = its bf16 rounding residual; `pack` = the shared latent
+ *                       tokens [T][C] as a packed hi/lo operand (avmoe_rf_pack_b, nb = 1, Nn_pad = Tp); `part` = workspace of
+ *                       BT * avmoe_rf_tok_parts(BT, Nk) * 2 * Tp floats; `lse` [BT][T] optional output.
+ *   avmoe_rf_tok_ds:    A12[b][n][Tp..Tp+T) = A1ᵀ ∘ (kv · dRᵀ − Dt[b][t]); `pack` = dR [BT][T][C] packed per sample (nb = BT), per_sample = 1.
+ * kv [BT][Nk][C] bf16, Nk % 16 == 0, C % 16 == 0, C <= 384, Tp = T rounded up to 8; avmoe_rf_tok_supported says whether a geometry is covered.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct {
+  int32_t BT, Nk, C, T, Tp;
+  int32_t per_sample;        /* 0: one packed operand shared by all samples; 1: one per sample */
+  const void* kv;
+  const void* pack;
+  float* part;
+  void* A12;                 /* [BT][Nk][2*Tp] bf16 */
+  const float* Dt;           /* [BT][T] (backward) */
+  float* lse;                /* [BT][T] or NULL (forward) */
+} avmoe_rf_tok_args;
+int avmoe_rf_tok_supported(int Nk, int C, int T);
+int avmoe_rf_tok_parts(int BT, int Nk);
+int avmoe_rf_tok_probs(const avmoe_rf_tok_args* a, avmoe_stream_t stream);
+int avmoe_rf_tok_ds(const avmoe_rf_tok_args* a, avmoe_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
  * Fused Adam on the flat parameter buffer (torch.optim.Adam semantics, AVMOE/AVE/main_trans_v3.py:311-323: default betas/eps,
  * L2 weight decay added to the gradient, bias correction by `step` >= 1).  p, g, m, v: n fp32 each (16-byte aligned).
  * grad_scale multiplies the gradient first (1/world of the data-parallel average, 1/accum of gradient accumulation);

@@ -305,3 +305,65 @@ def test_rf_front_bwd(geom, ln):
             assert _fro(lat[e][0][:, :, :T].float(), lat_ref[e][0][:, :, :T].float()) < tol, e
             assert _fro(lat[e][1][:, :, :T].float(), lat_ref[e][1][:, :, :T].float()) < 2 * tol, e
             assert lat[e][0][:, :, T:].abs().sum().item() == 0
+
+
+# ------------------------------------------------------------------------------------------------ latent-token update passes
+TOK_CASES = [(3, 256, 96, 32), (2, 4096, 96, 32), (2, 144, 384, 32), (2, 64, 384, 87), (2, 576, 192, 2), (1, 2304, 192, 32)]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("BT,Nk,C,T", TOK_CASES)
+def test_rf_token_update_passes(BT, Nk, C, T, monkeypatch):
+    """csrc/rf_tokens.cu against plain fp32 torch on the same bf16 kv: A1ᵀ = softmax over the Nk rows of kv·tokᵀ written as bf16
+    hi | lo blocks (hi + lo carries ~16 bits), and the backward's dS1ᵀ = A1ᵀ ∘ (kv·dRᵀ − D) written over the lo block."""
+    from avmoe_b200 import ops
+    from tests import util
+    g = torch.Generator().manual_seed(5)
+    kv = (torch.randn(BT, Nk, C, generator=g) + torch.randn(BT, 1, C, generator=g)).cuda().bfloat16()
+    tok = torch.rand(T, C, generator=g).cuda()                       # my_tokens ~ U[0,1) like the reference (net_trans_v3.py:315)
+    monkeypatch.setattr(ops, "_RF_TOK_MIN_NK", 16)                    # the size threshold is a speed choice; the kernels cover every Nk % 16 == 0
+    assert ops.rf_tok_supported(kv, T)
+    Tp = ops.round8(T)
+    A12 = ops.rf_tok_probs(kv, tok)
+    assert A12.shape == (BT, Nk, 2 * Tp)
+    S = kv.float() @ tok.t()                                          # [BT,Nk,T]
+    ref = torch.softmax(S, dim=1)
+    got = A12[:, :, :T].float() + A12[:, :, Tp:Tp + T].float()
+    assert util.rel_err(got, ref) < 2e-3, "probabilities (hi + lo)"
+    assert util.rel_err(A12[:, :, :T].float(), ref) < 6e-3, "hi block alone is the bf16 rounding"
+    if Tp > T:
+        assert A12[:, :, T:Tp].abs().sum() == 0 and A12[:, :, Tp + T:].abs().sum() == 0, "padding columns are zero"
+    assert util.rel_err(got.sum(dim=1), torch.ones(BT, T, device="cuda")) < 2e-3
+    # backward pass
+    dR = torch.randn(BT, T, C, generator=g).cuda()
+    Dt = torch.randn(BT, T, generator=g).cuda()
+    hi = A12[:, :, :T].float().clone()
+    ops.rf_tok_ds(kv, dR, A12, Dt, T)
+    dA = kv.float() @ dR.transpose(1, 2)                              # [BT,Nk,T]
+    want = hi * (dA - Dt[:, None, :])
+    assert torch.equal(A12[:, :, :T].float(), hi), "the probability block is left untouched"
+    assert util.rel_err(A12[:, :, Tp:Tp + T].float(), want) < 1e-2
+    if Tp > T:
+        assert A12[:, :, Tp + T:].abs().sum() == 0
+
+
+@pytest.mark.gpu
+def test_latent_token_update_fused_matches_gemm_form(monkeypatch):
+    """functional.gemm_latent_fwd/bwd with the row-fused token passes against the GEMM + column-softmax form on the same inputs"""
+    from avmoe_b200 import ops, functional as F
+    from tests import util
+    g = torch.Generator().manual_seed(11)
+    BT, Nk, C, T = 4, 1024, 192, 32
+    kv = (torch.randn(BT, Nk, C, generator=g) + torch.randn(BT, 1, C, generator=g)).cuda().bfloat16()
+    tok = torch.rand(T, C, generator=g).cuda()
+    dtokp = torch.randn(BT, T, C, generator=g).cuda()
+    res = []
+    for fused in (False, True):
+        monkeypatch.setattr(ops, "USE_ROWFUSED_TOKENS", fused)
+        tokp, tokp_op, A12 = F.gemm_latent_fwd(ops, kv, tok)
+        dkv, dtok = F.gemm_latent_bwd(ops, kv, tok, tokp, A12, dtokp.clone(), T)
+        res.append((tokp, dkv.float(), dtok))
+    (t0, k0, d0), (t1, k1, d1) = res
+    assert util.rel_err(t1, t0) < 1e-3
+    assert util.rel_err(k1, k0) < 2e-2 and util.fro_err(k1, k0) < 1e-2
+    assert util.rel_err(d1, d0) < 5e-3
