@@ -21,7 +21,7 @@
  * lines of their own files):
  *   avmoe_gemm / avmoe_resample_*  <- MoEAdapter.conv_adapter + fc      net_trans_v3.py:445-446,469-471
  *   avmoe_pool / avmoe_router_*    <- mean-pool, router MLP, softmax    net_trans_v3.py:460-466,472-479
- *   avmoe_latent_*                 <- ExpertAdapter latent attention    net_trans_v3.py:379-384
+ *   avmoe_latent_* / avmoe_rf_tok_* <- ExpertAdapter latent attention   net_trans_v3.py:379-384
  *   avmoe_expert_front_*           <- token<-latent attention, gate_av,
  *                                     ln_before, grouped down_sampler   net_trans_v3.py:386-395
  *   avmoe_bn_*                     <- bn1 / bn2 (train + eval)          net_trans_v3.py:397-403
@@ -157,7 +157,7 @@ int avmoe_rowsum(const float* w, float* out, int rows, int cols, avmoe_stream_t 
 int avmoe_broadcast_rows(const float* src, void* out, int BT, int N, int C, int dtype, avmoe_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
- * Router (fp32, one CTA per sample, fixed reduction order) and the load-balancing loss.
+ * Router (fp32, fixed reduction order; the wide first layer is tiled over samples) and the load-balancing loss.
  *   rin = [mean_N x | mean_N vis'] ; probs = softmax(W4 relu(W2 relu(W0 rin + b0) + b2) + b4 (+noise))
  *   idx = first argmax of probs (int64, bit-exact contract).
  * ------------------------------------------------------------------------------------------ */
