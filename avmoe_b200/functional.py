@@ -286,7 +286,7 @@ def gemm_latent_bwd(K, kv, tok, tokp, A12, dtokp, T: int, dkv_bias=None):
     else:
         dA1 = K.bgemm(kv, dR_s, out_dtype=f32)                                           # kv[b]·dR[b]ᵀ  (token-major)  [BT,Nk,W]
         K.softmax_cols_bwd(A12, dA1, Dt, T, off)                                         # A12[:, :, Tp:Tp+T] = dS1ᵀ
-    B12 = torch.zeros((BT, 2 * Tp, C), device=kv.device, dtype=dt)                       # [dR ; tok] stacked along K
+    B12 = (torch.empty if Tp == T else torch.zeros)((BT, 2 * Tp, C), device=kv.device, dtype=dt)   # [dR ; tok] stacked along K (padding rows zero)
     B12[:, :T] = dR_lp
     B12[:, Tp:Tp + T] = K.cast_to(tok, dt)
     dkv = K.bgemm(A12, B12, b_kmajor=False, col_bias=dkv_bias)                           # A1ᵀ·dR + dS1ᵀ·tok (+ bias)  [BT,Nk,C]

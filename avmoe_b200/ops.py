@@ -580,7 +580,8 @@ def split_operand(t: torch.Tensor, dtype: torch.dtype):
         buf[..., :T, :] = t
         return buf, 0, buf[..., :T, :]
     assert dtype == torch.bfloat16
-    buf = torch.zeros(lead + (2 * Tp, Cc), device=t.device, dtype=dtype)
+    alloc = torch.empty if Tp == T else torch.zeros       # cast_split writes rows [0,T) and [Tp,Tp+T): only padding rows need the zero fill
+    buf = alloc(lead + (2 * Tp, Cc), device=t.device, dtype=dtype)
     groups = t.numel() // (T * Cc)
     _lib_call("cast_split", _ptr(t), _ptr(buf), C.c_int64(groups), T, Tp, Cc, _stream())
     return buf, Tp, buf[..., :T, :]
@@ -591,7 +592,9 @@ def softmax_cols(S: torch.Tensor, T: int, off_lo: int, dtype: torch.dtype):
     [0,T), rest zero), lse [BT,T]."""
     BT, Nk, W = S.shape
     Tp = round8(T)
-    A12 = torch.zeros((BT, Nk, 2 * Tp), device=S.device, dtype=dtype)
+    # bf16 with Tp == T: the kernel writes every column (hi | lo blocks); otherwise padding / the second block start as zeros
+    alloc = torch.empty if (Tp == T and dtype == torch.bfloat16) else torch.zeros
+    A12 = alloc((BT, Nk, 2 * Tp), device=S.device, dtype=dtype)
     lse = torch.empty((BT, T), device=S.device, dtype=torch.float32)
     p_lo = Tp if dtype == torch.bfloat16 else 0      # bf16: rounding residual of A1 in columns [Tp,Tp+T) (until the backward reuses them)
     _lib_call("softmax_cols", _ptr(S), _ptr(A12), _ptr(lse), BT, Nk, T, W, 2 * Tp, off_lo, p_lo, _dt(A12), _stream(),
